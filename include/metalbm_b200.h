@@ -1,0 +1,181 @@
+/* metalbm_b200.h -- C-ABI of the B200-native fused collide-and-stream (pull) step.
+ *
+ * This is the drop-in boundary for ONE hot path of gtauzin/metaLBM: the per-step
+ * work of `lbm::Algorithm<T, AlgorithmType::Pull, Architecture::GPU, MemoryLayout::SoA,
+ * PartitionningType::OneD, CommunicationType::MPI, Overlapping>` and what it calls.
+ * Every entry point names the reference interface it replaces (file:line under the
+ * reference tree).  The reference's C++ template spellings are kept by the header-only
+ * shim `include/metaLBM_b200/`, which forwards to these functions.
+ *
+ * Conventions
+ *  - plain C types only; one opaque `mlbm_ctx` per rank == per GPU (the reference's
+ *    "one MPI rank <-> one GPU", CUDAInitializer.h:23-26);
+ *  - every function returns 0 on success or a negative `mlbm_status`; the message of the
+ *    last failure on the calling thread is `mlbm_last_error()`.  The reference prints and
+ *    exit(-1)s (Commons.h:6-28); the C++ shim re-applies that convention;
+ *  - a context is not thread-safe; all calls for one context come from one host thread
+ *    (same as the reference);
+ *  - there is NO CPU fallback: creating a context without a usable CUDA device fails.
+ */
+#ifndef METALBM_B200_H
+#define METALBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MLBM_ABI_VERSION 1
+
+typedef struct mlbm_ctx mlbm_ctx;
+
+typedef enum mlbm_status {
+  MLBM_OK = 0,
+  MLBM_ERR_INVALID = -1,      /* bad argument / unsupported combination */
+  MLBM_ERR_CUDA = -2,         /* CUDA runtime failure (or no device)     */
+  MLBM_ERR_COMM = -3,         /* NCCL / peer-access failure              */
+  MLBM_ERR_STATE = -4,        /* call made in the wrong state            */
+  MLBM_ERR_NOMEM = -5
+} mlbm_status;
+
+/* LatticeType (Options.h:13-14, descriptors Lattice.h:80,145,460,535,614) */
+typedef enum mlbm_lattice {
+  MLBM_D2Q5 = 0, MLBM_D2Q9 = 1, MLBM_D3Q15 = 2, MLBM_D3Q19 = 3, MLBM_D3Q27 = 4
+} mlbm_lattice;
+
+/* CollisionType (Options.h:35-38; Collision.h:103-180 BGK, :182-376 ELBM, :684-724 ForcedNR_ELBM) */
+typedef enum mlbm_collision {
+  MLBM_BGK = 0, MLBM_ELBM = 1, MLBM_FORCED_NR_ELBM = 2
+} mlbm_collision;
+
+/* EquilibriumType (Options.h:33; Equilibrium.h:14-34 TruncationMa3, :36-126 Exact) */
+typedef enum mlbm_equilibrium {
+  MLBM_TRUNCATION_MA3 = 0, MLBM_EXACT = 1
+} mlbm_equilibrium;
+
+/* ForcingSchemeType (Options.h:40; ForcingScheme.h:41-198) */
+typedef enum mlbm_forcing_scheme {
+  MLBM_SCHEME_NONE = 0, MLBM_GUO = 1, MLBM_SHAN_CHEN = 2, MLBM_EXACT_DIFFERENCE = 3
+} mlbm_forcing_scheme;
+
+/* ForceType (Options.h:41-43; Force.h:104-292) */
+typedef enum mlbm_force {
+  MLBM_FORCE_NONE = 0, MLBM_FORCE_CONSTANT = 1, MLBM_FORCE_SINUSOIDAL = 2, MLBM_FORCE_KOLMOGOROV = 3
+} mlbm_force;
+
+/* `dataT` (Input_prod.in:10).  F32 is FP32 storage of populations and fields with the moments,
+ * forcing and the entropic solve carried in FP64 registers (the reference never ran FP32). */
+typedef enum mlbm_dtype { MLBM_F64 = 0, MLBM_F32 = 1 } mlbm_dtype;
+
+/* Overlapping (Options.h:20): Off = exchange, then one kernel over the slab (Algorithm.h:326-358);
+ * On = boundary planes first, exchange overlapped with the bulk kernel (the intent of Algorithm.h:392-447). */
+typedef enum mlbm_overlap { MLBM_OVERLAP_OFF = 0, MLBM_OVERLAP_ON = 1 } mlbm_overlap;
+
+/* The compile-time globals of src/Input_*.in that the path reads, as one runtime struct.
+ * Kernels stay compile-time specialised; the combination is dispatched once in mlbm_create. */
+typedef struct mlbm_config {
+  int32_t abi_version;        /* MLBM_ABI_VERSION */
+  int32_t lattice;            /* mlbm_lattice        <- latticeT        */
+  int32_t collision;          /* mlbm_collision      <- collisionT      */
+  int32_t equilibrium;        /* mlbm_equilibrium    <- equilibriumT    */
+  int32_t forcing_scheme;     /* mlbm_forcing_scheme <- forcingSchemeT  */
+  int32_t force;              /* mlbm_force          <- forceT          */
+  int32_t dtype;              /* mlbm_dtype          <- dataT           */
+  int32_t overlap;            /* mlbm_overlap        <- overlappingT    */
+  int32_t global_length[3];   /* globalLengthX/Y/Z; unused trailing dimensions = 1 */
+  int32_t rank;               /* MPIInit::rank[d::X]  (MPIInitializer.h:53)       */
+  int32_t nranks;             /* numProcs; must divide global_length[0] (Domain.h:22-24) */
+  int32_t device;             /* CUDA ordinal, or -1 = rank % device count (CUDAInitializer.h:23-26) */
+  int32_t variant;            /* 0 = default kernel; other values select experimental kernels (bench only) */
+  double tau;                 /* relaxationTime  */
+  double force_amplitude[3];  /* forceAmplitude  */
+  double force_wavelength[3]; /* forceWaveLength */
+} mlbm_config;
+
+const char* mlbm_last_error(void);
+int mlbm_abi_version(void);
+
+/* Algorithm ctor (Algorithm.h:69-95, 225-240, 317-324) + Distribution ctor (Distribution.h:25-28) +
+ * FieldList ctor (FieldList.h:44-63): allocates the ping-pong SoA population pair and the
+ * density / velocity / alpha / force fields on the device, alpha initialised to 2 (Initialize.h:82-88). */
+int mlbm_create(const mlbm_config* config, mlbm_ctx** out);
+int mlbm_destroy(mlbm_ctx* ctx);
+
+/* Multi-GPU wiring; replaces MPIInitializer (MPIInitializer.h:27-58) and the Communication ctor.
+ * Rank 0 makes an id, the caller ships the 128 bytes to every rank (any transport), every rank attaches.
+ * Without it a context with nranks > 1 refuses to step. */
+int mlbm_comm_unique_id(void* id128);
+int mlbm_comm_init(mlbm_ctx* ctx, const void* id128);
+
+/* Algorithm::unpack (Algorithm.h:141-147, Boundary.h:26-38): host local-padded SoA -> device.
+ * Element (iQ, x, y, z) of the host array is host[iQ*component_stride + (x*padded_y + y)*padded_z + z]
+ * (lSD::getIndex, Domain.h:88-91; component stride FFTWInit::numberElements), in the context's dtype. */
+int mlbm_upload_distribution(mlbm_ctx* ctx, const void* host, size_t component_stride,
+                             size_t padded_y, size_t padded_z);
+/* Algorithm::pack (Algorithm.h:132-139, Boundary.h:11-24): device -> host, same layout. */
+int mlbm_download_distribution(mlbm_ctx* ctx, void* host, size_t component_stride,
+                               size_t padded_y, size_t padded_z);
+
+/* Initial state without a host round trip: f = feq(rho, u) (initDistribution, Initialize.h:106-117) from
+ * host density / velocity fields laid out like the FieldList arrays (velocity component iD at
+ * velocity + iD*component_stride). */
+int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* velocity,
+                          size_t component_stride, size_t padded_y, size_t padded_z);
+
+/* The alpha field the entropic solve warm-starts from (Algorithm.h:103-106; initAlpha, Initialize.h:82-88). */
+int mlbm_set_alpha(mlbm_ctx* ctx, const void* host, size_t padded_y, size_t padded_z);
+
+/* Algorithm::iterate (Algorithm.h:326-358 / 392-447): swap, halo exchange, periodic boundaries, fused node
+ * update; synchronous like the reference (returns after the device finished).  `is_stored` is
+ * Algorithm::isStored (Routine.h:122-124): when non-zero the step also stores density, hydrodynamic
+ * velocity, alpha and force (Algorithm::storeFields, Algorithm.h:150-194) and reduces the observables. */
+int mlbm_step(mlbm_ctx* ctx, unsigned iteration, int is_stored);
+
+/* `count` calls of iterate for iterations first..first+count-1 with isStored = (iteration % store_every == 0)
+ * (store_every == 0: never), enqueued without host synchronisation in between; returns immediately. */
+int mlbm_run_async(mlbm_ctx* ctx, unsigned first_iteration, unsigned count, unsigned store_every);
+int mlbm_sync(mlbm_ctx* ctx);
+
+/* FieldList arrays as of the last stored step (Algorithm::storeFields): any pointer may be NULL.
+ * Multi-component fields use component_stride between components. */
+int mlbm_download_fields(mlbm_ctx* ctx, void* density, void* velocity, void* alpha, void* force,
+                         size_t component_stride, size_t padded_y, size_t padded_z);
+
+/* ScalarAnalysisList::writeAnalyses (AnalysisList.h:55-73) as device reductions, of the last stored step,
+ * already summed over ranks (Communication::reduce, Communication.h:76-89) and normalised by the global
+ * volume (Analysis.h:30):
+ *   out[0] total energy     (Analysis.h:53-61)
+ *   out[1] total enstrophy  (Analysis.h:85-93; central-difference vorticity)
+ *   out[2] max Mach number  max |u_hydro| / c_s
+ *   out[3] total mass       sum of density (PerformanceAnalysisList mass, Routine.h:117-118) */
+int mlbm_observables(mlbm_ctx* ctx, double out[4]);
+
+/* Algorithm::getCommunicationTime / getComputationTime (Algorithm.h:128-130), seconds of the last step
+ * measured with CUDA events on the device. */
+int mlbm_timers(mlbm_ctx* ctx, double* communication_seconds, double* computation_seconds);
+
+/* Device-side access for callers that already hold device memory (zero-copy interop): the SoA buffer the
+ * next step will read.  Element (iQ, x, y, z) is at base[iQ*component_stride + (x + halo_x)*plane + y*row + z]. */
+typedef struct mlbm_device_layout {
+  void* populations;          /* device pointer, context dtype */
+  size_t component_stride;    /* elements between populations  */
+  size_t plane;               /* elements between x planes     */
+  size_t row;                 /* elements between y rows (== 1 in 2-D where y is the unit-stride axis) */
+  int32_t halo_x;             /* number of x halo planes on each side */
+  int32_t local_length[3];
+} mlbm_device_layout;
+int mlbm_device_distribution(mlbm_ctx* ctx, mlbm_device_layout* out);
+
+/* Bench support: number of kernels this library launched since the context was created, and the CUDA
+ * stream the fused kernel is launched on (for event timing by the caller). */
+int mlbm_launch_count(mlbm_ctx* ctx, uint64_t* launches);
+int mlbm_stream(mlbm_ctx* ctx, void** cuda_stream);
+/* Average device time (ms) of the fused kernel over the launches since the last call (CUDA events). */
+int mlbm_kernel_time(mlbm_ctx* ctx, double* average_ms, uint64_t* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* METALBM_B200_H */

@@ -1,0 +1,193 @@
+"""ctypes binding of the C-ABI declared in ``include/metalbm_b200.h``.
+
+This is the same boundary the C++ template shim (``include/metaLBM_b200/``) calls; Python uses
+it for the parity tests and the benchmark driver.  There is no fallback: if the CUDA library
+is missing, loading fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes
+import enum
+import os
+from pathlib import Path
+
+PACKAGE_DIR = Path(__file__).resolve().parent
+LIBRARY_PATH = PACKAGE_DIR / "libmetalbm_b200.so"
+ABI_VERSION = 1
+
+
+class Lattice(enum.IntEnum):
+    D2Q5 = 0
+    D2Q9 = 1
+    D3Q15 = 2
+    D3Q19 = 3
+    D3Q27 = 4
+
+
+class Collision(enum.IntEnum):
+    BGK = 0
+    ELBM = 1
+    ForcedNR_ELBM = 2
+
+
+class Equilibrium(enum.IntEnum):
+    TruncationMa3 = 0
+    Exact = 1
+
+
+class ForcingScheme(enum.IntEnum):
+    None_ = 0
+    Guo = 1
+    ShanChen = 2
+    ExactDifferenceMethod = 3
+
+
+class Force(enum.IntEnum):
+    None_ = 0
+    Constant = 1
+    Sinusoidal = 2
+    Kolmogorov = 3
+
+
+class DType(enum.IntEnum):
+    F64 = 0
+    F32 = 1
+
+
+class Overlapping(enum.IntEnum):
+    Off = 0
+    On = 1
+
+
+LATTICE_DQ = {Lattice.D2Q5: (2, 5), Lattice.D2Q9: (2, 9), Lattice.D3Q15: (3, 15),
+              Lattice.D3Q19: (3, 19), Lattice.D3Q27: (3, 27)}
+
+
+class MlbmConfig(ctypes.Structure):
+    """``mlbm_config`` (include/metalbm_b200.h)."""
+    _fields_ = [
+        ("abi_version", ctypes.c_int32),
+        ("lattice", ctypes.c_int32),
+        ("collision", ctypes.c_int32),
+        ("equilibrium", ctypes.c_int32),
+        ("forcing_scheme", ctypes.c_int32),
+        ("force", ctypes.c_int32),
+        ("dtype", ctypes.c_int32),
+        ("overlap", ctypes.c_int32),
+        ("global_length", ctypes.c_int32 * 3),
+        ("rank", ctypes.c_int32),
+        ("nranks", ctypes.c_int32),
+        ("device", ctypes.c_int32),
+        ("variant", ctypes.c_int32),
+        ("tau", ctypes.c_double),
+        ("force_amplitude", ctypes.c_double * 3),
+        ("force_wavelength", ctypes.c_double * 3),
+    ]
+
+
+class MlbmDeviceLayout(ctypes.Structure):
+    """``mlbm_device_layout`` (include/metalbm_b200.h)."""
+    _fields_ = [
+        ("populations", ctypes.c_void_p),
+        ("component_stride", ctypes.c_size_t),
+        ("plane", ctypes.c_size_t),
+        ("row", ctypes.c_size_t),
+        ("halo_x", ctypes.c_int32),
+        ("local_length", ctypes.c_int32 * 3),
+    ]
+
+
+def _lookup(enum_cls, value):
+    if isinstance(value, enum_cls):
+        return value
+    if isinstance(value, str):
+        name = value if value in enum_cls.__members__ else value + "_"
+        return enum_cls[name]
+    return enum_cls(int(value))
+
+
+def make_config(lattice="D2Q9", shape=(16, 16, 1), collision="BGK", equilibrium="TruncationMa3",
+                forcing_scheme="None", force="None", tau=0.7, amplitude=(0.0, 0.0, 0.0),
+                wavelength=(32.0, 32.0, 32.0), dtype="F64", overlap="Off", rank=0, nranks=1,
+                device=-1, variant=0) -> MlbmConfig:
+    cfg = MlbmConfig()
+    cfg.abi_version = ABI_VERSION
+    cfg.lattice = _lookup(Lattice, lattice)
+    cfg.collision = _lookup(Collision, collision)
+    cfg.equilibrium = _lookup(Equilibrium, equilibrium)
+    cfg.forcing_scheme = _lookup(ForcingScheme, forcing_scheme)
+    cfg.force = _lookup(Force, force)
+    cfg.dtype = _lookup(DType, dtype)
+    cfg.overlap = _lookup(Overlapping, overlap)
+    dim = LATTICE_DQ[Lattice(cfg.lattice)][0]
+    shape = tuple(shape) + (1,) * (3 - len(shape))
+    for i in range(3):
+        cfg.global_length[i] = int(shape[i]) if i < dim else 1
+        cfg.force_amplitude[i] = float(amplitude[i])
+        cfg.force_wavelength[i] = float(wavelength[i])
+    cfg.rank, cfg.nranks, cfg.device, cfg.variant = int(rank), int(nranks), int(device), int(variant)
+    cfg.tau = float(tau)
+    return cfg
+
+
+# every symbol include/metalbm_b200.h declares: name -> (restype, argtypes)
+_P = ctypes.c_void_p
+_SZ = ctypes.c_size_t
+PROTOTYPES = {
+    "mlbm_last_error": (ctypes.c_char_p, []),
+    "mlbm_abi_version": (ctypes.c_int, []),
+    "mlbm_create": (ctypes.c_int, [ctypes.POINTER(MlbmConfig), ctypes.POINTER(_P)]),
+    "mlbm_destroy": (ctypes.c_int, [_P]),
+    "mlbm_comm_unique_id": (ctypes.c_int, [_P]),
+    "mlbm_comm_init": (ctypes.c_int, [_P, _P]),
+    "mlbm_upload_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
+    "mlbm_download_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
+    "mlbm_init_equilibrium": (ctypes.c_int, [_P, _P, _P, _SZ, _SZ, _SZ]),
+    "mlbm_set_alpha": (ctypes.c_int, [_P, _P, _SZ, _SZ]),
+    "mlbm_step": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_int]),
+    "mlbm_run_async": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
+    "mlbm_sync": (ctypes.c_int, [_P]),
+    "mlbm_download_fields": (ctypes.c_int, [_P, _P, _P, _P, _P, _SZ, _SZ, _SZ]),
+    "mlbm_observables": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
+    "mlbm_timers": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "mlbm_device_distribution": (ctypes.c_int, [_P, ctypes.POINTER(MlbmDeviceLayout)]),
+    "mlbm_launch_count": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
+    "mlbm_stream": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
+    "mlbm_kernel_time": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+}
+
+_library = None
+
+
+class MlbmError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"metalbm_b200 error {status}: {message}")
+        self.status = status
+
+
+def load_library(path: os.PathLike | None = None) -> ctypes.CDLL:
+    """Load ``libmetalbm_b200.so`` (built in-tree by ``__graft_entry__.build()``) and type its symbols."""
+    global _library
+    if _library is not None and path is None:
+        return _library
+    lib_path = Path(path) if path else LIBRARY_PATH
+    if not lib_path.is_file():
+        raise FileNotFoundError(
+            f"{lib_path} not found: build the CUDA library first (python -c 'import __graft_entry__ as g; g.build()'); "
+            "there is no CPU fallback")
+    lib = ctypes.CDLL(str(lib_path), mode=ctypes.RTLD_GLOBAL)
+    for name, (restype, argtypes) in PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = restype
+        fn.argtypes = argtypes
+    if lib.mlbm_abi_version() != ABI_VERSION:
+        raise RuntimeError("libmetalbm_b200.so ABI version mismatch")
+    if path is None:
+        _library = lib
+    return lib
+
+
+def check(status: int) -> None:
+    if status != 0:
+        message = load_library().mlbm_last_error()
+        raise MlbmError(status, message.decode() if message else "")

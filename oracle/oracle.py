@@ -1,0 +1,180 @@
+"""oracle/oracle.py -- TEST INFRASTRUCTURE ONLY.
+
+Python face of the CPU checker: ctypes access to ``liboracle.so`` (the plain-C restatement in
+``lbm_oracle.c``), the reference's *spectral* vorticity / enstrophy restated with numpy
+(Transformer.h:118-295, Routine.h:129-132, Analysis.h:68-98) and the seeded synthetic initial
+fields of SURVEY.md section 8(d).
+
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline / reference legs may
+import this module.  The product package ``metalbm_b200`` never does.
+"""
+from __future__ import annotations
+
+import ctypes
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+from metalbm_b200.capi import LATTICE_DQ, Lattice, MlbmConfig, make_config  # config struct = the ABI's
+
+ORACLE_DIR = Path(__file__).resolve().parent
+_LIB = None
+
+
+def build() -> Path:
+    subprocess.run(["make", "-s", "-C", str(ORACLE_DIR)], check=True, capture_output=True)
+    return ORACLE_DIR / "liboracle.so"
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        path = ORACLE_DIR / "liboracle.so"
+        if not path.is_file():
+            build()
+        _LIB = ctypes.CDLL(str(path))
+        dp = ctypes.POINTER(ctypes.c_double)
+        ip = ctypes.POINTER(ctypes.c_int)
+        cp = ctypes.POINTER(MlbmConfig)
+        _LIB.mlbm_oracle_step.argtypes = [cp, dp, dp, dp, dp, dp, dp, ctypes.c_int, ip, ip]
+        _LIB.mlbm_oracle_init_equilibrium.argtypes = [cp, dp, dp, dp]
+        _LIB.mlbm_oracle_observables.argtypes = [cp, dp, dp, dp]
+        _LIB.mlbm_oracle_lattice.argtypes = [ctypes.c_int, ip, ip, ip, dp]
+    return _LIB
+
+
+def _dp(a: np.ndarray):
+    assert a.dtype == np.float64 and a.flags.c_contiguous
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+def _ip(a: np.ndarray):
+    assert a.dtype == np.int32 and a.flags.c_contiguous
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+
+
+def lattice(name) -> tuple:
+    """(D, Q, celerity[Q,3] int, weight[Q])."""
+    lat = Lattice[name] if isinstance(name, str) else Lattice(int(name))
+    d, q = ctypes.c_int(), ctypes.c_int()
+    c = np.zeros((27, 3), dtype=np.int32)
+    w = np.zeros(27, dtype=np.float64)
+    assert lib().mlbm_oracle_lattice(int(lat), ctypes.byref(d), ctypes.byref(q), _ip(c), _dp(w)) == 0
+    return d.value, q.value, c[:q.value].copy(), w[:q.value].copy()
+
+
+def shape_of(cfg: MlbmConfig) -> tuple:
+    dim = LATTICE_DQ[Lattice(cfg.lattice)][0]
+    return tuple(int(cfg.global_length[i]) if i < dim else 1 for i in range(3))
+
+
+class OracleState:
+    """Global-domain state advanced by the C restatement (one ``iterate`` per ``step``)."""
+
+    def __init__(self, cfg: MlbmConfig, populations: np.ndarray, alpha: np.ndarray | None = None):
+        self.cfg = cfg
+        self.shape = shape_of(cfg)
+        self.dim, self.q = LATTICE_DQ[Lattice(cfg.lattice)]
+        self.f = np.ascontiguousarray(populations, dtype=np.float64).reshape((self.q,) + self.shape).copy()
+        self.next = np.empty_like(self.f)
+        self.alpha = (np.full(self.shape, 2.0) if alpha is None
+                      else np.ascontiguousarray(alpha, dtype=np.float64).reshape(self.shape).copy())
+        self.density = np.zeros(self.shape)
+        self.velocity = np.zeros((self.dim,) + self.shape)
+        self.force = np.zeros((self.dim,) + self.shape)
+        self.branch = np.zeros(self.shape, dtype=np.int32)
+        self.iterations = np.zeros(self.shape, dtype=np.int32)
+
+    def step(self, is_stored: bool = True) -> None:
+        status = lib().mlbm_oracle_step(ctypes.byref(self.cfg), _dp(self.f), _dp(self.next), _dp(self.alpha),
+                                        _dp(self.density), _dp(self.velocity), _dp(self.force),
+                                        1 if is_stored else 0, _ip(self.branch), _ip(self.iterations))
+        if status != 0:
+            raise ValueError("oracle: unsupported configuration")
+        self.f, self.next = self.next, self.f
+
+    def observables(self) -> np.ndarray:
+        """[energy, enstrophy (spectral, reference definition), mach, mass] of the last stored step."""
+        out = np.zeros(4)
+        lib().mlbm_oracle_observables(ctypes.byref(self.cfg), _dp(self.density), _dp(self.velocity), _dp(out))
+        out[1] = spectral_enstrophy(self.velocity, self.dim)
+        return out
+
+
+def init_equilibrium(cfg: MlbmConfig, density: np.ndarray, velocity: np.ndarray) -> np.ndarray:
+    shape = shape_of(cfg)
+    dim, q = LATTICE_DQ[Lattice(cfg.lattice)]
+    rho = np.ascontiguousarray(density, dtype=np.float64).reshape(shape)
+    u = np.ascontiguousarray(velocity, dtype=np.float64).reshape((dim,) + shape)
+    f = np.empty((q,) + shape)
+    assert lib().mlbm_oracle_init_equilibrium(ctypes.byref(cfg), _dp(rho), _dp(u), _dp(f)) == 0
+    return f
+
+
+# ---------------------------------------------------------------------------------------------
+# The reference's vorticity and enstrophy (spectral, integer wavenumbers, double normalisation).
+#   Curl<...,2,2>  Transformer.h:118-187     Curl<...,3,3>  Transformer.h:189-295
+#   BackwardFFT::execute divides by V (Transformer.h:101-108); Curl::normalize divides by V again
+#   (Transformer.h:179-185, 284-294); TotalEnstrophy = sum 0.5*w^2 / V (Analysis.h:85-93, :30).
+# ---------------------------------------------------------------------------------------------
+def _wavenumbers(n: int, half: bool) -> np.ndarray:
+    count = n // 2 + 1 if half else n
+    i = np.arange(count)
+    return np.where(i <= n // 2, i, i - n).astype(np.float64)
+
+
+def spectral_vorticity(velocity: np.ndarray, dim: int) -> np.ndarray:
+    """velocity [D, nx, ny, nz] -> vorticity [2D-3, nx, ny, nz] exactly as the reference stores it."""
+    shape = velocity.shape[1:]
+    volume = float(np.prod(shape))
+    if dim == 2:
+        nx, ny = shape[0], shape[1]
+        ux = np.fft.rfft2(velocity[0, :, :, 0])
+        uy = np.fft.rfft2(velocity[1, :, :, 0])
+        kx = _wavenumbers(nx, False)[:, None]
+        ky = _wavenumbers(ny, True)[None, :]
+        # only the real part is formed, the imaginary part is forced to zero (Transformer.h:151-165)
+        w_hat = (-kx * uy.imag + ky * ux.imag).astype(np.complex128)
+        w = np.fft.irfft2(w_hat, s=(nx, ny)) * (nx * ny)  # FFTW c2r is unnormalised
+        return (w / volume / volume).reshape((1,) + shape)
+    nx, ny, nz = shape
+    u = [np.fft.rfftn(velocity[d]) for d in range(3)]
+    kx = _wavenumbers(nx, False)[:, None, None]
+    ky = _wavenumbers(ny, False)[None, :, None]
+    kz = _wavenumbers(nz, True)[None, None, :]
+    wx = 1j * (ky * u[2] - kz * u[1])
+    wy = 1j * (kz * u[0] - kx * u[2])
+    wz = 1j * (kx * u[1] - ky * u[0])
+    out = np.stack([np.fft.irfftn(w, s=shape) * volume for w in (wx, wy, wz)])
+    return out / volume / volume
+
+
+def spectral_enstrophy(velocity: np.ndarray, dim: int) -> float:
+    w = spectral_vorticity(velocity, dim)
+    return float((0.5 * w * w).sum() / np.prod(velocity.shape[1:]))
+
+
+# ---------------------------------------------------------------------------------------------
+# Seeded synthetic inputs ("Init B"): f = feq(rho, u) * (1 + eps * N(0,1))
+# ---------------------------------------------------------------------------------------------
+def synthetic_populations(cfg: MlbmConfig, eps: float = 1e-2, seed: int = 20261017,
+                          amplitude: float = 0.05) -> np.ndarray:
+    shape = shape_of(cfg)
+    dim, q = LATTICE_DQ[Lattice(cfg.lattice)]
+    nx, ny, nz = shape
+    x = (2 * np.pi * np.arange(nx) / nx)[:, None, None]
+    y = (2 * np.pi * np.arange(ny) / ny)[None, :, None]
+    z = (2 * np.pi * np.arange(nz) / nz)[None, None, :]
+    rho = 1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z) * np.ones(shape)
+    u = np.zeros((dim,) + shape)
+    if dim == 2:
+        u[0] = amplitude * np.sin(y) * np.ones(shape)
+        u[1] = amplitude * np.cos(x) * np.ones(shape)
+    else:
+        u[0] = amplitude * np.sin(x) * np.cos(y) * np.cos(z)
+        u[1] = -amplitude * np.cos(x) * np.sin(y) * np.cos(z)
+        u[2] = 0.5 * amplitude * np.cos(x) * np.cos(y) * np.sin(z)
+    f = init_equilibrium(cfg, rho, u)
+    rng = np.random.default_rng(seed)
+    return f * (1.0 + eps * rng.standard_normal(f.shape))

@@ -1,0 +1,232 @@
+"""oracle/refbuild.py -- TEST INFRASTRUCTURE ONLY.
+
+Compiles the reference's own CPU implementation of the fused step from the sources
+where they lie under /root/reference (never copied into this repository) into
+``oracle/_ref/`` and runs it.  Every physics choice of the reference is a compile-time
+``constexpr`` global read from ``Input.in`` (src/Input_prod.in:10-78), so each
+configuration is its own small binary; they are cached by configuration hash.
+
+Only ``tests/``, ``__graft_entry__`` (build/smoke) and ``bench.py``'s reference / cpu_baseline
+legs may use this module.  ``/root/reference`` exists only in the build container: on
+the GPU box only the binaries already present in ``oracle/_ref`` can be run.
+"""
+from __future__ import annotations
+
+import dataclasses
+import hashlib
+import json
+import os
+import subprocess
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+REFERENCE_ROOT = Path(os.environ.get("MLBM_REFERENCE_ROOT", "/root/reference"))
+ORACLE_DIR = Path(__file__).resolve().parent
+REF_DIR = ORACLE_DIR / "_ref"
+
+LATTICES = {
+    "D1Q3": (1, 3), "D2Q5": (2, 5), "D2Q9": (2, 9), "D3Q15": (3, 15), "D3Q19": (3, 19), "D3Q27": (3, 27),
+}
+
+
+@dataclasses.dataclass(frozen=True)
+class RefConfig:
+    """One compile-time configuration of the reference (names follow src/Input_prod.in)."""
+    lattice: str = "D2Q9"
+    nx: int = 16
+    ny: int = 16
+    nz: int = 1
+    collision: str = "BGK"              # BGK | ELBM | ForcedNR_ELBM
+    equilibrium: str = "TruncationMa3"  # TruncationMa3 | Exact
+    forcing_scheme: str = "Guo"         # None | Guo | ShanChen | ExactDifferenceMethod
+    force: str = "Kolmogorov"           # None | Kolmogorov  (Constant/Sinusoidal do not compile in the snapshot)
+    tau: float = 0.7
+    amplitude: tuple = (1e-5, 1e-5, 1e-5)
+    wavelength: tuple = (32.0, 32.0, 32.0)
+    init_density: str = "Homogeneous"   # Homogeneous | Peak
+    nprocs: int = 1
+    optimize: str = "-O2"               # "-O2" = parity build (no FMA contraction); "-O3 -march=native" = timing build
+
+    @property
+    def dim(self) -> int:
+        return LATTICES[self.lattice][0]
+
+    @property
+    def q(self) -> int:
+        return LATTICES[self.lattice][1]
+
+    @property
+    def shape(self) -> tuple:
+        return (self.nx, self.ny if self.dim > 1 else 1, self.nz if self.dim > 2 else 1)
+
+    def key(self) -> str:
+        blob = json.dumps(dataclasses.asdict(self), sort_keys=True, default=repr)
+        return hashlib.sha1(blob.encode()).hexdigest()[:12]
+
+    def name(self) -> str:
+        flags = "nat" if "native" in self.optimize else "par"
+        return (f"ref_{self.lattice}_{self.collision}_{self.equilibrium}_{self.forcing_scheme}_{self.force}"
+                f"_{self.nx}x{self.ny}x{self.nz}_p{self.nprocs}_{flags}_{self.key()}")
+
+
+def _vector(values) -> str:
+    return "{ {" + ", ".join(repr(float(v)) for v in values) + "} }"
+
+
+def input_in(cfg: RefConfig) -> str:
+    """The compile-time configuration header the reference headers read as globals."""
+    return f"""#pragma once
+#include <string>
+#include "metaLBM/Commons.h"
+#include "metaLBM/Options.h"
+#include "metaLBM/MathVector.h"
+namespace lbm {{
+  using dataT = double;
+  using Vector = MathVector<dataT, 3>;
+  constexpr int numProcs = NPROCS;
+  constexpr int numThreads = NTHREADS;
+  constexpr LatticeType latticeT = LatticeType::{cfg.lattice};
+  constexpr int globalLengthX = GLOBAL_LENGTH_X;
+  constexpr int globalLengthY = GLOBAL_LENGTH_Y;
+  constexpr int globalLengthZ = GLOBAL_LENGTH_Z;
+  constexpr unsigned int startIteration = 0;
+  constexpr unsigned int endIteration = 1;
+  constexpr unsigned int writeStep = 1000000000;
+  constexpr unsigned int backUpStep = 1000000000;
+  constexpr unsigned int scalarAnalysisStep = 1000000000;
+  constexpr unsigned int spectralAnalysisStep = 1000000000;
+  constexpr unsigned int performanceAnalysisStep = 1000000000;
+  constexpr unsigned int successiveWriteStep = 1;
+  constexpr AlgorithmType algorithmT = AlgorithmType::Pull;
+  constexpr PartitionningType partitionningT = PartitionningType::OneD;
+  constexpr CommunicationType communicationT = CommunicationType::MPI;
+  constexpr MemoryLayout memoryL = MemoryLayout::SoA;
+  constexpr Overlapping overlappingT = Overlapping::Off;
+  constexpr dataT relaxationTime = {cfg.tau!r};
+  constexpr CollisionType collisionT = CollisionType::{cfg.collision};
+  constexpr EquilibriumType equilibriumT = EquilibriumType::{cfg.equilibrium};
+  constexpr InitDensityType initDensityT = InitDensityType::{cfg.init_density};
+  constexpr dataT initDensityValue = 1.0;
+  constexpr InitVelocityType initVelocityT = InitVelocityType::Homogeneous;
+  constexpr Vector initVelocityVector = {{ {{0.0, 0.0, 0.0}} }};
+  constexpr ForcingSchemeType forcingSchemeT = ForcingSchemeType::{cfg.forcing_scheme};
+  constexpr ForceType forceT = ForceType::{cfg.force};
+  constexpr Vector forceAmplitude = {_vector(cfg.amplitude)};
+  constexpr Vector forceWaveLength = {_vector(cfg.wavelength)};
+  constexpr int forcekMin = 1;
+  constexpr int forcekMax = 2;
+  constexpr Vector removalForceAmplitude = {{ {{0.0, 0.0, 0.0}} }};
+  constexpr Vector removalForceWaveLength = {{ {{32.0, 32.0, 32.0}} }};
+  constexpr int removalForcekMin = 1;
+  constexpr int removalForcekMax = 2;
+  constexpr BoundaryType boundaryT = BoundaryType::Generic;
+  constexpr InputOutputFormat inputOutputFormatT = InputOutputFormat::ascii;
+  constexpr auto prefix = LBM_POSTFIX;
+  constexpr bool writeFieldInit = 0;
+  constexpr bool writeAnalysisInit = 0;
+  constexpr bool writeForce = 1;
+  constexpr bool writeEntropy = 0;
+  constexpr bool writeAlpha = 1;
+  constexpr bool writeT = 0;
+  constexpr bool writeVorticity = 1;
+  constexpr bool writeKinetics = 0;
+  constexpr bool analyzeTotalEnergy = 1;
+  constexpr bool analyzeTotalEnstrophy = 1;
+  constexpr bool analyzeEnergySpectra = 0;
+  constexpr bool analyzeEnstrophySpectra = 0;
+}}
+"""
+
+
+def reference_available() -> bool:
+    return (REFERENCE_ROOT / "include" / "metaLBM" / "Algorithm.h").is_file()
+
+
+def binary_path(cfg: RefConfig) -> Path:
+    return REF_DIR / cfg.name()
+
+
+def build_ref(cfg: RefConfig, force: bool = False) -> Path:
+    """Compile (or reuse) the reference binary for ``cfg``; returns its path."""
+    out = binary_path(cfg)
+    if out.is_file() and not force:
+        return out
+    if not reference_available():
+        raise FileNotFoundError(f"{out} is not prebuilt and {REFERENCE_ROOT} is absent")
+    REF_DIR.mkdir(parents=True, exist_ok=True)
+    with tempfile.TemporaryDirectory(prefix="mlbm_ref_") as tmp:
+        (Path(tmp) / "Input.in").write_text(input_in(cfg))
+        nx, ny, nz = cfg.shape
+        cmd = ["g++", "-std=c++14", *cfg.optimize.split(), "-ffp-contract=off" if "native" not in cfg.optimize else "-ffp-contract=fast",
+               "-w", "-DUSE_FFTW", f"-DNPROCS={cfg.nprocs}", "-DNTHREADS=1",
+               f"-DGLOBAL_LENGTH_X={nx}", f"-DGLOBAL_LENGTH_Y={ny}", f"-DGLOBAL_LENGTH_Z={nz}",
+               '-DLBM_POSTFIX="oracle"', f"-I{ORACLE_DIR / 'shim'}", f"-I{tmp}",
+               f"-I{REFERENCE_ROOT / 'include'}", str(ORACLE_DIR / "ref_driver.cpp"), "-o", str(out) + ".tmp"]
+        proc = subprocess.run(cmd, capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("reference build failed:\n" + " ".join(cmd) + "\n" + proc.stderr[-4000:])
+        os.replace(str(out) + ".tmp", out)
+    return out
+
+
+def run_ref(cfg: RefConfig, populations: np.ndarray | None, steps: int, store_every: int = 0,
+            observables: bool = True, timeout: float = 3600.0) -> dict:
+    """Run the reference binary.  ``populations`` is float64 [Q, nx, ny, nz] (global interior) or None
+    for the reference's own equilibrium initialisation.  Returns the final populations / fields and
+    the (iteration, energy, enstrophy) rows of every stored step."""
+    exe = build_ref(cfg)
+    nx, ny, nz = cfg.shape
+    q, dim = cfg.q, cfg.dim
+    with tempfile.TemporaryDirectory(prefix="mlbm_run_") as tmp:
+        tmp = Path(tmp)
+        if populations is None:
+            inp = "-"
+        else:
+            arr = np.ascontiguousarray(populations, dtype=np.float64).reshape(q, nx, ny, nz)
+            inp = str(tmp / "f0.bin")
+            arr.tofile(inp)
+        prefix = str(tmp / "out")
+        proc = subprocess.run([str(exe), inp, prefix, str(steps), str(store_every), "1" if observables else "0"],
+                              capture_output=True, text=True, timeout=timeout, cwd=tmp)
+        if proc.returncode != 0:
+            raise RuntimeError(f"reference run failed ({proc.returncode}):\n{proc.stdout[-2000:]}\n{proc.stderr[-2000:]}")
+        lx = nx // cfg.nprocs
+        nvort = 2 * dim - 3
+        nfields = q + 1 + dim + 1 + dim + nvort
+        slabs = [np.fromfile(f"{prefix}.r{r}.bin", dtype=np.float64).reshape(nfields, lx, ny, nz)
+                 for r in range(cfg.nprocs)]
+        full = np.concatenate(slabs, axis=1)
+        result = {
+            "f": full[:q].copy(),
+            "density": full[q].copy(),
+            "velocity": full[q + 1:q + 1 + dim].copy(),
+            "alpha": full[q + 1 + dim].copy(),
+            "force": full[q + 2 + dim:q + 2 + 2 * dim].copy(),
+            "vorticity": full[q + 2 + 2 * dim:].copy(),
+            "observables": [],
+        }
+        for line in Path(prefix + ".txt").read_text().splitlines():
+            parts = line.split()
+            if parts[0] == "obs":
+                result["observables"].append((int(parts[1]), float(parts[2]), float(parts[3])))
+            elif parts[0].startswith("time_"):
+                result[parts[0]] = float(parts[1])
+        return result
+
+
+# Configurations prebuilt by __graft_entry__.build() so that they travel to the GPU box
+# (bench.py --impl reference / cpu_baseline time these; tests use them when present).
+def timing_configs(nprocs: int = 1) -> list:
+    native = "-O3 -march=native"
+    return [
+        RefConfig(lattice="D3Q19", nx=128, ny=128, nz=128, collision="BGK", forcing_scheme="None", force="None",
+                  tau=0.55, nprocs=nprocs, optimize=native),
+    ]
+
+
+if __name__ == "__main__":
+    import sys
+    cfg = RefConfig()
+    print(build_ref(cfg, force="--force" in sys.argv))
