@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- MLUPS of the fused collide-and-stream pull step on B200 (BASELINE.json's metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repository's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU implementation
+
+N = 1 workload: BASELINE.json configs[1], D3Q19 SRT-BGK periodic 256^3 FP64 (one step = one pass of the
+fused kernel over all 256^3 nodes; the two 2.6 GB population buffers are far larger than the 126 MB L2,
+so every timed step streams from HBM -- no L2 flush needed).  N > 1 (launched with torchrun, one rank per
+GPU): weak scaling, the same 256^3 slab per GPU, global (256 N) x 256 x 256, x-slab halo exchange
+overlapped with the bulk kernel.
+
+One JSON line on stdout from rank 0 (see the keys at the bottom).  `value` is device-timed with inputs
+resident in HBM; `e2e` is the same metric through the public C-ABI with HOST buffers: the timed region
+uploads the populations from pinned host memory (Algorithm::unpack), runs the K steps reading the scalar
+observables back to the host after every step, and downloads the populations (Algorithm::pack).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "MLUPS (D3Q19, FP64)"
+UNIT = "MLUPS"
+LATTICE, Q, EDGE = "D3Q19", 19, 256
+BYTES_PER_NODE = 2 * Q * 8           # algorithmic HBM traffic per node-step: read + write every population once
+FALLBACK_PEAK_GBS = 6650.0           # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def measured_peak():
+    path = ROOT / "MEASURED_PEAKS.json"
+    if path.is_file():
+        try:
+            return float(json.loads(path.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_PEAK_GBS, "fallback (B200_PROFILING.md)"
+
+
+def recorded_traffic():
+    """dram bytes per launch of the fused kernel from the committed ncu capture, if there is one."""
+    path = ROOT / "profiles" / "traffic.json"
+    if path.is_file():
+        try:
+            return json.loads(path.read_text()).get("d3q19_bgk_f64_256_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons sampled DURING the timed region."""
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.device_index = device_index
+        self.lines = []
+        self.process = None
+        self.thread = None
+
+    def start(self):
+        try:
+            self.process = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(self.device_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.process = None
+            return
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
+
+    def _pump(self):
+        for line in self.process.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, begin: float, end: float) -> dict:
+        if self.process is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.process.terminate()
+        try:
+            self.process.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.process.kill()
+        clocks, maxima, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for t, l in self.lines if begin - 0.05 <= t <= end + 0.15] or [l for _, l in self.lines]
+        for row in rows:
+            parts = [p.strip() for p in row.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                clocks.append(float(parts[1]))
+                maxima.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(names, parts[5:9]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(clocks) if clocks else None,
+                "sm_max_mhz": max(maxima) if maxima else None,
+                "reasons": sorted(reasons), "samples": len(clocks)}
+
+
+def distributed_setup(gpus: int):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if gpus > 1 and world != gpus:
+        raise SystemExit(f"--gpus {gpus} needs torchrun with --nproc-per-node {gpus} (WORLD_SIZE={world})")
+    return rank, world, local_rank
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU implementation (oracle/_ref, compiled from /root/reference by
+# oracle/refbuild.py in the build container) on the host cores, on a bounded x-slab sample of the workload
+# --------------------------------------------------------------------------------------------------
+def run_reference(args) -> int:
+    rank, world, _ = distributed_setup(args.gpus)
+    if rank != 0:
+        return 0
+    from oracle import refbuild
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cfg = refbuild.best_timing_config(cores)
+    if cfg is None:
+        print(json.dumps({"impl": "reference", "unavailable": "no prebuilt reference binary in oracle/_ref"}))
+        return 0
+    result = refbuild.time_reference(cfg, args.steps, args.warmup)
+    sample = (f"reference CPU build ({refbuild.TIMING_FLAGS}), {cfg.nprocs} forked MPI-shim ranks x "
+              f"{refbuild.TIMING_PLANES_PER_RANK} x-planes of 256x256 D3Q19 BGK FP64 nodes per step "
+              f"({cfg.nx}x256x256 per step), timers of Algorithm::iterate")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": result["mlups"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": result["seconds"] / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"D3Q19 SRT-BGK periodic 256^3 FP64 per GPU (BASELINE configs[1]); bounded sample: {sample}",
+                   "lattice": LATTICE, "collision": "BGK", "host_cores": cores, "ranks": cfg.nprocs},
+        "cpu_baseline": {"value": result["mlups"], "unit": UNIT, "cores": cfg.nprocs, "kind": "reference",
+                         "sample": sample},
+        "e2e": {"value": result["mlups"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def cpu_baseline_leg() -> dict:
+    """The reference CPU build timed on this box's host cores on a bounded sample (about 10-20 s)."""
+    from oracle import refbuild
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    cfg = refbuild.best_timing_config(cores)
+    if cfg is None:
+        return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "no prebuilt reference binary"}
+    probe = refbuild.time_reference(cfg, 3, 1)
+    steps = int(max(5, min(200, 12.0 / max(probe["seconds"] / 3, 1e-3))))
+    result = refbuild.time_reference(cfg, steps, 2)
+    return {"value": result["mlups"], "unit": UNIT, "cores": cfg.nprocs, "kind": "reference",
+            "sample": (f"{steps} steps of {cfg.nx}x256x256 D3Q19 BGK FP64 ({refbuild.TIMING_PLANES_PER_RANK} x-planes per rank), "
+                       f"reference CPU build {refbuild.TIMING_FLAGS}, {cfg.nprocs} forked MPI-shim ranks on {cores} host cores")}
+
+
+# --------------------------------------------------------------------------------------------------
+# this repository's arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args) -> int:
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from metalbm_b200.algorithm import Algorithm, Communication
+    from metalbm_b200.capi import make_config
+
+    rank, world, local_rank = distributed_setup(args.gpus)
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group(backend="nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(value: float) -> float:
+        if world == 1:
+            return value
+        tensor = torch.tensor([value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tensor, op=dist.ReduceOp.MAX)
+        return float(tensor.item())
+
+    edge = args.edge
+    shape = (edge * world, edge, edge)
+    cfg = make_config(lattice=LATTICE, shape=shape, collision="BGK", equilibrium="TruncationMa3",
+                      forcing_scheme="None", force="None", tau=0.55, dtype="F64",
+                      overlap="On", rank=rank, nranks=world, device=local_rank, variant=args.variant)
+    algorithm = Algorithm(cfg, communication=Communication(rank, world))
+    domain = algorithm.domain
+    nodes_global = shape[0] * shape[1] * shape[2]
+    nodes_local = nodes_global // world
+
+    # synthetic initial field of the named grid size: Taylor-Green-like velocity, density ripple (SURVEY 8d "Init B-3D")
+    lx = domain.local_length[0]
+    x = (2 * np.pi * (np.arange(lx) + domain.offset_x) / shape[0])[:, None, None]
+    y = (2 * np.pi * np.arange(edge) / edge)[None, :, None]
+    z = (2 * np.pi * np.arange(edge) / edge)[None, None, :]
+    fields = algorithm.fieldList
+    domain.interior(fields.density)[0] = 1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z)
+    domain.interior(fields.velocity)[0] = 0.05 * np.sin(x) * np.cos(y) * np.cos(z)
+    domain.interior(fields.velocity)[1] = -0.05 * np.cos(x) * np.sin(y) * np.cos(z)
+    domain.interior(fields.velocity)[2] = 0.025 * np.cos(x) * np.cos(y) * np.sin(z)
+    algorithm.init_equilibrium()
+
+    # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------------
+    algorithm.run(1, args.warmup)
+    algorithm.kernel_time()                      # switches the per-launch CUDA event pairs on
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    launches_before = algorithm.launch_count()
+    barrier()
+    begin = time.time()
+    algorithm.mark(0)
+    algorithm.run(args.warmup + 1, args.steps, sync=False)
+    algorithm.mark(1)
+    algorithm.synchronize()
+    barrier()
+    end = time.time()
+    device_ms = max_over_ranks(algorithm.elapsed_ms(0, 1))
+    launches = algorithm.launch_count() - launches_before
+    kernel_ms, kernel_launches = algorithm.kernel_time()
+    clocks = sampler.stop(begin, end) if rank == 0 else None
+    value = nodes_global * args.steps / (device_ms * 1e-3) / 1e6
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
+    algorithm.pack()                             # current state -> host array (also first-touches the host pages)
+    host = algorithm.distribution.array
+    pinned = torch.empty(host.shape, dtype=torch.float64, pin_memory=True)
+    pinned.numpy()[...] = host
+    algorithm.distribution.array = pinned.numpy()
+    barrier()
+    t0 = time.perf_counter()
+    algorithm.unpack()                           # H2D of the whole SoA distribution from pinned host memory
+    energy = 0.0
+    for iteration in range(1, args.steps + 1):
+        algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
+        energy = algorithm.observables()[0]      # D2H read of the step's scalar results
+    algorithm.pack()                             # D2H of the whole distribution
+    barrier()
+    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
+    distribution_bytes = Q * nodes_local * 8
+    e2e = {"value": e2e_value, "unit": UNIT,
+           "h2d_bytes_per_step": distribution_bytes / args.steps,
+           "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
+           "note": "timed region: unpack (H2D of all populations from pinned host memory) + K synchronous mlbm_step calls each "
+                   "followed by a D2H read of the observables + pack (D2H of all populations); population bytes amortised over K",
+           "last_energy": energy}
+
+    peak, peak_source = measured_peak()
+    achieved = BYTES_PER_NODE * nodes_local / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak if achieved else None, "traffic": recorded_traffic(),
+                "peak_source": peak_source, "kernel": "fusedStepKernel<D3Q19,BGK,TruncationMa3,None,double>",
+                "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_launches,
+                "algorithmic_bytes_per_launch": BYTES_PER_NODE * nodes_local,
+                "roofline_mlups_per_gpu": peak * 1e9 / BYTES_PER_NODE / 1e6}
+
+    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    algorithm.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"D3Q19 SRT-BGK periodic {edge}^3 FP64 per GPU (BASELINE configs[1]); global {shape[0]}x{shape[1]}x{shape[2]}",
+                       "lattice": LATTICE, "collision": "BGK", "equilibrium": "TruncationMa3", "forcing": "None", "tau": 0.55,
+                       "global_length": list(shape), "parallelism": f"x-slab x{world}", "overlap": "On",
+                       "l2": "inputs (2 x 2.6 GB population buffers per GPU) larger than the 126 MB L2; no flush between steps"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+        }
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    return 0
+
+
+def main() -> int:
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=200)
+    parser.add_argument("--warmup", type=int, default=10)
+    parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    parser.add_argument("--edge", type=int, default=EDGE, help="edge of the per-GPU cube (default: the BASELINE 256)")
+    parser.add_argument("--variant", type=int, default=0)
+    parser.add_argument("--no-cpu-baseline", action="store_true")
+    args = parser.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

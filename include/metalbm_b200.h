@@ -109,6 +109,20 @@ int mlbm_destroy(mlbm_ctx* ctx);
 int mlbm_comm_unique_id(void* id128);
 int mlbm_comm_init(mlbm_ctx* ctx, const void* id128);
 
+/* The halo exchange of one step as data (pure host logic, no device needed): which planes of the SoA buffer
+ * this rank sends and receives, in issue order.  Mirrors Communication::sendAndReceiveHaloXRight / XLeft
+ * (Communication.h:134-180): populations faceQ+1..2*faceQ (c_x > 0) travel right, 1..faceQ (c_x < 0) left.
+ * Offsets and counts are in elements of the context dtype, relative to the buffer base. */
+typedef struct mlbm_halo_message {
+  int32_t population;   /* iQ */
+  int32_t peer;         /* rank of the neighbour (MPIInitializer.h:56-57) */
+  int32_t is_send;      /* 1 = send, 0 = receive */
+  int32_t reserved;
+  uint64_t offset;
+  uint64_t count;
+} mlbm_halo_message;
+int mlbm_halo_plan(const mlbm_config* config, mlbm_halo_message* out, int capacity, int* count);
+
 /* Algorithm::unpack (Algorithm.h:141-147, Boundary.h:26-38): host local-padded SoA -> device.
  * Element (iQ, x, y, z) of the host array is host[iQ*component_stride + (x*padded_y + y)*padded_z + z]
  * (lSD::getIndex, Domain.h:88-91; component stride FFTWInit::numberElements), in the context's dtype. */
@@ -172,8 +186,14 @@ int mlbm_device_distribution(mlbm_ctx* ctx, mlbm_device_layout* out);
  * stream the fused kernel is launched on (for event timing by the caller). */
 int mlbm_launch_count(mlbm_ctx* ctx, uint64_t* launches);
 int mlbm_stream(mlbm_ctx* ctx, void** cuda_stream);
-/* Average device time (ms) of the fused kernel over the launches since the last call (CUDA events). */
+/* Average device time (ms) of the fused kernel over the launches since the last call, from a CUDA event pair
+ * around every launch on that stream.  The first call switches the per-launch events on and returns zeros. */
 int mlbm_kernel_time(mlbm_ctx* ctx, double* average_ms, uint64_t* launches);
+
+/* Device-side stopwatch on the compute stream: mlbm_mark records CUDA event `slot` (0..7) after the work
+ * enqueued so far; mlbm_elapsed waits for event `to` and returns the milliseconds between two marks. */
+int mlbm_mark(mlbm_ctx* ctx, int slot);
+int mlbm_elapsed(mlbm_ctx* ctx, int from, int to, double* milliseconds);
 
 #ifdef __cplusplus
 }

@@ -97,6 +97,18 @@ class MlbmDeviceLayout(ctypes.Structure):
     ]
 
 
+class MlbmHaloMessage(ctypes.Structure):
+    """``mlbm_halo_message`` (include/metalbm_b200.h)."""
+    _fields_ = [
+        ("population", ctypes.c_int32),
+        ("peer", ctypes.c_int32),
+        ("is_send", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("offset", ctypes.c_uint64),
+        ("count", ctypes.c_uint64),
+    ]
+
+
 def _lookup(enum_cls, value):
     if isinstance(value, enum_cls):
         return value
@@ -138,6 +150,8 @@ PROTOTYPES = {
     "mlbm_abi_version": (ctypes.c_int, []),
     "mlbm_create": (ctypes.c_int, [ctypes.POINTER(MlbmConfig), ctypes.POINTER(_P)]),
     "mlbm_destroy": (ctypes.c_int, [_P]),
+    "mlbm_halo_plan": (ctypes.c_int, [ctypes.POINTER(MlbmConfig), ctypes.POINTER(MlbmHaloMessage), ctypes.c_int,
+                                      ctypes.POINTER(ctypes.c_int)]),
     "mlbm_comm_unique_id": (ctypes.c_int, [_P]),
     "mlbm_comm_init": (ctypes.c_int, [_P, _P]),
     "mlbm_upload_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
@@ -154,6 +168,8 @@ PROTOTYPES = {
     "mlbm_launch_count": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),
     "mlbm_stream": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
     "mlbm_kernel_time": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_uint64)]),
+    "mlbm_mark": (ctypes.c_int, [_P, ctypes.c_int]),
+    "mlbm_elapsed": (ctypes.c_int, [_P, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]),
 }
 
 _library = None
@@ -185,6 +201,16 @@ def load_library(path: os.PathLike | None = None) -> ctypes.CDLL:
     if path is None:
         _library = lib
     return lib
+
+
+def halo_plan(cfg: MlbmConfig) -> list:
+    """The halo messages of one step for ``cfg.rank`` (pure host logic, runs without a GPU)."""
+    lib = load_library()
+    count = ctypes.c_int()
+    check(lib.mlbm_halo_plan(ctypes.byref(cfg), None, 0, ctypes.byref(count)))
+    messages = (MlbmHaloMessage * max(count.value, 1))()
+    check(lib.mlbm_halo_plan(ctypes.byref(cfg), messages, count.value, ctypes.byref(count)))
+    return [messages[i] for i in range(count.value)]
 
 
 def check(status: int) -> None:

@@ -1,0 +1,946 @@
+// context.cu -- the C-ABI of include/metalbm_b200.h: device memory, the per-step orchestration
+// (Algorithm::iterate, Algorithm.h:326-358 / 392-447), the x-slab halo exchange (Communication.h:134-180)
+// and the scalar observables (AnalysisList.h:55-73) for one rank == one GPU.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/metalbm_b200.h"
+#include "nccl_loader.h"
+#include "step_kernel.cuh"
+
+namespace mlbm {
+
+StepKernel lookupStepKernel_d2q5_f64(int, int, int);
+StepKernel lookupStepKernel_d2q5_f32(int, int, int);
+StepKernel lookupStepKernel_d2q9_f64(int, int, int);
+StepKernel lookupStepKernel_d2q9_f32(int, int, int);
+StepKernel lookupStepKernel_d3q15_f64(int, int, int);
+StepKernel lookupStepKernel_d3q15_f32(int, int, int);
+StepKernel lookupStepKernel_d3q19_f64(int, int, int);
+StepKernel lookupStepKernel_d3q19_f32(int, int, int);
+StepKernel lookupStepKernel_d3q27_f64(int, int, int);
+StepKernel lookupStepKernel_d3q27_f32(int, int, int);
+
+StepKernel lookupStepKernel(int lattice, int collision, int equilibrium, int scheme, int dtype) {
+  const bool f64 = dtype == MLBM_F64;
+  switch (lattice) {
+    case kD2Q5: return f64 ? lookupStepKernel_d2q5_f64(collision, equilibrium, scheme) : lookupStepKernel_d2q5_f32(collision, equilibrium, scheme);
+    case kD2Q9: return f64 ? lookupStepKernel_d2q9_f64(collision, equilibrium, scheme) : lookupStepKernel_d2q9_f32(collision, equilibrium, scheme);
+    case kD3Q15: return f64 ? lookupStepKernel_d3q15_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q15_f32(collision, equilibrium, scheme);
+    case kD3Q19: return f64 ? lookupStepKernel_d3q19_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q19_f32(collision, equilibrium, scheme);
+    case kD3Q27: return f64 ? lookupStepKernel_d3q27_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q27_f32(collision, equilibrium, scheme);
+    default: return nullptr;
+  }
+}
+
+const NcclApi* loadNccl(const char** error) {
+  static NcclApi api;
+  static bool tried = false, ok = false;
+  static std::string message;
+  if (!tried) {
+    tried = true;
+    void* handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!handle) {
+      message = std::string("cannot load libnccl: ") + dlerror();
+    } else {
+      ok = true;
+      auto resolve = [&](const char* name) -> void* {
+        void* symbol = dlsym(handle, name);
+        if (!symbol) { ok = false; message = std::string("libnccl lacks ") + name; }
+        return symbol;
+      };
+      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(resolve("ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(resolve("ncclCommInitRank"));
+      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(resolve("ncclCommDestroy"));
+      api.Send = reinterpret_cast<decltype(api.Send)>(resolve("ncclSend"));
+      api.Recv = reinterpret_cast<decltype(api.Recv)>(resolve("ncclRecv"));
+      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(resolve("ncclGroupStart"));
+      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(resolve("ncclGroupEnd"));
+      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(resolve("ncclAllReduce"));
+      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(resolve("ncclGetErrorString"));
+    }
+  }
+  if (!ok) { if (error) *error = message.c_str(); return nullptr; }
+  return &api;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small device kernels around the fused step
+// ------------------------------------------------------------------------------------------------
+
+// deterministic final reduction of the per-block partials written by the fused kernel on stored steps
+__global__ void reduceObservablesKernel(const double* __restrict__ partials, long long blocks, double* __restrict__ out) {
+  __shared__ double scratch[kObservableSlots][256];
+  double e = 0.0, ms = 0.0, s2 = 0.0;
+  for (long long i = threadIdx.x; i < blocks; i += blockDim.x) {
+    e += partials[i * kObservableSlots + 0];
+    ms += partials[i * kObservableSlots + 1];
+    s2 = fmax(s2, partials[i * kObservableSlots + 2]);
+  }
+  scratch[0][threadIdx.x] = e;
+  scratch[1][threadIdx.x] = ms;
+  scratch[2][threadIdx.x] = s2;
+  __syncthreads();
+  for (int width = blockDim.x / 2; width > 0; width >>= 1) {
+    if ((int)threadIdx.x < width) {
+      scratch[0][threadIdx.x] += scratch[0][threadIdx.x + width];
+      scratch[1][threadIdx.x] += scratch[1][threadIdx.x + width];
+      scratch[2][threadIdx.x] = fmax(scratch[2][threadIdx.x], scratch[2][threadIdx.x + width]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[0] = scratch[0][0];
+    out[1] = scratch[1][0];
+    out[2] = scratch[2][0];
+  }
+}
+
+// total enstrophy of the stored hydrodynamic velocity with a 2nd-order central-difference curl on the
+// periodic slab (the reference's spectral definition, Transformer.h:118-295, is the "next" row N1).
+// x neighbours outside the slab are not available without a field halo: the x derivative is one-sided
+// at slab faces when nranks > 1 (documented in DESIGN.md).
+template <typename StoreT>
+__global__ void enstrophyKernel(const StoreT* __restrict__ velocity, long long fieldStride, int LX, int NM, int NR,
+                                int dim, int wrapX, double* __restrict__ blockSums) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y, x = blockIdx.z;
+  double value = 0.0;
+  if (r < NR) {
+    auto at = [&](int d, int xx, int mm, int rr) {
+      return (double)velocity[d * fieldStride + ((long long)xx * NM + mm) * NR + rr];
+    };
+    const int rp = r == NR - 1 ? 0 : r + 1, rm = r == 0 ? NR - 1 : r - 1;
+    const int mp = m == NM - 1 ? 0 : m + 1, mm = m == 0 ? NM - 1 : m - 1;
+    int xp = x + 1, xm = x - 1;
+    double hx = 0.5;
+    if (wrapX) { if (xp == LX) xp = 0; if (xm < 0) xm = LX - 1; }
+    else { if (xp == LX) { xp = x; hx = 1.0; } if (xm < 0) { xm = x; hx = 1.0; } }
+    if (dim == 2) {
+      // (x, r) = (x, y): w = d(uy)/dx - d(ux)/dy
+      const double w = hx * (at(1, xp, m, r) - at(1, xm, m, r)) - 0.5 * (at(0, x, m, rp) - at(0, x, m, rm));
+      value = 0.5 * w * w;
+    } else {
+      // (x, m, r) = (x, y, z)
+      const double wx = 0.5 * (at(2, x, mp, r) - at(2, x, mm, r)) - 0.5 * (at(1, x, m, rp) - at(1, x, m, rm));
+      const double wy = 0.5 * (at(0, x, m, rp) - at(0, x, m, rm)) - hx * (at(2, xp, m, r) - at(2, xm, m, r));
+      const double wz = hx * (at(1, xp, m, r) - at(1, xm, m, r)) - 0.5 * (at(0, x, mp, r) - at(0, x, mm, r));
+      value = 0.5 * (wx * wx + wy * wy + wz * wz);
+    }
+  }
+  for (int offset = 16; offset > 0; offset >>= 1) value += __shfl_xor_sync(0xffffffffu, value, offset);
+  __shared__ double scratch[32];
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = value;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double sum = 0.0;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sum += scratch[i];
+    blockSums[((long long)x * gridDim.y + m) * gridDim.x + blockIdx.x] = sum;
+  }
+}
+
+__global__ void sumKernel(const double* __restrict__ values, long long count, double* __restrict__ out) {
+  __shared__ double scratch[256];
+  double sum = 0.0;
+  for (long long i = threadIdx.x; i < count; i += blockDim.x) sum += values[i];
+  scratch[threadIdx.x] = sum;
+  __syncthreads();
+  for (int width = blockDim.x / 2; width > 0; width >>= 1) {
+    if ((int)threadIdx.x < width) scratch[threadIdx.x] += scratch[threadIdx.x + width];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = scratch[0];
+}
+
+template <typename StoreT> __global__ void fillKernel(StoreT* data, long long count, StoreT value) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) data[i] = value;
+}
+
+// f = feq(rho, u) (initDistribution, Initialize.h:106-117) into the interior of an SoA buffer
+template <class L, int EQ, typename StoreT>
+__global__ void initEquilibriumKernel(StoreT* __restrict__ populations, const StoreT* __restrict__ density,
+                                      const StoreT* __restrict__ velocity, long long stride, long long plane,
+                                      long long fieldStride, long long nodes) {
+  const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= nodes) return;
+  double u[3] = {0.0, 0.0, 0.0};
+  double u2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) {
+    u[d] = (double)velocity[d * fieldStride + node];
+    u2 += u[d] * u[d];
+  }
+  const double rho = (double)density[node];
+  EquilibriumCoefficients<L, EQ> eq;
+  eq.set(u, u2);
+  staticFor<0, L::Q>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    populations[q * stride + plane + node] = (StoreT)(rho * L::w(q) * eq.template shape<q>());
+  });
+}
+
+template <int EQ, typename StoreT>
+static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* populations, const StoreT* density,
+                                  const StoreT* velocity, long long stride, long long plane, long long fieldStride,
+                                  long long nodes) {
+  const int block = 128;
+  const unsigned grid = (unsigned)((nodes + block - 1) / block);
+  switch (lattice) {
+    case kD2Q5:
+      if (EQ == kTruncationMa3) initEquilibriumKernel<Lattice<kD2Q5>, kTruncationMa3, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes);
+      break;
+    case kD2Q9: initEquilibriumKernel<Lattice<kD2Q9>, EQ, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes); break;
+    case kD3Q15:
+      if (EQ == kTruncationMa3) initEquilibriumKernel<Lattice<kD3Q15>, kTruncationMa3, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes);
+      break;
+    case kD3Q19:
+      if (EQ == kTruncationMa3) initEquilibriumKernel<Lattice<kD3Q19>, kTruncationMa3, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes);
+      break;
+    case kD3Q27: initEquilibriumKernel<Lattice<kD3Q27>, EQ, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes); break;
+  }
+}
+
+}  // namespace mlbm
+
+using namespace mlbm;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_lastError;
+
+static int fail(int status, const char* format, ...) {
+  char buffer[1024];
+  va_list arguments;
+  va_start(arguments, format);
+  vsnprintf(buffer, sizeof(buffer), format, arguments);
+  va_end(arguments);
+  g_lastError = buffer;
+  return status;
+}
+
+#define MLBM_CUDA(call)                                                                                  \
+  do {                                                                                                   \
+    cudaError_t error_ = (call);                                                                         \
+    if (error_ != cudaSuccess)                                                                           \
+      return fail(error_ == cudaErrorMemoryAllocation ? MLBM_ERR_NOMEM : MLBM_ERR_CUDA, "[%s:%d] CUDA failed with %s", \
+                  __FILE__, __LINE__, cudaGetErrorString(error_));                                       \
+  } while (0)
+
+#define MLBM_NCCL(ctx, call)                                                                             \
+  do {                                                                                                   \
+    ncclResult_t result_ = (call);                                                                       \
+    if (result_ != ncclSuccess)                                                                          \
+      return fail(MLBM_ERR_COMM, "[%s:%d] NCCL failed with %s", __FILE__, __LINE__,                      \
+                  (ctx)->nccl->GetErrorString(result_));                                                 \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// the context
+// ------------------------------------------------------------------------------------------------
+struct mlbm_ctx {
+  mlbm_config config;
+  int device = 0;
+  int D = 0, Q = 0, faceQ = 0;
+  int LX = 0, NM = 0, NR = 0;           // local extents on the kernel axes (x, m, r)
+  size_t elementSize = 8;
+  long long plane = 0, stride = 0, fieldStride = 0, nodes = 0;
+  long long partialBlocks = 0;
+  int gridR = 0;
+
+  void* populations[2] = {nullptr, nullptr};  // ping-pong SoA pair (Distribution.h:19-20)
+  int current = 0;                             // buffer the next step reads ("previous")
+  void* alpha = nullptr;
+  void* density = nullptr;
+  void* velocity = nullptr;
+  void* force = nullptr;
+  bool fieldsStored = false;
+  double* partials = nullptr;
+  double* enstrophyBlocks = nullptr;
+  double* deviceObservables = nullptr;   // [energy sum, mass, max speed^2, enstrophy sum]
+  double* forceTables[3] = {nullptr, nullptr, nullptr};
+  int forceAxis[3] = {-1, -1, -1};
+  bool observablesValid = false;
+
+  StepKernel kernel = nullptr;
+  int hydroShift = 0;
+  cudaStream_t computeStream = nullptr;
+  cudaStream_t commStream = nullptr;
+  cudaEvent_t boundaryDone = nullptr, exchangeDone = nullptr, bulkDone = nullptr;
+  cudaEvent_t timeStart = nullptr, timeMid = nullptr, timeStop = nullptr;
+  cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  double lastCommunication = 0.0, lastComputation = 0.0;
+  unsigned long long launches = 0;
+
+  // per-launch timing of the fused kernel (mlbm_kernel_time)
+  bool profiling = false;
+  std::vector<cudaEvent_t> profileEvents;
+  size_t profileUsed = 0;
+  double profileMs = 0.0;
+  unsigned long long profileLaunches = 0;
+
+  const NcclApi* nccl = nullptr;
+  ncclComm_t comm = nullptr;
+  bool halosValid = false;  // halo planes of populations[current] hold the neighbours' data
+  std::vector<mlbm_halo_message> haloMessages;
+};
+
+static inline void* offsetElements(void* base, long long elements, size_t elementSize) {
+  return static_cast<char*>(base) + elements * (long long)elementSize;
+}
+
+static int collectProfile(mlbm_ctx* ctx) {
+  for (size_t i = 0; i + 1 < ctx->profileUsed; i += 2) {
+    float ms = 0.f;
+    MLBM_CUDA(cudaEventElapsedTime(&ms, ctx->profileEvents[i], ctx->profileEvents[i + 1]));
+    ctx->profileMs += ms;
+    ctx->profileLaunches += 1;
+  }
+  ctx->profileUsed = 0;
+  return MLBM_OK;
+}
+
+// one launch of the fused kernel over local planes [x0, x1)
+static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int isStored, bool profile) {
+  if (x1 <= x0) return MLBM_OK;
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  p.prev = ctx->populations[ctx->current];
+  p.next = ctx->populations[ctx->current ^ 1];
+  p.alpha = ctx->alpha;
+  p.density = ctx->density;
+  p.velocity = ctx->velocity;
+  p.force = ctx->force;
+  p.partials = ctx->partials;
+  for (int d = 0; d < 3; ++d) { p.forceTable[d] = ctx->forceTables[d]; p.forceAxis[d] = ctx->forceAxis[d]; }
+  p.stride = ctx->stride;
+  p.plane = ctx->plane;
+  p.fieldStride = ctx->fieldStride;
+  p.LX = ctx->LX; p.NM = ctx->NM; p.NR = ctx->NR;
+  p.x0 = x0;
+  p.wrapX = ctx->config.nranks == 1 ? 1 : 0;
+  p.isStored = isStored;
+  p.hydroShift = ctx->hydroShift;
+  p.hasForce = ctx->config.force != MLBM_FORCE_NONE;
+  p.beta = 1.0 / (2.0 * ctx->config.tau);
+  p.guoFactor = (1.0 - 1.0 / (2.0 * ctx->config.tau)) * 3.0;
+  dim3 grid((unsigned)ctx->gridR, (unsigned)ctx->NM, (unsigned)(x1 - x0));
+  cudaEvent_t start = nullptr, stop = nullptr;
+  if (profile) {
+    if (ctx->profileUsed + 2 > ctx->profileEvents.size()) {
+      if (ctx->profileEvents.size() >= 8192) {
+        MLBM_CUDA(cudaStreamSynchronize(stream));
+        if (int status = collectProfile(ctx)) return status;
+      } else {
+        for (int i = 0; i < 2; ++i) {
+          cudaEvent_t event;
+          MLBM_CUDA(cudaEventCreate(&event));
+          ctx->profileEvents.push_back(event);
+        }
+      }
+    }
+    start = ctx->profileEvents[ctx->profileUsed];
+    stop = ctx->profileEvents[ctx->profileUsed + 1];
+    ctx->profileUsed += 2;
+    MLBM_CUDA(cudaEventRecord(start, stream));
+  }
+  ctx->kernel<<<grid, kStepBlock, 0, stream>>>(p);
+  if (profile) MLBM_CUDA(cudaEventRecord(stop, stream));
+  MLBM_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  return MLBM_OK;
+}
+
+// geometry shared by the context and the (device-free) halo plan
+struct SlabGeometry {
+  int D, Q, faceQ, LX, NM, NR;
+  long long plane, stride;
+};
+
+static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
+  g->Q = latticeQ(config->lattice);
+  if (!g->Q || config->nranks < 1 || config->global_length[0] % config->nranks) return false;
+  g->D = latticeDim(config->lattice);
+  g->faceQ = latticeFaceQ(config->lattice);
+  g->LX = config->global_length[0] / config->nranks;
+  g->NM = g->D == 3 ? config->global_length[1] : 1;
+  g->NR = g->D == 3 ? config->global_length[2] : config->global_length[1];
+  g->plane = (long long)g->NM * g->NR;
+  const long long perPopulation = g->plane * (g->LX + 2);
+  g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
+  return true;
+}
+
+// Communication::communicateHalos (Communication.h:494-500) as a list of messages: the last interior plane of
+// the c_x > 0 populations goes to the right neighbour's plane 0, the first interior plane of the c_x < 0
+// populations to the left neighbour's plane LX+1 (Communication.h:134-180).
+static int haloPlan(const mlbm_config* config, std::vector<mlbm_halo_message>* plan) {
+  SlabGeometry g;
+  if (!slabGeometry(config, &g)) return MLBM_ERR_INVALID;
+  plan->clear();
+  if (config->nranks == 1) return MLBM_OK;
+  const int left = (config->rank + config->nranks - 1) % config->nranks;  // MPIInitializer.h:56
+  const int right = (config->rank + 1) % config->nranks;                  // MPIInitializer.h:57
+  auto add = [&](int q, int peer, int isSend, long long xPlane) {
+    mlbm_halo_message message;
+    message.population = q;
+    message.peer = peer;
+    message.is_send = isSend;
+    message.reserved = 0;
+    message.offset = (uint64_t)(q * g.stride + xPlane * g.plane);
+    message.count = (uint64_t)g.plane;
+    plan->push_back(message);
+  };
+  for (int q = g.faceQ + 1; q < 2 * g.faceQ + 1; ++q) {
+    add(q, right, 1, g.LX);  // last interior plane
+    add(q, left, 0, 0);      // left halo plane
+  }
+  for (int q = 1; q < g.faceQ + 1; ++q) {
+    add(q, left, 1, 1);          // first interior plane
+    add(q, right, 0, g.LX + 1);  // right halo plane
+  }
+  return MLBM_OK;
+}
+
+static int exchangeHalos(mlbm_ctx* ctx, int which, cudaStream_t stream) {
+  if (ctx->config.nranks == 1) return MLBM_OK;
+  if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
+  const ncclDataType_t type = ctx->config.dtype == MLBM_F64 ? ncclDouble : ncclFloat;
+  void* base = ctx->populations[which];
+  MLBM_NCCL(ctx, ctx->nccl->GroupStart());
+  for (const mlbm_halo_message& message : ctx->haloMessages) {
+    void* pointer = offsetElements(base, (long long)message.offset, ctx->elementSize);
+    if (message.is_send) MLBM_NCCL(ctx, ctx->nccl->Send(pointer, message.count, type, message.peer, ctx->comm, stream));
+    else MLBM_NCCL(ctx, ctx->nccl->Recv(pointer, message.count, type, message.peer, ctx->comm, stream));
+  }
+  MLBM_NCCL(ctx, ctx->nccl->GroupEnd());
+  ctx->launches += 1;
+  return MLBM_OK;
+}
+
+static int ensureFields(mlbm_ctx* ctx) {
+  if (ctx->density) return MLBM_OK;
+  const size_t bytes = (size_t)ctx->nodes * ctx->elementSize;
+  MLBM_CUDA(cudaMalloc(&ctx->density, bytes));
+  MLBM_CUDA(cudaMalloc(&ctx->velocity, bytes * ctx->D));
+  MLBM_CUDA(cudaMalloc(&ctx->force, bytes * ctx->D));
+  MLBM_CUDA(cudaMemsetAsync(ctx->density, 0, bytes, ctx->computeStream));
+  MLBM_CUDA(cudaMemsetAsync(ctx->velocity, 0, bytes * ctx->D, ctx->computeStream));
+  MLBM_CUDA(cudaMemsetAsync(ctx->force, 0, bytes * ctx->D, ctx->computeStream));
+  return MLBM_OK;
+}
+
+static int ensurePartials(mlbm_ctx* ctx) {
+  if (ctx->partials) return MLBM_OK;
+  MLBM_CUDA(cudaMalloc(&ctx->partials, sizeof(double) * kObservableSlots * (size_t)ctx->partialBlocks));
+  MLBM_CUDA(cudaMalloc(&ctx->enstrophyBlocks, sizeof(double) * (size_t)ctx->partialBlocks));
+  return MLBM_OK;
+}
+
+// enqueue one Algorithm::iterate; `timed` records the events behind mlbm_timers
+static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
+  const bool multi = ctx->config.nranks > 1;
+  if (isStored & 1) { if (int status = ensureFields(ctx)) return status; }
+  if (isStored) { if (int status = ensurePartials(ctx)) return status; }
+  cudaStream_t compute = ctx->computeStream;
+  if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeStart, compute));
+
+  if (!multi) {
+    if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
+    if (int status = launchStep(ctx, compute, 0, ctx->LX, isStored, profile)) return status;
+  } else if (ctx->config.overlap == MLBM_OVERLAP_OFF || ctx->LX < 3) {
+    // the reference's order (Algorithm.h:336-355): exchange the halos of the buffer about to be read, then compute
+    if (!ctx->halosValid) { if (int status = exchangeHalos(ctx, ctx->current, compute)) return status; }
+    if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
+    if (int status = launchStep(ctx, compute, 0, ctx->LX, isStored, profile)) return status;
+    ctx->halosValid = false;
+  } else {
+    // overlap (the intent of Algorithm.h:392-447): the two boundary planes first, their exchange on the
+    // communication stream while the bulk planes are computed.
+    if (!ctx->halosValid) {
+      if (int status = exchangeHalos(ctx, ctx->current, compute)) return status;
+    }
+    if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
+    if (int status = launchStep(ctx, compute, 0, 1, isStored, false)) return status;
+    if (int status = launchStep(ctx, compute, ctx->LX - 1, ctx->LX, isStored, false)) return status;
+    MLBM_CUDA(cudaEventRecord(ctx->boundaryDone, compute));
+    MLBM_CUDA(cudaStreamWaitEvent(ctx->commStream, ctx->boundaryDone, 0));
+    if (int status = exchangeHalos(ctx, ctx->current ^ 1, ctx->commStream)) return status;
+    MLBM_CUDA(cudaEventRecord(ctx->exchangeDone, ctx->commStream));
+    if (int status = launchStep(ctx, compute, 1, ctx->LX - 1, isStored, profile)) return status;
+    MLBM_CUDA(cudaStreamWaitEvent(compute, ctx->exchangeDone, 0));
+    ctx->halosValid = true;  // of the buffer that becomes current below
+  }
+  ctx->current ^= 1;  // std::swap(previous, next) (Algorithm.h:336), done after the step instead of before
+
+  if (isStored) {
+    reduceObservablesKernel<<<1, 256, 0, compute>>>(ctx->partials, ctx->partialBlocks, ctx->deviceObservables);
+    ctx->launches += 1;
+    if (isStored & 1) {
+      dim3 grid((unsigned)ctx->gridR, (unsigned)ctx->NM, (unsigned)ctx->LX);
+      const int wrapX = ctx->config.nranks == 1;
+      if (ctx->config.dtype == MLBM_F64)
+        enstrophyKernel<double><<<grid, kStepBlock, 0, compute>>>(static_cast<const double*>(ctx->velocity), ctx->fieldStride,
+                                                                  ctx->LX, ctx->NM, ctx->NR, ctx->D, wrapX, ctx->enstrophyBlocks);
+      else
+        enstrophyKernel<float><<<grid, kStepBlock, 0, compute>>>(static_cast<const float*>(ctx->velocity), ctx->fieldStride,
+                                                                 ctx->LX, ctx->NM, ctx->NR, ctx->D, wrapX, ctx->enstrophyBlocks);
+      sumKernel<<<1, 256, 0, compute>>>(ctx->enstrophyBlocks, ctx->partialBlocks, ctx->deviceObservables + 3);
+      ctx->launches += 2;
+      ctx->fieldsStored = true;
+    }
+    MLBM_CUDA(cudaGetLastError());
+    ctx->observablesValid = true;
+  }
+  if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeStop, compute));
+  return MLBM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// C entry points
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* mlbm_last_error(void) { return g_lastError.c_str(); }
+int mlbm_abi_version(void) { return MLBM_ABI_VERSION; }
+
+int mlbm_destroy(mlbm_ctx* ctx) {
+  if (!ctx) return MLBM_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->computeStream) cudaStreamSynchronize(ctx->computeStream);
+  if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
+  if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
+  for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
+                        (void*)ctx->partials, (void*)ctx->enstrophyBlocks, (void*)ctx->deviceObservables,
+                        (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
+    if (pointer) cudaFree(pointer);
+  for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->timeStart, ctx->timeMid, ctx->timeStop})
+    if (event) cudaEventDestroy(event);
+  for (cudaEvent_t event : ctx->profileEvents) cudaEventDestroy(event);
+  for (cudaEvent_t event : ctx->marks) if (event) cudaEventDestroy(event);
+  if (ctx->computeStream) cudaStreamDestroy(ctx->computeStream);
+  if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
+  delete ctx;
+  return MLBM_OK;
+}
+
+int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
+  if (!config || !out) return fail(MLBM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  if (config->abi_version != MLBM_ABI_VERSION) return fail(MLBM_ERR_INVALID, "mlbm_config.abi_version %d != %d", config->abi_version, MLBM_ABI_VERSION);
+  const int Q = latticeQ(config->lattice);
+  if (!Q) return fail(MLBM_ERR_INVALID, "unknown lattice %d", config->lattice);
+  const int D = latticeDim(config->lattice);
+  if (config->dtype != MLBM_F64 && config->dtype != MLBM_F32) return fail(MLBM_ERR_INVALID, "unknown dtype %d", config->dtype);
+  if (!(config->tau > 0.5)) return fail(MLBM_ERR_INVALID, "relaxation time must exceed 0.5 (got %g)", config->tau);
+  if (config->nranks < 1 || config->rank < 0 || config->rank >= config->nranks) return fail(MLBM_ERR_INVALID, "bad rank %d of %d", config->rank, config->nranks);
+  for (int d = 0; d < D; ++d)
+    if (config->global_length[d] < 1) return fail(MLBM_ERR_INVALID, "global_length[%d] = %d", d, config->global_length[d]);
+  if (config->global_length[0] % config->nranks) return fail(MLBM_ERR_INVALID, "nranks %d does not divide globalLengthX %d (Domain.h:22-24)", config->nranks, config->global_length[0]);
+
+  int collision, scheme, hydroShift;
+  switch (config->collision) {
+    case MLBM_BGK: collision = kBGK; break;
+    case MLBM_ELBM: case MLBM_FORCED_NR_ELBM: collision = kELBM; break;  // identical in the reference snapshot (Collision.h:239, 705-723)
+    default: return fail(MLBM_ERR_INVALID, "unknown collision %d", config->collision);
+  }
+  switch (config->forcing_scheme) {
+    case MLBM_SCHEME_NONE: scheme = kSchemeNone; hydroShift = 0; break;
+    case MLBM_SHAN_CHEN: scheme = kSchemeNone; hydroShift = 1; break;
+    case MLBM_GUO: scheme = kSchemeGuo; hydroShift = 1; break;
+    case MLBM_EXACT_DIFFERENCE: scheme = kSchemeEDM; hydroShift = 1; break;
+    default: return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
+  }
+  if (config->force < MLBM_FORCE_NONE || config->force > MLBM_FORCE_KOLMOGOROV) return fail(MLBM_ERR_INVALID, "unknown force %d", config->force);
+  if (config->equilibrium != MLBM_TRUNCATION_MA3 && config->equilibrium != MLBM_EXACT) return fail(MLBM_ERR_INVALID, "unknown equilibrium %d", config->equilibrium);
+  StepKernel kernel = lookupStepKernel(config->lattice, collision, config->equilibrium, scheme, config->dtype);
+  if (!kernel) return fail(MLBM_ERR_INVALID, "no kernel for this lattice/equilibrium combination (the exact equilibrium exists for D2Q9 and D3Q27 only, Equilibrium.h:36-126)");
+
+  int deviceCount = 0;
+  cudaError_t error = cudaGetDeviceCount(&deviceCount);
+  if (error != cudaSuccess || deviceCount == 0)
+    return fail(MLBM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                error == cudaSuccess ? "device count is 0" : cudaGetErrorString(error));
+  const int device = config->device >= 0 ? config->device : config->rank % deviceCount;  // CUDAInitializer.h:23-26
+  if (device >= deviceCount) return fail(MLBM_ERR_INVALID, "device %d of %d", device, deviceCount);
+  MLBM_CUDA(cudaSetDevice(device));
+
+  mlbm_ctx* ctx = new mlbm_ctx();
+  ctx->config = *config;
+  ctx->device = device;
+  ctx->D = D; ctx->Q = Q; ctx->faceQ = latticeFaceQ(config->lattice);
+  SlabGeometry geometry;
+  slabGeometry(config, &geometry);
+  ctx->LX = geometry.LX;
+  ctx->NM = geometry.NM;
+  ctx->NR = geometry.NR;
+  ctx->elementSize = config->dtype == MLBM_F64 ? 8 : 4;
+  ctx->plane = geometry.plane;
+  ctx->nodes = ctx->plane * ctx->LX;
+  ctx->fieldStride = ctx->nodes;
+  ctx->stride = geometry.stride;
+  haloPlan(config, &ctx->haloMessages);
+  ctx->gridR = (ctx->NR + kStepBlock - 1) / kStepBlock;
+  ctx->partialBlocks = (long long)ctx->gridR * ctx->NM * ctx->LX;
+  ctx->kernel = kernel;
+  ctx->hydroShift = hydroShift;
+
+  auto cleanup = [&](int status) { mlbm_destroy(ctx); return status; };
+#define MLBM_CREATE_CUDA(call)                                                                          \
+  do {                                                                                                  \
+    cudaError_t error_ = (call);                                                                        \
+    if (error_ != cudaSuccess)                                                                          \
+      return cleanup(fail(error_ == cudaErrorMemoryAllocation ? MLBM_ERR_NOMEM : MLBM_ERR_CUDA,         \
+                          "[%s:%d] CUDA failed with %s", __FILE__, __LINE__, cudaGetErrorString(error_))); \
+  } while (0)
+
+  int leastPriority = 0, greatestPriority = 0;
+  MLBM_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&leastPriority, &greatestPriority));
+  MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->computeStream, cudaStreamNonBlocking, leastPriority));
+  MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, greatestPriority));
+  for (cudaEvent_t* event : {&ctx->boundaryDone, &ctx->exchangeDone, &ctx->bulkDone})
+    MLBM_CREATE_CUDA(cudaEventCreateWithFlags(event, cudaEventDisableTiming));
+  for (cudaEvent_t* event : {&ctx->timeStart, &ctx->timeMid, &ctx->timeStop}) MLBM_CREATE_CUDA(cudaEventCreate(event));
+
+  const size_t bufferBytes = (size_t)ctx->stride * Q * ctx->elementSize;
+  for (int i = 0; i < 2; ++i) {
+    MLBM_CREATE_CUDA(cudaMalloc(&ctx->populations[i], bufferBytes));
+    MLBM_CREATE_CUDA(cudaMemsetAsync(ctx->populations[i], 0, bufferBytes, ctx->computeStream));
+  }
+  if (collision == kELBM) {
+    // initAlpha: the alpha field starts at 2 (Initialize.h:82-88)
+    MLBM_CREATE_CUDA(cudaMalloc(&ctx->alpha, (size_t)ctx->nodes * ctx->elementSize));
+    const unsigned grid = (unsigned)((ctx->nodes + 255) / 256);
+    if (config->dtype == MLBM_F64) fillKernel<double><<<grid, 256, 0, ctx->computeStream>>>(static_cast<double*>(ctx->alpha), ctx->nodes, 2.0);
+    else fillKernel<float><<<grid, 256, 0, ctx->computeStream>>>(static_cast<float*>(ctx->alpha), ctx->nodes, 2.0f);
+    MLBM_CREATE_CUDA(cudaGetLastError());
+  }
+  MLBM_CREATE_CUDA(cudaMalloc(&ctx->deviceObservables, 4 * sizeof(double)));
+  MLBM_CREATE_CUDA(cudaMemsetAsync(ctx->deviceObservables, 0, 4 * sizeof(double), ctx->computeStream));
+
+  // Force profiles, evaluated on the host with libm exactly like Force::setForce does per node
+  // (Force.h:154-159 Constant, :208-215 Sinusoidal, :262-267 Kolmogorov) at LOCAL coordinates (Collision.h:86).
+  if (config->force != MLBM_FORCE_NONE) {
+    const int extent[3] = {ctx->LX, D == 3 ? config->global_length[1] : config->global_length[1], D == 3 ? config->global_length[2] : 1};
+    const int kernelAxisOf[3] = {0, D == 3 ? 1 : 2, 2};  // physical axis -> kernel axis
+    for (int d = 0; d < D; ++d) {
+      int physicalAxis = -1;
+      if (config->force == MLBM_FORCE_CONSTANT) physicalAxis = 0;
+      if (config->force == MLBM_FORCE_SINUSOIDAL) physicalAxis = d;
+      if (config->force == MLBM_FORCE_KOLMOGOROV && d == 0) physicalAxis = 1;
+      if (physicalAxis < 0) continue;
+      std::vector<double> table((size_t)extent[physicalAxis]);
+      for (unsigned i = 0; i < (unsigned)table.size(); ++i) {
+        if (config->force == MLBM_FORCE_CONSTANT) table[i] = config->force_amplitude[d];
+        else if (config->force == MLBM_FORCE_SINUSOIDAL) table[i] = config->force_amplitude[d] * sin(i * 2 * M_PI / config->force_wavelength[d]);
+        else table[i] = config->force_amplitude[0] * sin(i * 2 * M_PI / config->force_wavelength[0]);
+      }
+      MLBM_CREATE_CUDA(cudaMalloc(&ctx->forceTables[d], table.size() * sizeof(double)));
+      MLBM_CREATE_CUDA(cudaMemcpy(ctx->forceTables[d], table.data(), table.size() * sizeof(double), cudaMemcpyHostToDevice));
+      ctx->forceAxis[d] = kernelAxisOf[physicalAxis];
+    }
+  }
+  MLBM_CREATE_CUDA(cudaStreamSynchronize(ctx->computeStream));
+#undef MLBM_CREATE_CUDA
+  *out = ctx;
+  return MLBM_OK;
+}
+
+int mlbm_halo_plan(const mlbm_config* config, mlbm_halo_message* out, int capacity, int* count) {
+  if (!config || !count) return fail(MLBM_ERR_INVALID, "null argument");
+  std::vector<mlbm_halo_message> plan;
+  if (haloPlan(config, &plan)) return fail(MLBM_ERR_INVALID, "bad lattice or nranks does not divide globalLengthX");
+  *count = (int)plan.size();
+  if (out) {
+    if (capacity < (int)plan.size()) return fail(MLBM_ERR_INVALID, "capacity %d < %d messages", capacity, (int)plan.size());
+    memcpy(out, plan.data(), plan.size() * sizeof(mlbm_halo_message));
+  }
+  return MLBM_OK;
+}
+
+int mlbm_comm_unique_id(void* id128) {
+  if (!id128) return fail(MLBM_ERR_INVALID, "null argument");
+  const char* error = nullptr;
+  const NcclApi* api = loadNccl(&error);
+  if (!api) return fail(MLBM_ERR_COMM, "%s", error);
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  ncclUniqueId id;
+  ncclResult_t result = api->GetUniqueId(&id);
+  if (result != ncclSuccess) return fail(MLBM_ERR_COMM, "ncclGetUniqueId: %s", api->GetErrorString(result));
+  memcpy(id128, &id, sizeof(id));
+  return MLBM_OK;
+}
+
+int mlbm_comm_init(mlbm_ctx* ctx, const void* id128) {
+  if (!ctx || !id128) return fail(MLBM_ERR_INVALID, "null argument");
+  if (ctx->comm) return fail(MLBM_ERR_STATE, "communicator already initialised");
+  const char* error = nullptr;
+  ctx->nccl = loadNccl(&error);
+  if (!ctx->nccl) return fail(MLBM_ERR_COMM, "%s", error);
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  ncclUniqueId id;
+  memcpy(&id, id128, sizeof(id));
+  MLBM_NCCL(ctx, ctx->nccl->CommInitRank(&ctx->comm, ctx->config.nranks, id, ctx->config.rank));
+  return MLBM_OK;
+}
+
+// host (reference local-padded SoA) <-> device interior planes, one strided copy per population
+static int copyDistribution(mlbm_ctx* ctx, void* host, size_t componentStride, size_t paddedY, size_t paddedZ, bool upload) {
+  if (!ctx || !host) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  const size_t es = ctx->elementSize;
+  const bool threeD = ctx->D == 3;
+  const size_t hostPitch = threeD ? paddedZ : paddedY;  // elements between consecutive host rows
+  if (hostPitch < (size_t)ctx->NR || (threeD && paddedY < (size_t)ctx->NM)) return fail(MLBM_ERR_INVALID, "padded lengths smaller than the local lengths");
+  const bool uniform = !threeD || paddedY == (size_t)ctx->NM;
+  for (int q = 0; q < ctx->Q; ++q) {
+    char* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->plane) * es;
+    char* hostQ = static_cast<char*>(host) + (size_t)q * componentStride * es;
+    const int chunks = uniform ? 1 : ctx->LX;
+    const size_t rows = uniform ? (size_t)ctx->LX * ctx->NM : (size_t)ctx->NM;
+    for (int chunk = 0; chunk < chunks; ++chunk) {
+      char* d = device + (size_t)chunk * ctx->plane * es;
+      char* h = hostQ + (size_t)chunk * paddedY * paddedZ * es;
+      if (upload) MLBM_CUDA(cudaMemcpy2DAsync(d, ctx->NR * es, h, hostPitch * es, ctx->NR * es, rows, cudaMemcpyHostToDevice, ctx->computeStream));
+      else MLBM_CUDA(cudaMemcpy2DAsync(h, hostPitch * es, d, ctx->NR * es, ctx->NR * es, rows, cudaMemcpyDeviceToHost, ctx->computeStream));
+    }
+  }
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  if (upload) ctx->halosValid = false;
+  return MLBM_OK;
+}
+
+int mlbm_upload_distribution(mlbm_ctx* ctx, const void* host, size_t componentStride, size_t paddedY, size_t paddedZ) {
+  return copyDistribution(ctx, const_cast<void*>(host), componentStride, paddedY, paddedZ, true);
+}
+
+int mlbm_download_distribution(mlbm_ctx* ctx, void* host, size_t componentStride, size_t paddedY, size_t paddedZ) {
+  return copyDistribution(ctx, host, componentStride, paddedY, paddedZ, false);
+}
+
+// a field [components][LX][paddedY][paddedZ] on the host <-> dense [components][LX][NM][NR] on the device
+static int copyField(mlbm_ctx* ctx, void* host, void* device, int components, size_t componentStride, size_t paddedY,
+                     size_t paddedZ, bool upload) {
+  const size_t es = ctx->elementSize;
+  const bool threeD = ctx->D == 3;
+  const size_t hostPitch = threeD ? paddedZ : paddedY;
+  if (hostPitch < (size_t)ctx->NR || (threeD && paddedY < (size_t)ctx->NM)) return fail(MLBM_ERR_INVALID, "padded lengths smaller than the local lengths");
+  const bool uniform = !threeD || paddedY == (size_t)ctx->NM;
+  for (int c = 0; c < components; ++c) {
+    const int chunks = uniform ? 1 : ctx->LX;
+    const size_t rows = uniform ? (size_t)ctx->LX * ctx->NM : (size_t)ctx->NM;
+    for (int chunk = 0; chunk < chunks; ++chunk) {
+      char* d = static_cast<char*>(device) + ((size_t)c * ctx->fieldStride + (size_t)chunk * ctx->plane) * es;
+      char* h = static_cast<char*>(host) + ((size_t)c * componentStride + (size_t)chunk * paddedY * paddedZ) * es;
+      if (upload) MLBM_CUDA(cudaMemcpy2DAsync(d, ctx->NR * es, h, hostPitch * es, ctx->NR * es, rows, cudaMemcpyHostToDevice, ctx->computeStream));
+      else MLBM_CUDA(cudaMemcpy2DAsync(h, hostPitch * es, d, ctx->NR * es, ctx->NR * es, rows, cudaMemcpyDeviceToHost, ctx->computeStream));
+    }
+  }
+  return MLBM_OK;
+}
+
+int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* velocity, size_t componentStride,
+                          size_t paddedY, size_t paddedZ) {
+  if (!ctx || !density || !velocity) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (int status = ensureFields(ctx)) return status;
+  if (int status = copyField(ctx, const_cast<void*>(density), ctx->density, 1, componentStride, paddedY, paddedZ, true)) return status;
+  if (int status = copyField(ctx, const_cast<void*>(velocity), ctx->velocity, ctx->D, componentStride, paddedY, paddedZ, true)) return status;
+  void* target = ctx->populations[ctx->current];
+  if (ctx->config.dtype == MLBM_F64) {
+    if (ctx->config.equilibrium == MLBM_EXACT)
+      launchInitEquilibrium<kExact, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), static_cast<const double*>(ctx->density), static_cast<const double*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+    else
+      launchInitEquilibrium<kTruncationMa3, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), static_cast<const double*>(ctx->density), static_cast<const double*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+  } else {
+    if (ctx->config.equilibrium == MLBM_EXACT)
+      launchInitEquilibrium<kExact, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+    else
+      launchInitEquilibrium<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+  }
+  MLBM_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  ctx->halosValid = false;
+  return MLBM_OK;
+}
+
+int mlbm_set_alpha(mlbm_ctx* ctx, const void* host, size_t paddedY, size_t paddedZ) {
+  if (!ctx || !host) return fail(MLBM_ERR_INVALID, "null argument");
+  if (!ctx->alpha) return fail(MLBM_ERR_STATE, "the BGK alpha field is the constant 2 (Collision.h:121)");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (int status = copyField(ctx, const_cast<void*>(host), ctx->alpha, 1, 0, paddedY, paddedZ, true)) return status;
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  return MLBM_OK;
+}
+
+int mlbm_step(mlbm_ctx* ctx, unsigned iteration, int isStored) {
+  (void)iteration;  // Force::update is a no-op for the time-independent forces of this path (Force.h:51-54)
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (int status = enqueueStep(ctx, isStored ? (isStored & 3 ? isStored & 3 : 1) : 0, true, ctx->profiling)) return status;
+  // the reference's iterate returns after cudaDeviceSynchronize (Algorithm.h:355)
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  float communication = 0.f, computation = 0.f;
+  MLBM_CUDA(cudaEventElapsedTime(&communication, ctx->timeStart, ctx->timeMid));
+  MLBM_CUDA(cudaEventElapsedTime(&computation, ctx->timeMid, ctx->timeStop));
+  ctx->lastCommunication = communication * 1e-3;
+  ctx->lastComputation = computation * 1e-3;
+  return MLBM_OK;
+}
+
+int mlbm_run_async(mlbm_ctx* ctx, unsigned firstIteration, unsigned count, unsigned storeEvery) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  const bool profile = ctx->profiling;
+  for (unsigned i = 0; i < count; ++i) {
+    const unsigned iteration = firstIteration + i;
+    const int isStored = (storeEvery && iteration % storeEvery == 0) ? 1 : 0;
+    if (int status = enqueueStep(ctx, isStored, false, profile)) return status;
+  }
+  return MLBM_OK;
+}
+
+int mlbm_sync(mlbm_ctx* ctx) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  MLBM_CUDA(cudaStreamSynchronize(ctx->commStream));
+  return MLBM_OK;
+}
+
+int mlbm_download_fields(mlbm_ctx* ctx, void* density, void* velocity, void* alpha, void* force, size_t componentStride,
+                         size_t paddedY, size_t paddedZ) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if ((density || velocity || force) && !ctx->fieldsStored) return fail(MLBM_ERR_STATE, "no stored step yet (Algorithm::isStored was never set)");
+  if (density) { if (int status = copyField(ctx, density, ctx->density, 1, componentStride, paddedY, paddedZ, false)) return status; }
+  if (velocity) { if (int status = copyField(ctx, velocity, ctx->velocity, ctx->D, componentStride, paddedY, paddedZ, false)) return status; }
+  if (force) { if (int status = copyField(ctx, force, ctx->force, ctx->D, componentStride, paddedY, paddedZ, false)) return status; }
+  if (alpha) {
+    if (ctx->alpha) {
+      if (int status = copyField(ctx, alpha, ctx->alpha, 1, componentStride, paddedY, paddedZ, false)) return status;
+    } else {
+      // BGK: alpha == 2 everywhere (Collision.h:121, Algorithm.h:105-106)
+      const size_t hostPitch = ctx->D == 3 ? paddedZ : paddedY;
+      for (int x = 0; x < ctx->LX; ++x)
+        for (int m = 0; m < ctx->NM; ++m)
+          for (int r = 0; r < ctx->NR; ++r) {
+            const size_t index = ctx->D == 3 ? ((size_t)x * paddedY + m) * paddedZ + r : (size_t)x * hostPitch + r;
+            if (ctx->config.dtype == MLBM_F64) static_cast<double*>(alpha)[index] = 2.0;
+            else static_cast<float*>(alpha)[index] = 2.0f;
+          }
+    }
+  }
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  return MLBM_OK;
+}
+
+int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
+  if (!ctx || !out) return fail(MLBM_ERR_INVALID, "null argument");
+  if (!ctx->observablesValid) return fail(MLBM_ERR_STATE, "no stored step yet (Algorithm::isStored was never set)");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  double local[4];
+  if (ctx->config.nranks > 1) {
+    if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
+    // Communication::reduce (Communication.h:76-89): sums over ranks (max for the Mach number)
+    double* values = ctx->deviceObservables;
+    const ncclDataType_t type = ncclDouble;
+    MLBM_NCCL(ctx, ctx->nccl->GroupStart());
+    MLBM_NCCL(ctx, ctx->nccl->AllReduce(values, values, 2, type, ncclSum, ctx->comm, ctx->computeStream));
+    MLBM_NCCL(ctx, ctx->nccl->AllReduce(values + 2, values + 2, 1, type, ncclMax, ctx->comm, ctx->computeStream));
+    MLBM_NCCL(ctx, ctx->nccl->AllReduce(values + 3, values + 3, 1, type, ncclSum, ctx->comm, ctx->computeStream));
+    MLBM_NCCL(ctx, ctx->nccl->GroupEnd());
+    ctx->observablesValid = false;  // reduced in place: valid again after the next stored step
+  }
+  MLBM_CUDA(cudaMemcpyAsync(local, ctx->deviceObservables, sizeof(local), cudaMemcpyDeviceToHost, ctx->computeStream));
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  double globalVolume = 1.0;
+  for (int d = 0; d < ctx->D; ++d) globalVolume *= ctx->config.global_length[d];
+  out[0] = local[0] / globalVolume;          // AnalysisScalar::normalize (Analysis.h:30)
+  out[1] = local[3] / globalVolume;
+  out[2] = sqrt(local[2] * 3.0);             // |u| / c_s, c_s^2 = 1/3
+  out[3] = local[1];
+  return MLBM_OK;
+}
+
+int mlbm_timers(mlbm_ctx* ctx, double* communicationSeconds, double* computationSeconds) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  if (communicationSeconds) *communicationSeconds = ctx->lastCommunication;
+  if (computationSeconds) *computationSeconds = ctx->lastComputation;
+  return MLBM_OK;
+}
+
+int mlbm_device_distribution(mlbm_ctx* ctx, mlbm_device_layout* out) {
+  if (!ctx || !out) return fail(MLBM_ERR_INVALID, "null argument");
+  out->populations = ctx->populations[ctx->current];
+  out->component_stride = (size_t)ctx->stride;
+  out->plane = (size_t)ctx->plane;
+  out->row = (size_t)ctx->NR;
+  out->halo_x = 1;
+  out->local_length[0] = ctx->LX;
+  out->local_length[1] = ctx->D == 3 ? ctx->NM : ctx->NR;
+  out->local_length[2] = ctx->D == 3 ? ctx->NR : 1;
+  return MLBM_OK;
+}
+
+int mlbm_launch_count(mlbm_ctx* ctx, uint64_t* launches) {
+  if (!ctx || !launches) return fail(MLBM_ERR_INVALID, "null argument");
+  *launches = ctx->launches;
+  return MLBM_OK;
+}
+
+int mlbm_stream(mlbm_ctx* ctx, void** cudaStream) {
+  if (!ctx || !cudaStream) return fail(MLBM_ERR_INVALID, "null argument");
+  *cudaStream = ctx->computeStream;
+  return MLBM_OK;
+}
+
+int mlbm_kernel_time(mlbm_ctx* ctx, double* averageMs, uint64_t* launches) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->profiling) {
+    // first call switches per-launch event timing on
+    ctx->profiling = true;
+    if (averageMs) *averageMs = 0.0;
+    if (launches) *launches = 0;
+    return MLBM_OK;
+  }
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  if (int status = collectProfile(ctx)) return status;
+  if (averageMs) *averageMs = ctx->profileLaunches ? ctx->profileMs / (double)ctx->profileLaunches : 0.0;
+  if (launches) *launches = ctx->profileLaunches;
+  ctx->profileMs = 0.0;
+  ctx->profileLaunches = 0;
+  return MLBM_OK;
+}
+
+int mlbm_mark(mlbm_ctx* ctx, int slot) {
+  if (!ctx || slot < 0 || slot >= 8) return fail(MLBM_ERR_INVALID, "bad mark slot");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->marks[slot]) MLBM_CUDA(cudaEventCreate(&ctx->marks[slot]));
+  MLBM_CUDA(cudaEventRecord(ctx->marks[slot], ctx->computeStream));
+  return MLBM_OK;
+}
+
+int mlbm_elapsed(mlbm_ctx* ctx, int from, int to, double* milliseconds) {
+  if (!ctx || !milliseconds || from < 0 || from >= 8 || to < 0 || to >= 8 || !ctx->marks[from] || !ctx->marks[to])
+    return fail(MLBM_ERR_INVALID, "bad mark slot");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  MLBM_CUDA(cudaEventSynchronize(ctx->marks[to]));
+  float ms = 0.f;
+  MLBM_CUDA(cudaEventElapsedTime(&ms, ctx->marks[from], ctx->marks[to]));
+  *milliseconds = ms;
+  return MLBM_OK;
+}
+
+}  // extern "C"

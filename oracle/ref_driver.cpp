@@ -12,7 +12,7 @@
 // TotalEnergy / TotalEnstrophy (Analysis.h:33-98), Curl (Transformer.h:118-295),
 // Communication::reduce (Communication.h:76-89).
 //
-// usage: ref_driver <populations.bin | -> <output prefix> <steps> <store every> [observables 0|1]
+// usage: ref_driver <populations.bin | -> <output prefix> <steps> <store every> [observables 0|1] [dump 0|1] [warm-up steps]
 //   populations.bin : float64 [Q][GX][GY][GZ] global interior populations ("-" = the
 //                     reference's own equilibrium initialisation, Initialize.h:91-118)
 #include "Input.in"
@@ -48,6 +48,8 @@ int main(int argc, char* argv[]) {
   const int steps = atoi(argv[3]);
   const int storeEvery = atoi(argv[4]);
   const bool withObservables = argc > 5 ? atoi(argv[5]) != 0 : true;
+  const bool withDump = argc > 6 ? atoi(argv[6]) != 0 : true;  // timing runs skip the dump and the stored step
+  const int warmup = argc > 7 ? atoi(argv[7]) : 0;             // leading steps left out of the timers
 
   auto mpiLauncher = MPIInitializer<numProcs>{argc, argv};
   auto fftwLauncher = FFTWInitializer<numThreads>{};
@@ -108,11 +110,13 @@ int main(int argc, char* argv[]) {
   double computationTime = 0.0, communicationTime = 0.0;
   const auto wallStart = std::chrono::high_resolution_clock::now();
   for (int iteration = 1; iteration <= steps; ++iteration) {
-    algorithm.isStored = (storeEvery > 0 && iteration % storeEvery == 0) || iteration == steps;
+    algorithm.isStored = (storeEvery > 0 && iteration % storeEvery == 0) || (withDump && iteration == steps);
     algorithm.iterate(iteration, defaultStream, bulkStream, leftStream, rightStream,
                       leftEvent, rightEvent);
-    computationTime += algorithm.getComputationTime();
-    communicationTime += algorithm.getCommunicationTime();
+    if (iteration > warmup) {
+      computationTime += algorithm.getComputationTime();
+      communicationTime += algorithm.getCommunicationTime();
+    }
 
     if (algorithm.isStored && withObservables) {
       // Routine.h:129-132 then ScalarAnalysisList::writeAnalyses (AnalysisList.h:55-73)
@@ -146,8 +150,9 @@ int main(int argc, char* argv[]) {
   // dump this rank's slab: f[Q], density, velocity[D], alpha, force[D], vorticity[2D-3]
   const int numberFields = L::dimQ + 1 + L::dimD + 1 + L::dimD + (2 * L::dimD - 3);
   std::vector<double> out;
-  out.reserve((size_t)numberFields * localVolume);
+  if (withDump) out.reserve((size_t)numberFields * localVolume);
   auto gather = [&](dataT* component) {
+    if (!withDump) return;
     for (unsigned int x = 0; x < local[d::X]; ++x)
       for (unsigned int y = 0; y < local[d::Y]; ++y)
         for (unsigned int z = 0; z < local[d::Z]; ++z)
@@ -159,7 +164,7 @@ int main(int argc, char* argv[]) {
   gather(fieldList.alpha.getData(numberElements));
   for (int iD = 0; iD < L::dimD; ++iD) gather(fieldList.force.getData(numberElements, iD));
   for (int iD = 0; iD < 2 * L::dimD - 3; ++iD) gather(fieldList.vorticity.getData(numberElements, iD));
-  writeRaw(outputPrefix + ".r" + std::to_string(rank) + ".bin", out);
+  if (withDump) writeRaw(outputPrefix + ".r" + std::to_string(rank) + ".bin", out);
 
   communication.reduce(&computationTime, 1);
   communication.reduce(&communicationTime, 1);

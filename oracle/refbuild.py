@@ -47,7 +47,7 @@ class RefConfig:
     wavelength: tuple = (32.0, 32.0, 32.0)
     init_density: str = "Homogeneous"   # Homogeneous | Peak
     nprocs: int = 1
-    optimize: str = "-O2"               # "-O2" = parity build (no FMA contraction); "-O3 -march=native" = timing build
+    optimize: str = "-O2"               # "-O2" = parity build (no FMA contraction); TIMING_FLAGS = timing build
 
     @property
     def dim(self) -> int:
@@ -66,7 +66,7 @@ class RefConfig:
         return hashlib.sha1(blob.encode()).hexdigest()[:12]
 
     def name(self) -> str:
-        flags = "nat" if "native" in self.optimize else "par"
+        flags = "opt" if self.optimize != "-O2" else "par"
         return (f"ref_{self.lattice}_{self.collision}_{self.equilibrium}_{self.forcing_scheme}_{self.force}"
                 f"_{self.nx}x{self.ny}x{self.nz}_p{self.nprocs}_{flags}_{self.key()}")
 
@@ -159,7 +159,7 @@ def build_ref(cfg: RefConfig, force: bool = False) -> Path:
     with tempfile.TemporaryDirectory(prefix="mlbm_ref_") as tmp:
         (Path(tmp) / "Input.in").write_text(input_in(cfg))
         nx, ny, nz = cfg.shape
-        cmd = ["g++", "-std=c++14", *cfg.optimize.split(), "-ffp-contract=off" if "native" not in cfg.optimize else "-ffp-contract=fast",
+        cmd = ["g++", "-std=c++14", *cfg.optimize.split(), "-ffp-contract=off" if cfg.optimize == "-O2" else "-ffp-contract=fast",
                "-w", "-DUSE_FFTW", f"-DNPROCS={cfg.nprocs}", "-DNTHREADS=1",
                f"-DGLOBAL_LENGTH_X={nx}", f"-DGLOBAL_LENGTH_Y={ny}", f"-DGLOBAL_LENGTH_Z={nz}",
                '-DLBM_POSTFIX="oracle"', f"-I{ORACLE_DIR / 'shim'}", f"-I{tmp}",
@@ -172,7 +172,7 @@ def build_ref(cfg: RefConfig, force: bool = False) -> Path:
 
 
 def run_ref(cfg: RefConfig, populations: np.ndarray | None, steps: int, store_every: int = 0,
-            observables: bool = True, timeout: float = 3600.0) -> dict:
+            observables: bool = True, timeout: float = 3600.0, dump: bool = True, warmup: int = 0) -> dict:
     """Run the reference binary.  ``populations`` is float64 [Q, nx, ny, nz] (global interior) or None
     for the reference's own equilibrium initialisation.  Returns the final populations / fields and
     the (iteration, energy, enstrophy) rows of every stored step."""
@@ -188,42 +188,74 @@ def run_ref(cfg: RefConfig, populations: np.ndarray | None, steps: int, store_ev
             inp = str(tmp / "f0.bin")
             arr.tofile(inp)
         prefix = str(tmp / "out")
-        proc = subprocess.run([str(exe), inp, prefix, str(steps), str(store_every), "1" if observables else "0"],
+        proc = subprocess.run([str(exe), inp, prefix, str(steps), str(store_every), "1" if observables else "0",
+                               "1" if dump else "0", str(warmup)],
                               capture_output=True, text=True, timeout=timeout, cwd=tmp)
         if proc.returncode != 0:
             raise RuntimeError(f"reference run failed ({proc.returncode}):\n{proc.stdout[-2000:]}\n{proc.stderr[-2000:]}")
-        lx = nx // cfg.nprocs
-        nvort = 2 * dim - 3
-        nfields = q + 1 + dim + 1 + dim + nvort
-        slabs = [np.fromfile(f"{prefix}.r{r}.bin", dtype=np.float64).reshape(nfields, lx, ny, nz)
-                 for r in range(cfg.nprocs)]
-        full = np.concatenate(slabs, axis=1)
-        result = {
-            "f": full[:q].copy(),
-            "density": full[q].copy(),
-            "velocity": full[q + 1:q + 1 + dim].copy(),
-            "alpha": full[q + 1 + dim].copy(),
-            "force": full[q + 2 + dim:q + 2 + 2 * dim].copy(),
-            "vorticity": full[q + 2 + 2 * dim:].copy(),
-            "observables": [],
-        }
+        result = {"observables": []}
         for line in Path(prefix + ".txt").read_text().splitlines():
             parts = line.split()
             if parts[0] == "obs":
                 result["observables"].append((int(parts[1]), float(parts[2]), float(parts[3])))
             elif parts[0].startswith("time_"):
                 result[parts[0]] = float(parts[1])
+        if not dump:
+            return result
+        lx = nx // cfg.nprocs
+        nvort = 2 * dim - 3
+        nfields = q + 1 + dim + 1 + dim + nvort
+        slabs = [np.fromfile(f"{prefix}.r{r}.bin", dtype=np.float64).reshape(nfields, lx, ny, nz)
+                 for r in range(cfg.nprocs)]
+        full = np.concatenate(slabs, axis=1)
+        result.update({
+            "f": full[:q].copy(),
+            "density": full[q].copy(),
+            "velocity": full[q + 1:q + 1 + dim].copy(),
+            "alpha": full[q + 1 + dim].copy(),
+            "force": full[q + 2 + dim:q + 2 + 2 * dim].copy(),
+            "vorticity": full[q + 2 + 2 * dim:].copy(),
+        })
         return result
 
 
-# Configurations prebuilt by __graft_entry__.build() so that they travel to the GPU box
-# (bench.py --impl reference / cpu_baseline time these; tests use them when present).
-def timing_configs(nprocs: int = 1) -> list:
-    native = "-O3 -march=native"
-    return [
-        RefConfig(lattice="D3Q19", nx=128, ny=128, nz=128, collision="BGK", forcing_scheme="None", force="None",
-                  tau=0.55, nprocs=nprocs, optimize=native),
-    ]
+# The reference's performance build.  x86-64-v3 (AVX2 + FMA) rather than -march=native because the binary is
+# compiled in the build container and timed on the GPU box, whose host CPU may differ.
+TIMING_FLAGS = "-O3 -march=x86-64-v3 -funroll-loops"
+TIMING_RANKS = (1, 2, 4, 8, 16, 32, 64, 128)
+TIMING_PLANES_PER_RANK = 2
+
+
+def timing_config(nprocs: int) -> RefConfig:
+    """The headline workload (D3Q19 SRT-BGK, 256 x 256 cross-section, FP64) as a bounded x-slab sample:
+    TIMING_PLANES_PER_RANK planes of 256 x 256 nodes per rank, one rank per host core."""
+    return RefConfig(lattice="D3Q19", nx=TIMING_PLANES_PER_RANK * nprocs, ny=256, nz=256, collision="BGK",
+                     forcing_scheme="None", force="None", tau=0.55, nprocs=nprocs, optimize=TIMING_FLAGS)
+
+
+def timing_configs() -> list:
+    """Prebuilt by __graft_entry__.build() so that they travel to the GPU box (one binary per rank count,
+    numProcs is a compile-time constant of the reference)."""
+    return [timing_config(n) for n in TIMING_RANKS]
+
+
+def best_timing_config(cores: int) -> RefConfig | None:
+    """Largest prebuilt rank count that fits the host cores."""
+    for n in sorted(TIMING_RANKS, reverse=True):
+        if n <= cores and binary_path(timing_config(n)).is_file():
+            return timing_config(n)
+    return None
+
+
+def time_reference(cfg: RefConfig, steps: int, warmup: int = 0, timeout: float = 3600.0) -> dict:
+    """MLUPS of the reference CPU build on cfg (its own initialisation, no observables) over `steps` timed
+    steps after `warmup` untimed ones."""
+    result = run_ref(cfg, None, steps + warmup, 0, observables=False, timeout=timeout, dump=False, warmup=warmup)
+    nodes = cfg.nx * cfg.ny * cfg.nz
+    # per-rank average of the reference's own timers (Algorithm.h:340-357) = time of the parallel run
+    seconds = result["time_computation"] + result["time_communication"]
+    return {"mlups": nodes * steps / seconds / 1e6, "seconds": seconds, "wall": result["time_wall"],
+            "nodes": nodes, "steps": steps, "ranks": cfg.nprocs}
 
 
 if __name__ == "__main__":
