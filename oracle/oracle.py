@@ -146,7 +146,7 @@ def spectral_vorticity(velocity: np.ndarray, dim: int) -> np.ndarray:
     wx = 1j * (ky * u[2] - kz * u[1])
     wy = 1j * (kz * u[0] - kx * u[2])
     wz = 1j * (kx * u[1] - ky * u[0])
-    out = np.stack([np.fft.irfftn(w, s=shape) * volume for w in (wx, wy, wz)])
+    out = np.stack([np.fft.irfftn(w, s=shape, axes=(0, 1, 2)) * volume for w in (wx, wy, wz)])
     return out / volume / volume
 
 
@@ -159,14 +159,14 @@ def spectral_enstrophy(velocity: np.ndarray, dim: int) -> float:
 # Seeded synthetic inputs ("Init B"): f = feq(rho, u) * (1 + eps * N(0,1))
 # ---------------------------------------------------------------------------------------------
 def synthetic_populations(cfg: MlbmConfig, eps: float = 1e-2, seed: int = 20261017,
-                          amplitude: float = 0.05) -> np.ndarray:
+                          amplitude: float = 0.05, ripple: float = 0.05) -> np.ndarray:
     shape = shape_of(cfg)
     dim, q = LATTICE_DQ[Lattice(cfg.lattice)]
     nx, ny, nz = shape
     x = (2 * np.pi * np.arange(nx) / nx)[:, None, None]
     y = (2 * np.pi * np.arange(ny) / ny)[None, :, None]
     z = (2 * np.pi * np.arange(nz) / nz)[None, None, :]
-    rho = 1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z) * np.ones(shape)
+    rho = 1.0 + ripple * np.sin(x) * np.cos(y) * np.cos(z) * np.ones(shape)
     u = np.zeros((dim,) + shape)
     if dim == 2:
         u[0] = amplitude * np.sin(y) * np.ones(shape)

@@ -1,0 +1,66 @@
+"""Generates the golden vectors in this directory by RUNNING THE REFERENCE ITSELF (oracle/_ref binaries compiled
+from /root/reference by oracle/refbuild.py, parity flags: -O2 -ffp-contract=off).  Only runs in the build
+container; the .npz files it writes are committed so that the GPU box (which has no /root/reference) can check
+the CUDA path and the C oracle against real reference outputs.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from metalbm_b200.capi import make_config  # noqa: E402
+from oracle import oracle as O  # noqa: E402
+from oracle.refbuild import RefConfig, run_ref  # noqa: E402
+
+HERE = Path(__file__).resolve().parent
+
+# name, lattice, shape, collision, equilibrium, scheme, force, tau, eps, flow amplitude, density ripple, steps, ranks
+CASES = [
+    ("d2q9_bgk_guo_kolmogorov", "D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.7, 1e-2, 0.05, 0.05, 3, 1),
+    ("d2q9_bgk_guo_kolmogorov_100", "D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.7, 1e-2, 0.05, 0.05, 100, 1),
+    ("d2q9_bgk_none", "D2Q9", (10, 14, 1), "BGK", "TruncationMa3", "None", "None", 0.6, 1e-2, 0.05, 0.05, 2, 1),
+    ("d2q9_bgk_exact_edm", "D2Q9", (12, 10, 1), "BGK", "Exact", "ExactDifferenceMethod", "Kolmogorov", 0.7, 1e-2, 0.05, 0.05, 2, 1),
+    ("d2q9_elbm_shanchen", "D2Q9", (16, 12, 1), "ELBM", "TruncationMa3", "ShanChen", "Kolmogorov", 0.51, 2e-2, 0.05, 0.05, 2, 1),
+    ("d2q9_elbm_edm", "D2Q9", (16, 12, 1), "ELBM", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.51, 2e-2, 0.05, 0.05, 2, 1),
+    ("d2q9_elbm_small_deviation", "D2Q9", (16, 12, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 4e-4, 0.0, 0.0, 2, 1),
+    ("d2q5_bgk_guo", "D2Q5", (8, 10, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.8, 1e-2, 0.05, 0.05, 2, 1),
+    ("d3q15_bgk_edm", "D3Q15", (6, 8, 4), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.6, 1e-2, 0.05, 0.05, 2, 1),
+    ("d3q19_bgk_none", "D3Q19", (8, 6, 10), "BGK", "TruncationMa3", "None", "None", 0.55, 1e-3, 0.05, 0.05, 3, 1),
+    ("d3q19_bgk_guo_kolmogorov", "D3Q19", (8, 6, 4), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 1e-3, 0.05, 0.05, 3, 1),
+    ("d3q19_bgk_guo_2ranks", "D3Q19", (8, 6, 4), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 1e-3, 0.05, 0.05, 3, 2),
+    ("d3q19_elbm_all_branches", "D3Q19", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 0.05, 0.05, 2, 1),
+    ("d3q27_elbm_guo", "D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+    ("d3q27_elbm_exact", "D3Q27", (8, 6, 4), "ELBM", "Exact", "Guo", "Kolmogorov", 0.50000032, 2e-2, 0.05, 0.05, 2, 1),
+    ("d3q27_forcednr_elbm", "D3Q27", (6, 6, 4), "ForcedNR_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+]
+AMPLITUDE = (1e-4, 2e-4, 3e-4)
+WAVELENGTH = (8.0, 4.0, 16.0)
+
+
+def main():
+    for name, lattice, shape, collision, equilibrium, scheme, force, tau, eps, flow, ripple, steps, ranks in CASES:
+        ref_cfg = RefConfig(lattice=lattice, nx=shape[0], ny=shape[1], nz=shape[2], collision=collision,
+                            equilibrium=equilibrium, forcing_scheme=scheme, force=force, tau=tau,
+                            amplitude=AMPLITUDE, wavelength=WAVELENGTH, nprocs=ranks)
+        cfg = make_config(lattice=lattice, shape=shape, collision=collision, equilibrium=equilibrium,
+                          forcing_scheme=scheme, force=force, tau=tau, amplitude=AMPLITUDE, wavelength=WAVELENGTH)
+        f0 = O.synthetic_populations(cfg, eps=eps, amplitude=flow, ripple=ripple)
+        out = run_ref(ref_cfg, f0, steps, store_every=1)
+        meta = dict(name=name, lattice=lattice, shape=list(shape), collision=collision, equilibrium=equilibrium,
+                    forcing_scheme=scheme, force=force, tau=tau, amplitude=list(AMPLITUDE), wavelength=list(WAVELENGTH),
+                    steps=steps, ranks=ranks, eps=eps,
+                    source="oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off), oracle/ref_driver.cpp")
+        np.savez_compressed(HERE / f"{name}.npz", meta=json.dumps(meta), f0=f0, f=out["f"], alpha=out["alpha"],
+                            density=out["density"], velocity=out["velocity"], force=out["force"],
+                            observables=np.array(out["observables"], dtype=np.float64))
+        print(name, out["f"].shape, out["observables"][-1])
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,173 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads and exports every symbol the header declares,
+refuses to run without a GPU (no CPU fallback), and its host logic (domain arithmetic, halo plan) is right.
+The two-rank halo plan is exercised over torch.distributed's gloo backend (world_size 2)."""
+import ctypes
+import os
+import re
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from metalbm_b200 import capi
+from metalbm_b200.algorithm import Communication, Domain, slab_of
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol(cuda_lib):
+    header = (ROOT / "include" / "metalbm_b200.h").read_text()
+    declared = set(re.findall(r"\b(mlbm_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(capi.PROTOTYPES), "ctypes prototypes and header out of sync"
+    for name in declared:
+        assert hasattr(cuda_lib, name), f"{name} not exported"
+    assert cuda_lib.mlbm_abi_version() == capi.ABI_VERSION
+
+
+def test_struct_layout_matches_header(cuda_lib):
+    assert ctypes.sizeof(capi.MlbmConfig) == 8 * 4 + 3 * 4 + 4 * 4 + 4 + 8 + 24 + 24  # includes 4 bytes of padding before tau
+    assert ctypes.sizeof(capi.MlbmHaloMessage) == 32
+
+
+def _no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+@pytest.mark.skipif(not _no_gpu(), reason="a GPU is present")
+def test_create_fails_loudly_without_a_gpu(cuda_lib):
+    cfg = capi.make_config("D3Q19", (8, 8, 8))
+    ctx = ctypes.c_void_p()
+    status = cuda_lib.mlbm_create(ctypes.byref(cfg), ctypes.byref(ctx))
+    assert status == -2 and not ctx.value
+    assert b"no CPU fallback" in cuda_lib.mlbm_last_error()
+
+
+def test_create_rejects_bad_configurations(cuda_lib):
+    ctx = ctypes.c_void_p()
+    bad = [capi.make_config("D3Q19", (8, 8, 8), equilibrium="Exact"),      # Exact exists for D2Q9 / D3Q27 only
+           capi.make_config("D3Q19", (9, 8, 8), nranks=2),                 # numProcs must divide globalLengthX
+           capi.make_config("D2Q9", (8, 8, 1), tau=0.5)]
+    for cfg in bad:
+        assert cuda_lib.mlbm_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1
+    cfg = capi.make_config("D2Q9", (8, 8, 1))
+    cfg.abi_version = 99
+    assert cuda_lib.mlbm_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1
+
+
+def test_domain_padding_follows_the_reference():
+    # lSD::pLength pads the LAST used dimension to 2 (n/2 + 1) (Domain.h:53-57, MathVector.h:330-344)
+    d3 = Domain(capi.make_config("D3Q19", (8, 6, 5), nranks=2, rank=1))
+    assert d3.local_length == (4, 6, 5) and d3.padded_length == (4, 6, 6) and d3.number_elements == 144 and d3.offset_x == 4
+    d2 = Domain(capi.make_config("D2Q9", (8, 6, 1)))
+    assert d2.local_length == (8, 6, 1) and d2.padded_length == (8, 8, 1)
+
+
+def test_halo_plan_single_rank_is_empty(cuda_lib):
+    assert capi.halo_plan(capi.make_config("D3Q19", (8, 8, 8))) == []
+
+
+@pytest.mark.parametrize("lattice,shape,face", [("D2Q9", (8, 6, 1), 3), ("D3Q19", (8, 6, 4), 5), ("D3Q27", (8, 6, 4), 9)])
+def test_halo_plan_messages(cuda_lib, lattice, shape, face):
+    cfg = capi.make_config(lattice, shape, nranks=4, rank=1)
+    plan = capi.halo_plan(cfg)
+    assert len(plan) == 4 * face
+    sends = [m for m in plan if m.is_send]
+    assert sorted(m.population for m in sends) == list(range(1, 2 * face + 1))
+    for m in sends:
+        assert m.peer == (0 if m.population <= face else 2)   # c_x < 0 travels left, c_x > 0 right
+    plane = shape[1] * shape[2]
+    assert all(m.count == plane for m in plan)
+
+
+WORKER = r'''
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from metalbm_b200 import capi
+from metalbm_b200.algorithm import Communication, slab_of
+from oracle import oracle as O
+
+rank, world, port = int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+lattice, shape = "D3Q19", (8, 6, 4)
+cfg = capi.make_config(lattice, shape, nranks=world, rank=rank)
+dim, q, c, w = O.lattice(lattice)
+
+# the 128-byte id hand-shake of Algorithm.__init__ over gloo
+communication = Communication(rank, world)
+payload = communication.broadcast_bytes(bytes(range(128)) if rank == 0 else None, 128)
+assert payload == bytes(range(128))
+assert communication.rank_left == (rank - 1) % world and communication.rank_right == (rank + 1) % world
+
+# a global field every rank can rebuild; the slab in the device layout [Q][LX + 2][plane]
+rng = np.random.default_rng(5)
+full = rng.standard_normal((q,) + shape)
+lx, plane = shape[0] // world, shape[1] * shape[2]
+perPopulation = (lx + 2) * plane
+stride = (perPopulation + 31) // 32 * 32
+buffer = np.zeros(q * stride)
+for iq in range(q):
+    buffer[iq * stride + plane: iq * stride + (lx + 1) * plane] = slab_of(full[iq], rank, world).ravel()
+
+# execute the plan with point-to-point messages (what exchangeHalos does with ncclSend / ncclRecv)
+plan = capi.halo_plan(cfg)
+requests, receives = [], []
+for m in plan:
+    if m.is_send:
+        t = torch.from_numpy(buffer[m.offset:m.offset + m.count].copy())
+        requests.append(dist.isend(t, dst=m.peer, tag=m.population))
+    else:
+        t = torch.zeros(m.count, dtype=torch.float64)
+        requests.append(dist.irecv(t, src=m.peer, tag=m.population))
+        receives.append((m, t))
+for r in requests:
+    r.wait()
+for m, t in receives:
+    buffer[m.offset:m.offset + m.count] = t.numpy()
+
+# every population that pulls across a slab face now finds its periodic upstream neighbour in the halo plane
+x0 = rank * lx
+for iq in range(q):
+    cx = c[iq, 0]
+    if cx == 1:
+        got = buffer[iq * stride: iq * stride + plane]
+        assert np.array_equal(got, full[iq, (x0 - 1) % shape[0]].ravel()), f"left halo of population {iq}"
+    if cx == -1:
+        got = buffer[iq * stride + (lx + 1) * plane: iq * stride + (lx + 2) * plane]
+        assert np.array_equal(got, full[iq, (x0 + lx) % shape[0]].ravel()), f"right halo of population {iq}"
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_halo_plan_over_gloo(cuda_lib, oracle_lib, tmp_path, world):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    procs = [subprocess.Popen([sys.executable, str(script), str(ROOT), str(r), str(world), str(port)],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env) for r in range(world)]
+    outputs = []
+    for p in procs:
+        try:
+            out, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            out, _ = p.communicate()
+        outputs.append(out)
+    for r, (p, out) in enumerate(zip(procs, outputs)):
+        assert p.returncode == 0 and f"ok {r}" in out, out[-2000:]

@@ -63,16 +63,23 @@ ELBM_CASES = [
     ("D3Q27", (16, 12, 10), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 2e-2),
     ("D3Q27", (8, 6, 4), "Exact", "Guo", "Kolmogorov", 0.50000032, "ForcedNR_ELBM", 2e-2),
     ("D3Q27", (8, 6, 4), "TruncationMa3", "None", "None", 0.55, "ELBM", 1e-5),
+    ("D2Q9", (16, 12, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 4e-4),
     ("D3Q19", (8, 6, 4), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 3e-1),
     ("D3Q15", (8, 6, 4), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 1e-1),
 ]
+
+
+def _flow(eps):
+    # small-noise cases use a fluid at rest with uniform density so that nodes fall below the 1e-3 deviation
+    # threshold of isDeviationSmall (branch 0); the others a 5 % density ripple and |u| = 0.05
+    return dict(amplitude=0.05, ripple=0.05) if eps > 1e-3 else dict(amplitude=0.0, ripple=0.0)
 
 
 @pytest.mark.parametrize("case", ELBM_CASES, ids=lambda c: "-".join(map(str, c[:1] + c[2:5] + c[6:])))
 def test_elbm_alpha_and_populations(case):
     lattice, shape, equilibrium, scheme, force, tau, collision, eps = case
     cfg = _config(lattice, shape, equilibrium, scheme, force, tau, collision)
-    f0 = O.synthetic_populations(cfg, eps=eps)
+    f0 = O.synthetic_populations(cfg, eps=eps, **_flow(eps))
     for steps in (1, 2):
         got = run_cuda(cfg, f0, steps)
         ref = run_oracle(cfg, f0, steps)
@@ -90,9 +97,9 @@ def test_elbm_branches_are_exercised():
     seen = set()
     for lattice, shape, equilibrium, scheme, force, tau, collision, eps in ELBM_CASES:
         cfg = _config(lattice, shape, equilibrium, scheme, force, tau, collision)
-        ref = run_oracle(cfg, O.synthetic_populations(cfg, eps=eps), 1)
+        ref = run_oracle(cfg, O.synthetic_populations(cfg, eps=eps, **_flow(eps)), 1)
         seen |= set(np.unique(ref.branch).tolist())
-    assert {0, 1, 2} <= seen
+    assert {0, 1, 2, 3} <= seen
 
 
 def test_energy_after_100_steps_d2q9_kolmogorov():
