@@ -36,6 +36,33 @@ LATTICE, Q, EDGE = "D3Q19", 19, 256
 BYTES_PER_NODE = 2 * Q * 8           # algorithmic HBM traffic per node-step: read + write every population once
 FALLBACK_PEAK_GBS = 6650.0           # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
+# BASELINE.json configs as named workloads.  `shape` is per GPU for weak scaling and global for strong scaling.
+# The default (and the only one the reference arm / cpu_baseline leg time) is configs[1].
+WORKLOADS = {
+    "d3q19_bgk_256": dict(config=1, lattice="D3Q19", q=19, shape=(256, 256, 256), scaling="weak", collision="BGK",
+                          equilibrium="TruncationMa3", scheme="None", force="None", tau=0.55, eps=0.0, store_every=0,
+                          text="D3Q19 SRT-BGK periodic 256^3 FP64 per GPU (BASELINE configs[1])"),
+    "d3q19_bgk_guo_256": dict(config=1, lattice="D3Q19", q=19, shape=(256, 256, 256), scaling="weak", collision="BGK",
+                              equilibrium="TruncationMa3", scheme="Guo", force="Kolmogorov", tau=0.55, eps=0.0, store_every=0,
+                              text="D3Q19 SRT-BGK Guo-forced Kolmogorov periodic 256^3 per GPU (second row of BASELINE configs[1])"),
+    "d3q27_elbm_512": dict(config=2, lattice="D3Q27", q=27, shape=(512, 512, 512), scaling="strong", collision="ELBM",
+                           equilibrium="TruncationMa3", scheme="Guo", force="Kolmogorov", tau=0.55, eps=2e-2, store_every=0,
+                           text="D3Q27 SRT-Entropic (alpha Newton solve) Guo Kolmogorov 512^3, x-slab (BASELINE configs[2])"),
+    "d2q9_elbm_shanchen_8192": dict(config=3, lattice="D2Q9", q=9, shape=(8192, 8192, 1), scaling="strong", collision="ELBM",
+                                    equilibrium="TruncationMa3", scheme="ShanChen", force="Kolmogorov", tau=0.55, eps=2e-2,
+                                    store_every=0, text="D2Q9 SRT-Entropic Shan-Chen Kolmogorov 8192^2 (BASELINE configs[3])"),
+    "d2q9_elbm_edm_8192": dict(config=3, lattice="D2Q9", q=9, shape=(8192, 8192, 1), scaling="strong", collision="ELBM",
+                               equilibrium="TruncationMa3", scheme="ExactDifferenceMethod", force="Kolmogorov", tau=0.55,
+                               eps=2e-2, store_every=0, text="D2Q9 SRT-Entropic EDM Kolmogorov 8192^2 (BASELINE configs[3])"),
+    "d3q19_bgk_1024": dict(config=4, lattice="D3Q19", q=19, shape=(1024, 1024, 1024), scaling="strong", collision="BGK",
+                           equilibrium="TruncationMa3", scheme="None", force="None", tau=0.55, eps=0.0, store_every=50,
+                           text="D3Q19 SRT-BGK 1024^3 strong-scaled, halo/interior overlap, on-line energy/enstrophy/Mach "
+                                "reductions every 50 steps (BASELINE configs[4])"),
+    "d3q19_bgk_512": dict(config=4, lattice="D3Q19", q=19, shape=(512, 512, 512), scaling="strong", collision="BGK",
+                          equilibrium="TruncationMa3", scheme="None", force="None", tau=0.55, eps=0.0, store_every=50,
+                          text="D3Q19 SRT-BGK 512^3 strong-scaled (reduced-size stand-in of BASELINE configs[4] that fits one GPU)"),
+}
+
 
 def measured_peak():
     path = ROOT / "MEASURED_PEAKS.json"
@@ -199,30 +226,55 @@ def run_ours(args) -> int:
         dist.all_reduce(tensor, op=dist.ReduceOp.MAX)
         return float(tensor.item())
 
-    edge = args.edge
-    shape = (edge * world, edge, edge)
-    cfg = make_config(lattice=LATTICE, shape=shape, collision="BGK", equilibrium="TruncationMa3",
-                      forcing_scheme="None", force="None", tau=0.55, dtype="F64",
-                      overlap="On", rank=rank, nranks=world, device=local_rank, variant=args.variant)
-    algorithm = Algorithm(cfg, communication=Communication(rank, world))
+    work = dict(WORKLOADS[args.workload])
+    if args.edge != EDGE and args.workload == "d3q19_bgk_256":
+        work["shape"] = (args.edge,) * 3
+        work["text"] = work["text"].replace("256^3", f"{args.edge}^3")
+    if args.eps is not None:
+        work["eps"] = args.eps
+    if args.store_every is not None:
+        work["store_every"] = args.store_every
+    dtype = args.dtype.upper()
+    element = 8 if dtype == "F64" else 4
+    q_count = work["q"]
+    entropic = work["collision"] != "BGK"
+    bytes_per_node = 2 * q_count * element + (2 * element if entropic else 0)
+    if work["scaling"] == "weak":
+        shape = (work["shape"][0] * world,) + tuple(work["shape"][1:])
+    else:
+        shape = tuple(work["shape"])
+    cfg = make_config(lattice=work["lattice"], shape=shape, collision=work["collision"], equilibrium=work["equilibrium"],
+                      forcing_scheme=work["scheme"], force=work["force"], tau=work["tau"], dtype=dtype,
+                      amplitude=(1e-5, 1e-5, 1e-5), wavelength=(32.0, 32.0, 32.0),
+                      overlap=args.overlap, rank=rank, nranks=world, device=local_rank, variant=args.variant)
+    algorithm = Algorithm(cfg, communication=Communication(rank, world), host_distribution=not args.no_e2e)
     domain = algorithm.domain
     nodes_global = shape[0] * shape[1] * shape[2]
     nodes_local = nodes_global // world
 
-    # synthetic initial field of the named grid size: Taylor-Green-like velocity, density ripple (SURVEY 8d "Init B-3D")
+    # synthetic initial field of the named grid size: Taylor-Green-like velocity, density ripple (SURVEY 8d "Init B"),
+    # f = feq(rho, u) on the device, then (entropic workloads) a multiplicative perturbation of relative size eps
     lx = domain.local_length[0]
     x = (2 * np.pi * (np.arange(lx) + domain.offset_x) / shape[0])[:, None, None]
-    y = (2 * np.pi * np.arange(edge) / edge)[None, :, None]
-    z = (2 * np.pi * np.arange(edge) / edge)[None, None, :]
+    y = (2 * np.pi * np.arange(shape[1]) / shape[1])[None, :, None]
+    z = (2 * np.pi * np.arange(shape[2]) / shape[2])[None, None, :]
     fields = algorithm.fieldList
-    domain.interior(fields.density)[0] = 1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z)
-    domain.interior(fields.velocity)[0] = 0.05 * np.sin(x) * np.cos(y) * np.cos(z)
-    domain.interior(fields.velocity)[1] = -0.05 * np.cos(x) * np.sin(y) * np.cos(z)
-    domain.interior(fields.velocity)[2] = 0.025 * np.cos(x) * np.cos(y) * np.sin(z)
+    field_dtype = domain.dtype
+    domain.interior(fields.density)[0] = (1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z)).astype(field_dtype)
+    if domain.dim == 3:
+        domain.interior(fields.velocity)[0] = (0.05 * np.sin(x) * np.cos(y) * np.cos(z)).astype(field_dtype)
+        domain.interior(fields.velocity)[1] = (-0.05 * np.cos(x) * np.sin(y) * np.cos(z)).astype(field_dtype)
+        domain.interior(fields.velocity)[2] = (0.025 * np.cos(x) * np.cos(y) * np.sin(z)).astype(field_dtype)
+    else:
+        domain.interior(fields.velocity)[0] = (0.05 * np.sin(y) * np.ones_like(x) * np.ones_like(z)).astype(field_dtype)
+        domain.interior(fields.velocity)[1] = (0.05 * np.cos(x) * np.ones_like(y) * np.ones_like(z)).astype(field_dtype)
     algorithm.init_equilibrium()
+    if work["eps"]:
+        algorithm.perturb(work["eps"])
+    store_every = int(work["store_every"])
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------------
-    algorithm.run(1, args.warmup)
+    algorithm.run(1, args.warmup, store_every)
     algorithm.kernel_time()                      # switches the per-launch CUDA event pairs on
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -232,7 +284,7 @@ def run_ours(args) -> int:
     barrier()
     begin = time.time()
     algorithm.mark(0)
-    algorithm.run(args.warmup + 1, args.steps, sync=False)
+    algorithm.run(args.warmup + 1, args.steps, store_every, sync=False)
     algorithm.mark(1)
     algorithm.synchronize()
     barrier()
@@ -244,54 +296,71 @@ def run_ours(args) -> int:
     value = nodes_global * args.steps / (device_ms * 1e-3) / 1e6
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
-    algorithm.pack()                             # current state -> host array (also first-touches the host pages)
-    host = algorithm.distribution.array
-    pinned = torch.empty(host.shape, dtype=torch.float64, pin_memory=True)
-    pinned.numpy()[...] = host
-    algorithm.distribution.array = pinned.numpy()
-    barrier()
-    t0 = time.perf_counter()
-    algorithm.unpack()                           # H2D of the whole SoA distribution from pinned host memory
-    energy = 0.0
-    for iteration in range(1, args.steps + 1):
-        algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
-        energy = algorithm.observables()[0]      # D2H read of the step's scalar results
-    algorithm.pack()                             # D2H of the whole distribution
-    barrier()
-    e2e_seconds = max_over_ranks(time.perf_counter() - t0)
-    e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
-    distribution_bytes = Q * nodes_local * 8
-    e2e = {"value": e2e_value, "unit": UNIT,
-           "h2d_bytes_per_step": distribution_bytes / args.steps,
-           "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
-           "note": "timed region: unpack (H2D of all populations from pinned host memory) + K synchronous mlbm_step calls each "
-                   "followed by a D2H read of the observables + pack (D2H of all populations); population bytes amortised over K",
-           "last_energy": energy}
+    e2e = None
+    if not args.no_e2e:
+        algorithm.pack()                         # current state -> host array (also first-touches the host pages)
+        host = algorithm.distribution.array
+        pinned = torch.empty(host.shape, dtype=torch.float64 if element == 8 else torch.float32, pin_memory=True)
+        pinned.numpy()[...] = host
+        algorithm.distribution.array = pinned.numpy()
+        barrier()
+        t0 = time.perf_counter()
+        algorithm.unpack()                       # H2D of the whole SoA distribution from pinned host memory
+        energy = 0.0
+        for iteration in range(1, args.steps + 1):
+            algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
+            energy = algorithm.observables()[0]  # D2H read of the step's scalar results
+        algorithm.pack()                         # D2H of the whole distribution
+        barrier()
+        e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+        e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
+        distribution_bytes = q_count * nodes_local * element
+        e2e = {"value": e2e_value, "unit": UNIT,
+               "h2d_bytes_per_step": distribution_bytes / args.steps,
+               "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
+               "note": "timed region: unpack (H2D of all populations from pinned host memory) + K synchronous mlbm_step calls "
+                       "each followed by a D2H read of the observables + pack (D2H of all populations); population bytes "
+                       "amortised over K", "last_energy": energy}
 
     peak, peak_source = measured_peak()
-    achieved = BYTES_PER_NODE * nodes_local / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    # the dominant kernel is the bulk launch of the fused step: all local planes at N = 1, all but the two boundary
+    # planes when the halo exchange is overlapped
+    overlapped = world > 1 and args.overlap == "On" and lx >= 3
+    kernel_nodes = nodes_local // lx * (lx - 2) if overlapped else nodes_local
+    achieved = bytes_per_node * kernel_nodes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+    kernel_name = (f"fusedStepKernel<{work['lattice']},{work['collision']},{work['equilibrium']},{work['scheme']},"
+                   f"{'double' if element == 8 else 'float'}>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak if achieved else None, "traffic": recorded_traffic(),
-                "peak_source": peak_source, "kernel": "fusedStepKernel<D3Q19,BGK,TruncationMa3,None,double>",
+                "frac": achieved / peak if achieved else None,
+                "traffic": recorded_traffic() if args.workload == "d3q19_bgk_256" and dtype == "F64" else None,
+                "peak_source": peak_source, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_launches,
-                "algorithmic_bytes_per_launch": BYTES_PER_NODE * nodes_local,
-                "roofline_mlups_per_gpu": peak * 1e9 / BYTES_PER_NODE / 1e6}
+                "algorithmic_bytes_per_node": bytes_per_node,
+                "algorithmic_bytes_per_launch": bytes_per_node * kernel_nodes,
+                "roofline_mlups_per_gpu": peak * 1e9 / bytes_per_node / 1e6}
 
-    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline) else None
+    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline
+                                 and args.workload == "d3q19_bgk_256") else None
     algorithm.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
 
     if rank == 0:
+        buffer_gb = q_count * nodes_local * element / 1e9
+        metric = METRIC if args.workload == "d3q19_bgk_256" and dtype == "F64" else \
+            f"MLUPS ({work['lattice']}, {'FP64' if element == 8 else 'FP32'})"
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"D3Q19 SRT-BGK periodic {edge}^3 FP64 per GPU (BASELINE configs[1]); global {shape[0]}x{shape[1]}x{shape[2]}",
-                       "lattice": LATTICE, "collision": "BGK", "equilibrium": "TruncationMa3", "forcing": "None", "tau": 0.55,
-                       "global_length": list(shape), "parallelism": f"x-slab x{world}", "overlap": "On",
-                       "l2": "inputs (2 x 2.6 GB population buffers per GPU) larger than the 126 MB L2; no flush between steps"},
+            "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": work["scaling"], "vs_baseline": None,
+            "dtype": "f64" if element == 8 else "f32 storage, f64 arithmetic", "data": "synthetic",
+            "config": {"workload": f"{work['text']}; global {shape[0]}x{shape[1]}x{shape[2]}", "name": args.workload,
+                       "lattice": work["lattice"], "collision": work["collision"], "equilibrium": work["equilibrium"],
+                       "forcing": f"{work['scheme']}/{work['force']}", "tau": work["tau"], "perturbation_eps": work["eps"],
+                       "store_every": store_every, "global_length": list(shape), "parallelism": f"x-slab x{world}",
+                       "overlap": args.overlap,
+                       "l2": f"inputs (2 x {buffer_gb:.2f} GB population buffers per GPU) larger than the 126 MB L2; "
+                             "no flush between steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
         if cpu is not None:
@@ -308,6 +377,12 @@ def main() -> int:
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--edge", type=int, default=EDGE, help="edge of the per-GPU cube (default: the BASELINE 256)")
     parser.add_argument("--variant", type=int, default=0)
+    parser.add_argument("--workload", default="d3q19_bgk_256", choices=sorted(WORKLOADS))
+    parser.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    parser.add_argument("--overlap", default="On", choices=["On", "Off"])
+    parser.add_argument("--eps", type=float, default=None, help="override the workload's initial perturbation")
+    parser.add_argument("--store-every", type=int, default=None, help="override the workload's observable cadence")
+    parser.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large workloads)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -138,6 +138,11 @@ int mlbm_download_distribution(mlbm_ctx* ctx, void* host, size_t component_strid
 int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* velocity,
                           size_t component_stride, size_t padded_y, size_t padded_z);
 
+/* Synthetic non-equilibrium state for benchmarks and size-independent property tests (no reference counterpart;
+ * SURVEY.md 8d "Init B"): multiplies every population by 1 + eps * n, n uniform with unit variance from a
+ * counter-based hash of (seed, iQ, global node index) -- the same field whatever the number of ranks. */
+int mlbm_perturb_distribution(mlbm_ctx* ctx, double eps, uint64_t seed);
+
 /* The alpha field the entropic solve warm-starts from (Algorithm.h:103-106; initAlpha, Initialize.h:82-88). */
 int mlbm_set_alpha(mlbm_ctx* ctx, const void* host, size_t padded_y, size_t padded_z);
 

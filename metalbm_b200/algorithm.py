@@ -58,9 +58,9 @@ class Distribution:
     """Host side of ``Distribution<T, Architecture::GPU>`` (Distribution.h:15-43): the local padded SoA array the
     reference checkpoints and initialises; the ping-pong halo pair lives on the device inside the context."""
 
-    def __init__(self, domain: Domain):
+    def __init__(self, domain: Domain, allocate: bool = True):
         self.domain = domain
-        self.array = domain.allocate(domain.q)
+        self.array = domain.allocate(domain.q) if allocate else None
 
     def set_interior(self, populations: np.ndarray) -> None:
         """populations: [Q, lx, ly, lz] of this rank's slab."""
@@ -120,12 +120,14 @@ class Algorithm:
     """``Algorithm<T, Pull, GPU, SoA, OneD, MPI, Overlapping>`` (Algorithm.h:300-452) over the C-ABI."""
 
     def __init__(self, config: MlbmConfig, field_list: FieldList | None = None,
-                 distribution: Distribution | None = None, communication: Communication | None = None):
+                 distribution: Distribution | None = None, communication: Communication | None = None,
+                 host_distribution: bool = True):
         self._lib = load_library()
         self.config = config
         self.domain = Domain(config)
         self.fieldList = field_list if field_list is not None else FieldList(self.domain)
-        self.distribution = distribution if distribution is not None else Distribution(self.domain)
+        self.distribution = (distribution if distribution is not None
+                             else Distribution(self.domain, allocate=host_distribution))
         self.communication = communication or Communication(int(config.rank), int(config.nranks))
         self.isStored = False
         self._ctx = ctypes.c_void_p()
@@ -173,6 +175,10 @@ class Algorithm:
         stride, py, pz = self._layout()
         check(self._lib.mlbm_init_equilibrium(self._ctx, self.fieldList.density.ctypes.data,
                                               self.fieldList.velocity.ctypes.data, stride, py, pz))
+
+    def perturb(self, eps: float, seed: int = 20261017) -> None:
+        """f *= 1 + eps * noise on the device (synthetic non-equilibrium fields, decomposition independent)."""
+        check(self._lib.mlbm_perturb_distribution(self._ctx, float(eps), int(seed)))
 
     def set_alpha(self) -> None:
         _, py, pz = self._layout()

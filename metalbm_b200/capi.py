@@ -157,6 +157,7 @@ PROTOTYPES = {
     "mlbm_upload_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_download_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_init_equilibrium": (ctypes.c_int, [_P, _P, _P, _SZ, _SZ, _SZ]),
+    "mlbm_perturb_distribution": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_uint64]),
     "mlbm_set_alpha": (ctypes.c_int, [_P, _P, _SZ, _SZ]),
     "mlbm_step": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_int]),
     "mlbm_run_async": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),

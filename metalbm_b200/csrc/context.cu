@@ -188,6 +188,29 @@ __global__ void initEquilibriumKernel(StoreT* __restrict__ populations, const St
   });
 }
 
+// f *= 1 + eps * n, n uniform with unit variance from a counter-based hash of (seed, population, GLOBAL node):
+// the synthetic non-equilibrium initial fields of the benchmark, independent of the decomposition.
+__device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <typename StoreT>
+__global__ void perturbKernel(StoreT* __restrict__ populations, long long stride, long long plane, long long nodes,
+                              long long globalNodeOffset, int Q, double eps, unsigned long long seed) {
+  const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= nodes) return;
+  for (int q = 0; q < Q; ++q) {
+    const unsigned long long bits = splitmix64(splitmix64(seed + (unsigned long long)q) ^ (unsigned long long)(globalNodeOffset + node));
+    const double uniform = (double)(bits >> 11) * (1.0 / 9007199254740992.0);  // [0, 1)
+    const double n = (2.0 * uniform - 1.0) * 1.7320508075688772;
+    StoreT* p = populations + q * stride + plane + node;
+    *p = (StoreT)((double)*p * (1.0 + eps * n));
+  }
+}
+
 template <int EQ, typename StoreT>
 static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* populations, const StoreT* density,
                                   const StoreT* velocity, long long stride, long long plane, long long fieldStride,
@@ -767,6 +790,23 @@ int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* veloci
     else
       launchInitEquilibrium<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
   }
+  MLBM_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  ctx->halosValid = false;
+  return MLBM_OK;
+}
+
+int mlbm_perturb_distribution(mlbm_ctx* ctx, double eps, uint64_t seed) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  const unsigned grid = (unsigned)((ctx->nodes + 255) / 256);
+  const long long offset = (long long)ctx->config.rank * ctx->nodes;
+  void* target = ctx->populations[ctx->current];
+  if (ctx->config.dtype == MLBM_F64)
+    perturbKernel<double><<<grid, 256, 0, ctx->computeStream>>>(static_cast<double*>(target), ctx->stride, ctx->plane, ctx->nodes, offset, ctx->Q, eps, seed);
+  else
+    perturbKernel<float><<<grid, 256, 0, ctx->computeStream>>>(static_cast<float*>(target), ctx->stride, ctx->plane, ctx->nodes, offset, ctx->Q, eps, seed);
   MLBM_CUDA(cudaGetLastError());
   ctx->launches += 1;
   MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));

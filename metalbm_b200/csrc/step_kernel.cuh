@@ -158,7 +158,7 @@ __device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const d
   // The a-independent sum is hoisted and ln((f - a fNeq)/w) is shared between F and F'.
   double hoisted = 0.0;
 #pragma unroll
-  for (int q = 0; q < L::Q; ++q) hoisted += f[q] * (log(f[q]) - log(L::w(q)));
+  for (int q = 0; q < L::Q; ++q) hoisted += f[q] * log(f[q] * (1.0 / L::w(q)));
 
   double x = alphaGuess, step = 0.0;
   bool converged = false;
@@ -168,7 +168,7 @@ __device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const d
 #pragma unroll
     for (int q = 0; q < L::Q; ++q) {
       const double g = f[q] - x * fNeq[q];
-      const double lg = log(g) - log(L::w(q));
+      const double lg = log(g * (1.0 / L::w(q)));
       sum += g * lg;
       derivative += fNeq[q] * (1.0 + lg);
     }

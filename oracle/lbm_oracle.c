@@ -225,6 +225,23 @@ static double calculate_alpha(const lattice_t* L, const double* f, const double*
   return ok ? alpha : 2.0;
 }
 
+/* Checker-side diagnostic (not in the reference): how far double rounding alone can move the Newton iterate.
+ * F(alpha) is a difference of two sums of magnitude ~rho that cancel to O(fNeq^2) and F'(alpha) is O(fNeq^2) as
+ * well (sum fNeq = 0), so one Newton step carries an absolute uncertainty of about
+ *     eps * sum_q (|f_q| (1 + |ln f_q/w_q|) + |g_q| (1 + |ln g_q/w_q|)) / |F'(alpha)|,   g = f - alpha fNeq.
+ * Two implementations that differ only in rounding (libm vs device log, FMA contraction) cannot agree on alpha
+ * better than a small multiple of this number; the parity tests add it to the 1e-10 alpha tolerance. */
+static double alpha_rounding_noise(const lattice_t* L, const double* f, const double* fNeq, double alpha) {
+  double magnitude = 0.0;
+  for (int q = 0; q < L->Q; ++q) {
+    const double g = f[q] - alpha * fNeq[q];
+    if (!(f[q] > 0.0) || !(g > 0.0)) return 1.0;
+    magnitude += fabs(f[q]) * (1.0 + fabs(log(f[q] / L->w[q]))) + fabs(g) * (1.0 + fabs(log(g / L->w[q])));
+  }
+  const double derivative = fabs(entropic_derivative(L, f, fNeq, alpha));
+  return derivative > 0.0 ? 2.220446049250313e-16 * magnitude / derivative : 1.0;
+}
+
 static size_t wrap(long i, long n) { return (size_t)((i % n + n) % n); }
 
 /* One Algorithm::iterate (Algorithm.h:326-358) over the global domain = the per-node functor
@@ -232,8 +249,9 @@ static size_t wrap(long i, long n) { return (size_t)((i % n + n) % n); }
  *   prev, next : [Q][nx][ny][nz]      alpha : [nx][ny][nz] read (warm start) and written every step
  *   density, velocity[D], force[D] : written when is_stored (Algorithm::storeFields, Algorithm.h:150-194)
  *   branch, iterations (optional, [nx][ny][nz] int32): which alpha branch each node took. */
-int mlbm_oracle_step(const mlbm_config* cfg, const double* prev, double* next, double* alpha, double* density,
-                     double* velocity, double* force, int is_stored, int* branchOut, int* iterationsOut) {
+int mlbm_oracle_step_ex(const mlbm_config* cfg, const double* prev, double* next, double* alpha, double* density,
+                        double* velocity, double* force, int is_stored, int* branchOut, int* iterationsOut,
+                        double* alphaNoiseOut, double* fNeqMaxOut) {
   lattice_t L;
   if (lattice_table(cfg->lattice, &L)) return -1;
   if (cfg->equilibrium == MLBM_EXACT && !(cfg->lattice == MLBM_D2Q9 || cfg->lattice == MLBM_D3Q27)) return -1;
@@ -275,6 +293,12 @@ int mlbm_oracle_step(const mlbm_config* cfg, const double* prev, double* next, d
           a = calculate_alpha(&L, f, fNeq, alpha[idx], &branch, &iterations);
           if (branchOut) branchOut[idx] = branch;
           if (iterationsOut) iterationsOut[idx] = iterations;
+          if (alphaNoiseOut) alphaNoiseOut[idx] = branch >= 2 ? alpha_rounding_noise(&L, f, fNeq, a) : 0.0;
+          if (fNeqMaxOut) {
+            double m = 0.0;
+            for (int q = 0; q < L.Q; ++q) if (fabs(fNeq[q]) > m) m = fabs(fNeq[q]);
+            fNeqMaxOut[idx] = m;
+          }
           const double tau = 1.0 / (a * beta);
           /* Collision<ELBM>::collideAndStream (Collision.h:243-258) */
           for (int q = 0; q < L.Q; ++q) {
@@ -303,6 +327,12 @@ int mlbm_oracle_step(const mlbm_config* cfg, const double* prev, double* next, d
         }
       }
   return 0;
+}
+
+int mlbm_oracle_step(const mlbm_config* cfg, const double* prev, double* next, double* alpha, double* density,
+                     double* velocity, double* force, int is_stored, int* branchOut, int* iterationsOut) {
+  return mlbm_oracle_step_ex(cfg, prev, next, alpha, density, velocity, force, is_stored, branchOut, iterationsOut,
+                             NULL, NULL);
 }
 
 /* initDistribution, equilibrium branch (Initialize.h:106-117): f = feq(rho, u) */

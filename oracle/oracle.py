@@ -38,6 +38,7 @@ def lib() -> ctypes.CDLL:
         ip = ctypes.POINTER(ctypes.c_int)
         cp = ctypes.POINTER(MlbmConfig)
         _LIB.mlbm_oracle_step.argtypes = [cp, dp, dp, dp, dp, dp, dp, ctypes.c_int, ip, ip]
+        _LIB.mlbm_oracle_step_ex.argtypes = [cp, dp, dp, dp, dp, dp, dp, ctypes.c_int, ip, ip, dp, dp]
         _LIB.mlbm_oracle_init_equilibrium.argtypes = [cp, dp, dp, dp]
         _LIB.mlbm_oracle_observables.argtypes = [cp, dp, dp, dp]
         _LIB.mlbm_oracle_lattice.argtypes = [ctypes.c_int, ip, ip, ip, dp]
@@ -85,11 +86,15 @@ class OracleState:
         self.force = np.zeros((self.dim,) + self.shape)
         self.branch = np.zeros(self.shape, dtype=np.int32)
         self.iterations = np.zeros(self.shape, dtype=np.int32)
+        # checker-side diagnostics of the last step: rounding-noise floor of the Newton iterate and max_q |fNeq_q|
+        self.alpha_noise = np.zeros(self.shape)
+        self.fneq_max = np.zeros(self.shape)
 
     def step(self, is_stored: bool = True) -> None:
-        status = lib().mlbm_oracle_step(ctypes.byref(self.cfg), _dp(self.f), _dp(self.next), _dp(self.alpha),
-                                        _dp(self.density), _dp(self.velocity), _dp(self.force),
-                                        1 if is_stored else 0, _ip(self.branch), _ip(self.iterations))
+        status = lib().mlbm_oracle_step_ex(ctypes.byref(self.cfg), _dp(self.f), _dp(self.next), _dp(self.alpha),
+                                           _dp(self.density), _dp(self.velocity), _dp(self.force),
+                                           1 if is_stored else 0, _ip(self.branch), _ip(self.iterations),
+                                           _dp(self.alpha_noise), _dp(self.fneq_max))
         if status != 0:
             raise ValueError("oracle: unsupported configuration")
         self.f, self.next = self.next, self.f

@@ -3,7 +3,7 @@ import numpy as np
 import pytest
 
 from golden_util import golden_names, load_golden
-from helpers import relative_error, run_cuda
+from helpers import check_entropic, relative_error, run_cuda, run_oracle
 
 pytestmark = pytest.mark.gpu
 
@@ -14,11 +14,11 @@ def test_cuda_reproduces_reference_outputs(name):
     got = run_cuda(cfg, data["f0"], meta["steps"])
     entropic = meta["collision"] != "BGK"
     if entropic:
-        alpha_error = np.abs(got["alpha"] - data["alpha"])
-        mismatched = alpha_error > 1e-10
-        assert mismatched.mean() <= 5e-3, f"{mismatched.sum()} alpha mismatches, max {alpha_error.max():.3e}"
-        node_error = np.abs(got["f"] - data["f"]).max(axis=0)
-        assert node_error[~mismatched].max() <= 1e-12 * np.abs(data["f"]).max()
+        # the oracle (bit-identical to the reference: tests/test_oracle_golden.py) supplies the conditioning of the
+        # Newton solve at every node; the values compared are the reference's own (the golden file)
+        ref = run_oracle(cfg, data["f0"], meta["steps"])
+        assert np.array_equal(ref.alpha, data["alpha"]) and np.array_equal(ref.f, data["f"])
+        check_entropic(got, ref, cfg, meta["steps"], mismatch_budget=5e-3)
     else:
         tolerance = 1e-12 if meta["steps"] <= 3 else 1e-11
         assert relative_error(got["f"], data["f"]) <= tolerance
