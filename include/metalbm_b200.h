@@ -171,6 +171,15 @@ int mlbm_download_fields(mlbm_ctx* ctx, void* density, void* velocity, void* alp
  *   out[3] total mass       sum of density (PerformanceAnalysisList mass, Routine.h:117-118) */
 int mlbm_observables(mlbm_ctx* ctx, double out[4]);
 
+/* Communication::reduce(T* localSumPtr, numberComponents) (Communication.h:76-89): element-wise sum of `count` host
+ * doubles over all ranks, result on EVERY rank (the reference leaves it on rank 0 only); a no-op for one rank. */
+int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count);
+
+/* DynamicArray<U, Architecture::CPUPinned> (DynamicArray.cuh:88-127): page-locked host memory, which is where the
+ * reference keeps the GPU build's fields (Field.h:62-79) and what makes pack/unpack run at PCIe speed. */
+int mlbm_alloc_pinned(size_t bytes, void** out);
+int mlbm_free_pinned(void* pointer);
+
 /* Algorithm::getCommunicationTime / getComputationTime (Algorithm.h:128-130), seconds of the last step
  * measured with CUDA events on the device. */
 int mlbm_timers(mlbm_ctx* ctx, double* communication_seconds, double* computation_seconds);

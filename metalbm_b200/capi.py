@@ -164,6 +164,9 @@ PROTOTYPES = {
     "mlbm_sync": (ctypes.c_int, [_P]),
     "mlbm_download_fields": (ctypes.c_int, [_P, _P, _P, _P, _P, _SZ, _SZ, _SZ]),
     "mlbm_observables": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
+    "mlbm_reduce_sum": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
+    "mlbm_alloc_pinned": (ctypes.c_int, [_SZ, ctypes.POINTER(_P)]),
+    "mlbm_free_pinned": (ctypes.c_int, [_P]),
     "mlbm_timers": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "mlbm_device_distribution": (ctypes.c_int, [_P, ctypes.POINTER(MlbmDeviceLayout)]),
     "mlbm_launch_count": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_uint64)]),

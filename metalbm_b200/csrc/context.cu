@@ -913,6 +913,43 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
   return MLBM_OK;
 }
 
+int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count) {
+  if (!ctx || !values || count < 0) return fail(MLBM_ERR_INVALID, "null argument");
+  if (ctx->config.nranks == 1 || count == 0) return MLBM_OK;
+  if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  double* staging = nullptr;
+  MLBM_CUDA(cudaMalloc(&staging, sizeof(double) * (size_t)count));
+  int status = MLBM_OK;
+  cudaError_t error = cudaMemcpyAsync(staging, values, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->computeStream);
+  if (error == cudaSuccess) {
+    ncclResult_t result = ctx->nccl->AllReduce(staging, staging, (size_t)count, ncclDouble, ncclSum, ctx->comm, ctx->computeStream);
+    if (result != ncclSuccess) status = fail(MLBM_ERR_COMM, "ncclAllReduce: %s", ctx->nccl->GetErrorString(result));
+  }
+  if (error == cudaSuccess && status == MLBM_OK)
+    error = cudaMemcpyAsync(values, staging, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->computeStream);
+  if (error == cudaSuccess) error = cudaStreamSynchronize(ctx->computeStream);
+  cudaFree(staging);
+  if (error != cudaSuccess) return fail(MLBM_ERR_CUDA, "mlbm_reduce_sum: %s", cudaGetErrorString(error));
+  ctx->launches += 1;
+  return status;
+}
+
+int mlbm_alloc_pinned(size_t bytes, void** out) {
+  if (!out) return fail(MLBM_ERR_INVALID, "null argument");
+  *out = nullptr;
+  cudaError_t error = cudaMallocHost(out, bytes ? bytes : 1);
+  if (error != cudaSuccess) return fail(MLBM_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(error));
+  return MLBM_OK;
+}
+
+int mlbm_free_pinned(void* pointer) {
+  if (!pointer) return MLBM_OK;
+  cudaError_t error = cudaFreeHost(pointer);
+  if (error != cudaSuccess) return fail(MLBM_ERR_CUDA, "cudaFreeHost: %s", cudaGetErrorString(error));
+  return MLBM_OK;
+}
+
 int mlbm_timers(mlbm_ctx* ctx, double* communicationSeconds, double* computationSeconds) {
   if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
   if (communicationSeconds) *communicationSeconds = ctx->lastCommunication;

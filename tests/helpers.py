@@ -54,7 +54,7 @@ def check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3):
     if good.any():
         assert node_error[good].max() <= population_tolerance, \
             f"population error {node_error[good].max():.3e} > {population_tolerance:.3e}"
-    return mismatched
+    return mismatched, population_tolerance
 
 
 def run_oracle(cfg, f0, steps, alpha0=None):

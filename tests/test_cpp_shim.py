@@ -1,0 +1,178 @@
+"""The C++ drop-in layer (include/metaLBM_b200/metaLBM/*.h): reference spellings over the C-ABI.
+
+CPU part: the headers compile with g++ -std=c++14 against an Input.in in the reference's format, the lattice / domain
+descriptors equal the reference's tables (through the oracle, which restates Lattice.h), and the reference-style
+main links against libmetalbm_b200.so.  GPU part: populations injected through Distribution, advanced with
+Algorithm::iterate and read back with Algorithm::pack match the oracle within BASELINE.json's tolerances, on one rank
+and on two ranks (processes) exchanging halos over NVLink."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import relative_error, run_oracle
+from metalbm_b200.capi import make_config
+from oracle import oracle as O
+
+ROOT = Path(__file__).resolve().parent.parent
+INCLUDE = ROOT / "include" / "metaLBM_b200"
+LIBDIR = ROOT / "metalbm_b200"
+
+
+def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equilibrium="TruncationMa3", scheme="Guo",
+                    force="Kolmogorov", tau=0.55, nprocs=1, overlap="Off", link=True, input_file="Input_generic.in", steps=100):
+    output = tmp_path / name
+    command = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
+               f"-DNPROCS={nprocs}", "-DNTHREADS=1", f"-DGLOBAL_LENGTH_X={shape[0]}", f"-DGLOBAL_LENGTH_Y={shape[1]}",
+               f"-DGLOBAL_LENGTH_Z={shape[2]}", '-DLBM_POSTFIX="test"', f"-DLBM_LATTICE={lattice}", f"-DLBM_COLLISION={collision}",
+               f"-DLBM_EQUILIBRIUM={equilibrium}", f"-DLBM_SCHEME={scheme}", f"-DLBM_FORCE={force}", f"-DLBM_TAU={tau}",
+               f"-DLBM_OVERLAP={overlap}", f"-DLBM_STEPS={steps}",
+               "-include", str(ROOT / "examples" / input_file), "-I", str(INCLUDE), str(ROOT / "examples" / source),
+               "-o", str(output)]
+    if link:
+        command += ["-L", str(LIBDIR), "-lmetalbm_b200", f"-Wl,-rpath,{LIBDIR}"]
+    result = subprocess.run(command, capture_output=True, text=True)
+    assert result.returncode == 0, result.stderr[-4000:]
+    return output
+
+
+@pytest.mark.parametrize("lattice,shape", [("D2Q5", (8, 6, 1)), ("D2Q9", (8, 6, 1)), ("D3Q15", (8, 6, 4)),
+                                           ("D3Q19", (8, 6, 4)), ("D3Q27", (8, 6, 5))])
+def test_lattice_descriptor_equals_reference_tables(tmp_path, oracle_lib, lattice, shape):
+    binary = compile_example(tmp_path, "lattice_dump.cpp", "lattice_dump", lattice, shape, link=False)
+    lines = subprocess.run([str(binary)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
+    dim, q, c, w = O.lattice(lattice)
+    head = list(map(int, lines[0].split()))
+    face = {"D2Q5": 1, "D2Q9": 3, "D3Q15": 5, "D3Q19": 5, "D3Q27": 9}[lattice]
+    assert head == [dim, q, 1, face]
+    for iq in range(q):
+        parts = lines[1 + iq].split()
+        assert list(map(int, parts[:3])) == c[iq].tolist()
+        assert float(parts[3]) == w[iq]
+    faces = [list(map(int, part.split())) for part in lines[1 + q].split("|")]
+    expect = [[i for i in range(q) if c[i, axis] == sign] if axis < dim else [] for axis, sign in ((1, -1), (1, 1), (2, -1), (2, 1))]
+    assert faces == expect
+    # lSD::pLength pads the last used dimension to 2 (n / 2 + 1) (Domain.h:53-57); hSD::volume has a halo of 1 per used side
+    px, py, pz, pvolume, hvolume = map(int, lines[2 + q].split())
+    padded = list(shape)
+    padded[dim - 1] = 2 * (shape[dim - 1] // 2 + 1)
+    assert [px, py, pz] == padded and pvolume == int(np.prod(padded))
+    assert hvolume == int(np.prod([n + 2 if i < dim else n for i, n in enumerate(shape)]))
+    assert int(lines[3 + q]) == 2 ** 32 - 1
+
+
+def test_reference_style_main_compiles_and_links(tmp_path, cuda_lib):
+    compile_example(tmp_path, "main_gpu.cpp", "main_gpu", "D2Q9", (64, 64, 1), input_file="Input_d2q9_kolmogorov.in")
+    compile_example(tmp_path, "shim_check.cpp", "shim_check", "D3Q27", (8, 6, 4), collision="ELBM", equilibrium="Exact")
+
+
+def test_unsupported_choices_fail_at_compile_time(tmp_path):
+    with pytest.raises(AssertionError):
+        compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), equilibrium="Exact", link=False)
+    with pytest.raises(AssertionError):
+        compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), collision="Malaspinas_ELBM", link=False)
+
+
+def _run_shim(tmp_path, binary, f0_slabs, steps, env_extra=None):
+    procs = []
+    world = len(f0_slabs)
+    for rank, slab in enumerate(f0_slabs):
+        slab.astype(np.float64).tofile(tmp_path / f"in{rank}.bin")
+        env = dict(os.environ, MLBM_RANK=str(rank), MLBM_NRANKS=str(world), MLBM_RENDEZVOUS_DIR=str(tmp_path),
+                   MLBM_SESSION=f"shim{os.getpid()}")
+        env.update(env_extra or {})
+        procs.append(subprocess.Popen([str(binary), str(tmp_path / f"in{rank}.bin"), str(steps), str(tmp_path / f"out{rank}.bin"),
+                                       str(tmp_path / f"fields{rank}.bin")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                      text=True, env=env))
+    outputs = []
+    for rank, p in enumerate(procs):
+        try:
+            out, _ = p.communicate(timeout=300)
+        except subprocess.TimeoutExpired:
+            for other in procs:
+                other.kill()
+            out, _ = p.communicate()
+        assert p.returncode == 0 and f"ok rank {rank}" in out, out[-3000:]
+        outputs.append(out)
+    return outputs
+
+
+SHIM_CASES = [
+    ("D3Q19", (16, 12, 10), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 3),
+    ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 3),
+    ("D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 1),
+]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2])
+@pytest.mark.parametrize("case", SHIM_CASES, ids=lambda c: "-".join(map(str, c[:1] + c[2:6])))
+def test_template_api_reproduces_the_oracle(tmp_path, cuda_lib, world, case):
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    lattice, shape, collision, equilibrium, scheme, force, steps = case
+    binary = compile_example(tmp_path, "shim_check.cpp", "shim_check", lattice, shape, collision, equilibrium, scheme, force,
+                             tau=0.55, nprocs=world, overlap="On" if world > 1 else "Off")
+    cfg = make_config(lattice=lattice, shape=shape, collision=collision, equilibrium=equilibrium, forcing_scheme=scheme,
+                      force=force, tau=0.55, amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0))
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    lx = shape[0] // world
+    outputs = _run_shim(tmp_path, binary, [np.ascontiguousarray(f0[:, r * lx:(r + 1) * lx]) for r in range(world)], steps)
+    ref = run_oracle(cfg, f0, steps)
+    dim, q = ref.dim, ref.q
+    got = np.concatenate([np.fromfile(tmp_path / f"out{r}.bin").reshape((q, lx) + tuple(shape[1:])) for r in range(world)], axis=1)
+    if collision == "BGK":
+        assert relative_error(got, ref.f) <= 1e-12 * steps
+    else:
+        node_error = np.abs(got - ref.f).max(axis=0)
+        alpha_ok = np.ones(shape, dtype=bool)
+    volume = lx * shape[1] * shape[2]
+    for r in range(world):
+        raw = np.fromfile(tmp_path / f"fields{r}.bin")
+        density = raw[:volume].reshape((lx,) + tuple(shape[1:]))
+        alpha = raw[(1 + dim) * volume:(2 + dim) * volume].reshape((lx,) + tuple(shape[1:]))
+        observables = raw[(2 + dim) * volume:]
+        assert relative_error(density, ref.density[r * lx:(r + 1) * lx]) <= 1e-12 * steps
+        if collision == "BGK":
+            assert np.all(alpha == 2.0)
+        else:
+            tolerance = 1e-10 + 4.0 * ref.alpha_noise[r * lx:(r + 1) * lx]
+            alpha_ok[r * lx:(r + 1) * lx] = np.abs(alpha - ref.alpha[r * lx:(r + 1) * lx]) <= tolerance
+        obs = ref.observables()
+        assert abs(observables[0] - obs[0]) <= 1e-9 * abs(obs[0])
+        assert abs(observables[3] - obs[3]) <= 1e-12 * abs(obs[3])
+        # Communication::reduce of the stored density == the reduced mass observable
+        mass = float(outputs[r].split("mass")[1].split()[0])
+        assert abs(mass - obs[3]) <= 1e-12 * abs(obs[3])
+    if collision != "BGK":
+        assert (~alpha_ok).mean() <= 1e-3
+        assert node_error[alpha_ok].max() <= 1e-12 * np.abs(ref.f).max() + 2e-10 * ref.fneq_max.max()
+
+
+@pytest.mark.gpu
+def test_reference_style_routine_runs(tmp_path, cuda_lib):
+    """src/main.cu with Architecture::GPU: Routine::compute from a density peak, observables against the oracle."""
+    shape = (64, 48, 1)
+    binary = compile_example(tmp_path, "main_gpu.cpp", "main_gpu", "D2Q9", shape, scheme="Guo", force="Kolmogorov", tau=0.55,
+                             steps=100)
+    result = subprocess.run([str(binary)], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    table = np.loadtxt(tmp_path / "observables_test.dat", skiprows=1)
+    assert table.shape == (2, 5) and table[:, 0].tolist() == [50, 100]
+    # the same run on the oracle: rho = 1 with a 3x peak at (0.4, 0.3)(L - 1) (Initialize.h:30-46), u = 0, f = feq
+    cfg = make_config(lattice="D2Q9", shape=shape, collision="BGK", forcing_scheme="Guo", force="Kolmogorov", tau=0.55,
+                      amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0))
+    density = np.ones(shape)
+    density[int((shape[0] - 1) * 0.4), int((shape[1] - 1) * 0.3), 0] = 3.0
+    state = O.OracleState(cfg, O.init_equilibrium(cfg, density, np.zeros((2,) + shape)))
+    for iteration in range(1, 101):
+        state.step(iteration % 50 == 0)
+        if iteration % 50 == 0:
+            obs = state.observables()
+            row = table[iteration // 50 - 1]
+            assert abs(row[1] - obs[0]) <= 1e-9 * abs(obs[0])
+            assert abs(row[4] - obs[3]) <= 1e-12 * abs(obs[3])
