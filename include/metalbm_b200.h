@@ -175,6 +175,10 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]);
  * doubles over all ranks, result on EVERY rank (the reference leaves it on rank 0 only); a no-op for one rank. */
 int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count);
 
+/* Self-test hook: out[i] = the kernels' table-driven logarithm of in[i] (host arrays), so that the parity suite can pin
+ * the one transcendental of the entropic solve (std::log in EntropicStep.h:31-62) against a high-precision value. */
+int mlbm_selftest_log(const double* in, double* out, size_t count);
+
 /* DynamicArray<U, Architecture::CPUPinned> (DynamicArray.cuh:88-127): page-locked host memory, which is where the
  * reference keeps the GPU build's fields (Field.h:62-79) and what makes pack/unpack run at PCIe speed. */
 int mlbm_alloc_pinned(size_t bytes, void** out);

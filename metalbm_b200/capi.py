@@ -165,6 +165,7 @@ PROTOTYPES = {
     "mlbm_download_fields": (ctypes.c_int, [_P, _P, _P, _P, _P, _SZ, _SZ, _SZ]),
     "mlbm_observables": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "mlbm_reduce_sum": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
+    "mlbm_selftest_log": (ctypes.c_int, [_P, _P, _SZ]),
     "mlbm_alloc_pinned": (ctypes.c_int, [_SZ, ctypes.POINTER(_P)]),
     "mlbm_free_pinned": (ctypes.c_int, [_P]),
     "mlbm_timers": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),

@@ -211,6 +211,14 @@ __global__ void perturbKernel(StoreT* __restrict__ populations, long long stride
   }
 }
 
+__global__ void fastLogKernel(const double* __restrict__ in, double* __restrict__ out, long long count) {
+  __shared__ double2 table[128];
+  if (threadIdx.x < 128) table[threadIdx.x] = kLogTable[threadIdx.x];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = fastLog(in[i], table);
+}
+
 template <int EQ, typename StoreT>
 static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* populations, const StoreT* density,
                                   const StoreT* velocity, long long stride, long long plane, long long fieldStride,
@@ -933,6 +941,24 @@ int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count) {
   if (error != cudaSuccess) return fail(MLBM_ERR_CUDA, "mlbm_reduce_sum: %s", cudaGetErrorString(error));
   ctx->launches += 1;
   return status;
+}
+
+int mlbm_selftest_log(const double* in, double* out, size_t count) {
+  if (!in || !out) return fail(MLBM_ERR_INVALID, "null argument");
+  if (!count) return MLBM_OK;
+  double *deviceIn = nullptr, *deviceOut = nullptr;
+  MLBM_CUDA(cudaMalloc(&deviceIn, count * sizeof(double)));
+  cudaError_t error = cudaMalloc(&deviceOut, count * sizeof(double));
+  if (error == cudaSuccess) error = cudaMemcpy(deviceIn, in, count * sizeof(double), cudaMemcpyHostToDevice);
+  if (error == cudaSuccess) {
+    fastLogKernel<<<(unsigned)((count + 127) / 128), 128>>>(deviceIn, deviceOut, (long long)count);
+    error = cudaGetLastError();
+  }
+  if (error == cudaSuccess) error = cudaMemcpy(out, deviceOut, count * sizeof(double), cudaMemcpyDeviceToHost);
+  cudaFree(deviceIn);
+  cudaFree(deviceOut);
+  if (error != cudaSuccess) return fail(MLBM_ERR_CUDA, "mlbm_selftest_log: %s", cudaGetErrorString(error));
+  return MLBM_OK;
 }
 
 int mlbm_alloc_pinned(size_t bytes, void** out) {

@@ -126,10 +126,47 @@ template <int I, int N, class F> __device__ __forceinline__ void staticFor(F&& f
 }
 
 // ------------------------------------------------------------------------------------------------
+// fastLog: natural logarithm of a positive normal double with an absolute error of a few 1e-17 * (1 + |ln v|),
+// about 12 FP64 instructions instead of the ~30 FP64 + ~25 integer instructions of the CUDA math library's log().
+// The entropic solve evaluates (1 + iterations) * Q logarithms per node, which makes it FP64-pipe bound (SURVEY.md
+// section 7); this is what moves it back towards the HBM roofline.
+//   v = 2^k z, z in [0.6875, 1.375): integer arithmetic on the bit pattern; the top 7 bits below the exponent pick
+//   one of 128 sub-intervals with centre c; invc = double(1/c), logc = double(-ln invc) (log_table.inc, generated with
+//   100-digit arithmetic by gen_log_table.py); r = fma(z, invc, -1) is exact to rounding and |r| < 2^-8, so
+//   ln v = k ln2 + logc + (r - r^2/2 + ... + r^7/7) with a truncation error below 1e-20.
+// Zero, negative, subnormal, infinite and NaN arguments take the library path so that the Newton iteration sees the
+// same NaNs the reference's std::log produces for a mirror state that left the positive cone (EntropicStep.h:31-62).
+// ------------------------------------------------------------------------------------------------
+static __device__ const double2 kLogTable[128] = {
+#include "log_table.inc"
+};
+
+static __device__ __noinline__ double libraryLog(double v) { return log(v); }
+
+__device__ __forceinline__ double fastLog(double v, const double2* __restrict__ table) {
+  if (!(v >= 2.2250738585072014e-308 && v <= 1.7976931348623157e308)) return libraryLog(v);
+  const long long ix = __double_as_longlong(v);
+  const long long tmp = ix - 0x3FE6000000000000LL;
+  const double kd = (double)(int)(tmp >> 52);
+  const int i = (int)(tmp >> 45) & 127;
+  const double z = __longlong_as_double(ix - (tmp & (long long)0xFFF0000000000000ULL));
+  const double2 entry = table[i];
+  const double r = fma(z, entry.x, -1.0);
+  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
+  p = fma(r, p, 0.2);
+  p = fma(r, p, -0.25);
+  p = fma(r, p, 1.0 / 3.0);
+  p = fma(r, p, -0.5);
+  const double hi = fma(kd, 0x1.62e42fefa3800p-1, entry.y);
+  return hi + fma(r * r, p, fma(kd, 0x1.ef35793c76730p-45, r));
+}
+
+// ------------------------------------------------------------------------------------------------
 // Entropic alpha: Collision<ELBM>::calculateAlpha (Collision.h:351-375).
 // ------------------------------------------------------------------------------------------------
 template <class L>
-__device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const double (&fNeq)[L::Q], double alphaGuess) {
+__device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const double (&fNeq)[L::Q], double alphaGuess,
+                                                const double2* __restrict__ logTable) {
   // isDeviationSmall (Collision.h:284-303): no |fNeq_q| / f_q above 1e-3
   bool small = true;
 #pragma unroll
@@ -158,7 +195,7 @@ __device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const d
   // The a-independent sum is hoisted and ln((f - a fNeq)/w) is shared between F and F'.
   double hoisted = 0.0;
 #pragma unroll
-  for (int q = 0; q < L::Q; ++q) hoisted += f[q] * log(f[q] * (1.0 / L::w(q)));
+  for (int q = 0; q < L::Q; ++q) hoisted = fma(f[q], fastLog(f[q] * (1.0 / L::w(q)), logTable), hoisted);
 
   double x = alphaGuess, step = 0.0;
   bool converged = false;
@@ -167,10 +204,10 @@ __device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const d
     double sum = 0.0, derivative = 0.0;
 #pragma unroll
     for (int q = 0; q < L::Q; ++q) {
-      const double g = f[q] - x * fNeq[q];
-      const double lg = log(g * (1.0 / L::w(q)));
-      sum += g * lg;
-      derivative += fNeq[q] * (1.0 + lg);
+      const double g = fma(-x, fNeq[q], f[q]);
+      const double lg = fastLog(g * (1.0 / L::w(q)), logTable);
+      sum = fma(g, lg, sum);
+      derivative = fma(fNeq[q], 1.0 + lg, derivative);
     }
     step = (hoisted - sum) / derivative;
     if (fabs(step) <= 1e-8) { converged = (x > 1.0 && x < alphaMax); break; }
@@ -192,6 +229,13 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
   const int m = blockIdx.y;
   const int x = p.x0 + blockIdx.z;
   const bool active = r < p.NR;
+
+  __shared__ double2 logTable[COLLISION == kELBM ? 128 : 1];
+  if (COLLISION == kELBM) {
+    static_assert(kStepBlock == 128, "one table entry per thread");
+    logTable[threadIdx.x] = kLogTable[threadIdx.x];
+    __syncthreads();
+  }
 
   double rho = 0.0, energy = 0.0, speed2 = 0.0;
 
@@ -284,7 +328,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
         fNeq[q] = f[q] - rho * L::w(q) * eq.template shape<q>();
       });
       StoreT* alphaField = static_cast<StoreT*>(p.alpha);
-      alpha = entropicAlpha<L>(f, fNeq, (double)alphaField[node]);
+      alpha = entropicAlpha<L>(f, fNeq, (double)alphaField[node], logTable);
       alphaField[node] = (StoreT)alpha;
       const double omega = alpha * p.beta;  // 1 / tau_eff (Collision.h:240)
       // Collision<ELBM>::collideAndStream (Collision.h:243-258)

@@ -25,7 +25,8 @@ def test_cuda_reproduces_reference_outputs(name):
         tolerance = 1e-12 if meta["steps"] <= 3 else 1e-11
         assert relative_error(got["f"], data["f"]) <= tolerance
         assert np.all(got["alpha"] == 2.0)
-    assert relative_error(got["density"], data["density"]) <= 1e-12
+        density_tolerance = 1e-12
+    assert relative_error(got["density"], data["density"]) <= density_tolerance
     assert np.array_equal(got["force"], data["force"])
     energy = data["observables"][-1][1]
     assert abs(got["observables"][0] - energy) <= 1e-9 * abs(energy)

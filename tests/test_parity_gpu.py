@@ -117,3 +117,25 @@ def test_fp32_storage_against_fp64_oracle():
     got = run_cuda(cfg32, f0, 1)
     ref = run_oracle(cfg64, f0, 1)
     assert relative_error(got["f"], ref.f) <= 1e-6
+
+
+def test_table_logarithm_against_high_precision():
+    """The kernels' logarithm (fastLog, step_kernel.cuh) against mpmath: absolute error <= 4e-16 (1 + |ln v|) over the
+    range the entropic solve visits and far outside it; non-positive / non-finite arguments behave like std::log."""
+    import ctypes
+    import mpmath
+    from metalbm_b200.capi import check, load_library
+    rng = np.random.default_rng(7)
+    v = np.concatenate([rng.uniform(0.2, 4.0, 4000), 1.0 + rng.uniform(-1e-3, 1e-3, 2000), 10.0 ** rng.uniform(-300, 300, 2000),
+                        np.array([1.0, 0.6875, 1.375, np.nextafter(1.0, 0), np.nextafter(1.0, 2), 2.0 ** -1022, 1.7e308])])
+    special = np.array([0.0, -1.0, np.inf, np.nan, 5e-324, -np.inf])
+    data = np.ascontiguousarray(np.concatenate([v, special]))
+    out = np.empty_like(data)
+    check(load_library().mlbm_selftest_log(data.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), data.size))
+    mpmath.mp.dps = 40
+    for value, got in zip(v, out[:v.size]):
+        exact = mpmath.log(mpmath.mpf(float(value)))
+        assert abs(mpmath.mpf(float(got)) - exact) <= 4e-16 * (1 + abs(exact)), (value, got)
+    tail = out[v.size:]
+    assert tail[0] == -np.inf and np.isnan(tail[1]) and tail[2] == np.inf and np.isnan(tail[3]) and np.isnan(tail[5])
+    assert abs(tail[4] - np.log(5e-324)) <= 1e-12
