@@ -212,8 +212,8 @@ __global__ void perturbKernel(StoreT* __restrict__ populations, long long stride
 }
 
 __global__ void fastLogKernel(const double* __restrict__ in, double* __restrict__ out, long long count) {
-  __shared__ double2 table[128];
-  if (threadIdx.x < 128) table[threadIdx.x] = kLogTable[threadIdx.x];
+  __shared__ double2 table[kLogTableEntries];
+  for (int i = threadIdx.x; i < kLogTableEntries; i += blockDim.x) table[i] = kLogTable[i];
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) out[i] = fastLog(in[i], table);
@@ -303,6 +303,7 @@ struct mlbm_ctx {
   bool observablesValid = false;
 
   StepKernel kernel = nullptr;
+  int sharedBytes = 0;  // dynamic shared memory of the fused kernel (entropic kernels stage f / fNeq there)
   int hydroShift = 0;
   cudaStream_t computeStream = nullptr;
   cudaStream_t commStream = nullptr;
@@ -384,7 +385,7 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
     ctx->profileUsed += 2;
     MLBM_CUDA(cudaEventRecord(start, stream));
   }
-  ctx->kernel<<<grid, kStepBlock, 0, stream>>>(p);
+  ctx->kernel<<<grid, kStepBlock, ctx->sharedBytes, stream>>>(p);
   if (profile) MLBM_CUDA(cudaEventRecord(stop, stream));
   MLBM_CUDA(cudaGetLastError());
   ctx->launches += 1;
@@ -624,6 +625,15 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   ctx->partialBlocks = (long long)ctx->gridR * ctx->NM * ctx->LX;
   ctx->kernel = kernel;
   ctx->hydroShift = hydroShift;
+  if (collision == kELBM) {
+    ctx->sharedBytes = entropicSharedBytes(Q, logTableInShared(Q));
+    cudaError_t attributeError = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->sharedBytes);
+    if (attributeError != cudaSuccess) {
+      const int bytes = ctx->sharedBytes;
+      delete ctx;
+      return fail(MLBM_ERR_CUDA, "cudaFuncSetAttribute(%d bytes of shared memory): %s", bytes, cudaGetErrorString(attributeError));
+    }
+  }
 
   auto cleanup = [&](int status) { mlbm_destroy(ctx); return status; };
 #define MLBM_CREATE_CUDA(call)                                                                          \

@@ -126,101 +126,185 @@ template <int I, int N, class F> __device__ __forceinline__ void staticFor(F&& f
 }
 
 // ------------------------------------------------------------------------------------------------
-// fastLog: natural logarithm of a positive normal double with an absolute error of a few 1e-17 * (1 + |ln v|),
-// about 12 FP64 instructions instead of the ~30 FP64 + ~25 integer instructions of the CUDA math library's log().
-// The entropic solve evaluates (1 + iterations) * Q logarithms per node, which makes it FP64-pipe bound (SURVEY.md
-// section 7); this is what moves it back towards the HBM roofline.
-//   v = 2^k z, z in [0.6875, 1.375): integer arithmetic on the bit pattern; the top 7 bits below the exponent pick
-//   one of 128 sub-intervals with centre c; invc = double(1/c), logc = double(-ln invc) (log_table.inc, generated with
-//   100-digit arithmetic by gen_log_table.py); r = fma(z, invc, -1) is exact to rounding and |r| < 2^-8, so
-//   ln v = k ln2 + logc + (r - r^2/2 + ... + r^7/7) with a truncation error below 1e-20.
-// Zero, negative, subnormal, infinite and NaN arguments take the library path so that the Newton iteration sees the
-// same NaNs the reference's std::log produces for a mirror state that left the positive cone (EntropicStep.h:31-62).
+// fastLogCore: natural logarithm of doubles in [0.25, 4) with an absolute error below 2.5e-16, 9 FP64 + 4 integer
+// instructions instead of the ~30 FP64 + ~25 integer instructions of the CUDA math library's log().
+// The entropic solve evaluates (1 + iterations) * Q logarithms per node, which makes it FP64-issue bound (SURVEY.md
+// section 7); this is what moves it back towards the HBM roofline.  The arguments are f_q / w_q and
+// (f_q - alpha fNeq_q) / w_q, i.e. the local density times 1 + O(Mach) + O(non-equilibrium): [0.25, 4) covers every
+// state a lattice-Boltzmann run can sensibly be in, and anything else takes the library path (entropicNewtonLibrary).
+//   The top bits of the double (exponent and 7 mantissa bits, minus those of 0.25) index one of 512 sub-intervals with
+//   centre c; invc = double(1/c), logc = double(-ln invc) (log_table.inc, generated with 100-digit arithmetic by
+//   gen_log_table.py); r = fma(v, invc, -1) is exact to rounding and |r| < 2^-8, so
+//   ln v = logc + (r - r^2/2 + ... + r^7/7) with a truncation error below 1e-20.
+// N independent arguments advance in lock step: every Horner step is issued for all N before the next one, which
+// gives the FP64 pipe N independent dependency chains per warp.
+// `range` accumulates the maximum table index as an unsigned number: it stays below 512 exactly when every argument
+// was inside [0.25, 4) (smaller, negative, infinite and NaN arguments all map to indices >= 512).
 // ------------------------------------------------------------------------------------------------
-static __device__ const double2 kLogTable[128] = {
+constexpr int kLogTableEntries = 512;
+static __device__ const double2 kLogTable[kLogTableEntries] = {
 #include "log_table.inc"
 };
 
-static __device__ __noinline__ double libraryLog(double v) { return log(v); }
+template <int N>
+__device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[N], const double2* __restrict__ table,
+                                            unsigned& range) {
+  double2 entry[N];
+  double r[N], p[N];
+#pragma unroll
+  for (int j = 0; j < N; ++j) {
+    const unsigned index = (unsigned)((__double2hiint(v[j]) - 0x3FD00000) >> 13);
+    range = max(range, index);
+    entry[j] = table[index & (kLogTableEntries - 1)];
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) r[j] = fma(v[j], entry[j].x, -1.0);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fma(r[j], 1.0 / 7.0, -1.0 / 6.0);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], 0.2);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], -0.25);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], 1.0 / 3.0);
+#pragma unroll
+  for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], -0.5);
+#pragma unroll
+  for (int j = 0; j < N; ++j) out[j] = entry[j].y + fma(r[j] * r[j], p[j], r[j]);
+}
 
+// general entry point (self-test, tools): library logarithm outside [0.25, 4)
 __device__ __forceinline__ double fastLog(double v, const double2* __restrict__ table) {
-  if (!(v >= 2.2250738585072014e-308 && v <= 1.7976931348623157e308)) return libraryLog(v);
-  const long long ix = __double_as_longlong(v);
-  const long long tmp = ix - 0x3FE6000000000000LL;
-  const double kd = (double)(int)(tmp >> 52);
-  const int i = (int)(tmp >> 45) & 127;
-  const double z = __longlong_as_double(ix - (tmp & (long long)0xFFF0000000000000ULL));
-  const double2 entry = table[i];
-  const double r = fma(z, entry.x, -1.0);
-  double p = fma(r, 1.0 / 7.0, -1.0 / 6.0);
-  p = fma(r, p, 0.2);
-  p = fma(r, p, -0.25);
-  p = fma(r, p, 1.0 / 3.0);
-  p = fma(r, p, -0.5);
-  const double hi = fma(kd, 0x1.62e42fefa3800p-1, entry.y);
-  return hi + fma(r * r, p, fma(kd, 0x1.ef35793c76730p-45, r));
+  const double in[1] = {v};
+  double out[1];
+  unsigned range = 0;
+  fastLogCore<1>(in, out, table, range);
+  return range < kLogTableEntries ? out[0] : log(v);
 }
 
 // ------------------------------------------------------------------------------------------------
 // Entropic alpha: Collision<ELBM>::calculateAlpha (Collision.h:351-375).
+//
+// Work layout.  The populations f_q and their non-equilibrium parts of one node live in SHARED memory while alpha is
+// solved for ([q][thread], conflict-free), not in registers: the Newton loops over q are then rolled (a few dozen
+// instructions, three-way unrolled for instruction-level parallelism) instead of Q copies of the logarithm per
+// evaluation, which had overflowed the instruction cache (ncu: 'no_instructions' was the second stall reason) and
+// kept 108 registers alive through the solve.
 // ------------------------------------------------------------------------------------------------
-template <class L>
-__device__ __forceinline__ double entropicAlpha(const double (&f)[L::Q], const double (&fNeq)[L::Q], double alphaGuess,
-                                                const double2* __restrict__ logTable) {
-  // isDeviationSmall (Collision.h:284-303): no |fNeq_q| / f_q above 1e-3
-  bool small = true;
-#pragma unroll
-  for (int q = 0; q < L::Q; ++q) {
-    const double a = fabs(fNeq[q]);
-    const bool large = f[q] > 0.0 ? (a > 1.0e-3 * f[q]) : (f[q] == 0.0 ? a > 0.0 : false);
-    small = small && !large;
-  }
-  if (small) return 2.0;
+struct EntropicScratch {
+  const double* f;       // f[q * kStepBlock]     (this thread's column)
+  const double* fNeq;    // fNeq[q * kStepBlock]
+  const double* invW;    // 1 / w_q, one copy per block
+  const double2* table;  // fastLog table (shared or global memory)
+};
 
-  // calculateAlphaMax (Collision.h:305-326): min(2.5, min over fNeq_q > 0 of |f_q| / fNeq_q), tracked as a fraction
-  double num = 2.5, den = 1.0;
-#pragma unroll
-  for (int q = 0; q < L::Q; ++q) {
-    if (fNeq[q] > 0.0) {
-      const double a = fabs(f[q]);
-      if (a * den < num * fNeq[q]) { num = a; den = fNeq[q]; }
+// The same solve with the CUDA math library's logarithm, for the rare node whose arguments fall outside fastLogCore's
+// table.  Kept out of line and rolled: it is cold code.
+template <int Q>
+__device__ __noinline__ double entropicNewtonLibrary(const EntropicScratch& s, double alphaGuess, double alphaMax) {
+  double hoisted = 0.0;
+#pragma unroll 1
+  for (int q = 0; q < Q; ++q) {
+    const double fq = s.f[q * kStepBlock];
+    hoisted = fma(fq, log(fq * s.invW[q]), hoisted);
+  }
+  double x = alphaGuess, step = 0.0;
+  for (int iteration = 1; iteration <= 50; ++iteration) {
+    x = x - step;
+    double sum = 0.0, derivative = 0.0;
+#pragma unroll 1
+    for (int q = 0; q < Q; ++q) {
+      const double nq = s.fNeq[q * kStepBlock];
+      const double g = fma(-x, nq, s.f[q * kStepBlock]);
+      const double lg = log(g * s.invW[q]);
+      sum = fma(g, lg, sum);
+      derivative = fma(nq, 1.0 + lg, derivative);
     }
+    step = (hoisted - sum) / derivative;
+    if (fabs(step) <= 1e-8) return (x > 1.0 && x < alphaMax) ? x : 2.0;
   }
-  const double alphaMax = num / den;
-  if (alphaMax < 2.0) return 0.95 * alphaMax;
+  return 2.0;
+}
 
+// The q loops are rolled over groups of three populations (the three logarithms of a group advance in lock step,
+// see fastLogCore); Q = 9, 15, 27 are multiples of three, the others end with a partial group whose unused slots
+// are fed the harmless argument 1 and contribute exact zeros.
+template <int Q>
+__device__ __forceinline__ double entropicNewton(const EntropicScratch& s, double alphaGuess, double alphaMax) {
   // solveAlpha (Collision.h:328-349) -> NewtonRaphsonSolver (EntropicStep.h:111-140) on
   //   F(a)  = sum f ln(f/w) - (f - a fNeq) ln((f - a fNeq)/w)      (EntropicStep.h:31-45)
   //   F'(a) = sum fNeq (1 + ln((f - a fNeq)/w))                     (EntropicStep.h:47-62)
-  // The a-independent sum is hoisted and ln((f - a fNeq)/w) is shared between F and F'.
-  double hoisted = 0.0;
+  // The a-independent sum is hoisted and ln((f - a fNeq)/w) is shared between F and F'.  Each slot of a group keeps
+  // its own partial sums.
+  // As soon as a logarithm argument leaves the table's range the node is handed to entropicNewtonLibrary, which
+  // restarts the solve with the library logarithm (and with it the reference's NaN behaviour for mirror states that
+  // leave the positive cone: the iteration produces NaNs, gives up after 50 iterations and alpha falls back to 2,
+  // EntropicStep.h:126-138, Collision.h:344-346).
+  constexpr int G = 3;
+  constexpr int groups = (Q + G - 1) / G;
+  unsigned range = 0;
+  double h[G] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+  for (int group = 0; group < groups; ++group) {
+    double fq[G], v[G], lg[G];
 #pragma unroll
-  for (int q = 0; q < L::Q; ++q) hoisted = fma(f[q], fastLog(f[q] * (1.0 / L::w(q)), logTable), hoisted);
+    for (int j = 0; j < G; ++j) {
+      const int q = group * G + j;
+      const bool live = Q % G == 0 || q < Q;
+      fq[j] = live ? s.f[q * kStepBlock] : 0.0;
+      v[j] = live ? fq[j] * s.invW[q] : 1.0;
+    }
+    fastLogCore<G>(v, lg, s.table, range);
+#pragma unroll
+    for (int j = 0; j < G; ++j) h[j] = fma(fq[j], lg[j], h[j]);
+  }
+  if (range >= kLogTableEntries) return entropicNewtonLibrary<Q>(s, alphaGuess, alphaMax);
+  const double hoisted = (h[0] + h[1]) + h[2];
 
   double x = alphaGuess, step = 0.0;
   bool converged = false;
   for (int iteration = 1; iteration <= 50; ++iteration) {
     x = x - step;
-    double sum = 0.0, derivative = 0.0;
+    double sum[G] = {0.0, 0.0, 0.0}, derivative[G] = {0.0, 0.0, 0.0};
+#pragma unroll 1
+    for (int group = 0; group < groups; ++group) {
+      double g[G], nq[G], v[G], lg[G];
 #pragma unroll
-    for (int q = 0; q < L::Q; ++q) {
-      const double g = fma(-x, fNeq[q], f[q]);
-      const double lg = fastLog(g * (1.0 / L::w(q)), logTable);
-      sum = fma(g, lg, sum);
-      derivative = fma(fNeq[q], 1.0 + lg, derivative);
+      for (int j = 0; j < G; ++j) {
+        const int q = group * G + j;
+        const bool live = Q % G == 0 || q < Q;
+        nq[j] = live ? s.fNeq[q * kStepBlock] : 0.0;
+        g[j] = live ? fma(-x, nq[j], s.f[q * kStepBlock]) : 0.0;
+        v[j] = live ? g[j] * s.invW[q] : 1.0;
+      }
+      fastLogCore<G>(v, lg, s.table, range);
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        sum[j] = fma(g[j], lg[j], sum[j]);
+        derivative[j] = fma(nq[j], 1.0 + lg[j], derivative[j]);
+      }
     }
-    step = (hoisted - sum) / derivative;
+    if (range >= kLogTableEntries) return entropicNewtonLibrary<Q>(s, alphaGuess, alphaMax);
+    step = (hoisted - ((sum[0] + sum[1]) + sum[2])) / ((derivative[0] + derivative[1]) + derivative[2]);
     if (fabs(step) <= 1e-8) { converged = (x > 1.0 && x < alphaMax); break; }
   }
   return converged ? x : 2.0;
 }
+
+// bytes of dynamic shared memory the entropic kernels need (see fusedStepKernel)
+constexpr int kLogTableBytes = kLogTableEntries * 16;
+constexpr int entropicSharedBytes(int Q, bool tableInShared) {
+  return 2 * Q * kStepBlock * 8 + ((Q * 8 + 15) / 16) * 16 + (tableInShared ? kLogTableBytes : 0);
+}
+// the fastLog table is staged in shared memory whenever four blocks per SM still fit (228 KB, 1 KB reserved per block)
+constexpr bool logTableInShared(int Q) { return 4 * (entropicSharedBytes(Q, true) + 1024) <= 233472; }
 
 // ------------------------------------------------------------------------------------------------
 // The fused step.
 // grid = (ceil(NR / kStepBlock), NM, number of x planes), block = kStepBlock threads along r.
 // ------------------------------------------------------------------------------------------------
 template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
-__global__ void __launch_bounds__(kStepBlock)
+__global__ void __launch_bounds__(kStepBlock, COLLISION == kELBM ? 4 : 1)
 fusedStepKernel(const __grid_constant__ StepParams p) {
   constexpr int Q = L::Q;
   constexpr int D = L::D;
@@ -230,10 +314,29 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
   const int x = p.x0 + blockIdx.z;
   const bool active = r < p.NR;
 
-  __shared__ double2 logTable[COLLISION == kELBM ? 128 : 1];
+  // entropic kernels: dynamic shared memory = f[Q][block] | fNeq[Q][block] | 1/w[Q] | (fastLog table)
+  extern __shared__ __align__(16) unsigned char dynamicShared[];
+  EntropicScratch scratchPointers = {nullptr, nullptr, nullptr, kLogTable};
+  double* sharedF = nullptr;
+  double* sharedFNeq = nullptr;
   if (COLLISION == kELBM) {
-    static_assert(kStepBlock == 128, "one table entry per thread");
-    logTable[threadIdx.x] = kLogTable[threadIdx.x];
+    static_assert(kLogTableEntries % kStepBlock == 0, "whole table entries per thread");
+    sharedF = reinterpret_cast<double*>(dynamicShared) + threadIdx.x;
+    sharedFNeq = sharedF + Q * kStepBlock;
+    double* invW = reinterpret_cast<double*>(dynamicShared) + 2 * Q * kStepBlock;
+    staticFor<0, Q>([&](auto qc) {
+      constexpr int q = decltype(qc)::value;
+      if (threadIdx.x == q) invW[q] = 1.0 / L::w(q);
+    });
+    scratchPointers.f = sharedF;
+    scratchPointers.fNeq = sharedFNeq;
+    scratchPointers.invW = invW;
+    if (logTableInShared(Q)) {
+      double2* table = reinterpret_cast<double2*>(dynamicShared + 2 * Q * kStepBlock * 8 + ((Q * 8 + 15) / 16) * 16);
+#pragma unroll
+      for (int i = 0; i < kLogTableEntries / kStepBlock; ++i) table[i * kStepBlock + threadIdx.x] = kLogTable[i * kStepBlock + threadIdx.x];
+      scratchPointers.table = table;
+    }
     __syncthreads();
   }
 
@@ -321,20 +424,39 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
 
     double alpha = 2.0;
     if (COLLISION == kELBM) {
-      // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241)
-      double fNeq[Q];
+      // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241): fNeq, then alpha.  While fNeq is formed the
+      // two cheap screens of calculateAlpha run on the register values:
+      //   isDeviationSmall (Collision.h:284-303): no |fNeq_q| / f_q above 1e-3
+      //   calculateAlphaMax (Collision.h:305-326): min(2.5, min over fNeq_q > 0 of |f_q| / fNeq_q), tracked as a fraction
+      bool small = true;
+      double num = 2.5, den = 1.0;
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        fNeq[q] = f[q] - rho * L::w(q) * eq.template shape<q>();
+        const double fq = f[q];
+        const double nq = fq - rho * L::w(q) * eq.template shape<q>();
+        sharedF[q * kStepBlock] = fq;
+        sharedFNeq[q * kStepBlock] = nq;
+        const double a = fabs(nq);
+        const bool large = fq > 0.0 ? (a > 1.0e-3 * fq) : (fq == 0.0 ? a > 0.0 : false);
+        small = small && !large;
+        if (nq > 0.0) {
+          const double af = fabs(fq);
+          if (af * den < num * nq) { num = af; den = nq; }
+        }
       });
       StoreT* alphaField = static_cast<StoreT*>(p.alpha);
-      alpha = entropicAlpha<L>(f, fNeq, (double)alphaField[node], logTable);
+      if (!small) {
+        // Collision<ELBM>::calculateAlpha (Collision.h:351-375)
+        const double alphaMax = num / den;
+        alpha = alphaMax < 2.0 ? 0.95 * alphaMax : entropicNewton<Q>(scratchPointers, (double)alphaField[node], alphaMax);
+      }
       alphaField[node] = (StoreT)alpha;
       const double omega = alpha * p.beta;  // 1 / tau_eff (Collision.h:240)
       // Collision<ELBM>::collideAndStream (Collision.h:243-258)
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        double value = f[q] - omega * fNeq[q];
+        const double fq = sharedF[q * kStepBlock], nq = sharedFNeq[q * kStepBlock];
+        double value = fq - omega * nq;
         if (SCHEME == kSchemeGuo) {
           double cF = 0.0, cu = 0.0;
 #pragma unroll
@@ -345,7 +467,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
           value += p.guoFactor * L::w(q) * (cF - uF + 3.0 * cu * cF);
         }
         if (SCHEME == kSchemeEDM) {
-          value += rho * L::w(q) * eqShifted.template shape<q>() - (f[q] - fNeq[q]);
+          value += rho * L::w(q) * eqShifted.template shape<q>() - (fq - nq);
         }
         storePopulation(next + q * p.stride + out, value);
       });
