@@ -3,7 +3,7 @@
 // to an ASCII table "iteration total_energy total_enstrophy".  The reference loops over the host field arrays
 // (Analysis.h:53-61, 85-93) and calls MPI_Reduce; here the sums were already formed on the device by the step
 // kernel (warp shuffles + block partials) and reduced across GPUs by NCCL -- writeAnalyses only fetches them.
-// Enstrophy uses a central-difference vorticity (the reference's is spectral).
+// Enstrophy is the reference's spectral one (Curl, Transformer.h:118-295), evaluated on the device (csrc/spectral.cu).
 #pragma once
 
 #include <fstream>

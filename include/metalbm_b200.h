@@ -149,7 +149,9 @@ int mlbm_set_alpha(mlbm_ctx* ctx, const void* host, size_t padded_y, size_t padd
 /* Algorithm::iterate (Algorithm.h:326-358 / 392-447): swap, halo exchange, periodic boundaries, fused node
  * update; synchronous like the reference (returns after the device finished).  `is_stored` is
  * Algorithm::isStored (Routine.h:122-124): when non-zero the step also stores density, hydrodynamic
- * velocity, alpha and force (Algorithm::storeFields, Algorithm.h:150-194) and reduces the observables. */
+ * velocity, alpha and force (Algorithm::storeFields, Algorithm.h:150-194) and reduces the observables.
+ * Bit 0 (value 1, the reference's `true`) = fields + all observables; value 2 = energy / mass / Mach only, no field
+ * arrays are allocated or written (what fits when the populations fill the GPU). */
 int mlbm_step(mlbm_ctx* ctx, unsigned iteration, int is_stored);
 
 /* `count` calls of iterate for iterations first..first+count-1 with isStored = (iteration % store_every == 0)
@@ -166,7 +168,9 @@ int mlbm_download_fields(mlbm_ctx* ctx, void* density, void* velocity, void* alp
  * already summed over ranks (Communication::reduce, Communication.h:76-89) and normalised by the global
  * volume (Analysis.h:30):
  *   out[0] total energy     (Analysis.h:53-61)
- *   out[1] total enstrophy  (Analysis.h:85-93; central-difference vorticity)
+ *   out[1] total enstrophy  (Analysis.h:85-93) of the reference's SPECTRAL vorticity (Curl, Transformer.h:118-295,
+ *          Routine.h:129-132: integer wave numbers, divided by the volume twice); needs the stored velocity field,
+ *          i.e. bit 0 of is_stored -- NaN after a step stored with is_stored == 2
  *   out[2] max Mach number  max |u_hydro| / c_s
  *   out[3] total mass       sum of density (PerformanceAnalysisList mass, Routine.h:117-118) */
 int mlbm_observables(mlbm_ctx* ctx, double out[4]);

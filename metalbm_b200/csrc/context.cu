@@ -13,6 +13,7 @@
 
 #include "../../include/metalbm_b200.h"
 #include "nccl_loader.h"
+#include "spectral.h"
 #include "step_kernel.cuh"
 
 namespace mlbm {
@@ -76,88 +77,65 @@ const NcclApi* loadNccl(const char** error) {
 // small device kernels around the fused step
 // ------------------------------------------------------------------------------------------------
 
-// deterministic final reduction of the per-block partials written by the fused kernel on stored steps
-__global__ void reduceObservablesKernel(const double* __restrict__ partials, long long blocks, double* __restrict__ out) {
-  __shared__ double scratch[kObservableSlots][256];
+// Deterministic reduction of the per-block partials written by the fused kernel on stored steps: every block sums a
+// fixed contiguous share into `stage`, the block that finishes last (atomic ticket) adds the shares in index order.
+constexpr int kReduceBlocks = 296;  // two per SM
+constexpr int kReduceThreads = 256;
+
+__global__ void __launch_bounds__(kReduceThreads)
+reduceObservablesKernel(const double* __restrict__ partials, long long blocks, double* __restrict__ stage,
+                        unsigned* __restrict__ ticket, double* __restrict__ out) {
+  __shared__ double scratch[kObservableSlots][kReduceThreads];
+  __shared__ bool last;
+  const long long share = (blocks + gridDim.x - 1) / gridDim.x;
+  const long long begin = share * blockIdx.x;
+  const long long end = begin + share < blocks ? begin + share : blocks;
   double e = 0.0, ms = 0.0, s2 = 0.0;
-  for (long long i = threadIdx.x; i < blocks; i += blockDim.x) {
+  for (long long i = begin + threadIdx.x; i < end; i += blockDim.x) {
     e += partials[i * kObservableSlots + 0];
     ms += partials[i * kObservableSlots + 1];
     s2 = fmax(s2, partials[i * kObservableSlots + 2]);
   }
-  scratch[0][threadIdx.x] = e;
-  scratch[1][threadIdx.x] = ms;
-  scratch[2][threadIdx.x] = s2;
-  __syncthreads();
-  for (int width = blockDim.x / 2; width > 0; width >>= 1) {
-    if ((int)threadIdx.x < width) {
-      scratch[0][threadIdx.x] += scratch[0][threadIdx.x + width];
-      scratch[1][threadIdx.x] += scratch[1][threadIdx.x + width];
-      scratch[2][threadIdx.x] = fmax(scratch[2][threadIdx.x], scratch[2][threadIdx.x + width]);
-    }
+  auto blockReduce = [&](double& a, double& b, double& c) {
+    scratch[0][threadIdx.x] = a;
+    scratch[1][threadIdx.x] = b;
+    scratch[2][threadIdx.x] = c;
     __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    out[0] = scratch[0][0];
-    out[1] = scratch[1][0];
-    out[2] = scratch[2][0];
-  }
-}
-
-// total enstrophy of the stored hydrodynamic velocity with a 2nd-order central-difference curl on the
-// periodic slab (the reference's spectral definition, Transformer.h:118-295, is the "next" row N1).
-// x neighbours outside the slab are not available without a field halo: the x derivative is one-sided
-// at slab faces when nranks > 1 (documented in DESIGN.md).
-template <typename StoreT>
-__global__ void enstrophyKernel(const StoreT* __restrict__ velocity, long long fieldStride, int LX, int NM, int NR,
-                                int dim, int wrapX, double* __restrict__ blockSums) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  const int m = blockIdx.y, x = blockIdx.z;
-  double value = 0.0;
-  if (r < NR) {
-    auto at = [&](int d, int xx, int mm, int rr) {
-      return (double)velocity[d * fieldStride + ((long long)xx * NM + mm) * NR + rr];
-    };
-    const int rp = r == NR - 1 ? 0 : r + 1, rm = r == 0 ? NR - 1 : r - 1;
-    const int mp = m == NM - 1 ? 0 : m + 1, mm = m == 0 ? NM - 1 : m - 1;
-    int xp = x + 1, xm = x - 1;
-    double hx = 0.5;
-    if (wrapX) { if (xp == LX) xp = 0; if (xm < 0) xm = LX - 1; }
-    else { if (xp == LX) { xp = x; hx = 1.0; } if (xm < 0) { xm = x; hx = 1.0; } }
-    if (dim == 2) {
-      // (x, r) = (x, y): w = d(uy)/dx - d(ux)/dy
-      const double w = hx * (at(1, xp, m, r) - at(1, xm, m, r)) - 0.5 * (at(0, x, m, rp) - at(0, x, m, rm));
-      value = 0.5 * w * w;
-    } else {
-      // (x, m, r) = (x, y, z)
-      const double wx = 0.5 * (at(2, x, mp, r) - at(2, x, mm, r)) - 0.5 * (at(1, x, m, rp) - at(1, x, m, rm));
-      const double wy = 0.5 * (at(0, x, m, rp) - at(0, x, m, rm)) - hx * (at(2, xp, m, r) - at(2, xm, m, r));
-      const double wz = hx * (at(1, xp, m, r) - at(1, xm, m, r)) - 0.5 * (at(0, x, mp, r) - at(0, x, mm, r));
-      value = 0.5 * (wx * wx + wy * wy + wz * wz);
+    for (int width = kReduceThreads / 2; width > 0; width >>= 1) {
+      if ((int)threadIdx.x < width) {
+        scratch[0][threadIdx.x] += scratch[0][threadIdx.x + width];
+        scratch[1][threadIdx.x] += scratch[1][threadIdx.x + width];
+        scratch[2][threadIdx.x] = fmax(scratch[2][threadIdx.x], scratch[2][threadIdx.x + width]);
+      }
+      __syncthreads();
     }
-  }
-  for (int offset = 16; offset > 0; offset >>= 1) value += __shfl_xor_sync(0xffffffffu, value, offset);
-  __shared__ double scratch[32];
-  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = value;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    double sum = 0.0;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) sum += scratch[i];
-    blockSums[((long long)x * gridDim.y + m) * gridDim.x + blockIdx.x] = sum;
-  }
-}
-
-__global__ void sumKernel(const double* __restrict__ values, long long count, double* __restrict__ out) {
-  __shared__ double scratch[256];
-  double sum = 0.0;
-  for (long long i = threadIdx.x; i < count; i += blockDim.x) sum += values[i];
-  scratch[threadIdx.x] = sum;
-  __syncthreads();
-  for (int width = blockDim.x / 2; width > 0; width >>= 1) {
-    if ((int)threadIdx.x < width) scratch[threadIdx.x] += scratch[threadIdx.x + width];
+    a = scratch[0][0]; b = scratch[1][0]; c = scratch[2][0];
     __syncthreads();
+  };
+  blockReduce(e, ms, s2);
+  if (threadIdx.x == 0) {
+    stage[blockIdx.x * kObservableSlots + 0] = e;
+    stage[blockIdx.x * kObservableSlots + 1] = ms;
+    stage[blockIdx.x * kObservableSlots + 2] = s2;
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
   }
-  if (threadIdx.x == 0) *out = scratch[0];
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  e = 0.0; ms = 0.0; s2 = 0.0;
+  for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
+    e += __ldcg(stage + i * kObservableSlots + 0);
+    ms += __ldcg(stage + i * kObservableSlots + 1);
+    s2 = fmax(s2, __ldcg(stage + i * kObservableSlots + 2));
+  }
+  blockReduce(e, ms, s2);
+  if (threadIdx.x == 0) {
+    out[0] = e;
+    out[1] = ms;
+    out[2] = s2;
+    *ticket = 0;
+  }
 }
 
 template <typename StoreT> __global__ void fillKernel(StoreT* data, long long count, StoreT value) {
@@ -296,8 +274,11 @@ struct mlbm_ctx {
   void* force = nullptr;
   bool fieldsStored = false;
   double* partials = nullptr;
-  double* enstrophyBlocks = nullptr;
+  double* reduceStage = nullptr;         // [kReduceBlocks][kObservableSlots] second-stage partials
+  unsigned* reduceTicket = nullptr;
   double* deviceObservables = nullptr;   // [energy sum, mass, max speed^2, enstrophy sum]
+  SpectralEnstrophy* spectral = nullptr; // created on the first step that stores the fields
+  bool enstrophyValid = false;           // the last stored step stored the velocity field (bit 0 of isStored)
   double* forceTables[3] = {nullptr, nullptr, nullptr};
   int forceAxis[3] = {-1, -1, -1};
   bool observablesValid = false;
@@ -461,7 +442,7 @@ static int exchangeHalos(mlbm_ctx* ctx, int which, cudaStream_t stream) {
 
 static int ensureFields(mlbm_ctx* ctx) {
   if (ctx->density) return MLBM_OK;
-  const size_t bytes = (size_t)ctx->nodes * ctx->elementSize;
+  const size_t bytes = (size_t)ctx->fieldStride * ctx->elementSize;
   MLBM_CUDA(cudaMalloc(&ctx->density, bytes));
   MLBM_CUDA(cudaMalloc(&ctx->velocity, bytes * ctx->D));
   MLBM_CUDA(cudaMalloc(&ctx->force, bytes * ctx->D));
@@ -474,7 +455,9 @@ static int ensureFields(mlbm_ctx* ctx) {
 static int ensurePartials(mlbm_ctx* ctx) {
   if (ctx->partials) return MLBM_OK;
   MLBM_CUDA(cudaMalloc(&ctx->partials, sizeof(double) * kObservableSlots * (size_t)ctx->partialBlocks));
-  MLBM_CUDA(cudaMalloc(&ctx->enstrophyBlocks, sizeof(double) * (size_t)ctx->partialBlocks));
+  MLBM_CUDA(cudaMalloc(&ctx->reduceStage, sizeof(double) * kObservableSlots * kReduceBlocks));
+  MLBM_CUDA(cudaMalloc(&ctx->reduceTicket, sizeof(unsigned)));
+  MLBM_CUDA(cudaMemsetAsync(ctx->reduceTicket, 0, sizeof(unsigned), ctx->computeStream));
   return MLBM_OK;
 }
 
@@ -515,20 +498,22 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
   ctx->current ^= 1;  // std::swap(previous, next) (Algorithm.h:336), done after the step instead of before
 
   if (isStored) {
-    reduceObservablesKernel<<<1, 256, 0, compute>>>(ctx->partials, ctx->partialBlocks, ctx->deviceObservables);
+    reduceObservablesKernel<<<kReduceBlocks, kReduceThreads, 0, compute>>>(ctx->partials, ctx->partialBlocks, ctx->reduceStage,
+                                                                          ctx->reduceTicket, ctx->deviceObservables);
     ctx->launches += 1;
+    ctx->enstrophyValid = false;
     if (isStored & 1) {
-      dim3 grid((unsigned)ctx->gridR, (unsigned)ctx->NM, (unsigned)ctx->LX);
-      const int wrapX = ctx->config.nranks == 1;
-      if (ctx->config.dtype == MLBM_F64)
-        enstrophyKernel<double><<<grid, kStepBlock, 0, compute>>>(static_cast<const double*>(ctx->velocity), ctx->fieldStride,
-                                                                  ctx->LX, ctx->NM, ctx->NR, ctx->D, wrapX, ctx->enstrophyBlocks);
-      else
-        enstrophyKernel<float><<<grid, kStepBlock, 0, compute>>>(static_cast<const float*>(ctx->velocity), ctx->fieldStride,
-                                                                 ctx->LX, ctx->NM, ctx->NR, ctx->D, wrapX, ctx->enstrophyBlocks);
-      sumKernel<<<1, 256, 0, compute>>>(ctx->enstrophyBlocks, ctx->partialBlocks, ctx->deviceObservables + 3);
-      ctx->launches += 2;
+      // Routine.h:129-132 + TotalEnstrophy (Analysis.h:68-98): spectral vorticity of the stored velocity
+      std::string error;
+      if (!ctx->spectral) {
+        SpectralGeometry geometry = {ctx->D, ctx->LX, ctx->NM, ctx->NR, ctx->config.rank, ctx->config.nranks, (int)ctx->elementSize};
+        ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->comm, &error);
+        if (!ctx->spectral) return fail(MLBM_ERR_CUDA, "spectral enstrophy: %s", error.c_str());
+      }
+      if (spectralEnqueue(ctx->spectral, ctx->velocity, ctx->fieldStride, ctx->deviceObservables + 3, compute, &ctx->launches, &error))
+        return fail(MLBM_ERR_CUDA, "spectral enstrophy: %s", error.c_str());
       ctx->fieldsStored = true;
+      ctx->enstrophyValid = true;
     }
     MLBM_CUDA(cudaGetLastError());
     ctx->observablesValid = true;
@@ -550,9 +535,10 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->computeStream) cudaStreamSynchronize(ctx->computeStream);
   if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
+  if (ctx->spectral) spectralDestroy(ctx->spectral);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
-                        (void*)ctx->partials, (void*)ctx->enstrophyBlocks, (void*)ctx->deviceObservables,
+                        (void*)ctx->partials, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
                         (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
     if (pointer) cudaFree(pointer);
   for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->timeStart, ctx->timeMid, ctx->timeStop})
@@ -618,7 +604,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   ctx->elementSize = config->dtype == MLBM_F64 ? 8 : 4;
   ctx->plane = geometry.plane;
   ctx->nodes = ctx->plane * ctx->LX;
-  ctx->fieldStride = ctx->nodes;
+  ctx->fieldStride = (ctx->nodes + 31) / 32 * 32;  // every field component 128-byte aligned (cuFFT reads them as double2)
   ctx->stride = geometry.stride;
   haloPlan(config, &ctx->haloMessages);
   ctx->gridR = (ctx->NR + kStepBlock - 1) / kStepBlock;
@@ -925,7 +911,7 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
   double globalVolume = 1.0;
   for (int d = 0; d < ctx->D; ++d) globalVolume *= ctx->config.global_length[d];
   out[0] = local[0] / globalVolume;          // AnalysisScalar::normalize (Analysis.h:30)
-  out[1] = local[3] / globalVolume;
+  out[1] = ctx->enstrophyValid ? local[3] / globalVolume : NAN;  // Analysis.h:85-93; needs the stored velocity field
   out[2] = sqrt(local[2] * 3.0);             // |u| / c_s, c_s^2 = 1/3
   out[3] = local[1];
   return MLBM_OK;

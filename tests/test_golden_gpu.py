@@ -30,3 +30,6 @@ def test_cuda_reproduces_reference_outputs(name):
     assert np.array_equal(got["force"], data["force"])
     energy = data["observables"][-1][1]
     assert abs(got["observables"][0] - energy) <= 1e-9 * abs(energy)
+    if meta["ranks"] == 1 and not entropic:   # the reference's own TotalEnstrophy (its Curl ran on the oracle's DFT stub)
+        enstrophy = data["observables"][-1][2]
+        assert abs(got["observables"][1] - enstrophy) <= 1e-9 * abs(enstrophy)

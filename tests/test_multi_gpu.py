@@ -137,6 +137,7 @@ def test_slabs_reproduce_the_single_rank_result(tmp_path, world, case):
     obs = ref.observables()
     for rank_observables in got["observables"]:   # every rank holds the reduced values
         assert abs(rank_observables[0] - obs[0]) <= 1e-9 * abs(obs[0])
+        assert abs(rank_observables[1] - obs[1]) <= 1e-9 * abs(obs[1])   # spectral enstrophy, distributed transform
         assert abs(rank_observables[3] - obs[3]) <= 1e-12 * abs(obs[3])
         assert abs(rank_observables[2] - obs[2]) <= 1e-12 * abs(obs[2])
         assert np.array_equal(rank_observables, got["observables"][0])

@@ -52,6 +52,7 @@ def test_bgk_one_and_three_steps(case):
         assert np.all(got["alpha"] == 2.0)
         obs = ref.observables()
         assert abs(got["observables"][0] - obs[0]) <= ENERGY_TOLERANCE * abs(obs[0])
+        assert abs(got["observables"][1] - obs[1]) <= ENERGY_TOLERANCE * abs(obs[1])   # spectral enstrophy
         assert abs(got["observables"][3] - obs[3]) <= 1e-12 * abs(obs[3])
         assert abs(got["observables"][2] - obs[2]) <= 1e-12 * abs(obs[2])
 
@@ -106,7 +107,46 @@ def test_energy_after_100_steps_d2q9_kolmogorov():
     ref = run_oracle(cfg, f0, 100)
     obs = ref.observables()
     assert abs(got["observables"][0] - obs[0]) <= ENERGY_TOLERANCE * abs(obs[0])
+    assert abs(got["observables"][1] - obs[1]) <= ENERGY_TOLERANCE * abs(obs[1])
     assert relative_error(got["f"], ref.f) <= 1e-11
+
+
+@pytest.mark.parametrize("lattice,shape", [("D2Q9", (12, 10, 1)), ("D2Q9", (9, 7, 1)), ("D2Q9", (8, 9, 1)), ("D2Q9", (7, 8, 1)),
+                                           ("D3Q19", (8, 6, 4)), ("D3Q19", (5, 6, 7)), ("D3Q19", (6, 5, 8)), ("D3Q19", (7, 9, 5)),
+                                           ("D3Q19", (16, 16, 16))])
+def test_spectral_enstrophy_with_energy_at_every_wave_number(lattice, shape):
+    """Total enstrophy against the reference's literal algorithm (r2c, i k x u with integer wave numbers, c2r, / V,
+    / V again, sum 0.5 w^2 / V: Transformer.h:118-295, Analysis.h:68-98) restated in oracle.spectral_enstrophy, on a
+    velocity field with 10 % white noise so that the Nyquist planes of even and odd grids carry energy."""
+    cfg = _config(lattice, shape, "TruncationMa3", "Guo", "Kolmogorov", 0.8)
+    f0 = O.synthetic_populations(cfg, eps=1e-1)
+    got = run_cuda(cfg, f0, 1)
+    ref = run_oracle(cfg, f0, 1)
+    obs = ref.observables()
+    assert abs(got["observables"][1] - obs[1]) <= ENERGY_TOLERANCE * abs(obs[1])
+    # the stored velocity the transform starts from is the reference's
+    assert np.abs(got["velocity"] - ref.velocity).max() <= 1e-13
+
+
+def test_enstrophy_needs_the_stored_velocity_field():
+    """isStored = 2 reduces energy / mass / Mach only (no field arrays, as 1024^3 on 2 GPUs requires): enstrophy is NaN."""
+    from metalbm_b200.algorithm import Algorithm
+    cfg = _config("D2Q9", (16, 12, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.7)
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.set_interior(O.synthetic_populations(cfg, eps=1e-2))
+        algorithm.unpack()
+        algorithm._lib.mlbm_step(algorithm._ctx, 1, 2)
+        observables = algorithm.observables()
+        assert np.isfinite(observables[0]) and np.isnan(observables[1])
+
+
+def test_fp32_spectral_enstrophy():
+    cfg32 = _config("D3Q19", (12, 10, 8), "TruncationMa3", "Guo", "Kolmogorov", 0.7, dtype="F32")
+    cfg64 = _config("D3Q19", (12, 10, 8), "TruncationMa3", "Guo", "Kolmogorov", 0.7)
+    f0 = O.synthetic_populations(cfg64, eps=1e-2).astype(np.float32).astype(np.float64)
+    got = run_cuda(cfg32, f0, 1)
+    ref = run_oracle(cfg64, f0, 1)
+    assert abs(got["observables"][1] - ref.observables()[1]) <= 1e-5 * abs(ref.observables()[1])
 
 
 def test_fp32_storage_against_fp64_oracle():
