@@ -207,7 +207,7 @@ def run_ours(args) -> int:
     import torch.distributed as dist
 
     from metalbm_b200.algorithm import Algorithm, Communication
-    from metalbm_b200.capi import make_config
+    from metalbm_b200.capi import check, make_config
 
     rank, world, local_rank = distributed_setup(args.gpus)
     torch.cuda.set_device(local_rank)
@@ -247,7 +247,8 @@ def run_ours(args) -> int:
                       forcing_scheme=work["scheme"], force=work["force"], tau=work["tau"], dtype=dtype,
                       amplitude=(1e-5, 1e-5, 1e-5), wavelength=(32.0, 32.0, 32.0),
                       overlap=args.overlap, rank=rank, nranks=world, device=local_rank, variant=args.variant)
-    algorithm = Algorithm(cfg, communication=Communication(rank, world), host_distribution=not args.no_e2e)
+    algorithm = Algorithm(cfg, communication=Communication(rank, world), host_distribution=not args.no_e2e,
+                          peer_halos=(args.halo == "peer" and args.overlap == "On") if world > 1 else False)
     domain = algorithm.domain
     nodes_global = shape[0] * shape[1] * shape[2]
     nodes_local = nodes_global // world
@@ -274,6 +275,9 @@ def run_ours(args) -> int:
     store_every = int(work["store_every"])
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------------
+    if store_every:
+        # the first stored step allocates the field arrays and plans the transforms of the spectral enstrophy: warm-up
+        check(algorithm._lib.mlbm_step(algorithm._ctx, 0, 1))
     algorithm.run(1, args.warmup, store_every)
     algorithm.kernel_time()                      # switches the per-launch CUDA event pairs on
     sampler = ClockSampler(local_rank)
@@ -294,6 +298,16 @@ def run_ours(args) -> int:
     kernel_ms, kernel_launches = algorithm.kernel_time()
     clocks = sampler.stop(begin, end) if rank == 0 else None
     value = nodes_global * args.steps / (device_ms * 1e-3) / 1e6
+
+    # ---- cost of one stored step (fields + energy / spectral enstrophy / Mach reductions), timed on its own -------------
+    stored_ms = None
+    if store_every:
+        barrier()
+        algorithm.mark(2)
+        check(algorithm._lib.mlbm_run_async(algorithm._ctx, store_every, 1, store_every))
+        algorithm.mark(3)
+        algorithm.synchronize()
+        stored_ms = max_over_ranks(algorithm.elapsed_ms(2, 3))
 
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
     e2e = None
@@ -341,6 +355,7 @@ def run_ours(args) -> int:
 
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline
                                  and args.workload == "d3q19_bgk_256") else None
+    algorithm_peer = algorithm.peer_halos
     algorithm.close()
     if world > 1:
         dist.barrier()
@@ -357,8 +372,10 @@ def run_ours(args) -> int:
             "config": {"workload": f"{work['text']}; global {shape[0]}x{shape[1]}x{shape[2]}", "name": args.workload,
                        "lattice": work["lattice"], "collision": work["collision"], "equilibrium": work["equilibrium"],
                        "forcing": f"{work['scheme']}/{work['force']}", "tau": work["tau"], "perturbation_eps": work["eps"],
-                       "store_every": store_every, "global_length": list(shape), "parallelism": f"x-slab x{world}",
+                       "store_every": store_every, "stored_step_ms": stored_ms, "global_length": list(shape), "parallelism": f"x-slab x{world}",
                        "overlap": args.overlap,
+                       "halo": ("direct peer stores over NVLink from the boundary kernel" if algorithm_peer else
+                                "NCCL send/recv") if world > 1 else "none (single rank: periodic wrap in the kernel)",
                        "l2": f"inputs (2 x {buffer_gb:.2f} GB population buffers per GPU) larger than the 126 MB L2; "
                              "no flush between steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
@@ -380,6 +397,8 @@ def main() -> int:
     parser.add_argument("--workload", default="d3q19_bgk_256", choices=sorted(WORKLOADS))
     parser.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     parser.add_argument("--overlap", default="On", choices=["On", "Off"])
+    parser.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                        help="N > 1 with overlap On: boundary kernel stores into the neighbours' halo planes (peer) or NCCL send/recv")
     parser.add_argument("--eps", type=float, default=None, help="override the workload's initial perturbation")
     parser.add_argument("--store-every", type=int, default=None, help="override the workload's observable cadence")
     parser.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large workloads)")

@@ -6,6 +6,9 @@
 // use from those globals and MPIInit::rank, and destroyed at exit.
 #pragma once
 
+#include <cstdlib>
+#include <vector>
+
 #include "Commons.h"
 #include "Domain.h"
 #include "FFTWInitializer.h"
@@ -68,6 +71,17 @@ class Context {
       if (MPIInit::rank[d::X] == 0) LBM_B200_CALL(mlbm_comm_unique_id(id));
       MPIInit::broadcastFromRoot(id, sizeof(id));
       LBM_B200_CALL(mlbm_comm_init(handle, id));
+      // Overlapping::On: the boundary kernel stores into the neighbours' halo planes over NVLink (CUDA IPC mappings);
+      // MLBM_PEER_HALOS=0 keeps the NCCL send/recv exchange
+      const char* peerHalos = std::getenv("MLBM_PEER_HALOS");
+      if (overlappingT == Overlapping::On && !(peerHalos && peerHalos[0] == '0')) {
+        unsigned char mine[MLBM_PEER_HANDLE_BYTES];
+        std::vector<unsigned char> all((size_t)MLBM_PEER_HANDLE_BYTES * numProcs);
+        LBM_B200_CALL(mlbm_comm_peer_export(handle, mine));
+        MPIInit::allGather(mine, all.data(), sizeof(mine), id, sizeof(id));
+        LBM_B200_CALL(mlbm_comm_peer_attach(handle, all.data() + (size_t)MLBM_PEER_HANDLE_BYTES * MPIInit::rankLeft,
+                                            all.data() + (size_t)MLBM_PEER_HANDLE_BYTES * MPIInit::rankRight));
+      }
     }
   }
   ~Context() { mlbm_destroy(handle); }

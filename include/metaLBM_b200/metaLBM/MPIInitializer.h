@@ -103,6 +103,39 @@ struct MPIInitializer {
     }
 #endif
   }
+
+  // every rank's `count` bytes -> `all` (size * count bytes) on every rank; used once, for the CUDA IPC handles of the
+  // direct peer halos.  `salt` (the NCCL id, unique per run) keeps the rendezvous files of different runs apart.
+  static void allGather(const void* mine, void* all, size_t count, const unsigned char* salt, size_t saltCount) {
+    if (size[d::X] <= 1) { std::memcpy(all, mine, count); return; }
+#ifdef LBM_B200_USE_MPI
+    (void)salt; (void)saltCount;
+    MPI_Allgather(mine, (int)count, MPI_BYTE, all, (int)count, MPI_BYTE, MPI_COMM_WORLD);
+#else
+    unsigned long long hash = 1469598103934665603ull;  // FNV-1a
+    for (size_t i = 0; i < saltCount; ++i) hash = (hash ^ salt[i]) * 1099511628211ull;
+    const char* directory = std::getenv("MLBM_RENDEZVOUS_DIR");
+    const std::string base = std::string(directory ? directory : "/tmp") + "/metalbm_b200_" + std::to_string(hash) + ".peer.";
+    {
+      const std::string path = base + std::to_string(rank[d::X]), temporary = path + ".tmp";
+      { std::ofstream out(temporary, std::ios::binary | std::ios::trunc); out.write(static_cast<const char*>(mine), (std::streamsize)count); }
+      std::rename(temporary.c_str(), path.c_str());
+    }
+    for (int other = 0; other < size[d::X]; ++other) {
+      char* target = static_cast<char*>(all) + (size_t)other * count;
+      bool done = false;
+      for (int attempt = 0; attempt < 60000 && !done; ++attempt) {
+        std::ifstream in(base + std::to_string(other), std::ios::binary);
+        if (in && in.read(target, (std::streamsize)count)) done = true;
+        else std::this_thread::sleep_for(std::chrono::milliseconds(1));
+      }
+      if (!done) {
+        std::fprintf(stderr, "[%s:%d] rendezvous file %s%d never appeared\n", __FILE__, __LINE__, base.c_str(), other);
+        std::exit(-1);
+      }
+    }
+#endif
+  }
 };
 
 using MPIInit = MPIInitializer<numProcs>;

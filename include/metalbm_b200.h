@@ -109,6 +109,18 @@ int mlbm_destroy(mlbm_ctx* ctx);
 int mlbm_comm_unique_id(void* id128);
 int mlbm_comm_init(mlbm_ctx* ctx, const void* id128);
 
+/* Direct peer halos (optional, one process per GPU on one NVLink/NVSwitch box).  Every rank exports a
+ * MLBM_PEER_HANDLE_BYTES blob (CUDA IPC handles of its two population buffers and of its handshake words), the
+ * caller ships the blobs between ranks (any transport, like the NCCL id) and every rank attaches the blobs of its
+ * LEFT and RIGHT ring neighbours (MPIInitializer.h:56-57).  From then on, with overlap == MLBM_OVERLAP_ON, the kernel
+ * that computes the two boundary planes stores their outgoing populations straight into the neighbours' halo planes
+ * over NVLink -- the whole of Communication::communicateHalos (Communication.h:134-180, 494-500) without a single
+ * copy or send/recv -- while the bulk kernel runs; NCCL is only used for the first exchange after an upload, for the
+ * observables and as the shutdown barrier.  All ranks must issue the same sequence of calls (as with MPI). */
+#define MLBM_PEER_HANDLE_BYTES 256
+int mlbm_comm_peer_export(mlbm_ctx* ctx, void* handle);
+int mlbm_comm_peer_attach(mlbm_ctx* ctx, const void* left_handle, const void* right_handle);
+
 /* The halo exchange of one step as data (pure host logic, no device needed): which planes of the SoA buffer
  * this rank sends and receives, in issue order.  Mirrors Communication::sendAndReceiveHaloXRight / XLeft
  * (Communication.h:134-180): populations faceQ+1..2*faceQ (c_x > 0) travel right, 1..faceQ (c_x < 0) left.

@@ -16,6 +16,7 @@ numpy host arrays in the reference's layouts and forwards calls.  There is no CP
 from __future__ import annotations
 
 import ctypes
+import os
 
 import numpy as np
 
@@ -87,8 +88,9 @@ class Communication:
     rank: ring neighbours and the NCCL id hand-shake.  ``broadcast`` ships 128 bytes from rank 0 to all ranks;
     by default it uses ``torch.distributed`` (any backend, gloo works)."""
 
-    def __init__(self, rank: int = 0, nranks: int = 1, broadcast=None):
+    def __init__(self, rank: int = 0, nranks: int = 1, broadcast=None, all_gather=None):
         self.rank, self.nranks = rank, nranks
+        self._all_gather = all_gather
         self.rank_left = (rank + nranks - 1) % nranks    # MPIInitializer.h:56
         self.rank_right = (rank + 1) % nranks            # MPIInitializer.h:57
         self._broadcast = broadcast
@@ -108,6 +110,21 @@ class Communication:
         dist.broadcast(buffer, src=0)
         return bytes(buffer.cpu().numpy().tobytes())
 
+    def all_gather_bytes(self, payload: bytes) -> list:
+        """Every rank's ``payload`` (equal sizes) on every rank: ships the CUDA IPC handles of the direct peer halos."""
+        if self.nranks == 1:
+            return [payload]
+        if self._all_gather is not None:
+            return self._all_gather(payload)
+        import torch
+        import torch.distributed as dist
+        mine = torch.frombuffer(bytearray(payload), dtype=torch.uint8).clone()
+        if dist.get_backend() == "nccl":
+            mine = mine.cuda()
+        everyone = [torch.zeros_like(mine) for _ in range(self.nranks)]
+        dist.all_gather(everyone, mine)
+        return [bytes(t.cpu().numpy().tobytes()) for t in everyone]
+
 
 def slab_of(global_array: np.ndarray, rank: int, nranks: int) -> np.ndarray:
     """x-slab of rank ``rank`` of a [..., nx, ny, nz] global array (Domain.h:22-24)."""
@@ -121,7 +138,7 @@ class Algorithm:
 
     def __init__(self, config: MlbmConfig, field_list: FieldList | None = None,
                  distribution: Distribution | None = None, communication: Communication | None = None,
-                 host_distribution: bool = True):
+                 host_distribution: bool = True, peer_halos: bool | None = None):
         self._lib = load_library()
         self.config = config
         self.domain = Domain(config)
@@ -130,6 +147,7 @@ class Algorithm:
                              else Distribution(self.domain, allocate=host_distribution))
         self.communication = communication or Communication(int(config.rank), int(config.nranks))
         self.isStored = False
+        self.peer_halos = False
         self._ctx = ctypes.c_void_p()
         check(self._lib.mlbm_create(ctypes.byref(config), ctypes.byref(self._ctx)))
         if config.nranks > 1:
@@ -138,6 +156,22 @@ class Algorithm:
                 check(self._lib.mlbm_comm_unique_id(unique))
             payload = self.communication.broadcast_bytes(unique.raw if config.rank == 0 else None, 128)
             check(self._lib.mlbm_comm_init(self._ctx, ctypes.create_string_buffer(payload, 128)))
+            # direct peer halos (boundary kernel stores into the neighbours' halo planes over NVLink): default on with
+            # Overlapping::On; MLBM_PEER_HALOS=0 or peer_halos=False keeps the NCCL send/recv exchange
+            if peer_halos is None:
+                peer_halos = int(config.overlap) == 1 and os.environ.get("MLBM_PEER_HALOS", "1") != "0"
+            self.peer_halos = False
+            if peer_halos:
+                self._attach_peers()
+
+    def _attach_peers(self) -> None:
+        mine = ctypes.create_string_buffer(capi.PEER_HANDLE_BYTES)
+        check(self._lib.mlbm_comm_peer_export(self._ctx, mine))
+        blobs = self.communication.all_gather_bytes(mine.raw)
+        left = ctypes.create_string_buffer(blobs[self.communication.rank_left], capi.PEER_HANDLE_BYTES)
+        right = ctypes.create_string_buffer(blobs[self.communication.rank_right], capi.PEER_HANDLE_BYTES)
+        check(self._lib.mlbm_comm_peer_attach(self._ctx, left, right))
+        self.peer_halos = True
 
     # -- life cycle -------------------------------------------------------------------------------
     def close(self) -> None:

@@ -14,6 +14,7 @@ from pathlib import Path
 PACKAGE_DIR = Path(__file__).resolve().parent
 LIBRARY_PATH = PACKAGE_DIR / "libmetalbm_b200.so"
 ABI_VERSION = 1
+PEER_HANDLE_BYTES = 256
 
 
 class Lattice(enum.IntEnum):
@@ -154,6 +155,8 @@ PROTOTYPES = {
                                       ctypes.POINTER(ctypes.c_int)]),
     "mlbm_comm_unique_id": (ctypes.c_int, [_P]),
     "mlbm_comm_init": (ctypes.c_int, [_P, _P]),
+    "mlbm_comm_peer_export": (ctypes.c_int, [_P, _P]),
+    "mlbm_comm_peer_attach": (ctypes.c_int, [_P, _P, _P]),
     "mlbm_upload_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_download_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_init_equilibrium": (ctypes.c_int, [_P, _P, _P, _SZ, _SZ, _SZ]),

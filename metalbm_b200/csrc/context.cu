@@ -3,6 +3,7 @@
 // and the scalar observables (AnalysisList.h:55-73) for one rank == one GPU.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdarg>
@@ -136,6 +137,31 @@ reduceObservablesKernel(const double* __restrict__ partials, long long blocks, d
     out[2] = s2;
     *ticket = 0;
   }
+}
+
+// Direct peer halos: per-step handshake through two 64-bit words in every rank's memory.
+//   flags[0] = number of steps whose halo plane 0 the LEFT neighbour has delivered, flags[1] likewise for plane LX+1 / RIGHT.
+// A neighbour raises the word only after its boundary kernel has finished, so `flags >= step - 1` also says that the
+// neighbour is done reading the halo planes this rank is about to overwrite.
+__global__ void waitPeerFlagsKernel(const unsigned long long* flags, unsigned long long target, int* timedOut) {
+  const volatile unsigned long long* word = flags + threadIdx.x;
+  const long long begin = clock64();
+  while (*word < target) {
+    if (clock64() - begin > 40000000000ll) {  // ~20 s at 2 GHz: a lost neighbour must not hang the box
+      *timedOut = 1;
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+
+__global__ void signalPeersKernel(unsigned long long* leftNeighbourFlags, unsigned long long* rightNeighbourFlags, unsigned long long step) {
+  __threadfence_system();  // the boundary kernel before this one in the stream has completed: order its peer stores first
+  if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(leftNeighbourFlags + 1) = step;   // I am its RIGHT neighbour
+  if (threadIdx.x == 1) *reinterpret_cast<volatile unsigned long long*>(rightNeighbourFlags + 0) = step;  // I am its LEFT neighbour
+  __threadfence_system();
 }
 
 template <typename StoreT> __global__ void fillKernel(StoreT* data, long long count, StoreT value) {
@@ -303,6 +329,14 @@ struct mlbm_ctx {
 
   const NcclApi* nccl = nullptr;
   ncclComm_t comm = nullptr;
+  // direct peer halos (mlbm_comm_peer_export / _attach)
+  unsigned long long* peerFlags = nullptr;       // this rank's two handshake words (+ padding), written by the neighbours
+  int* peerTimedOut = nullptr;
+  void* mapped[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [left, right][populations 0, 1, flags]
+  bool mappedOwned[2] = {false, false};          // right shares left's mapping when both are the same rank
+  bool peerAttached = false;
+  unsigned long long peerEpoch = 0;
+  cudaEvent_t stepStart = nullptr;
   bool halosValid = false;  // halo planes of populations[current] hold the neighbours' data
   std::vector<mlbm_halo_message> haloMessages;
 };
@@ -323,7 +357,8 @@ static int collectProfile(mlbm_ctx* ctx) {
 }
 
 // one launch of the fused kernel over local planes [x0, x1)
-static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int isStored, bool profile) {
+static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int isStored, bool profile, int planeStep = 1,
+                      void* peerLow = nullptr, void* peerHigh = nullptr) {
   if (x1 <= x0) return MLBM_OK;
   StepParams p;
   memset(&p, 0, sizeof(p));
@@ -340,6 +375,9 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
   p.fieldStride = ctx->fieldStride;
   p.LX = ctx->LX; p.NM = ctx->NM; p.NR = ctx->NR;
   p.x0 = x0;
+  p.planeStep = planeStep;
+  p.peerLow = peerLow;
+  p.peerHigh = peerHigh;
   p.wrapX = ctx->config.nranks == 1 ? 1 : 0;
   p.isStored = isStored;
   p.hydroShift = ctx->hydroShift;
@@ -472,6 +510,36 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
   if (!multi) {
     if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
     if (int status = launchStep(ctx, compute, 0, ctx->LX, isStored, profile)) return status;
+  } else if (ctx->peerAttached && ctx->config.overlap == MLBM_OVERLAP_ON) {
+    // Direct peer halos: ONE kernel computes the two boundary planes and stores their outgoing populations straight
+    // into the neighbours' halo planes over NVLink (no pack, no send/recv, no staging); it runs on the high-priority
+    // stream next to the bulk kernel.  Replaces Communication::communicateHalos (Communication.h:134-180, 494-500).
+    const unsigned long long step = ++ctx->peerEpoch;
+    if (!ctx->halosValid) {
+      // first step after an upload: the halo planes of the buffer about to be read were never delivered
+      if (int status = exchangeHalos(ctx, ctx->current, compute)) return status;
+    }
+    MLBM_CUDA(cudaEventRecord(ctx->stepStart, compute));
+    MLBM_CUDA(cudaStreamWaitEvent(ctx->commStream, ctx->stepStart, 0));
+    if (ctx->halosValid) {
+      waitPeerFlagsKernel<<<1, 2, 0, ctx->commStream>>>(ctx->peerFlags, step - 1, ctx->peerTimedOut);
+      ctx->launches += 1;
+    }
+    if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
+    const int next = ctx->current ^ 1;
+    const bool twoPlanes = ctx->LX >= 2;
+    {
+      // launchStep reads ctx->current; the boundary launch goes to the communication stream
+      if (int status = launchStep(ctx, ctx->commStream, 0, twoPlanes ? 2 : 1, isStored, false, twoPlanes ? ctx->LX - 1 : 1,
+                                  ctx->mapped[0][next], ctx->mapped[1][next])) return status;
+    }
+    signalPeersKernel<<<1, 2, 0, ctx->commStream>>>(static_cast<unsigned long long*>(ctx->mapped[0][2]),
+                                                    static_cast<unsigned long long*>(ctx->mapped[1][2]), step);
+    ctx->launches += 1;
+    MLBM_CUDA(cudaEventRecord(ctx->boundaryDone, ctx->commStream));
+    if (int status = launchStep(ctx, compute, 1, ctx->LX - 1, isStored, profile)) return status;
+    MLBM_CUDA(cudaStreamWaitEvent(compute, ctx->boundaryDone, 0));
+    ctx->halosValid = true;  // the neighbours deliver the halo planes of the buffer that becomes current; waited for next step
   } else if (ctx->config.overlap == MLBM_OVERLAP_OFF || ctx->LX < 3) {
     // the reference's order (Algorithm.h:336-355): exchange the halos of the buffer about to be read, then compute
     if (!ctx->halosValid) { if (int status = exchangeHalos(ctx, ctx->current, compute)) return status; }
@@ -535,13 +603,23 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->computeStream) cudaStreamSynchronize(ctx->computeStream);
   if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
+  if (ctx->peerAttached && ctx->comm && ctx->nccl && ctx->deviceObservables) {
+    // the neighbours store into this rank's halo planes and flags: nobody frees before everybody has drained its streams
+    if (ctx->nccl->AllReduce(ctx->deviceObservables, ctx->deviceObservables, 1, ncclDouble, ncclSum, ctx->comm, ctx->computeStream) == ncclSuccess)
+      cudaStreamSynchronize(ctx->computeStream);
+  }
+  for (int side = 0; side < 2; ++side)
+    if (ctx->mappedOwned[side])
+      for (void* pointer : ctx->mapped[side]) if (pointer) cudaIpcCloseMemHandle(pointer);
+  if (ctx->peerFlags) cudaFree(ctx->peerFlags);
+  if (ctx->peerTimedOut) cudaFreeHost(ctx->peerTimedOut);
   if (ctx->spectral) spectralDestroy(ctx->spectral);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
                         (void*)ctx->partials, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
                         (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
     if (pointer) cudaFree(pointer);
-  for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->timeStart, ctx->timeMid, ctx->timeStop})
+  for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->stepStart, ctx->timeStart, ctx->timeMid, ctx->timeStop})
     if (event) cudaEventDestroy(event);
   for (cudaEvent_t event : ctx->profileEvents) cudaEventDestroy(event);
   for (cudaEvent_t event : ctx->marks) if (event) cudaEventDestroy(event);
@@ -634,7 +712,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   MLBM_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&leastPriority, &greatestPriority));
   MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->computeStream, cudaStreamNonBlocking, leastPriority));
   MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, greatestPriority));
-  for (cudaEvent_t* event : {&ctx->boundaryDone, &ctx->exchangeDone, &ctx->bulkDone})
+  for (cudaEvent_t* event : {&ctx->boundaryDone, &ctx->exchangeDone, &ctx->bulkDone, &ctx->stepStart})
     MLBM_CREATE_CUDA(cudaEventCreateWithFlags(event, cudaEventDisableTiming));
   for (cudaEvent_t* event : {&ctx->timeStart, &ctx->timeMid, &ctx->timeStop}) MLBM_CREATE_CUDA(cudaEventCreate(event));
 
@@ -717,6 +795,88 @@ int mlbm_comm_init(mlbm_ctx* ctx, const void* id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   MLBM_NCCL(ctx, ctx->nccl->CommInitRank(&ctx->comm, ctx->config.nranks, id, ctx->config.rank));
+  return MLBM_OK;
+}
+
+// ---- direct peer halos ---------------------------------------------------------------------------
+struct PeerBlob {  // MLBM_PEER_HANDLE_BYTES = 256
+  cudaIpcMemHandle_t populations[2];
+  cudaIpcMemHandle_t flags;
+  uint64_t bufferBytes;
+  int32_t rank, device;
+  int64_t process;
+  char padding[256 - 3 * sizeof(cudaIpcMemHandle_t) - 8 - 8 - 8];
+};
+static_assert(sizeof(PeerBlob) == MLBM_PEER_HANDLE_BYTES, "peer handle blob size");
+
+int mlbm_comm_peer_export(mlbm_ctx* ctx, void* handle) {
+  if (!ctx || !handle) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->peerFlags) {
+    MLBM_CUDA(cudaMalloc(&ctx->peerFlags, 256));
+    MLBM_CUDA(cudaMemset(ctx->peerFlags, 0, 256));
+    MLBM_CUDA(cudaHostAlloc(&ctx->peerTimedOut, sizeof(int), cudaHostAllocMapped));
+    *ctx->peerTimedOut = 0;
+  }
+  PeerBlob blob;
+  memset(&blob, 0, sizeof(blob));
+  for (int i = 0; i < 2; ++i) {
+    cudaError_t error = cudaIpcGetMemHandle(&blob.populations[i], ctx->populations[i]);
+    if (error != cudaSuccess) return fail(MLBM_ERR_COMM, "cudaIpcGetMemHandle: %s", cudaGetErrorString(error));
+  }
+  cudaError_t error = cudaIpcGetMemHandle(&blob.flags, ctx->peerFlags);
+  if (error != cudaSuccess) return fail(MLBM_ERR_COMM, "cudaIpcGetMemHandle: %s", cudaGetErrorString(error));
+  blob.bufferBytes = (uint64_t)ctx->stride * ctx->Q * ctx->elementSize;
+  blob.rank = ctx->config.rank;
+  blob.device = ctx->device;
+  blob.process = (int64_t)getpid();
+  memcpy(handle, &blob, sizeof(blob));
+  return MLBM_OK;
+}
+
+int mlbm_comm_peer_attach(mlbm_ctx* ctx, const void* leftHandle, const void* rightHandle) {
+  if (!ctx || !leftHandle || !rightHandle) return fail(MLBM_ERR_INVALID, "null argument");
+  if (ctx->config.nranks < 2) return fail(MLBM_ERR_STATE, "a single rank has no neighbours");
+  if (ctx->peerAttached) return fail(MLBM_ERR_STATE, "peer halos already attached");
+  if (!ctx->peerFlags) return fail(MLBM_ERR_STATE, "mlbm_comm_peer_export has to be called first");
+  if (!ctx->comm) return fail(MLBM_ERR_STATE, "mlbm_comm_init has to be called first (initial halo exchange and shutdown barrier)");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  PeerBlob blobs[2];
+  memcpy(&blobs[0], leftHandle, sizeof(PeerBlob));
+  memcpy(&blobs[1], rightHandle, sizeof(PeerBlob));
+  const int expected[2] = {(ctx->config.rank + ctx->config.nranks - 1) % ctx->config.nranks, (ctx->config.rank + 1) % ctx->config.nranks};
+  const uint64_t bufferBytes = (uint64_t)ctx->stride * ctx->Q * ctx->elementSize;
+  for (int side = 0; side < 2; ++side) {
+    if (blobs[side].rank != expected[side]) return fail(MLBM_ERR_INVALID, "handle of rank %d where the %s neighbour %d was expected", blobs[side].rank, side ? "right" : "left", expected[side]);
+    if (blobs[side].bufferBytes != bufferBytes) return fail(MLBM_ERR_INVALID, "neighbour %d has a different slab geometry", blobs[side].rank);
+    if (blobs[side].process == (int64_t)getpid()) return fail(MLBM_ERR_INVALID, "peer halos need one process per rank (CUDA IPC)");
+  }
+  auto closeAll = [&]() {
+    for (int side = 0; side < 2; ++side) {
+      if (ctx->mappedOwned[side]) for (void*& pointer : ctx->mapped[side]) if (pointer) cudaIpcCloseMemHandle(pointer);
+      for (void*& pointer : ctx->mapped[side]) pointer = nullptr;
+      ctx->mappedOwned[side] = false;
+    }
+  };
+  for (int side = 0; side < 2; ++side) {
+    if (side == 1 && expected[1] == expected[0]) {  // two ranks: both neighbours are the same process, map it once
+      for (int i = 0; i < 3; ++i) ctx->mapped[1][i] = ctx->mapped[0][i];
+      break;
+    }
+    ctx->mappedOwned[side] = true;
+    const cudaIpcMemHandle_t* handles[3] = {&blobs[side].populations[0], &blobs[side].populations[1], &blobs[side].flags};
+    for (int i = 0; i < 3; ++i) {
+      cudaError_t error = cudaIpcOpenMemHandle(&ctx->mapped[side][i], *handles[i], cudaIpcMemLazyEnablePeerAccess);
+      if (error != cudaSuccess) {
+        cudaGetLastError();
+        closeAll();
+        return fail(MLBM_ERR_COMM, "cudaIpcOpenMemHandle (rank %d, device %d): %s", blobs[side].rank, blobs[side].device, cudaGetErrorString(error));
+      }
+    }
+  }
+  ctx->peerAttached = true;
+  ctx->peerEpoch = 0;
+  ctx->halosValid = false;
   return MLBM_OK;
 }
 

@@ -48,7 +48,13 @@ struct StepParams {
   long long plane;         // elements between x planes (= NM * NR)
   long long fieldStride;   // elements between field components
   int LX, NM, NR;          // local interior extents along x, m, r
-  int x0;                  // first local x plane of this launch (blockIdx.z counts from it)
+  int x0;                  // first local x plane of this launch
+  int planeStep;           // blockIdx.z-th plane of the launch is x0 + blockIdx.z * planeStep (1: a contiguous range;
+                           // LX - 1 with two planes: the two boundary planes of the slab in one launch)
+  void* peerLow;           // direct peer halos: the LEFT neighbour's `next` buffer, mapped over NVLink;
+                           // plane x = 0 stores its c_x < 0 populations into that buffer's halo plane LX + 1 as well
+  void* peerHigh;          // the RIGHT neighbour's `next` buffer; plane x = LX - 1 stores its c_x > 0 populations into
+                           // that buffer's halo plane 0 (what Communication.h:134-180 sends); nullptr = no peer stores
   int wrapX;               // 1: single rank, x is periodic inside the slab; 0: halo planes hold the neighbours' data
   int isStored;            // Algorithm::isStored (Routine.h:122-124): bit 0 = store fields, bit 1 = reduce observables
   int hydroShift;          // 1: stored velocity = u + F/(2 rho) (ForcingScheme.h:26-33); 0: u (scheme None, :50-57)
@@ -311,7 +317,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
 
   const int r = blockIdx.x * kStepBlock + threadIdx.x;
   const int m = blockIdx.y;
-  const int x = p.x0 + blockIdx.z;
+  const int x = p.x0 + (int)blockIdx.z * p.planeStep;
   const bool active = r < p.NR;
 
   // entropic kernels: dynamic shared memory = f[Q][block] | fNeq[Q][block] | 1/w[Q] | (fastLog table)
@@ -403,6 +409,15 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
 
     const long long node = (long long)x * p.plane + (long long)m * p.NR + r;  // field / alpha index
     const long long out = (long long)xh * p.plane + (long long)m * p.NR + r;
+    // halo planes of the neighbours this node's outgoing populations belong to (block-uniform conditions)
+    StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
+    StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
+    auto storeOutgoing = [&](auto qc, double value) {
+      constexpr int q = decltype(qc)::value;
+      storePopulation(next + q * p.stride + out, value);
+      if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
+      if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
+    };
 
     // collision source helpers
     double uF = 0.0;
@@ -469,7 +484,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
         if (SCHEME == kSchemeEDM) {
           value += rho * L::w(q) * eqShifted.template shape<q>() - (fq - nq);
         }
-        storePopulation(next + q * p.stride + out, value);
+        storeOutgoing(qc, value);
       });
     } else {
       // Collision<BGK>::collideAndStream (Collision.h:134-151)
@@ -491,7 +506,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
         if (SCHEME == kSchemeEDM) {
           value += rho * L::w(q) * eqShifted.template shape<q>() - feq;
         }
-        storePopulation(next + q * p.stride + out, value);
+        storeOutgoing(qc, value);
       });
     }
 

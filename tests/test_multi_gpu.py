@@ -35,7 +35,8 @@ case = json.load(open(out + "/case.json"))
 f0 = np.load(out + "/f0.npy")
 dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
 cfg = make_config(rank=rank, nranks=world, device=rank, **case["config"])
-algorithm = Algorithm(cfg, communication=Communication(rank, world))
+algorithm = Algorithm(cfg, communication=Communication(rank, world), peer_halos=case["peer"])
+assert algorithm.peer_halos == case["peer"]
 domain = algorithm.domain
 algorithm.distribution.set_interior(slab_of(f0, rank, world).astype(domain.dtype))
 algorithm.unpack()
@@ -68,9 +69,9 @@ def _device_count():
         return 0
 
 
-def _run_ranks(tmp_path, world, config, f0, steps, mode):
+def _run_ranks(tmp_path, world, config, f0, steps, mode, peer=False):
     import json
-    (tmp_path / "case.json").write_text(json.dumps({"config": config, "steps": steps, "mode": mode}))
+    (tmp_path / "case.json").write_text(json.dumps({"config": config, "steps": steps, "mode": mode, "peer": peer}))
     np.save(tmp_path / "f0.npy", f0)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
@@ -99,7 +100,12 @@ def _run_ranks(tmp_path, world, config, f0, steps, mode):
 
 
 CASES = [
-    # lattice, shape, collision, scheme, force, overlap, steps, mode
+    # lattice, shape, collision, scheme, force, overlap, steps, mode[, halo]
+    ("D3Q19", (16, 6, 10), "BGK", "Guo", "Kolmogorov", "On", 5, "sync", "peer"),
+    ("D3Q19", (16, 6, 10), "BGK", "None", "None", "On", 12, "async", "peer"),
+    ("D2Q9", (24, 20, 1), "BGK", "Guo", "Kolmogorov", "On", 9, "async", "peer"),
+    ("D3Q27", (8, 6, 4), "ELBM", "Guo", "Kolmogorov", "On", 2, "sync", "peer"),
+    ("D2Q9", (8, 140, 1), "ELBM", "ShanChen", "Kolmogorov", "On", 3, "async", "peer"),
     ("D3Q19", (16, 6, 10), "BGK", "Guo", "Kolmogorov", "On", 5, "sync"),
     ("D3Q19", (16, 6, 10), "BGK", "Guo", "Kolmogorov", "Off", 5, "sync"),
     ("D3Q19", (16, 6, 10), "BGK", "None", "None", "On", 6, "async"),
@@ -110,18 +116,19 @@ CASES = [
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(map(str, (c[0], c[2], c[3], c[5], c[7]))))
+@pytest.mark.parametrize("case", CASES, ids=lambda c: "-".join(map(str, (c[0], c[2], c[3], c[5], c[7]) + c[8:])))
 def test_slabs_reproduce_the_single_rank_result(tmp_path, world, case):
     if _device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    lattice, shape, collision, scheme, force, overlap, steps, mode = case
+    lattice, shape, collision, scheme, force, overlap, steps, mode = case[:8]
+    peer = len(case) > 8 and case[8] == "peer"   # boundary kernel stores into the neighbours' halo planes (CUDA IPC)
     if shape[0] % world or shape[0] // world < 1:
         pytest.skip("slab too thin")
     config = dict(lattice=lattice, shape=list(shape), collision=collision, forcing_scheme=scheme, force=force, tau=0.55,
                   amplitude=[1e-4, 2e-4, 3e-4], wavelength=[8.0, 4.0, 16.0], overlap=overlap)
     single = make_config(**config)
     f0 = O.synthetic_populations(single, eps=1e-2)
-    got = _run_ranks(tmp_path, world, config, f0, steps, mode)
+    got = _run_ranks(tmp_path, world, config, f0, steps, mode, peer)
 
     # (b) bit-identical to the single-GPU CUDA path.  The force profile is evaluated at LOCAL x (Collision.h:86), which
     # only Sinusoidal forces along x would notice; the cases here are x-independent.
