@@ -13,11 +13,14 @@ from pathlib import Path
 
 PACKAGE_DIR = Path(__file__).resolve().parent
 CSRC = PACKAGE_DIR / "csrc"
-BUILD = PACKAGE_DIR / "_build"
-LIBRARY = PACKAGE_DIR / "libmetalbm_b200.so"
+# experiments: MLBM_VARIANT=name MLBM_EXTRA_FLAGS="-DX=1 ..." builds libmetalbm_b200_name.so next to the product library
+VARIANT = os.environ.get("MLBM_VARIANT", "")
+BUILD = PACKAGE_DIR / ("_build" + ("_" + VARIANT if VARIANT else ""))
+LIBRARY = PACKAGE_DIR / ("libmetalbm_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v",
+         *os.environ.get("MLBM_EXTRA_FLAGS", "").split()]
 
 
 def _stale(target: Path, sources: list) -> bool:

@@ -12,7 +12,8 @@ import os
 from pathlib import Path
 
 PACKAGE_DIR = Path(__file__).resolve().parent
-LIBRARY_PATH = PACKAGE_DIR / "libmetalbm_b200.so"
+# MLBM_VARIANT selects an experimental build (metalbm_b200/build.py); the product library otherwise
+LIBRARY_PATH = PACKAGE_DIR / ("libmetalbm_b200" + ("_" + os.environ["MLBM_VARIANT"] if os.environ.get("MLBM_VARIANT") else "") + ".so")
 ABI_VERSION = 1
 PEER_HANDLE_BYTES = 256
 

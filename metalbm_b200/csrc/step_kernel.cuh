@@ -51,6 +51,8 @@ struct StepParams {
   int x0;                  // first local x plane of this launch
   int planeStep;           // blockIdx.z-th plane of the launch is x0 + blockIdx.z * planeStep (1: a contiguous range;
                            // LX - 1 with two planes: the two boundary planes of the slab in one launch)
+  int planeCount;          // number of planes of the launch
+  int planesPerBlock;      // entropic kernels: consecutive planes walked by one block (gridDim.z = ceil(planeCount / planesPerBlock))
   void* peerLow;           // direct peer halos: the LEFT neighbour's `next` buffer, mapped over NVLink;
                            // plane x = 0 stores its c_x < 0 populations into that buffer's halo plane LX + 1 as well
   void* peerHigh;          // the RIGHT neighbour's `next` buffer; plane x = LX - 1 stores its c_x > 0 populations into
@@ -65,6 +67,11 @@ struct StepParams {
 
 template <typename StoreT> __device__ __forceinline__ double loadPopulation(const StoreT* p) {
   return (double)__ldg(p);
+}
+// L2-only load: the entropic kernels keep their logarithm table (and little else) in what the shared-memory carve-out
+// leaves of L1; the once-read population stream must not evict it
+template <typename StoreT> __device__ __forceinline__ double loadPopulationStreaming(const StoreT* p) {
+  return (double)__ldcg(p);
 }
 template <typename StoreT> __device__ __forceinline__ void storePopulation(StoreT* p, double v) {
   __stcs(p, (StoreT)v);
@@ -191,40 +198,127 @@ __device__ __forceinline__ double fastLog(double v, const double2* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // Entropic alpha: Collision<ELBM>::calculateAlpha (Collision.h:351-375).
 //
-// Work layout.  The populations f_q and their non-equilibrium parts of one node live in SHARED memory while alpha is
-// solved for ([q][thread], conflict-free), not in registers: the Newton loops over q are then rolled (a few dozen
-// instructions, three-way unrolled for instruction-level parallelism) instead of Q copies of the logarithm per
-// evaluation, which had overflowed the instruction cache (ncu: 'no_instructions' was the second stall reason) and
-// kept 108 registers alive through the solve.
+// Work layout.  The populations f_q and their non-equilibrium parts of the block's nodes live in SHARED memory
+// ([row][node], conflict-free) while alpha is solved for.  That buys three things:
+//   * the Newton loops over q are rolled (a few dozen instructions, G logarithms in lock step for instruction-level
+//     parallelism) instead of Q copies of the logarithm per evaluation, which had overflowed the instruction cache;
+//   * the solve is COMPACTED over the block: the nodes that need it are listed in shared memory and thread i solves
+//     the i-th listed node (any thread can read any node's column), so the FP64 cost follows the number of such nodes
+//     instead of the number of warps that contain at least one of them;
+//   * one block handles several x planes in a row, staging the logarithm table and the per-row constants once.
+//
+// Arithmetic of one evaluation.  The populations of one speed class c (|c_q|^2 = 0, 1, 2, 3: same weight w_c) are
+// stored next to each other and SCALED by 2^k_c, k_c the integer with w_c 2^k_c in [0.7, 1.4): the scaling is exact
+// (it commutes with every rounding below), and with C_c = -ln(w_c 2^k_c)
+//     ln(g_q / w_q) = ln(v_q) + C_c,    v_q = 2^k_c g_q = F2_q - a N2_q     (F2 = 2^k f, N2 = 2^k fNeq as stored),
+// so the logarithm's argument comes out of ONE fused multiply-add, stays inside the table's [0.25, 4) for any
+// sensible state, and the C_c terms collapse into per-node constants:
+//   F(a)  = sum f ln(f/w) - g ln(g/w) = H - [sum_c 2^-k_c sum_{q in c} v_q L_q + A - a B]          (EntropicStep.h:31-45)
+//   F'(a) = sum fNeq (1 + ln(g/w))    = sum fNeq + B + sum_c 2^-k_c sum_{q in c} N2_q L_q             (EntropicStep.h:47-62)
+// with L_q = fastLog(v_q), A = sum_c 2^-k_c C_c sum_{q in c} F2_q, B likewise over N2, and H = F's first sum, hoisted
+// out of the iteration: 12 FP64 instructions per population and evaluation (1 + 9 + 2), against ~3 x 60 as the
+// reference writes it, and no per-population integer or constant traffic besides the table lookup.
 // ------------------------------------------------------------------------------------------------
-struct EntropicScratch {
-  const double* f;       // f[q * kStepBlock]     (this thread's column)
-  const double* fNeq;    // fNeq[q * kStepBlock]
-  const double* invW;    // 1 / w_q, one copy per block
+constexpr int logShift(double w) {
+  int k = 0;
+  while (w < 0.7) { w *= 2.0; ++k; }
+  while (w >= 1.4) { w *= 0.5; --k; }
+  return k;
+}
+constexpr double powerOfTwo(int k) {
+  double value = 1.0;
+  for (int i = 0; i < (k < 0 ? -k : k); ++i) value *= (k < 0 ? 0.5 : 2.0);
+  return value;
+}
+// natural logarithm of y in [0.7, 1.4) at compile time: 2 atanh((y - 1) / (y + 1)), 40 terms (|s| < 0.18)
+constexpr double constexprLog(double y) {
+  const double s = (y - 1.0) / (y + 1.0), s2 = s * s;
+  double term = s, sum = 0.0;
+  for (int n = 1; n < 80; n += 2) { sum += term / n; term *= s2; }
+  return 2.0 * sum;
+}
+
+// speed classes of a lattice: populations sorted by |c|^2 (stable), the order of the shared-memory rows
+template <class L> struct SpeedClasses {
+  static constexpr int count(int n2) {
+    int n = 0;
+    for (int q = 0; q < L::Q; ++q) n += L::norm2(q) == n2 ? 1 : 0;
+    return n;
+  }
+  static constexpr int first(int n2) {
+    int n = 0;
+    for (int q = 0; q < L::Q; ++q) n += L::norm2(q) < n2 ? 1 : 0;
+    return n;
+  }
+  static constexpr int row(int q) {
+    int n = first(L::norm2(q));
+    for (int other = 0; other < q; ++other) n += L::norm2(other) == L::norm2(q) ? 1 : 0;
+    return n;
+  }
+  static constexpr double weight(int n2) { return detail::weightByNorm<L::id>(n2); }
+  static constexpr int shift(int n2) { return logShift(weight(n2)); }
+  static constexpr double scale(int n2) { return powerOfTwo(shift(n2)); }        // 2^k_c
+  static constexpr double inverseScale(int n2) { return powerOfTwo(-shift(n2)); }  // 2^-k_c
+  static constexpr double offset(int n2) { return -constexprLog(weight(n2) * scale(n2)); }  // C_c
+  // logarithms advanced in lock step inside a class
+  static constexpr int group(int n2) {
+    const int n = count(n2);
+#ifdef MLBM_LOG_GROUP_WIDE
+    return n % 6 == 0 ? 6 : (n % 4 == 0 ? 4 : (n < 3 ? (n > 0 ? n : 1) : 3));
+#else
+    return n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n < 3 ? (n > 0 ? n : 1) : 3));
+#endif
+  }
+};
+
+struct EntropicShared {
+  double* f;             // [Q][kStepBlock]  F2, rows sorted by speed class
+  double* fNeq;          // [Q][kStepBlock]  N2
+  double* alpha;         // [kStepBlock]     in: alphaMax of the nodes to solve, out: their alpha
+  double* rowOffset;     // [32]  C_c of the row's class          (library fallback only)
+  double* rowInverse;    // [32]  2^-k_c of the row's class       (library fallback only)
+  int* warpCount;        // [kStepBlock / 32]
+  unsigned char* list;   // [kStepBlock]     nodes (thread indices) that need the Newton solve, ascending
   const double2* table;  // fastLog table (shared or global memory)
 };
 
+constexpr int kLogTableBytes = kLogTableEntries * 16;
+constexpr int entropicSharedBytes(int Q, bool tableInShared) {
+  return 2 * Q * kStepBlock * 8 + kStepBlock * 8 + 2 * 32 * 8 + 16 + kStepBlock + (tableInShared ? kLogTableBytes : 0);
+}
+// blocks per SM the entropic kernels are compiled for (registers) and sized for (shared memory)
+// (measured, D3Q27 512^3: three blocks with the table in shared memory beat four blocks with the table in L1 by 10-14 %)
+#ifndef MLBM_ENTROPIC_BLOCKS_Q9
+#define MLBM_ENTROPIC_BLOCKS_Q9 5
+#endif
+constexpr int entropicBlocksPerSM(int Q) { return Q <= 9 ? MLBM_ENTROPIC_BLOCKS_Q9 : (Q == 27 ? 3 : 4); }
+// the fastLog table is staged in shared memory whenever those blocks still fit (228 KB, 1 KB reserved per block)
+constexpr bool logTableInShared(int Q) { return entropicBlocksPerSM(Q) * (entropicSharedBytes(Q, true) + 1024) <= 233472; }
+
 // The same solve with the CUDA math library's logarithm, for the rare node whose arguments fall outside fastLogCore's
-// table.  Kept out of line and rolled: it is cold code.
+// table (and with it the reference's NaN behaviour for mirror states that leave the positive cone: the iteration produces
+// NaNs, gives up after 50 iterations and alpha falls back to 2, EntropicStep.h:126-138, Collision.h:344-346).
+// Kept out of line and rolled: it is cold code.
 template <int Q>
-__device__ __noinline__ double entropicNewtonLibrary(const EntropicScratch& s, double alphaGuess, double alphaMax) {
+__device__ __noinline__ double entropicNewtonLibrary(const double* fColumn, const double* nColumn, const double* rowOffset,
+                                                     const double* rowInverse, double alphaGuess, double alphaMax) {
   double hoisted = 0.0;
 #pragma unroll 1
-  for (int q = 0; q < Q; ++q) {
-    const double fq = s.f[q * kStepBlock];
-    hoisted = fma(fq, log(fq * s.invW[q]), hoisted);
+  for (int row = 0; row < Q; ++row) {
+    const double v = fColumn[row * kStepBlock];
+    hoisted = fma(v * rowInverse[row], log(v) + rowOffset[row], hoisted);
   }
   double x = alphaGuess, step = 0.0;
   for (int iteration = 1; iteration <= 50; ++iteration) {
     x = x - step;
     double sum = 0.0, derivative = 0.0;
 #pragma unroll 1
-    for (int q = 0; q < Q; ++q) {
-      const double nq = s.fNeq[q * kStepBlock];
-      const double g = fma(-x, nq, s.f[q * kStepBlock]);
-      const double lg = log(g * s.invW[q]);
-      sum = fma(g, lg, sum);
-      derivative = fma(nq, 1.0 + lg, derivative);
+    for (int row = 0; row < Q; ++row) {
+      const double n2 = nColumn[row * kStepBlock];
+      const double v = fma(-x, n2, fColumn[row * kStepBlock]);
+      const double lg = log(v) + rowOffset[row];
+      sum = fma(v * rowInverse[row], lg, sum);
+      derivative = fma(n2 * rowInverse[row], 1.0 + lg, derivative);
     }
     step = (hoisted - sum) / derivative;
     if (fabs(step) <= 1e-8) return (x > 1.0 && x < alphaMax) ? x : 2.0;
@@ -232,213 +326,337 @@ __device__ __noinline__ double entropicNewtonLibrary(const EntropicScratch& s, d
   return 2.0;
 }
 
-// The q loops are rolled over groups of three populations (the three logarithms of a group advance in lock step,
-// see fastLogCore); Q = 9, 15, 27 are multiples of three, the others end with a partial group whose unused slots
-// are fed the harmless argument 1 and contribute exact zeros.
-template <int Q>
-__device__ __forceinline__ double entropicNewton(const EntropicScratch& s, double alphaGuess, double alphaMax) {
-  // solveAlpha (Collision.h:328-349) -> NewtonRaphsonSolver (EntropicStep.h:111-140) on
-  //   F(a)  = sum f ln(f/w) - (f - a fNeq) ln((f - a fNeq)/w)      (EntropicStep.h:31-45)
-  //   F'(a) = sum fNeq (1 + ln((f - a fNeq)/w))                     (EntropicStep.h:47-62)
-  // The a-independent sum is hoisted and ln((f - a fNeq)/w) is shared between F and F'.  Each slot of a group keeps
-  // its own partial sums.
-  // As soon as a logarithm argument leaves the table's range the node is handed to entropicNewtonLibrary, which
-  // restarts the solve with the library logarithm (and with it the reference's NaN behaviour for mirror states that
-  // leave the positive cone: the iteration produces NaNs, gives up after 50 iterations and alpha falls back to 2,
-  // EntropicStep.h:126-138, Collision.h:344-346).
-  constexpr int G = 3;
-  constexpr int groups = (Q + G - 1) / G;
-  unsigned range = 0;
-  double h[G] = {0.0, 0.0, 0.0};
+// one speed class of the hoisted sums: hC = sum v ln v, sF = sum F2, sN = sum N2 over the class rows
+template <int FIRST, int COUNT, int G>
+__device__ __forceinline__ void entropicHoistClass(const double* fColumn, const double* nColumn, const double2* table, unsigned& range,
+                                                   double& hC, double& sF, double& sN) {
+  constexpr int groups = (COUNT + G - 1) / G;
+  double h[G], a[G], b[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) h[j] = a[j] = b[j] = 0.0;
 #pragma unroll 1
   for (int group = 0; group < groups; ++group) {
-    double fq[G], v[G], lg[G];
+    double v[G], lg[G];
 #pragma unroll
     for (int j = 0; j < G; ++j) {
-      const int q = group * G + j;
-      const bool live = Q % G == 0 || q < Q;
-      fq[j] = live ? s.f[q * kStepBlock] : 0.0;
-      v[j] = live ? fq[j] * s.invW[q] : 1.0;
+      const int row = FIRST + group * G + j;
+      const bool live = COUNT % G == 0 || group * G + j < COUNT;
+      v[j] = live ? fColumn[row * kStepBlock] : 1.0;
+      a[j] += live ? v[j] : 0.0;
+      b[j] += live ? nColumn[row * kStepBlock] : 0.0;
     }
-    fastLogCore<G>(v, lg, s.table, range);
+    fastLogCore<G>(v, lg, table, range);
 #pragma unroll
-    for (int j = 0; j < G; ++j) h[j] = fma(fq[j], lg[j], h[j]);
+    for (int j = 0; j < G; ++j) h[j] = fma(v[j], lg[j], h[j]);
   }
-  if (range >= kLogTableEntries) return entropicNewtonLibrary<Q>(s, alphaGuess, alphaMax);
-  const double hoisted = (h[0] + h[1]) + h[2];
+  hC = h[0]; sF = a[0]; sN = b[0];
+#pragma unroll
+  for (int j = 1; j < G; ++j) { hC += h[j]; sF += a[j]; sN += b[j]; }
+}
+
+// one speed class of an evaluation: sC = sum v L, dC = sum N2 L with v = F2 - x N2
+template <int FIRST, int COUNT, int G>
+__device__ __forceinline__ void entropicEvaluateClass(const double* fColumn, const double* nColumn, const double2* table, unsigned& range,
+                                                      double x, double& sC, double& dC) {
+  constexpr int groups = (COUNT + G - 1) / G;
+  double sum[G], derivative[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) sum[j] = derivative[j] = 0.0;
+#pragma unroll 1
+  for (int group = 0; group < groups; ++group) {
+    double n2[G], v[G], lg[G];
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      const int row = FIRST + group * G + j;
+      const bool live = COUNT % G == 0 || group * G + j < COUNT;
+      n2[j] = live ? nColumn[row * kStepBlock] : 0.0;
+      v[j] = live ? fma(-x, n2[j], fColumn[row * kStepBlock]) : 1.0;
+    }
+    fastLogCore<G>(v, lg, table, range);
+#pragma unroll
+    for (int j = 0; j < G; ++j) {
+      sum[j] = fma(v[j], lg[j], sum[j]);
+      derivative[j] = fma(n2[j], lg[j], derivative[j]);
+    }
+  }
+  sC = sum[0]; dC = derivative[0];
+#pragma unroll
+  for (int j = 1; j < G; ++j) { sC += sum[j]; dC += derivative[j]; }
+}
+
+// solveAlpha (Collision.h:328-349) -> NewtonRaphsonSolver (EntropicStep.h:111-140), see the banner above.
+template <class L>
+__device__ __forceinline__ double entropicNewton(const EntropicShared& s, int column, double alphaGuess, double alphaMax) {
+  using C = SpeedClasses<L>;
+  const double* fColumn = s.f + column;
+  const double* nColumn = s.fNeq + column;
+  unsigned range = 0;
+  double hoisted = 0.0, offsetF = 0.0, offsetN = 0.0, sumN = 0.0;
+  staticFor<0, 4>([&](auto nc) {
+    constexpr int n2 = decltype(nc)::value;
+    if constexpr (C::count(n2) > 0) {
+      double hC, sF, sN;
+      entropicHoistClass<C::first(n2), C::count(n2), C::group(n2)>(fColumn, nColumn, s.table, range, hC, sF, sN);
+      hoisted = fma(C::inverseScale(n2), hC, hoisted);
+      offsetF = fma(C::inverseScale(n2) * C::offset(n2), sF, offsetF);
+      offsetN = fma(C::inverseScale(n2) * C::offset(n2), sN, offsetN);
+      sumN = fma(C::inverseScale(n2), sN, sumN);
+    }
+  });
+  if (range >= kLogTableEntries) return entropicNewtonLibrary<L::Q>(fColumn, nColumn, s.rowOffset, s.rowInverse, alphaGuess, alphaMax);
+  hoisted += offsetF;
+  const double derivativeBase = sumN + offsetN;
 
   double x = alphaGuess, step = 0.0;
   bool converged = false;
   for (int iteration = 1; iteration <= 50; ++iteration) {
     x = x - step;
-    double sum[G] = {0.0, 0.0, 0.0}, derivative[G] = {0.0, 0.0, 0.0};
-#pragma unroll 1
-    for (int group = 0; group < groups; ++group) {
-      double g[G], nq[G], v[G], lg[G];
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const int q = group * G + j;
-        const bool live = Q % G == 0 || q < Q;
-        nq[j] = live ? s.fNeq[q * kStepBlock] : 0.0;
-        g[j] = live ? fma(-x, nq[j], s.f[q * kStepBlock]) : 0.0;
-        v[j] = live ? g[j] * s.invW[q] : 1.0;
+    double total = 0.0, slope = 0.0;
+    staticFor<0, 4>([&](auto nc) {
+      constexpr int n2 = decltype(nc)::value;
+      if constexpr (C::count(n2) > 0) {
+        double sC, dC;
+        entropicEvaluateClass<C::first(n2), C::count(n2), C::group(n2)>(fColumn, nColumn, s.table, range, x, sC, dC);
+        total = fma(C::inverseScale(n2), sC, total);
+        slope = fma(C::inverseScale(n2), dC, slope);
       }
-      fastLogCore<G>(v, lg, s.table, range);
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        sum[j] = fma(g[j], lg[j], sum[j]);
-        derivative[j] = fma(nq[j], 1.0 + lg[j], derivative[j]);
-      }
-    }
-    if (range >= kLogTableEntries) return entropicNewtonLibrary<Q>(s, alphaGuess, alphaMax);
-    step = (hoisted - ((sum[0] + sum[1]) + sum[2])) / ((derivative[0] + derivative[1]) + derivative[2]);
+    });
+    if (range >= kLogTableEntries) return entropicNewtonLibrary<L::Q>(fColumn, nColumn, s.rowOffset, s.rowInverse, alphaGuess, alphaMax);
+    step = (hoisted - (total + fma(-x, offsetN, offsetF))) / (derivativeBase + slope);
     if (fabs(step) <= 1e-8) { converged = (x > 1.0 && x < alphaMax); break; }
   }
   return converged ? x : 2.0;
 }
 
-// bytes of dynamic shared memory the entropic kernels need (see fusedStepKernel)
-constexpr int kLogTableBytes = kLogTableEntries * 16;
-constexpr int entropicSharedBytes(int Q, bool tableInShared) {
-  return 2 * Q * kStepBlock * 8 + ((Q * 8 + 15) / 16) * 16 + (tableInShared ? kLogTableBytes : 0);
-}
-// the fastLog table is staged in shared memory whenever four blocks per SM still fit (228 KB, 1 KB reserved per block)
-constexpr bool logTableInShared(int Q) { return 4 * (entropicSharedBytes(Q, true) + 1024) <= 233472; }
-
 // ------------------------------------------------------------------------------------------------
-// The fused step.
-// grid = (ceil(NR / kStepBlock), NM, number of x planes), block = kStepBlock threads along r.
+// Pieces shared by the two kernel bodies
 // ------------------------------------------------------------------------------------------------
-template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
-__global__ void __launch_bounds__(kStepBlock, COLLISION == kELBM ? 4 : 1)
-fusedStepKernel(const __grid_constant__ StepParams p) {
-  constexpr int Q = L::Q;
-  constexpr int D = L::D;
+struct NodeIndex {
+  int xPrev, xh, xNext, mPrev, m, mNext, rPrev, r, rNext;
+};
 
-  const int r = blockIdx.x * kStepBlock + threadIdx.x;
-  const int m = blockIdx.y;
-  const int x = p.x0 + (int)blockIdx.z * p.planeStep;
-  const bool active = r < p.NR;
-
-  // entropic kernels: dynamic shared memory = f[Q][block] | fNeq[Q][block] | 1/w[Q] | (fastLog table)
-  extern __shared__ __align__(16) unsigned char dynamicShared[];
-  EntropicScratch scratchPointers = {nullptr, nullptr, nullptr, kLogTable};
-  double* sharedF = nullptr;
-  double* sharedFNeq = nullptr;
-  if (COLLISION == kELBM) {
-    static_assert(kLogTableEntries % kStepBlock == 0, "whole table entries per thread");
-    sharedF = reinterpret_cast<double*>(dynamicShared) + threadIdx.x;
-    sharedFNeq = sharedF + Q * kStepBlock;
-    double* invW = reinterpret_cast<double*>(dynamicShared) + 2 * Q * kStepBlock;
-    staticFor<0, Q>([&](auto qc) {
-      constexpr int q = decltype(qc)::value;
-      if (threadIdx.x == q) invW[q] = 1.0 / L::w(q);
-    });
-    scratchPointers.f = sharedF;
-    scratchPointers.fNeq = sharedFNeq;
-    scratchPointers.invW = invW;
-    if (logTableInShared(Q)) {
-      double2* table = reinterpret_cast<double2*>(dynamicShared + 2 * Q * kStepBlock * 8 + ((Q * 8 + 15) / 16) * 16);
-#pragma unroll
-      for (int i = 0; i < kLogTableEntries / kStepBlock; ++i) table[i * kStepBlock + threadIdx.x] = kLogTable[i * kStepBlock + threadIdx.x];
-      scratchPointers.table = table;
-    }
-    __syncthreads();
+__device__ __forceinline__ NodeIndex nodeIndex(const StepParams& p, int x, int m, int r) {
+  // upstream coordinates: pull from (x - cx, m - cm, r - cr) of the periodic image
+  NodeIndex n;
+  n.xh = x + 1;  // halo plane 0 precedes the interior
+  n.xPrev = n.xh - 1;
+  n.xNext = n.xh + 1;
+  if (p.wrapX) {
+    if (n.xPrev == 0) n.xPrev = p.LX;
+    if (n.xNext == p.LX + 1) n.xNext = 1;
   }
+  n.m = m;
+  n.mPrev = m == 0 ? p.NM - 1 : m - 1;
+  n.mNext = m == p.NM - 1 ? 0 : m + 1;
+  n.r = r;
+  n.rPrev = r == 0 ? p.NR - 1 : r - 1;
+  n.rNext = r == p.NR - 1 ? 0 : r + 1;
+  return n;
+}
 
-  double rho = 0.0, energy = 0.0, speed2 = 0.0;
+template <class L, typename StoreT, bool STREAMING = false>
+__device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeIndex& n, double (&f)[L::Q]) {
+  const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) {
+    const int xs = L::cx(q) == 1 ? n.xPrev : (L::cx(q) == -1 ? n.xNext : n.xh);
+    const int ms = L::cm(q) == 1 ? n.mPrev : (L::cm(q) == -1 ? n.mNext : n.m);
+    const int rs = L::cr(q) == 1 ? n.rPrev : (L::cr(q) == -1 ? n.rNext : n.r);
+    const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
+    f[q] = STREAMING ? loadPopulationStreaming(source) : loadPopulation(source);
+  }
+}
 
-  if (active) {
-    // upstream coordinates: pull from (x - cx, m - cm, r - cr) of the periodic image
-    const int xh = x + 1;  // halo plane 0 precedes the interior
-    int xPrev = xh - 1, xNext = xh + 1;
-    if (p.wrapX) {
-      if (xPrev == 0) xPrev = p.LX;
-      if (xNext == p.LX + 1) xNext = 1;
+// Moment::calculateDensity / calculateVelocity (Moment.h:14-47)
+template <class L>
+__device__ __forceinline__ void moments(const double (&f)[L::Q], double& rho, double& invRho, double (&u)[3], double& u2) {
+  rho = f[0];
+#pragma unroll
+  for (int q = 1; q < L::Q; ++q) rho += f[q];
+  u[0] = u[1] = u[2] = 0.0;
+#pragma unroll
+  for (int q = 1; q < L::Q; ++q) {
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) {
+      if (L::c(q, d) == 1) u[d] += f[q];
+      if (L::c(q, d) == -1) u[d] -= f[q];
     }
-    const int mPrev = m == 0 ? p.NM - 1 : m - 1;
-    const int mNext = m == p.NM - 1 ? 0 : m + 1;
-    const int rPrev = r == 0 ? p.NR - 1 : r - 1;
-    const int rNext = r == p.NR - 1 ? 0 : r + 1;
-
-    const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
-    StoreT* __restrict__ next = static_cast<StoreT*>(p.next);
-
-    double f[Q];
+  }
+  invRho = 1.0 / rho;
+  u2 = 0.0;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const int xs = L::cx(q) == 1 ? xPrev : (L::cx(q) == -1 ? xNext : xh);
-      const int ms = L::cm(q) == 1 ? mPrev : (L::cm(q) == -1 ? mNext : m);
-      const int rs = L::cr(q) == 1 ? rPrev : (L::cr(q) == -1 ? rNext : r);
-      f[q] = loadPopulation(prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs);
+  for (int d = 0; d < L::D; ++d) {
+    u[d] *= invRho;
+    u2 += u[d] * u[d];
+  }
+}
+
+// Force::setForce at local interior coordinates (Collision.h:81-88); profiles precomputed on the host
+template <class L>
+__device__ __forceinline__ void bodyForce(const StepParams& p, int x, int m, int r, double (&F)[3]) {
+  F[0] = F[1] = F[2] = 0.0;
+  if (p.hasForce) {
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) {
+      const int axis = p.forceAxis[d];
+      if (axis >= 0) F[d] = __ldg(p.forceTable[d] + (axis == 0 ? x : (axis == 1 ? m : r)));
     }
+  }
+}
 
-    // Moment::calculateDensity / calculateVelocity (Moment.h:14-47)
-    rho = f[0];
+// collision source term S_q (ForcingScheme.h:99-117 Guo, :184-197 ExactDifferenceMethod; None / ShanChen: 0)
+template <class L, int EQ, int SCHEME> struct SourceTerm {
+  double uF = 0.0, guoFactor = 0.0, rho = 0.0;
+  double u[3], F[3];
+  EquilibriumCoefficients<L, EQ> shifted;  // EDM: feq at u + F / rho
+  __device__ __forceinline__ void set(const StepParams& p, double density, double invRho, const double (&velocity)[3], const double (&force)[3]) {
+    rho = density;
+    guoFactor = p.guoFactor;
 #pragma unroll
-    for (int q = 1; q < Q; ++q) rho += f[q];
-    double u[3] = {0.0, 0.0, 0.0};
-#pragma unroll
-    for (int q = 1; q < Q; ++q) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        if (L::c(q, d) == 1) u[d] += f[q];
-        if (L::c(q, d) == -1) u[d] -= f[q];
-      }
-    }
-    const double invRho = 1.0 / rho;
-    double u2 = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      u[d] *= invRho;
-      u2 += u[d] * u[d];
-    }
-
-    // Force::setForce at local interior coordinates (Collision.h:81-88); profiles precomputed on the host
-    double F[3] = {0.0, 0.0, 0.0};
-    if (p.hasForce) {
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const int axis = p.forceAxis[d];
-        if (axis >= 0) F[d] = __ldg(p.forceTable[d] + (axis == 0 ? x : (axis == 1 ? m : r)));
-      }
-    }
-
-    EquilibriumCoefficients<L, EQ> eq;
-    eq.set(u, u2);
-
-    const long long node = (long long)x * p.plane + (long long)m * p.NR + r;  // field / alpha index
-    const long long out = (long long)xh * p.plane + (long long)m * p.NR + r;
-    // halo planes of the neighbours this node's outgoing populations belong to (block-uniform conditions)
-    StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
-    StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
-    auto storeOutgoing = [&](auto qc, double value) {
-      constexpr int q = decltype(qc)::value;
-      storePopulation(next + q * p.stride + out, value);
-      if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
-      if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
-    };
-
-    // collision source helpers
-    double uF = 0.0;
-    EquilibriumCoefficients<L, EQ> eqShifted;  // EDM: feq at u + F / rho (ForcingScheme.h:184-197)
+    for (int d = 0; d < 3; ++d) { u[d] = velocity[d]; F[d] = force[d]; }
     if (SCHEME == kSchemeGuo) {
 #pragma unroll
-      for (int d = 0; d < D; ++d) uF += u[d] * F[d];
+      for (int d = 0; d < L::D; ++d) uF += u[d] * F[d];
     }
     if (SCHEME == kSchemeEDM) {
       double v[3] = {0.0, 0.0, 0.0};
       double v2 = 0.0;
 #pragma unroll
-      for (int d = 0; d < D; ++d) {
+      for (int d = 0; d < L::D; ++d) {
         v[d] = u[d] + F[d] * invRho;
         v2 += v[d] * v[d];
       }
-      eqShifted.set(v, v2);
+      shifted.set(v, v2);
     }
+  }
+  // feq is the equilibrium the scheme is handed: feq_q for BGK, f_q - fNeq_q for ELBM (Collision.h:252)
+  template <int q> __device__ __forceinline__ double value(double feq) const {
+    if (SCHEME == kSchemeGuo) {
+      double cF = 0.0, cu = 0.0;
+#pragma unroll
+      for (int d = 0; d < L::D; ++d) {
+        if (L::c(q, d) == 1) { cF += F[d]; cu += u[d]; }
+        if (L::c(q, d) == -1) { cF -= F[d]; cu -= u[d]; }
+      }
+      return guoFactor * L::w(q) * (cF - uF + 3.0 * cu * cF);
+    }
+    if (SCHEME == kSchemeEDM) return rho * L::w(q) * shifted.template shape<q>() - feq;
+    return 0.0;
+  }
+};
 
-    double alpha = 2.0;
-    if (COLLISION == kELBM) {
+// Algorithm::storeFields (Algorithm.h:150-194) and the per-node terms of the scalar analyses (Analysis.h:53-61)
+template <class L, typename StoreT>
+__device__ __forceinline__ void storeNodeFields(const StepParams& p, long long node, double rho, double invRho, const double (&u)[3],
+                                                const double (&F)[3], double& energy, double& speed2) {
+  const bool fields = (p.isStored & 1) != 0;
+  if (fields) static_cast<StoreT*>(p.density)[node] = (StoreT)rho;
+  const double half = p.hydroShift ? 0.5 * invRho : 0.0;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) {
+    const double v = u[d] + half * F[d];
+    if (fields) {
+      static_cast<StoreT*>(p.velocity)[d * p.fieldStride + node] = (StoreT)v;
+      static_cast<StoreT*>(p.force)[d * p.fieldStride + node] = (StoreT)F[d];
+    }
+    energy += 0.5 * rho * v * v;  // TotalEnergy (Analysis.h:53-61)
+    speed2 += v * v;
+  }
+}
+
+// block reduction of the observables: warp shuffles, then one value per warp through shared memory
+__device__ __forceinline__ void reduceBlockObservables(const StepParams& p, int x, double energy, double mass, double speed2) {
+#pragma unroll
+  for (int offset = 16; offset > 0; offset >>= 1) {
+    energy += __shfl_xor_sync(0xffffffffu, energy, offset);
+    mass += __shfl_xor_sync(0xffffffffu, mass, offset);
+    speed2 = fmax(speed2, __shfl_xor_sync(0xffffffffu, speed2, offset));
+  }
+  __shared__ double scratch[kObservableSlots][kStepBlock / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();  // the scratch array may still be read by the previous plane of this block
+  if (lane == 0) {
+    scratch[0][warp] = energy;
+    scratch[1][warp] = mass;
+    scratch[2][warp] = speed2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double e = 0.0, ms = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int i = 0; i < kStepBlock / 32; ++i) {
+      e += scratch[0][i];
+      ms += scratch[1][i];
+      s2 = fmax(s2, scratch[2][i]);
+    }
+    const long long block = ((long long)x * p.NM + blockIdx.y) * gridDim.x + blockIdx.x;
+    p.partials[block * kObservableSlots + 0] = e;
+    p.partials[block * kObservableSlots + 1] = ms;
+    p.partials[block * kObservableSlots + 2] = s2;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Entropic body: Collision<ELBM> (Collision.h:182-376); see the banner above entropicNewton.
+// grid = (ceil(NR / kStepBlock), NM, ceil(planes / planesPerBlock)); the block walks planesPerBlock planes.
+// ------------------------------------------------------------------------------------------------
+template <class L, int EQ, int SCHEME, typename StoreT>
+__device__ __forceinline__ void entropicStepBody(const StepParams& p) {
+  constexpr int Q = L::Q;
+  using C = SpeedClasses<L>;
+  extern __shared__ __align__(16) unsigned char dynamicShared[];
+  EntropicShared s;
+  s.f = reinterpret_cast<double*>(dynamicShared);
+  s.fNeq = s.f + Q * kStepBlock;
+  s.alpha = s.fNeq + Q * kStepBlock;
+  s.rowOffset = s.alpha + kStepBlock;
+  s.rowInverse = s.rowOffset + 32;
+  s.warpCount = reinterpret_cast<int*>(s.rowInverse + 32);
+  s.list = reinterpret_cast<unsigned char*>(s.warpCount + 4);
+  s.table = kLogTable;
+  staticFor<0, Q>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    if (threadIdx.x == q) {
+      s.rowOffset[C::row(q)] = C::offset(L::norm2(q));
+      s.rowInverse[C::row(q)] = C::inverseScale(L::norm2(q));
+    }
+  });
+  if (logTableInShared(Q)) {
+    static_assert(kLogTableEntries % kStepBlock == 0, "whole table entries per thread");
+    double2* table = reinterpret_cast<double2*>(dynamicShared + entropicSharedBytes(Q, false));
+#pragma unroll
+    for (int i = 0; i < kLogTableEntries / kStepBlock; ++i) table[i * kStepBlock + threadIdx.x] = kLogTable[i * kStepBlock + threadIdx.x];
+    s.table = table;
+  }
+
+  const int t = threadIdx.x;
+  const int r = blockIdx.x * kStepBlock + t;
+  const int m = blockIdx.y;
+  const bool active = r < p.NR;
+  double* const myF = s.f + t;
+  double* const myN = s.fNeq + t;
+  StoreT* __restrict__ next = static_cast<StoreT*>(p.next);
+  StoreT* alphaField = static_cast<StoreT*>(p.alpha);
+
+  for (int i = 0; i < p.planesPerBlock; ++i) {
+    const int planeIndex = blockIdx.z * p.planesPerBlock + i;
+    if (planeIndex >= p.planeCount) break;  // block-uniform
+    const int x = p.x0 + planeIndex * p.planeStep;
+    const long long rowNode = (long long)x * p.plane + (long long)m * p.NR;  // field / alpha index of r = 0
+    __syncthreads();  // constants staged (first plane) / shared columns of the previous plane no longer read
+
+    double rho = 0.0, invRho = 0.0, energy = 0.0, speed2 = 0.0, alpha = 2.0;
+    double u[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
+    bool needsNewton = false;
+    if (active) {
+      const NodeIndex n = nodeIndex(p, x, m, r);
+      double f[Q];
+      pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
+      double u2;
+      moments<L>(f, rho, invRho, u, u2);
+      bodyForce<L>(p, x, m, r, F);
+      EquilibriumCoefficients<L, EQ> eq;
+      eq.set(u, u2);
       // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241): fNeq, then alpha.  While fNeq is formed the
       // two cheap screens of calculateAlpha run on the register values:
       //   isDeviationSmall (Collision.h:284-303): no |fNeq_q| / f_q above 1e-3
@@ -447,10 +665,11 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
       double num = 2.5, den = 1.0;
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
+        constexpr double scale = C::scale(L::norm2(q));
         const double fq = f[q];
         const double nq = fq - rho * L::w(q) * eq.template shape<q>();
-        sharedF[q * kStepBlock] = fq;
-        sharedFNeq[q * kStepBlock] = nq;
+        myF[C::row(q) * kStepBlock] = fq * scale;  // exact
+        myN[C::row(q) * kStepBlock] = nq * scale;
         const double a = fabs(nq);
         const bool large = fq > 0.0 ? (a > 1.0e-3 * fq) : (fq == 0.0 ? a > 0.0 : false);
         small = small && !large;
@@ -459,105 +678,112 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
           if (af * den < num * nq) { num = af; den = nq; }
         }
       });
-      StoreT* alphaField = static_cast<StoreT*>(p.alpha);
       if (!small) {
         // Collision<ELBM>::calculateAlpha (Collision.h:351-375)
         const double alphaMax = num / den;
-        alpha = alphaMax < 2.0 ? 0.95 * alphaMax : entropicNewton<Q>(scratchPointers, (double)alphaField[node], alphaMax);
+        if (alphaMax < 2.0) alpha = 0.95 * alphaMax;
+        else { needsNewton = true; s.alpha[t] = alphaMax; }
       }
+    }
+
+    // compaction: the i-th node (in thread order) that needs the Newton solve is solved by thread i
+    const unsigned ballot = __ballot_sync(0xffffffffu, needsNewton);
+    const int warp = t >> 5, lane = t & 31;
+    if (lane == 0) s.warpCount[warp] = __popc(ballot);
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kStepBlock / 32; ++w) {
+      const int count = s.warpCount[w];
+      if (w < warp) before += count;
+      total += count;
+    }
+    if (total > 0) {  // block-uniform
+      if (needsNewton) s.list[before + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)t;
+      __syncthreads();
+      if (t < total) {
+        const int column = s.list[t];
+        const double guess = (double)alphaField[rowNode + blockIdx.x * kStepBlock + column];  // previous step's alpha (Algorithm.h:103-106)
+        s.alpha[column] = entropicNewton<L>(s, column, guess, s.alpha[column]);
+      }
+      __syncthreads();
+      if (needsNewton) alpha = s.alpha[t];
+    }
+
+    if (active) {
+      const long long node = rowNode + r;
+      const long long out = (long long)(x + 1) * p.plane + (long long)m * p.NR + r;
+      StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
+      StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
       alphaField[node] = (StoreT)alpha;
       const double omega = alpha * p.beta;  // 1 / tau_eff (Collision.h:240)
-      // Collision<ELBM>::collideAndStream (Collision.h:243-258)
+      SourceTerm<L, EQ, SCHEME> source;
+      source.set(p, rho, invRho, u, F);
+      // Collision<ELBM>::collideAndStream (Collision.h:243-258); the 2^k scaling of the stored values is undone exactly
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const double fq = sharedF[q * kStepBlock], nq = sharedFNeq[q * kStepBlock];
-        double value = fq - omega * nq;
-        if (SCHEME == kSchemeGuo) {
-          double cF = 0.0, cu = 0.0;
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            if (L::c(q, d) == 1) { cF += F[d]; cu += u[d]; }
-            if (L::c(q, d) == -1) { cF -= F[d]; cu -= u[d]; }
-          }
-          value += p.guoFactor * L::w(q) * (cF - uF + 3.0 * cu * cF);
-        }
-        if (SCHEME == kSchemeEDM) {
-          value += rho * L::w(q) * eqShifted.template shape<q>() - (fq - nq);
-        }
-        storeOutgoing(qc, value);
+        constexpr double inverse = C::inverseScale(L::norm2(q));
+        const double f2 = myF[C::row(q) * kStepBlock], n2 = myN[C::row(q) * kStepBlock];
+        const double value = (f2 - omega * n2) * inverse + source.template value<q>((f2 - n2) * inverse);
+        storePopulation(next + q * p.stride + out, value);
+        if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
+        if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
       });
-    } else {
+      if (p.isStored) storeNodeFields<L, StoreT>(p, node, rho, invRho, u, F, energy, speed2);
+    }
+    if (p.isStored) reduceBlockObservables(p, x, energy, active ? rho : 0.0, speed2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The fused step.
+// grid = (ceil(NR / kStepBlock), NM, number of x planes [/ planesPerBlock]), block = kStepBlock threads along r.
+// ------------------------------------------------------------------------------------------------
+template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
+__global__ void __launch_bounds__(kStepBlock, COLLISION == kELBM ? entropicBlocksPerSM(L::Q) : 1)
+fusedStepKernel(const __grid_constant__ StepParams p) {
+  if constexpr (COLLISION == kELBM) {
+    entropicStepBody<L, EQ, SCHEME, StoreT>(p);
+  } else {
+    constexpr int Q = L::Q;
+    const int r = blockIdx.x * kStepBlock + threadIdx.x;
+    const int m = blockIdx.y;
+    const int x = p.x0 + (int)blockIdx.z * p.planeStep;
+    const bool active = r < p.NR;
+    double rho = 0.0, energy = 0.0, speed2 = 0.0;
+    if (active) {
+      const NodeIndex n = nodeIndex(p, x, m, r);
+      StoreT* __restrict__ next = static_cast<StoreT*>(p.next);
+      double f[Q];
+      pullPopulations<L, StoreT>(p, n, f);
+      double invRho, u2, u[3], F[3];
+      moments<L>(f, rho, invRho, u, u2);
+      bodyForce<L>(p, x, m, r, F);
+      EquilibriumCoefficients<L, EQ> eq;
+      eq.set(u, u2);
+      SourceTerm<L, EQ, SCHEME> source;
+      source.set(p, rho, invRho, u, F);
+
+      const long long node = (long long)x * p.plane + (long long)m * p.NR + r;  // field index
+      const long long out = (long long)n.xh * p.plane + (long long)m * p.NR + r;
+      // halo planes of the neighbours this node's outgoing populations belong to (block-uniform conditions)
+      StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
+      StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
       // Collision<BGK>::collideAndStream (Collision.h:134-151)
       const double keep = 1.0 - 2.0 * p.beta;
       const double relax = 2.0 * p.beta;
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         const double feq = rho * L::w(q) * eq.template shape<q>();
-        double value = keep * f[q] + relax * feq;
-        if (SCHEME == kSchemeGuo) {
-          double cF = 0.0, cu = 0.0;
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            if (L::c(q, d) == 1) { cF += F[d]; cu += u[d]; }
-            if (L::c(q, d) == -1) { cF -= F[d]; cu -= u[d]; }
-          }
-          value += p.guoFactor * L::w(q) * (cF - uF + 3.0 * cu * cF);
-        }
-        if (SCHEME == kSchemeEDM) {
-          value += rho * L::w(q) * eqShifted.template shape<q>() - feq;
-        }
-        storeOutgoing(qc, value);
+        const double value = keep * f[q] + relax * feq + source.template value<q>(feq);
+        storePopulation(next + q * p.stride + out, value);
+        if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
+        if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
       });
+      // BGK's alpha field is the constant 2 (Collision.h:121) and is not stored
+      if (p.isStored) storeNodeFields<L, StoreT>(p, node, rho, invRho, u, F, energy, speed2);
     }
-
-    if (p.isStored) {
-      // Algorithm::storeFields (Algorithm.h:150-194); BGK's alpha field is the constant 2 (Collision.h:121)
-      const bool fields = (p.isStored & 1) != 0;
-      if (fields) static_cast<StoreT*>(p.density)[node] = (StoreT)rho;
-      const double half = p.hydroShift ? 0.5 * invRho : 0.0;
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        const double v = u[d] + half * F[d];
-        if (fields) {
-          static_cast<StoreT*>(p.velocity)[d * p.fieldStride + node] = (StoreT)v;
-          static_cast<StoreT*>(p.force)[d * p.fieldStride + node] = (StoreT)F[d];
-        }
-        energy += 0.5 * rho * v * v;  // TotalEnergy (Analysis.h:53-61)
-        speed2 += v * v;
-      }
-    }
-  }
-
-  if (p.isStored) {
-    // block reduction: warp shuffles, then one value per warp through shared memory
-    double mass = active ? rho : 0.0;
-#pragma unroll
-    for (int offset = 16; offset > 0; offset >>= 1) {
-      energy += __shfl_xor_sync(0xffffffffu, energy, offset);
-      mass += __shfl_xor_sync(0xffffffffu, mass, offset);
-      speed2 = fmax(speed2, __shfl_xor_sync(0xffffffffu, speed2, offset));
-    }
-    __shared__ double scratch[kObservableSlots][kStepBlock / 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (lane == 0) {
-      scratch[0][warp] = energy;
-      scratch[1][warp] = mass;
-      scratch[2][warp] = speed2;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double e = 0.0, ms = 0.0, s2 = 0.0;
-#pragma unroll
-      for (int i = 0; i < kStepBlock / 32; ++i) {
-        e += scratch[0][i];
-        ms += scratch[1][i];
-        s2 = fmax(s2, scratch[2][i]);
-      }
-      const long long block = ((long long)x * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-      p.partials[block * kObservableSlots + 0] = e;
-      p.partials[block * kObservableSlots + 1] = ms;
-      p.partials[block * kObservableSlots + 2] = s2;
-    }
+    if (p.isStored) reduceBlockObservables(p, x, energy, active ? rho : 0.0, speed2);
   }
 }
 
