@@ -109,6 +109,24 @@ int mlbm_destroy(mlbm_ctx* ctx);
 int mlbm_comm_unique_id(void* id128);
 int mlbm_comm_init(mlbm_ctx* ctx, const void* id128);
 
+/* The device-independent part of one launch of the fused kernel over local planes x0 + i * plane_step, i < x1 - x0:
+ * grid, block, dynamic shared memory and every scalar kernel parameter, exactly as mlbm_step assembles them (pure host
+ * logic, no device needed).  The CPU test-suite pins these against the configuration: a launch with, say, beta = 0
+ * or without the periodic wrap would still run at full speed and only a GPU parity test could tell. */
+typedef struct mlbm_launch_plan {
+  int32_t grid[3];
+  int32_t block;
+  int32_t shared_bytes;
+  int32_t x0, plane_step, plane_count, planes_per_block;
+  int32_t local_length[3];      /* LX, NM, NR: extents on the kernel axes (slab, middle, unit stride) */
+  int32_t wrap_x;               /* 1: single rank, x wraps inside the slab; 0: halo planes hold the neighbours' data */
+  int32_t is_stored, hydro_shift, has_force;
+  uint64_t stride, plane;       /* elements between populations / between x planes */
+  double beta;                  /* 1 / (2 tau)                 (Collision.h:122) */
+  double guo_factor;            /* (1 - 1/(2 tau)) * inv_cs2   (ForcingScheme.h:115) */
+} mlbm_launch_plan;
+int mlbm_launch_plan_for(const mlbm_config* config, int x0, int x1, int is_stored, int plane_step, mlbm_launch_plan* out);
+
 /* Direct peer halos (optional, one process per GPU on one NVLink/NVSwitch box).  Every rank exports a
  * MLBM_PEER_HANDLE_BYTES blob (CUDA IPC handles of its two population buffers and of its handshake words), the
  * caller ships the blobs between ranks (any transport, like the NCCL id) and every rank attaches the blobs of its

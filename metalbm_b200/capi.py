@@ -99,6 +99,28 @@ class MlbmDeviceLayout(ctypes.Structure):
     ]
 
 
+class MlbmLaunchPlan(ctypes.Structure):
+    """``mlbm_launch_plan`` (include/metalbm_b200.h)."""
+    _fields_ = [
+        ("grid", ctypes.c_int32 * 3),
+        ("block", ctypes.c_int32),
+        ("shared_bytes", ctypes.c_int32),
+        ("x0", ctypes.c_int32),
+        ("plane_step", ctypes.c_int32),
+        ("plane_count", ctypes.c_int32),
+        ("planes_per_block", ctypes.c_int32),
+        ("local_length", ctypes.c_int32 * 3),
+        ("wrap_x", ctypes.c_int32),
+        ("is_stored", ctypes.c_int32),
+        ("hydro_shift", ctypes.c_int32),
+        ("has_force", ctypes.c_int32),
+        ("stride", ctypes.c_uint64),
+        ("plane", ctypes.c_uint64),
+        ("beta", ctypes.c_double),
+        ("guo_factor", ctypes.c_double),
+    ]
+
+
 class MlbmHaloMessage(ctypes.Structure):
     """``mlbm_halo_message`` (include/metalbm_b200.h)."""
     _fields_ = [
@@ -154,6 +176,8 @@ PROTOTYPES = {
     "mlbm_destroy": (ctypes.c_int, [_P]),
     "mlbm_halo_plan": (ctypes.c_int, [ctypes.POINTER(MlbmConfig), ctypes.POINTER(MlbmHaloMessage), ctypes.c_int,
                                       ctypes.POINTER(ctypes.c_int)]),
+    "mlbm_launch_plan_for": (ctypes.c_int, [ctypes.POINTER(MlbmConfig), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            ctypes.POINTER(MlbmLaunchPlan)]),
     "mlbm_comm_unique_id": (ctypes.c_int, [_P]),
     "mlbm_comm_init": (ctypes.c_int, [_P, _P]),
     "mlbm_comm_peer_export": (ctypes.c_int, [_P, _P]),
@@ -220,6 +244,13 @@ def halo_plan(cfg: MlbmConfig) -> list:
     messages = (MlbmHaloMessage * max(count.value, 1))()
     check(lib.mlbm_halo_plan(ctypes.byref(cfg), messages, count.value, ctypes.byref(count)))
     return [messages[i] for i in range(count.value)]
+
+
+def launch_plan(cfg: MlbmConfig, x0: int, x1: int, is_stored: int = 0, plane_step: int = 1) -> MlbmLaunchPlan:
+    """Grid and scalar kernel parameters of one fused-kernel launch (pure host logic, runs without a GPU)."""
+    plan = MlbmLaunchPlan()
+    check(load_library().mlbm_launch_plan_for(ctypes.byref(cfg), x0, x1, is_stored, plane_step, ctypes.byref(plan)))
+    return plan
 
 
 def check(status: int) -> None:

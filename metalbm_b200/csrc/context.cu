@@ -357,6 +357,68 @@ static int collectProfile(mlbm_ctx* ctx) {
   return MLBM_OK;
 }
 
+// geometry shared by the context and the (device-free) halo plan
+struct SlabGeometry {
+  int D, Q, faceQ, LX, NM, NR;
+  long long plane, stride;
+};
+
+static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
+  g->Q = latticeQ(config->lattice);
+  if (!g->Q || config->nranks < 1 || config->global_length[0] % config->nranks) return false;
+  g->D = latticeDim(config->lattice);
+  g->faceQ = latticeFaceQ(config->lattice);
+  g->LX = config->global_length[0] / config->nranks;
+  g->NM = g->D == 3 ? config->global_length[1] : 1;
+  g->NR = g->D == 3 ? config->global_length[2] : config->global_length[1];
+  g->plane = (long long)g->NM * g->NR;
+  const long long perPopulation = g->plane * (g->LX + 2);
+  g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
+  return true;
+}
+
+// Everything of a launch that does not depend on device memory: the scalar kernel parameters and the grid.  Shared by
+// launchStep and by mlbm_launch_plan_for, the device-free mirror the CPU test-suite checks (a launch whose scalars are
+// silently wrong -- beta = 0, no periodic wrap -- still runs at full speed and only a GPU parity test would notice).
+static void fillLaunchScalars(const mlbm_config& config, const SlabGeometry& g, int gridR, bool entropic, int hydroShift, int x0,
+                              int x1, int isStored, int planeStep, StepParams* p, dim3* grid) {
+  p->stride = g.stride;
+  p->plane = g.plane;
+  p->LX = g.LX; p->NM = g.NM; p->NR = g.NR;
+  p->x0 = x0;
+  p->planeStep = planeStep;
+  p->planeCount = x1 - x0;
+  p->wrapX = config.nranks == 1 ? 1 : 0;
+  p->isStored = isStored;
+  p->hydroShift = hydroShift;
+  p->hasForce = config.force != MLBM_FORCE_NONE;
+  p->beta = 1.0 / (2.0 * config.tau);
+  p->guoFactor = (1.0 - 1.0 / (2.0 * config.tau)) * 3.0;
+  // entropic kernels stage their logarithm table and constants once per block: let a block walk up to 16 planes
+  // (measured: +30 % on D2Q9 8192^2, +11 % on D3Q27 512^3 against one plane per block) while the grid keeps >= ~20 waves
+  static const int planesOverride = getenv("MLBM_PLANES_PER_BLOCK") ? atoi(getenv("MLBM_PLANES_PER_BLOCK")) : 0;  // experiments
+  p->planesPerBlock = 1;
+  if (entropic && planeStep == 1) {
+    const long long blocks = (long long)gridR * g.NM * p->planeCount;
+    const long long wanted = 148LL * 4 * 20;
+    long long planes = blocks / wanted;
+    planes = planes < 1 ? 1 : (planes > 16 ? 16 : planes);
+    p->planesPerBlock = planesOverride > 0 ? planesOverride : (int)planes;
+  }
+  *grid = dim3((unsigned)gridR, (unsigned)g.NM, (unsigned)((p->planeCount + p->planesPerBlock - 1) / p->planesPerBlock));
+}
+
+// forcing scheme -> (kernel scheme, hydrodynamic velocity shift); ShanChen shares the kernel of None (ForcingScheme.h:141-151)
+static bool schemeOf(int forcingScheme, int* scheme, int* hydroShift) {
+  switch (forcingScheme) {
+    case MLBM_SCHEME_NONE: *scheme = kSchemeNone; *hydroShift = 0; return true;
+    case MLBM_SHAN_CHEN: *scheme = kSchemeNone; *hydroShift = 1; return true;
+    case MLBM_GUO: *scheme = kSchemeGuo; *hydroShift = 1; return true;
+    case MLBM_EXACT_DIFFERENCE: *scheme = kSchemeEDM; *hydroShift = 1; return true;
+    default: return false;
+  }
+}
+
 // one launch of the fused kernel over local planes [x0, x1)
 static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int isStored, bool profile, int planeStep = 1,
                       void* peerLow = nullptr, void* peerHigh = nullptr) {
@@ -371,26 +433,13 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
   p.force = ctx->force;
   p.partials = ctx->partials;
   for (int d = 0; d < 3; ++d) { p.forceTable[d] = ctx->forceTables[d]; p.forceAxis[d] = ctx->forceAxis[d]; }
-  p.stride = ctx->stride;
-  p.plane = ctx->plane;
   p.fieldStride = ctx->fieldStride;
-  p.LX = ctx->LX; p.NM = ctx->NM; p.NR = ctx->NR;
-  p.x0 = x0;
-  p.planeStep = planeStep;
-  p.planeCount = x1 - x0;
-  // entropic kernels stage their logarithm table once per block: let a block walk a few planes when there are plenty
-  // entropic kernels stage their logarithm table and constants once per block: let a block walk up to 16 planes
-  // (measured: +30 % on D2Q9 8192^2, +11 % on D3Q27 512^3 against one plane per block) while the grid keeps >= ~20 waves
-  static const int planesOverride = getenv("MLBM_PLANES_PER_BLOCK") ? atoi(getenv("MLBM_PLANES_PER_BLOCK")) : 0;  // experiments
-  p.planesPerBlock = 1;
-  if (ctx->alpha && planeStep == 1) {
-    const long long blocks = (long long)ctx->gridR * ctx->NM * p.planeCount;
-    const long long wanted = 148LL * 4 * 20;
-    long long planes = blocks / wanted;
-    planes = planes < 1 ? 1 : (planes > 16 ? 16 : planes);
-    p.planesPerBlock = planesOverride > 0 ? planesOverride : (int)planes;
-  }
-  dim3 grid((unsigned)ctx->gridR, (unsigned)ctx->NM, (unsigned)((p.planeCount + p.planesPerBlock - 1) / p.planesPerBlock));
+  p.peerLow = peerLow;
+  p.peerHigh = peerHigh;
+  SlabGeometry geometry;
+  slabGeometry(&ctx->config, &geometry);
+  dim3 grid;
+  fillLaunchScalars(ctx->config, geometry, ctx->gridR, ctx->alpha != nullptr, ctx->hydroShift, x0, x1, isStored, planeStep, &p, &grid);
   cudaEvent_t start = nullptr, stop = nullptr;
   if (profile) {
     if (ctx->profileUsed + 2 > ctx->profileEvents.size()) {
@@ -415,26 +464,6 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
   MLBM_CUDA(cudaGetLastError());
   ctx->launches += 1;
   return MLBM_OK;
-}
-
-// geometry shared by the context and the (device-free) halo plan
-struct SlabGeometry {
-  int D, Q, faceQ, LX, NM, NR;
-  long long plane, stride;
-};
-
-static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
-  g->Q = latticeQ(config->lattice);
-  if (!g->Q || config->nranks < 1 || config->global_length[0] % config->nranks) return false;
-  g->D = latticeDim(config->lattice);
-  g->faceQ = latticeFaceQ(config->lattice);
-  g->LX = config->global_length[0] / config->nranks;
-  g->NM = g->D == 3 ? config->global_length[1] : 1;
-  g->NR = g->D == 3 ? config->global_length[2] : config->global_length[1];
-  g->plane = (long long)g->NM * g->NR;
-  const long long perPopulation = g->plane * (g->LX + 2);
-  g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
-  return true;
 }
 
 // Communication::communicateHalos (Communication.h:494-500) as a list of messages: the last interior plane of
@@ -655,13 +684,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
     case MLBM_ELBM: case MLBM_FORCED_NR_ELBM: collision = kELBM; break;  // identical in the reference snapshot (Collision.h:239, 705-723)
     default: return fail(MLBM_ERR_INVALID, "unknown collision %d", config->collision);
   }
-  switch (config->forcing_scheme) {
-    case MLBM_SCHEME_NONE: scheme = kSchemeNone; hydroShift = 0; break;
-    case MLBM_SHAN_CHEN: scheme = kSchemeNone; hydroShift = 1; break;
-    case MLBM_GUO: scheme = kSchemeGuo; hydroShift = 1; break;
-    case MLBM_EXACT_DIFFERENCE: scheme = kSchemeEDM; hydroShift = 1; break;
-    default: return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
-  }
+  if (!schemeOf(config->forcing_scheme, &scheme, &hydroShift)) return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
   if (config->force < MLBM_FORCE_NONE || config->force > MLBM_FORCE_KOLMOGOROV) return fail(MLBM_ERR_INVALID, "unknown force %d", config->force);
   if (config->equilibrium != MLBM_TRUNCATION_MA3 && config->equilibrium != MLBM_EXACT) return fail(MLBM_ERR_INVALID, "unknown equilibrium %d", config->equilibrium);
   StepKernel kernel = lookupStepKernel(config->lattice, collision, config->equilibrium, scheme, config->dtype);
@@ -775,6 +798,32 @@ int mlbm_halo_plan(const mlbm_config* config, mlbm_halo_message* out, int capaci
     if (capacity < (int)plan.size()) return fail(MLBM_ERR_INVALID, "capacity %d < %d messages", capacity, (int)plan.size());
     memcpy(out, plan.data(), plan.size() * sizeof(mlbm_halo_message));
   }
+  return MLBM_OK;
+}
+
+int mlbm_launch_plan_for(const mlbm_config* config, int x0, int x1, int isStored, int planeStep, mlbm_launch_plan* out) {
+  if (!config || !out) return fail(MLBM_ERR_INVALID, "null argument");
+  SlabGeometry g;
+  if (!slabGeometry(config, &g)) return fail(MLBM_ERR_INVALID, "bad lattice or nranks does not divide globalLengthX");
+  int scheme, hydroShift;
+  if (!schemeOf(config->forcing_scheme, &scheme, &hydroShift)) return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
+  if (!(config->tau > 0.5)) return fail(MLBM_ERR_INVALID, "relaxation time must exceed 0.5 (got %g)", config->tau);
+  if (x0 < 0 || x1 > g.LX || x1 <= x0 || planeStep < 1 || x0 + (x1 - x0 - 1) * planeStep >= g.LX) return fail(MLBM_ERR_INVALID, "bad plane range");
+  const bool entropic = config->collision != MLBM_BGK;
+  const int gridR = (g.NR + kStepBlock - 1) / kStepBlock;
+  StepParams p;
+  memset(&p, 0, sizeof(p));
+  dim3 grid;
+  fillLaunchScalars(*config, g, gridR, entropic, hydroShift, x0, x1, isStored, planeStep, &p, &grid);
+  memset(out, 0, sizeof(*out));
+  out->grid[0] = (int32_t)grid.x; out->grid[1] = (int32_t)grid.y; out->grid[2] = (int32_t)grid.z;
+  out->block = kStepBlock;
+  out->shared_bytes = entropic ? entropicSharedBytes(g.Q, logTableInShared(g.Q)) : 0;
+  out->x0 = p.x0; out->plane_step = p.planeStep; out->plane_count = p.planeCount; out->planes_per_block = p.planesPerBlock;
+  out->local_length[0] = p.LX; out->local_length[1] = p.NM; out->local_length[2] = p.NR;
+  out->wrap_x = p.wrapX; out->is_stored = p.isStored; out->hydro_shift = p.hydroShift; out->has_force = p.hasForce;
+  out->stride = (uint64_t)p.stride; out->plane = (uint64_t)p.plane;
+  out->beta = p.beta; out->guo_factor = p.guoFactor;
   return MLBM_OK;
 }
 

@@ -171,3 +171,65 @@ def test_halo_plan_over_gloo(cuda_lib, oracle_lib, tmp_path, world):
         outputs.append(out)
     for r, (p, out) in enumerate(zip(procs, outputs)):
         assert p.returncode == 0 and f"ok {r}" in out, out[-2000:]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The scalar kernel parameters and the grid of a launch, as mlbm_step assembles them (device-free mirror).  A launch
+# whose scalars are silently wrong (beta = 0, no periodic wrap, stored flag dropped) runs at full speed and produces
+# plausible-looking numbers: this is the CPU-side guard.
+# ---------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("lattice,shape,collision,scheme,force,tau,nranks", [
+    ("D3Q19", (256, 256, 256), "BGK", "None", "None", 0.55, 1),
+    ("D3Q19", (1024, 1024, 1024), "BGK", "Guo", "Kolmogorov", 0.55, 8),
+    ("D3Q27", (512, 512, 512), "ELBM", "Guo", "Kolmogorov", 0.50000032, 1),
+    ("D2Q9", (8192, 8192, 1), "ELBM", "ShanChen", "Kolmogorov", 0.7, 8),
+    ("D2Q9", (24, 130, 1), "ForcedNR_ELBM", "ExactDifferenceMethod", "Constant", 0.9, 2),
+])
+def test_launch_plan_scalars_follow_the_configuration(cuda_lib, lattice, shape, collision, scheme, force, tau, nranks):
+    cfg = capi.make_config(lattice=lattice, shape=shape, collision=collision, forcing_scheme=scheme, force=force, tau=tau,
+                           nranks=nranks, rank=nranks - 1, overlap="On")
+    dim, q = capi.LATTICE_DQ[capi.Lattice(cfg.lattice)]
+    lx = shape[0] // nranks
+    nm, nr = (shape[1], shape[2]) if dim == 3 else (1, shape[1])
+    for is_stored in (0, 1, 2):
+        plan = capi.launch_plan(cfg, 0, lx, is_stored)
+        assert plan.beta == 1.0 / (2.0 * tau)                                  # Collision.h:122
+        assert plan.guo_factor == (1.0 - 1.0 / (2.0 * tau)) * 3.0              # ForcingScheme.h:115
+        assert plan.wrap_x == (1 if nranks == 1 else 0)
+        assert plan.is_stored == is_stored
+        assert plan.hydro_shift == (0 if scheme == "None" else 1)              # ForcingScheme.h:26-33 / :50-57
+        assert plan.has_force == (0 if force == "None" else 1)
+        assert list(plan.local_length) == [lx, nm, nr]
+        assert plan.plane == nm * nr and plan.stride >= plan.plane * (lx + 2) and plan.stride % 32 == 0
+        assert plan.block == 128 and plan.grid[0] == -(-nr // 128) and plan.grid[1] == nm
+        assert plan.x0 == 0 and plan.plane_step == 1 and plan.plane_count == lx
+        # every plane is covered exactly once
+        assert plan.grid[2] == -(-lx // plan.planes_per_block)
+        entropic = collision != "BGK"
+        assert (plan.shared_bytes > 2 * q * 128 * 8) == entropic
+        assert plan.shared_bytes <= 227 * 1024
+        if not entropic:
+            assert plan.planes_per_block == 1
+        else:
+            assert 1 <= plan.planes_per_block <= 16
+            # the grid keeps at least ~20 waves of 4 blocks on 148 SMs whenever blocks walk several planes
+            assert plan.planes_per_block == 1 or plan.grid[0] * plan.grid[1] * plan.grid[2] >= 148 * 4 * 20 // 2
+
+
+def test_launch_plan_of_the_two_boundary_planes(cuda_lib):
+    """Overlapped multi-GPU steps compute planes 0 and LX - 1 in one launch (plane_step = LX - 1), one plane per block."""
+    cfg = capi.make_config(lattice="D3Q27", shape=(512, 512, 512), collision="ELBM", forcing_scheme="Guo", force="Kolmogorov",
+                           tau=0.55, nranks=8, rank=3, overlap="On")
+    lx = 64
+    plan = capi.launch_plan(cfg, 0, 2, 1, lx - 1)
+    assert (plan.x0, plan.plane_step, plan.plane_count, plan.planes_per_block, plan.grid[2]) == (0, lx - 1, 2, 1, 2)
+    assert plan.wrap_x == 0 and plan.is_stored == 1 and plan.beta == 1.0 / 1.1
+    bulk = capi.launch_plan(cfg, 1, lx - 1, 0)
+    assert bulk.x0 == 1 and bulk.plane_count == lx - 2 and bulk.grid[2] * bulk.planes_per_block >= lx - 2
+
+
+def test_launch_plan_rejects_bad_ranges(cuda_lib):
+    cfg = capi.make_config(lattice="D2Q9", shape=(16, 12, 1), tau=0.7)
+    plan = capi.MlbmLaunchPlan()
+    for x0, x1, step in ((0, 0, 1), (-1, 4, 1), (0, 17, 1), (0, 2, 16), (3, 2, 1)):
+        assert cuda_lib.mlbm_launch_plan_for(ctypes.byref(cfg), x0, x1, 0, step, ctypes.byref(plan)) == -1

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from helpers import check_entropic, relative_error, run_cuda, run_oracle
-from metalbm_b200.capi import make_config
+from metalbm_b200.capi import check, make_config
 from oracle import oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -135,7 +135,7 @@ def test_enstrophy_needs_the_stored_velocity_field():
     with Algorithm(cfg) as algorithm:
         algorithm.distribution.set_interior(O.synthetic_populations(cfg, eps=1e-2))
         algorithm.unpack()
-        algorithm._lib.mlbm_step(algorithm._ctx, 1, 2)
+        check(algorithm._lib.mlbm_step(algorithm._ctx, 1, 2))
         observables = algorithm.observables()
         assert np.isfinite(observables[0]) and np.isnan(observables[1])
 
@@ -179,3 +179,97 @@ def test_table_logarithm_against_high_precision():
     tail = out[v.size:]
     assert tail[0] == -np.inf and np.isnan(tail[1]) and tail[2] == np.inf and np.isnan(tail[3]) and np.isnan(tail[5])
     assert abs(tail[4] - np.log(5e-324)) <= 1e-12
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Edge cases: extents of 2 and 3 (both neighbours of a node are the same periodic image), rows that are not a multiple
+# of the 128-thread block, and entropic launches whose blocks walk several planes.
+# ---------------------------------------------------------------------------------------------------------------
+EDGE_CASES = [
+    ("D2Q9", (2, 2, 1), "BGK"), ("D2Q9", (2, 3, 1), "BGK"), ("D2Q9", (3, 2, 1), "ELBM"), ("D2Q9", (2, 257, 1), "ELBM"),
+    ("D3Q19", (2, 2, 2), "BGK"), ("D3Q19", (2, 2, 3), "BGK"), ("D3Q19", (3, 2, 2), "ELBM"), ("D3Q19", (2, 3, 127), "ELBM"),
+    ("D3Q27", (2, 2, 129), "BGK"), ("D3Q27", (2, 2, 2), "ELBM"),
+]
+
+
+@pytest.mark.parametrize("case", EDGE_CASES, ids=lambda c: f"{c[0]}-{'x'.join(map(str, c[1]))}-{c[2]}")
+def test_degenerate_and_ragged_extents(case):
+    lattice, shape, collision = case
+    cfg = _config(lattice, shape, "TruncationMa3", "Guo", "Kolmogorov", 0.6, collision)
+    f0 = O.synthetic_populations(cfg, eps=2e-2)
+    for steps in (1, 3):
+        got = run_cuda(cfg, f0, steps)
+        ref = run_oracle(cfg, f0, steps)
+        if collision == "BGK":
+            assert relative_error(got["f"], ref.f) <= POPULATION_TOLERANCE
+        else:
+            check_entropic(got, ref, cfg, steps, mismatch_budget=0.02 if np.prod(shape) >= 100 else 0.0)
+        obs = ref.observables()
+        assert abs(got["observables"][0] - obs[0]) <= ENERGY_TOLERANCE * abs(obs[0])
+        if obs[1] > 0:
+            assert abs(got["observables"][1] - obs[1]) <= 1e-8 * abs(obs[1])
+
+
+def test_entropic_blocks_walking_several_planes():
+    """Enough blocks (gridR * planes >= 2 * 148 * 4 * 20) that every block of the entropic kernel walks two planes, with an odd
+    plane count so that the last block stops early; dense Newton regime."""
+    cfg = _config("D2Q9", (12001, 256, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM")
+    f0 = O.synthetic_populations(cfg, eps=2e-2)
+    got = run_cuda(cfg, f0, 1)
+    ref = run_oracle(cfg, f0, 1)
+    check_entropic(got, ref, cfg, 1, mismatch_budget=1e-3)
+    assert (ref.branch >= 2).mean() > 0.5   # most nodes take the Newton solve (branch 2: converged, 3: fell back to 2)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE sizes: properties that do not need the (slow) CPU oracle.
+# ---------------------------------------------------------------------------------------------------------------
+def _device_run(cfg, eps, steps, store_every):
+    from metalbm_b200.algorithm import Algorithm
+    with Algorithm(cfg, host_distribution=False) as algorithm:
+        domain = algorithm.domain
+        shape = domain.local_length
+        x = (2 * np.pi * np.arange(shape[0]) / shape[0])[:, None, None]
+        y = (2 * np.pi * np.arange(shape[1]) / shape[1])[None, :, None]
+        z = (2 * np.pi * np.arange(shape[2]) / shape[2])[None, None, :]
+        fields = algorithm.fieldList
+        domain.interior(fields.density)[0] = 1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z)
+        domain.interior(fields.velocity)[0] = 0.05 * np.sin(x) * np.cos(y) * np.cos(z)
+        domain.interior(fields.velocity)[1] = -0.05 * np.cos(x) * np.sin(y) * np.cos(z)
+        if domain.dim == 3:
+            domain.interior(fields.velocity)[2] = 0.025 * np.cos(x) * np.cos(y) * np.sin(z)
+        algorithm.init_equilibrium()
+        if eps:
+            algorithm.perturb(eps)
+        rows = []
+        for iteration in range(1, steps + 1):
+            stored = iteration == 1 or iteration % store_every == 0
+            check(algorithm._lib.mlbm_step(algorithm._ctx, iteration, 1 if stored else 0))
+            if stored:
+                rows.append(algorithm.observables())
+        return np.array(rows)
+
+
+def test_mass_conservation_at_256_cubed():
+    """BASELINE configs[1] at full size (D3Q19 BGK 256^3, unforced): total mass is conserved to rounding by every step
+    (the reference's own invariant, SURVEY.md 8c: drift <= 5e-15 per 100 steps on 64^3); energy, enstrophy and the Mach
+    number stay finite, positive and subsonic."""
+    cfg = make_config(lattice="D3Q19", shape=(256, 256, 256), collision="BGK", forcing_scheme="None", force="None", tau=0.55)
+    rows = _device_run(cfg, 0.0, 40, 10)
+    mass = rows[:, 3]
+    assert np.abs(mass / mass[0] - 1.0).max() <= 1e-12
+    assert np.all(np.isfinite(rows)) and np.all(rows[:, 0] > 0) and np.all(rows[:, 1] > 0)
+    assert np.all(rows[:, 2] < 0.3)
+
+
+def test_entropic_mass_conservation_at_baseline_sizes():
+    """BASELINE configs[2] / configs[3] shapes, reduced to what finishes in seconds (D3Q27 ELBM Guo 256^3 and D2Q9 ELBM
+    Shan-Chen 4096^2, 2 % noise so that the Newton branch runs everywhere): the entropic relaxation conserves mass whatever
+    alpha is, and alpha stays inside (1, 2.5]."""
+    for lattice, shape, scheme in (("D3Q27", (256, 256, 256), "Guo"), ("D2Q9", (4096, 4096, 1), "ShanChen")):
+        cfg = make_config(lattice=lattice, shape=shape, collision="ELBM", forcing_scheme=scheme, force="Kolmogorov", tau=0.55,
+                          amplitude=(1e-5, 1e-5, 1e-5), wavelength=(32.0, 32.0, 32.0))
+        rows = _device_run(cfg, 2e-2, 6, 3)
+        mass = rows[:, 3]
+        assert np.abs(mass / mass[0] - 1.0).max() <= 1e-12, lattice
+        assert np.all(np.isfinite(rows))
