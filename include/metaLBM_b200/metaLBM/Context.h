@@ -21,7 +21,12 @@ namespace b200 {
 
 constexpr int abiCollision(CollisionType c) {
   return c == CollisionType::BGK ? (int)MLBM_BGK : c == CollisionType::ELBM ? (int)MLBM_ELBM
-       : c == CollisionType::ForcedNR_ELBM ? (int)MLBM_FORCED_NR_ELBM : -1;
+       : c == CollisionType::ForcedNR_ELBM ? (int)MLBM_FORCED_NR_ELBM
+       : c == CollisionType::Approached_ELBM ? (int)MLBM_APPROACHED_ELBM
+       : c == CollisionType::Malaspinas_ELBM ? (int)MLBM_MALASPINAS_ELBM
+       : c == CollisionType::Essentially1_ELBM ? (int)MLBM_ESSENTIALLY1_ELBM
+       : c == CollisionType::Essentially2_ELBM ? (int)MLBM_ESSENTIALLY2_ELBM
+       : c == CollisionType::ForcedBNR_ELBM ? (int)MLBM_FORCED_BNR_ELBM : -1;
 }
 constexpr int abiEquilibrium(EquilibriumType e) {
   return e == EquilibriumType::TruncationMa3 ? (int)MLBM_TRUNCATION_MA3 : e == EquilibriumType::Exact ? (int)MLBM_EXACT : -1;
@@ -36,7 +41,7 @@ constexpr int abiForce(ForceType f) {
        : f == ForceType::Sinusoidal ? (int)MLBM_FORCE_SINUSOIDAL : f == ForceType::Kolmogorov ? (int)MLBM_FORCE_KOLMOGOROV : -1;
 }
 
-static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or ForcedNR_ELBM (SURVEY.md 8a a9-a10)");
+static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or one of the entropic variants that behave like ELBM in the reference (Approached_, Malaspinas_, Essentially1_, Essentially2_, ForcedNR_, ForcedBNR_ELBM); ForcedNR_ELBM_Forcing has no device kernel yet");
 static_assert(abiEquilibrium(equilibriumT) >= 0, "metalbm_b200: equilibriumT must be TruncationMa3 or Exact");
 static_assert(abiScheme(forcingSchemeT) >= 0, "metalbm_b200: forcingSchemeT must be None, Guo, ShanChen or ExactDifferenceMethod");
 static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal or Kolmogorov (spectral forces are out of scope)");

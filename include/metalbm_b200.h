@@ -45,9 +45,17 @@ typedef enum mlbm_lattice {
   MLBM_D2Q5 = 0, MLBM_D2Q9 = 1, MLBM_D3Q15 = 2, MLBM_D3Q19 = 3, MLBM_D3Q27 = 4
 } mlbm_lattice;
 
-/* CollisionType (Options.h:35-38; Collision.h:103-180 BGK, :182-376 ELBM, :684-724 ForcedNR_ELBM) */
+/* CollisionType (Options.h:35-38; Collision.h:103-180 BGK, :182-376 ELBM).
+ * In the reference snapshot Approached_ELBM (:378-459), Malaspinas_ELBM (:461-539), Essentially1/2_ELBM (:543-682),
+ * ForcedNR_ELBM (:684-724) and ForcedBNR_ELBM (:864-909) only override the PRIVATE, non-virtual calculateAlpha, which the
+ * inherited Collision<ELBM>::calculateRelaxationTime (:227-241) never calls: they compile and run bit-identically to
+ * ELBM (checked against the compiled reference, tests/test_oracle_vs_reference.py) and share its kernel here.
+ * ForcedNR_ELBM_Forcing (:727-857) is a different algorithm (alpha solved on the FORCED populations f + S with the
+ * mirror functor EntropicStep.h:65-108, no small-deviation shortcut): restated in the oracle and pinned by golden
+ * vectors; its device kernel is not built yet and mlbm_create refuses it. */
 typedef enum mlbm_collision {
-  MLBM_BGK = 0, MLBM_ELBM = 1, MLBM_FORCED_NR_ELBM = 2
+  MLBM_BGK = 0, MLBM_ELBM = 1, MLBM_FORCED_NR_ELBM = 2, MLBM_APPROACHED_ELBM = 3, MLBM_MALASPINAS_ELBM = 4,
+  MLBM_ESSENTIALLY1_ELBM = 5, MLBM_ESSENTIALLY2_ELBM = 6, MLBM_FORCED_BNR_ELBM = 7, MLBM_FORCED_NR_ELBM_FORCING = 8
 } mlbm_collision;
 
 /* EquilibriumType (Options.h:33; Equilibrium.h:14-34 TruncationMa3, :36-126 Exact) */

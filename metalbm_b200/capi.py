@@ -30,6 +30,12 @@ class Collision(enum.IntEnum):
     BGK = 0
     ELBM = 1
     ForcedNR_ELBM = 2
+    Approached_ELBM = 3
+    Malaspinas_ELBM = 4
+    Essentially1_ELBM = 5
+    Essentially2_ELBM = 6
+    ForcedBNR_ELBM = 7
+    ForcedNR_ELBM_Forcing = 8
 
 
 class Equilibrium(enum.IntEnum):

@@ -681,7 +681,11 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   int collision, scheme, hydroShift;
   switch (config->collision) {
     case MLBM_BGK: collision = kBGK; break;
-    case MLBM_ELBM: case MLBM_FORCED_NR_ELBM: collision = kELBM; break;  // identical in the reference snapshot (Collision.h:239, 705-723)
+    // identical to ELBM in the reference snapshot: their calculateAlpha overrides are dead code (Collision.h:239, 705-723)
+    case MLBM_ELBM: case MLBM_FORCED_NR_ELBM: case MLBM_APPROACHED_ELBM: case MLBM_MALASPINAS_ELBM:
+    case MLBM_ESSENTIALLY1_ELBM: case MLBM_ESSENTIALLY2_ELBM: case MLBM_FORCED_BNR_ELBM: collision = kELBM; break;
+    case MLBM_FORCED_NR_ELBM_FORCING:
+      return fail(MLBM_ERR_INVALID, "ForcedNR_ELBM_Forcing (Collision.h:727-857) has an oracle and golden vectors but no device kernel yet");
     default: return fail(MLBM_ERR_INVALID, "unknown collision %d", config->collision);
   }
   if (!schemeOf(config->forcing_scheme, &scheme, &hydroShift)) return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);

@@ -225,6 +225,28 @@ static double calculate_alpha(const lattice_t* L, const double* f, const double*
   return ok ? alpha : 2.0;
 }
 
+/* Collision<ForcedNR_ELBM_Forcing>::calculateAlpha (Collision.h:792-808) with its own calculateAlphaMax (:810-832,
+ * min over fNeq_q > 0 of |ff_q / fNeq_q|, start 2.5) and solveAlpha (:835-855) on the mirror functor
+ * EntropicStepFunctor<T,true> (EntropicStep.h:65-108), i.e. the ELBM entropy condition written for the FORCED
+ * populations ff = f + S.  No small-deviation shortcut.  branch: 1 = alphaMax < 2, 2 = Newton converged in range,
+ * 3 = Newton failed (alpha = 2). */
+static double calculate_alpha_forcing(const lattice_t* L, const double* ff, const double* fNeq, double alphaGuess,
+                                      int* branch, int* iterations) {
+  double alphaMax = 2.5;
+  for (int q = 0; q < L->Q; ++q) {
+    if (fNeq[q] > 0) {
+      double t = fabs(ff[q] / fNeq[q]);
+      if (t < alphaMax) alphaMax = t;
+    }
+  }
+  if (iterations) *iterations = 0;
+  if (alphaMax < 2.) { if (branch) *branch = 1; return 0.95 * alphaMax; }
+  double alpha = alphaGuess;
+  int ok = newton_raphson(L, ff, fNeq, 1e-8, 50, &alpha, 1., alphaMax, iterations);
+  if (branch) *branch = ok ? 2 : 3;
+  return ok ? alpha : 2.0;
+}
+
 /* Checker-side diagnostic (not in the reference): how far double rounding alone can move the Newton iterate.
  * F(alpha) is a difference of two sums of magnitude ~rho that cancel to O(fNeq^2) and F'(alpha) is O(fNeq^2) as
  * well (sum fNeq = 0), so one Newton step carries an absolute uncertainty of about
@@ -286,7 +308,29 @@ int mlbm_oracle_step_ex(const mlbm_config* cfg, const double* prev, double* next
         body_force(&L, cfg, p, F);
 
         double a = 2.0;
-        if (entropic) {
+        if (cfg->collision == MLBM_FORCED_NR_ELBM_FORCING) {
+          /* Collision<ForcedNR_ELBM_Forcing>::calculateRelaxationTime (Collision.h:757-778): next = f + S(feq), the pulled
+           * population of `prev` is overwritten by fNeq = f - feq; then alpha on (next, fNeq) and
+           * collideAndStream (:780-789): next -= 1/tau * fNeq */
+          double ff[MAXQ];
+          for (int q = 0; q < L.Q; ++q) {
+            const double feq_q = equilibrium(&L, cfg->equilibrium, rho, u, u2, q);
+            ff[q] = f[q] + collision_source(&L, cfg, F, rho, u, u2, feq_q, q);
+            fNeq[q] = f[q] - feq_q;
+          }
+          int branch = 0, iterations = 0;
+          a = calculate_alpha_forcing(&L, ff, fNeq, alpha[idx], &branch, &iterations);
+          if (branchOut) branchOut[idx] = branch;
+          if (iterationsOut) iterationsOut[idx] = iterations;
+          if (alphaNoiseOut) alphaNoiseOut[idx] = branch >= 2 ? alpha_rounding_noise(&L, ff, fNeq, a) : 0.0;
+          if (fNeqMaxOut) {
+            double m = 0.0;
+            for (int q = 0; q < L.Q; ++q) if (fabs(fNeq[q]) > m) m = fabs(fNeq[q]);
+            fNeqMaxOut[idx] = m;
+          }
+          const double tau = 1.0 / (a * beta);
+          for (int q = 0; q < L.Q; ++q) next[(size_t)q * V + idx] = ff[q] - 1.0 / tau * fNeq[q];
+        } else if (entropic) {
           /* Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241) */
           for (int q = 0; q < L.Q; ++q) fNeq[q] = f[q] - equilibrium(&L, cfg->equilibrium, rho, u, u2, q);
           int branch = 0, iterations = 0;

@@ -38,13 +38,26 @@ CASES = [
     ("d3q27_elbm_guo", "D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
     ("d3q27_elbm_exact", "D3Q27", (8, 6, 4), "ELBM", "Exact", "Guo", "Kolmogorov", 0.50000032, 2e-2, 0.05, 0.05, 2, 1),
     ("d3q27_forcednr_elbm", "D3Q27", (6, 6, 4), "ForcedNR_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+    # the remaining alpha models of Collision.h: dead overrides, the reference runs them exactly like ELBM
+    ("d2q9_approached_elbm", "D2Q9", (12, 10, 1), "Approached_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 0.05, 0.05, 2, 1),
+    ("d2q9_malaspinas_elbm", "D2Q9", (12, 10, 1), "Malaspinas_ELBM", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.51, 2e-2, 0.05, 0.05, 2, 1),
+    ("d3q19_essentially1_elbm", "D3Q19", (6, 4, 4), "Essentially1_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 0.05, 0.05, 2, 1),
+    ("d3q19_essentially2_elbm", "D3Q19", (6, 4, 4), "Essentially2_ELBM", "TruncationMa3", "ShanChen", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+    ("d3q27_forcedbnr_elbm", "D3Q27", (6, 6, 4), "ForcedBNR_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+    # ForcedNR_ELBM_Forcing (Collision.h:727-857): alpha solved on the forced populations (oracle only, no device kernel yet)
+    ("d2q9_forcednr_elbm_forcing", "D2Q9", (12, 10, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 0.05, 0.05, 3, 1),
+    ("d3q19_forcednr_elbm_forcing", "D3Q19", (6, 4, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 0.05, 0.05, 2, 1),
+    ("d3q27_forcednr_elbm_forcing_edm", "D3Q27", (6, 6, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
 ]
+ONLY = set(sys.argv[1:])   # optional: names of the cases to (re)generate; default all
 AMPLITUDE = (1e-4, 2e-4, 3e-4)
 WAVELENGTH = (8.0, 4.0, 16.0)
 
 
 def main():
     for name, lattice, shape, collision, equilibrium, scheme, force, tau, eps, flow, ripple, steps, ranks in CASES:
+        if ONLY and name not in ONLY:
+            continue
         ref_cfg = RefConfig(lattice=lattice, nx=shape[0], ny=shape[1], nz=shape[2], collision=collision,
                             equilibrium=equilibrium, forcing_scheme=scheme, force=force, tau=tau,
                             amplitude=AMPLITUDE, wavelength=WAVELENGTH, nprocs=ranks)

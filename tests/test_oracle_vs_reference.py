@@ -14,7 +14,33 @@ CASES = [
     ("D3Q19", (8, 6, 4), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 1e-3, 4),
     ("D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 1),
     ("D2Q9", (16, 12, 1), "ELBM", "Exact", "ExactDifferenceMethod", "Kolmogorov", 0.51, 2e-2, 2),
+    # alpha models whose overrides are dead code in the snapshot (== ELBM) and the one that is not
+    ("D2Q9", (12, 10, 1), "Approached_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
+    ("D2Q9", (12, 10, 1), "Malaspinas_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
+    ("D2Q9", (12, 10, 1), "Essentially1_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
+    ("D2Q9", (12, 10, 1), "Essentially2_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
+    ("D2Q9", (12, 10, 1), "ForcedBNR_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
+    ("D2Q9", (12, 10, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
+    ("D3Q27", (6, 6, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 1),
+    ("D3Q19", (6, 4, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 1),
 ]
+
+
+def test_dead_alpha_overrides_equal_elbm_in_the_reference(oracle_lib):
+    """Approached_, Malaspinas_, Essentially1/2_, ForcedNR_ and ForcedBNR_ELBM only override the private non-virtual
+    calculateAlpha that Collision<ELBM>::calculateRelaxationTime never calls (Collision.h:239): the compiled reference
+    produces bit-identical populations and alpha for all of them, which is why they share the ELBM kernel."""
+    base = dict(lattice="D2Q9", nx=12, ny=10, nz=1, equilibrium="TruncationMa3", forcing_scheme="Guo", force="Kolmogorov", tau=0.51)
+    _reference_or_skip(refbuild.RefConfig(collision="ELBM", **base))
+    cfg = make_config(lattice="D2Q9", shape=(12, 10, 1), collision="ELBM", forcing_scheme="Guo", force="Kolmogorov", tau=0.51,
+                      amplitude=(1e-5, 1e-5, 1e-5))
+    f0 = O.synthetic_populations(cfg, eps=2e-2)
+    expected = refbuild.run_ref(refbuild.RefConfig(collision="ELBM", **base), f0, 2)
+    for collision in ("Approached_ELBM", "Malaspinas_ELBM", "Essentially1_ELBM", "Essentially2_ELBM", "ForcedNR_ELBM", "ForcedBNR_ELBM"):
+        got = refbuild.run_ref(refbuild.RefConfig(collision=collision, **base), f0, 2)
+        assert np.array_equal(got["f"], expected["f"]) and np.array_equal(got["alpha"], expected["alpha"]), collision
+    different = refbuild.run_ref(refbuild.RefConfig(collision="ForcedNR_ELBM_Forcing", **base), f0, 2)
+    assert not np.array_equal(different["alpha"], expected["alpha"])
 
 
 def _reference_or_skip(ref_cfg):
