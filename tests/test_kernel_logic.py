@@ -1,0 +1,359 @@
+"""The LOGIC of the fused step kernels, checked on the CPU: the kernel source (metalbm_b200/csrc/step_kernel.cuh) is compiled
+for the host under a small CUDA-execution-model emulator (tests/emu: every CUDA thread is a fiber, __syncthreads and the warp
+collectives are real rendezvous, shared memory is NaN-poisoned per block) and run on arrays laid out exactly as
+csrc/context.cu lays them out, with the launch scalars taken from the library's own device-free mirror (mlbm_launch_plan_for)
+and the halo messages from mlbm_halo_plan.  Compared with the oracle at BASELINE.json's tolerances.
+
+This is test infrastructure: it catches index, barrier, plane-loop, compaction and halo-store mistakes without a GPU.  It
+is NOT a CPU fallback (nothing under metalbm_b200/ can reach it) and proves nothing about hardware behaviour or speed: the
+`-m gpu` suite remains the parity gate for the CUDA build."""
+import ctypes
+import math
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from helpers import check_entropic, relative_error, run_oracle
+from metalbm_b200 import capi
+from metalbm_b200.capi import LATTICE_DQ, Lattice, make_config
+from oracle import oracle as O
+
+sys.path.insert(0, str(Path(__file__).resolve().parent / "emu"))
+import build as emu_build  # noqa: E402
+
+
+class EmuLaunch(ctypes.Structure):
+    _fields_ = [("lattice", ctypes.c_int), ("collision", ctypes.c_int), ("equilibrium", ctypes.c_int), ("scheme", ctypes.c_int),
+                ("f32", ctypes.c_int),
+                ("prev", ctypes.c_void_p), ("next", ctypes.c_void_p), ("alpha", ctypes.c_void_p), ("density", ctypes.c_void_p),
+                ("velocity", ctypes.c_void_p), ("force", ctypes.c_void_p), ("partials", ctypes.c_void_p),
+                ("forceTable", ctypes.c_void_p * 3), ("forceAxis", ctypes.c_int * 3),
+                ("stride", ctypes.c_longlong), ("plane", ctypes.c_longlong), ("fieldStride", ctypes.c_longlong),
+                ("LX", ctypes.c_int), ("NM", ctypes.c_int), ("NR", ctypes.c_int), ("x0", ctypes.c_int), ("planeCount", ctypes.c_int),
+                ("planeStep", ctypes.c_int), ("planesPerBlock", ctypes.c_int),
+                ("peerLow", ctypes.c_void_p), ("peerHigh", ctypes.c_void_p),
+                ("wrapX", ctypes.c_int), ("isStored", ctypes.c_int), ("hydroShift", ctypes.c_int), ("hasForce", ctypes.c_int),
+                ("beta", ctypes.c_double), ("guoFactor", ctypes.c_double)]
+
+
+@pytest.fixture(scope="session")
+def emu(cuda_lib):
+    lib = ctypes.CDLL(str(emu_build.build()))
+    lib.emu_fused_step.argtypes = [ctypes.POINTER(EmuLaunch)]
+    lib.emu_fused_step.restype = ctypes.c_int
+    return lib
+
+
+SCHEME_KERNEL = {0: 0, 1: 1, 2: 0, 3: 2}   # None, Guo, ShanChen (kernel of None), ExactDifferenceMethod  (context.cu: schemeOf)
+
+
+class Slab:
+    """One rank's device state as csrc/context.cu allocates it: two SoA population buffers with one halo plane on each
+    side in x, the alpha field, the stored fields, the per-block observable partials and the host-libm force tables."""
+
+    def __init__(self, emu, cfg, dtype=np.float64):
+        self.emu, self.cfg, self.dtype = emu, cfg, dtype
+        self.dim, self.q = LATTICE_DQ[Lattice(cfg.lattice)]
+        self.plan = capi.launch_plan(cfg, 0, cfg.global_length[0] // cfg.nranks)
+        self.lx, self.nm, self.nr = self.plan.local_length
+        self.stride, self.plane = int(self.plan.stride), int(self.plan.plane)
+        self.nodes = self.lx * self.plane
+        self.field_stride = (self.nodes + 31) // 32 * 32
+        self.populations = [np.zeros(self.q * self.stride, dtype=dtype) for _ in range(2)]
+        self.current = 0
+        self.alpha = np.full(self.nodes, 2.0, dtype=dtype)              # initAlpha (Initialize.h:82-88)
+        self.density = np.zeros(self.field_stride, dtype=dtype)
+        self.velocity = np.zeros(self.dim * self.field_stride, dtype=dtype)
+        self.force = np.zeros(self.dim * self.field_stride, dtype=dtype)
+        grid_r = -(-self.nr // 128)
+        self.partials = np.full(grid_r * self.nm * self.lx * 3, np.nan)
+        self.entropic = cfg.collision != capi.Collision.BGK
+        # force profiles exactly as mlbm_create evaluates them (context.cu), at LOCAL coordinates (Collision.h:86)
+        extent = [self.lx, cfg.global_length[1], cfg.global_length[2] if self.dim == 3 else 1]
+        kernel_axis_of = [0, 1 if self.dim == 3 else 2, 2]
+        self.force_tables, self.force_axis = [None, None, None], [-1, -1, -1]
+        for d in range(self.dim):
+            axis = -1
+            if cfg.force == capi.Force.Constant:
+                axis = 0
+            if cfg.force == capi.Force.Sinusoidal:
+                axis = d
+            if cfg.force == capi.Force.Kolmogorov and d == 0:
+                axis = 1
+            if axis < 0:
+                continue
+            if cfg.force == capi.Force.Constant:
+                table = [cfg.force_amplitude[d]] * extent[axis]
+            elif cfg.force == capi.Force.Sinusoidal:
+                table = [cfg.force_amplitude[d] * math.sin(i * 2 * math.pi / cfg.force_wavelength[d]) for i in range(extent[axis])]
+            else:
+                table = [cfg.force_amplitude[0] * math.sin(i * 2 * math.pi / cfg.force_wavelength[0]) for i in range(extent[axis])]
+            self.force_tables[d] = np.array(table, dtype=np.float64)
+            self.force_axis[d] = kernel_axis_of[axis]
+
+    # -- upload / download of the interior planes (Algorithm::unpack / pack) --
+    def view(self, which):
+        """[Q, LX + 2, NM, NR] window (no copy) onto buffer `which`: population q starts at q * stride."""
+        item = self.populations[which].itemsize
+        return np.lib.stride_tricks.as_strided(
+            self.populations[which], shape=(self.q, self.lx + 2, self.nm, self.nr),
+            strides=(self.stride * item, self.plane * item, self.nr * item, item))
+
+    def upload(self, f):
+        self.view(self.current)[:, 1:self.lx + 1] = f.reshape(self.q, self.lx, self.nm, self.nr)
+
+    def download(self):
+        return self.view(self.current)[:, 1:self.lx + 1].astype(np.float64).copy()
+
+    def launch(self, x0, x1, is_stored, plane_step=1, planes_per_block=None, peer_low=None, peer_high=None):
+        plan = capi.launch_plan(self.cfg, x0, x1, is_stored, plane_step)
+        e = EmuLaunch()
+        e.lattice, e.collision = int(self.cfg.lattice), 1 if self.entropic else 0
+        e.equilibrium, e.scheme = int(self.cfg.equilibrium), SCHEME_KERNEL[int(self.cfg.forcing_scheme)]
+        e.f32 = 1 if self.dtype == np.float32 else 0
+        e.prev = self.populations[self.current].ctypes.data
+        e.next = self.populations[self.current ^ 1].ctypes.data
+        e.alpha, e.density = self.alpha.ctypes.data, self.density.ctypes.data
+        e.velocity, e.force, e.partials = self.velocity.ctypes.data, self.force.ctypes.data, self.partials.ctypes.data
+        for d in range(3):
+            e.forceTable[d] = self.force_tables[d].ctypes.data if self.force_tables[d] is not None else None
+            e.forceAxis[d] = self.force_axis[d]
+        e.stride, e.plane, e.fieldStride = self.stride, self.plane, self.field_stride
+        e.LX, e.NM, e.NR = self.lx, self.nm, self.nr
+        e.x0, e.planeCount, e.planeStep = plan.x0, plan.plane_count, plan.plane_step
+        e.planesPerBlock = planes_per_block if planes_per_block else plan.planes_per_block
+        e.peerLow = peer_low.ctypes.data if peer_low is not None else None
+        e.peerHigh = peer_high.ctypes.data if peer_high is not None else None
+        e.wrapX, e.isStored, e.hydroShift, e.hasForce = plan.wrap_x, plan.is_stored, plan.hydro_shift, plan.has_force
+        e.beta, e.guoFactor = plan.beta, plan.guo_factor
+        assert self.emu.emu_fused_step(ctypes.byref(e)) == 0, "no such kernel instantiation"
+
+    def fields(self):
+        shape = (self.lx, self.nm, self.nr)
+        return dict(density=self.density[:self.nodes].reshape(shape).astype(np.float64),
+                    velocity=np.stack([self.velocity[d * self.field_stride:d * self.field_stride + self.nodes].reshape(shape)
+                                       for d in range(self.dim)]).astype(np.float64),
+                    force=np.stack([self.force[d * self.field_stride:d * self.field_stride + self.nodes].reshape(shape)
+                                    for d in range(self.dim)]).astype(np.float64),
+                    alpha=self.alpha.reshape(shape).astype(np.float64))
+
+    def observables(self, global_volume):
+        partials = self.partials.reshape(-1, 3)
+        return partials[:, 0].sum() / global_volume, partials[:, 1].sum(), math.sqrt(partials[:, 2].max() * 3.0)
+
+
+def kernel_shape(cfg, array):
+    """[..., nx, ny, nz] (oracle order) -> [..., x, m, r] (kernel axes): the same memory order; 2-D has m == 1."""
+    dim = LATTICE_DQ[Lattice(cfg.lattice)][0]
+    nx, ny, nz = (int(cfg.global_length[i]) for i in range(3))
+    lead = array.shape[:-3]
+    return array.reshape(lead + ((nx, ny, nz) if dim == 3 else (nx, 1, ny)))
+
+
+def run_single(emu, cfg, f0, steps, planes_per_block=None, dtype=np.float64):
+    slab = Slab(emu, cfg, dtype)
+    slab.upload(kernel_shape(cfg, f0).astype(dtype))
+    for step in range(1, steps + 1):
+        slab.launch(0, slab.lx, 1 if step == steps else 0, planes_per_block=planes_per_block)
+        slab.current ^= 1
+    out = slab.fields()
+    shape = f0.shape[1:]
+    got = {"f": slab.download().reshape(f0.shape), "alpha": out["alpha"].reshape(shape), "density": out["density"].reshape(shape),
+           "velocity": out["velocity"].reshape((slab.dim,) + shape), "force": out["force"].reshape((slab.dim,) + shape)}
+    got["observables"] = slab.observables(float(np.prod(shape)))
+    return got
+
+
+def _config(lattice, shape, collision, equilibrium="TruncationMa3", scheme="Guo", force="Kolmogorov", tau=0.55, **extra):
+    return make_config(lattice=lattice, shape=shape, collision=collision, equilibrium=equilibrium, forcing_scheme=scheme,
+                       force=force, tau=tau, amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0), **extra)
+
+
+def _compare(cfg, got, ref, steps, entropic):
+    if entropic:
+        check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3)
+    else:
+        assert relative_error(got["f"], ref.f) <= 1e-12
+        assert np.all(got["alpha"] == 2.0)      # untouched initial field: BGK never stores alpha
+    assert relative_error(got["density"], ref.density) <= 1e-12
+    assert np.abs(got["velocity"] - ref.velocity).max() <= 1e-13
+    assert np.array_equal(got["force"], ref.force)
+    obs = ref.observables()
+    energy, mass, mach = got["observables"]
+    assert abs(energy - obs[0]) <= 1e-9 * abs(obs[0]) and abs(mass - obs[3]) <= 1e-12 * abs(obs[3]) and abs(mach - obs[2]) <= 1e-12 * obs[2] + 1e-13
+
+
+SINGLE_CASES = [
+    # lattice, shape, collision, equilibrium, scheme, force, tau, eps, steps
+    ("D2Q9", (12, 10, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.7, 1e-2, 3),
+    ("D2Q9", (5, 130, 1), "BGK", "Exact", "ExactDifferenceMethod", "Sinusoidal", 0.7, 1e-2, 2),
+    ("D2Q5", (6, 7, 1), "BGK", "TruncationMa3", "Guo", "Constant", 0.8, 1e-2, 2),
+    ("D3Q15", (4, 3, 5), "BGK", "TruncationMa3", "ShanChen", "Kolmogorov", 0.6, 1e-2, 2),
+    ("D3Q19", (6, 4, 5), "BGK", "TruncationMa3", "None", "None", 0.55, 1e-2, 3),
+    ("D3Q19", (2, 2, 2), "BGK", "TruncationMa3", "Guo", "Sinusoidal", 0.9, 1e-2, 2),
+    ("D3Q27", (3, 4, 3), "BGK", "Exact", "Guo", "Kolmogorov", 0.55, 1e-2, 2),
+    ("D2Q9", (8, 12, 1), "ELBM", "TruncationMa3", "ShanChen", "Kolmogorov", 0.51, 2e-2, 2),
+    ("D2Q9", (6, 129, 1), "ELBM", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.51, 2e-2, 2),
+    ("D2Q9", (8, 12, 1), "ELBM", "Exact", "Guo", "Kolmogorov", 0.50000032, 5e-2, 2),
+    ("D2Q9", (8, 12, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 4e-4, 2),      # small-deviation shortcut
+    ("D2Q5", (6, 7, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.6, 2e-2, 2),
+    ("D3Q15", (4, 3, 5), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 1e-1, 2),
+    ("D3Q19", (4, 3, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 2),      # every alpha branch
+    ("D3Q27", (4, 3, 4), "ForcedNR_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 2),
+    ("D3Q27", (3, 2, 3), "Malaspinas_ELBM", "Exact", "ExactDifferenceMethod", "Kolmogorov", 0.50000032, 2e-2, 2),
+]
+
+
+def _flow(eps):
+    return dict(amplitude=0.05, ripple=0.05) if eps > 1e-3 else dict(amplitude=0.0, ripple=0.0)
+
+
+@pytest.mark.parametrize("case", SINGLE_CASES, ids=lambda c: "-".join(map(str, (c[0], "x".join(map(str, c[1])), c[2], c[3], c[4], c[5]))))
+def test_kernel_source_reproduces_the_oracle(emu, case):
+    lattice, shape, collision, equilibrium, scheme, force, tau, eps, steps = case
+    cfg = _config(lattice, shape, collision, equilibrium, scheme, force, tau)
+    f0 = O.synthetic_populations(cfg, eps=eps, **_flow(eps))
+    got = run_single(emu, cfg, f0, steps)
+    ref = run_oracle(cfg, f0, steps)
+    _compare(cfg, got, ref, steps, collision != "BGK")
+
+
+@pytest.mark.parametrize("planes_per_block", [2, 3, 16])
+@pytest.mark.parametrize("lattice,shape", [("D2Q9", (7, 140, 1)), ("D3Q19", (5, 2, 4))])
+def test_entropic_blocks_walking_several_planes(emu, lattice, shape, planes_per_block):
+    """One block of the entropic kernel handles `planes_per_block` consecutive planes, re-using its shared-memory columns,
+    list and counters; the plane count is not a multiple, so the last block stops early."""
+    cfg = _config(lattice, shape, "ELBM", tau=0.55)
+    f0 = O.synthetic_populations(cfg, eps=2e-2)
+    got = run_single(emu, cfg, f0, 2, planes_per_block=planes_per_block)
+    ref = run_oracle(cfg, f0, 2)
+    _compare(cfg, got, ref, 2, True)
+
+
+def test_sparse_newton_nodes_are_compacted_correctly(emu):
+    """A fluid at rest with a few strongly perturbed nodes: most threads of a block skip the solve, the listed ones are
+    solved by OTHER threads (block-level compaction) and must land in the right columns."""
+    cfg = _config("D2Q9", (6, 200, 1), "ELBM", tau=0.55)
+    f0 = O.synthetic_populations(cfg, eps=1e-5, amplitude=0.0, ripple=0.0)
+    rng = np.random.default_rng(3)
+    for _ in range(40):
+        x, y = rng.integers(0, 6), rng.integers(0, 200)
+        f0[:, x, y, 0] *= 1.0 + 0.05 * rng.standard_normal(9)
+    got = run_single(emu, cfg, f0, 1)
+    ref = run_oracle(cfg, f0, 1)
+    assert 0 < (ref.branch >= 2).sum() < 0.5 * ref.branch.size and (ref.branch == 0).any()
+    _compare(cfg, got, ref, 1, True)
+
+
+def test_fp32_storage(emu):
+    cfg = _config("D2Q9", (8, 12, 1), "BGK", tau=0.7)
+    f0 = O.synthetic_populations(cfg, eps=1e-2).astype(np.float32).astype(np.float64)
+    got = run_single(emu, cfg, f0, 1, dtype=np.float32)
+    ref = run_oracle(cfg, f0, 1)
+    assert relative_error(got["f"], ref.f) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# x-slabs: the decomposition logic of csrc/context.cu (enqueueStep) replayed on the host around the emulated kernel.
+# ---------------------------------------------------------------------------------------------------------------
+def _slabs(emu, config, world, f0):
+    slabs = []
+    for rank in range(world):
+        cfg = _config(rank=rank, nranks=world, **config)
+        slab = Slab(emu, cfg)
+        lx = slab.lx
+        slab.upload(kernel_shape(cfg, f0)[:, rank * lx:(rank + 1) * lx])
+        slabs.append(slab)
+    return slabs
+
+
+def _exchange(slabs, which_of):
+    """Communication::communicateHalos as mlbm_halo_plan lists it: every send of rank r is matched, in order, with the
+    corresponding receive of its peer (what NCCL does inside one group)."""
+    world = len(slabs)
+    plans = [capi.halo_plan(s.cfg) for s in slabs]
+    for rank, slab in enumerate(slabs):
+        for peer in {(rank + 1) % world, (rank + world - 1) % world}:
+            sends = [m for m in plans[rank] if m.is_send and m.peer == peer]
+            receives = [m for m in plans[peer] if not m.is_send and m.peer == rank]
+            # with two ranks both neighbours are the same peer: right-going messages pair with left-halo receives by position
+            assert len(sends) == len(receives)
+            source, target = slab.populations[which_of(slab)], slabs[peer].populations[which_of(slabs[peer])]
+            for s, r in zip(sends, receives):
+                assert s.population == r.population and s.count == r.count
+                target[r.offset:r.offset + r.count] = source[s.offset:s.offset + s.count]
+
+
+def _gather(slabs, f0_shape):
+    f = np.concatenate([s.download() for s in slabs], axis=1).reshape(f0_shape)
+    alpha = np.concatenate([s.fields()["alpha"] for s in slabs], axis=0).reshape(f0_shape[1:])
+    return f, alpha
+
+
+MULTI_CASES = [
+    ("D3Q19", (8, 3, 4), "BGK", "Guo", "Kolmogorov"), ("D2Q9", (8, 10, 1), "BGK", "Guo", "Kolmogorov"),
+    ("D3Q27", (8, 2, 3), "ELBM", "Guo", "Kolmogorov"), ("D2Q9", (8, 9, 1), "ELBM", "ExactDifferenceMethod", "Kolmogorov"),
+]
+
+
+@pytest.mark.parametrize("mode", ["off", "overlap", "peer"])
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("case", MULTI_CASES, ids=lambda c: "-".join(map(str, (c[0], c[2], c[3]))))
+def test_slab_decomposition_logic(emu, case, world, mode):
+    """enqueueStep's three exchange modes on slabs down to ONE plane per rank (world 8 on 8 planes):
+    off     = exchange the halos of the buffer about to be read, then one launch over the slab (Algorithm.h:336-355);
+    overlap = boundary planes first (one launch, plane_step = LX - 1), exchange of the WRITTEN buffer, bulk launch;
+    peer    = the boundary launch stores its outgoing populations straight into the neighbours' halo planes.
+    The gathered result must equal the single-slab run of the same emulated kernel bit for bit, and the oracle within
+    BASELINE.json's tolerances."""
+    lattice, shape, collision, scheme, force = case
+    config = dict(lattice=lattice, shape=shape, collision=collision, scheme=scheme, force=force, tau=0.55)
+    single = _config(**config)
+    f0 = O.synthetic_populations(single, eps=1e-2)
+    steps = 3
+    slabs = _slabs(emu, config, world, f0)
+    lx = slabs[0].lx
+    halos_valid = False
+    for step in range(1, steps + 1):
+        stored = 1 if step == steps else 0
+        if mode == "off" or (mode == "overlap" and lx < 3):
+            _exchange(slabs, lambda s: s.current)
+            for s in slabs:
+                s.launch(0, lx, stored)
+        elif mode == "overlap":
+            if not halos_valid:
+                _exchange(slabs, lambda s: s.current)
+            for s in slabs:
+                s.launch(0, 1, stored)
+                s.launch(lx - 1, lx, stored)
+            _exchange(slabs, lambda s: s.current ^ 1)
+            for s in slabs:
+                s.launch(1, lx - 1, stored)
+            halos_valid = True
+        else:
+            if not halos_valid:
+                _exchange(slabs, lambda s: s.current)
+            for rank, s in enumerate(slabs):
+                left, right = slabs[(rank + world - 1) % world], slabs[(rank + 1) % world]
+                two = lx >= 2
+                s.launch(0, 2 if two else 1, stored, lx - 1 if two else 1,
+                         peer_low=left.populations[left.current ^ 1], peer_high=right.populations[right.current ^ 1])
+            for s in slabs:
+                if lx > 2:
+                    s.launch(1, lx - 1, stored)
+            halos_valid = True
+        for s in slabs:
+            s.current ^= 1
+    f, alpha = _gather(slabs, f0.shape)
+
+    one = run_single(emu, single, f0, steps)
+    assert np.array_equal(f, one["f"]) and np.array_equal(alpha, one["alpha"])
+    ref = run_oracle(single, f0, steps)
+    if collision == "BGK":
+        assert relative_error(f, ref.f) <= 1e-12 * steps
+    else:
+        check_entropic({"f": f, "alpha": alpha}, ref, single, steps, mismatch_budget=1e-3)
+    energy = sum(s.partials.reshape(-1, 3)[:, 0].sum() for s in slabs) / float(np.prod(shape))
+    assert abs(energy - ref.observables()[0]) <= 1e-9 * abs(ref.observables()[0])
