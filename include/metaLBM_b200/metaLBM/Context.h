@@ -26,7 +26,8 @@ constexpr int abiCollision(CollisionType c) {
        : c == CollisionType::Malaspinas_ELBM ? (int)MLBM_MALASPINAS_ELBM
        : c == CollisionType::Essentially1_ELBM ? (int)MLBM_ESSENTIALLY1_ELBM
        : c == CollisionType::Essentially2_ELBM ? (int)MLBM_ESSENTIALLY2_ELBM
-       : c == CollisionType::ForcedBNR_ELBM ? (int)MLBM_FORCED_BNR_ELBM : -1;
+       : c == CollisionType::ForcedBNR_ELBM ? (int)MLBM_FORCED_BNR_ELBM
+       : c == CollisionType::ForcedNR_ELBM_Forcing ? (int)MLBM_FORCED_NR_ELBM_FORCING : -1;
 }
 constexpr int abiEquilibrium(EquilibriumType e) {
   return e == EquilibriumType::TruncationMa3 ? (int)MLBM_TRUNCATION_MA3 : e == EquilibriumType::Exact ? (int)MLBM_EXACT : -1;
@@ -41,7 +42,7 @@ constexpr int abiForce(ForceType f) {
        : f == ForceType::Sinusoidal ? (int)MLBM_FORCE_SINUSOIDAL : f == ForceType::Kolmogorov ? (int)MLBM_FORCE_KOLMOGOROV : -1;
 }
 
-static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or one of the entropic variants that behave like ELBM in the reference (Approached_, Malaspinas_, Essentially1_, Essentially2_, ForcedNR_, ForcedBNR_ELBM); ForcedNR_ELBM_Forcing has no device kernel yet");
+static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or one of the entropic variants that behave like ELBM in the reference (Approached_, Malaspinas_, Essentially1_, Essentially2_, ForcedNR_, ForcedBNR_ELBM) or ForcedNR_ELBM_Forcing");
 static_assert(abiEquilibrium(equilibriumT) >= 0, "metalbm_b200: equilibriumT must be TruncationMa3 or Exact");
 static_assert(abiScheme(forcingSchemeT) >= 0, "metalbm_b200: forcingSchemeT must be None, Guo, ShanChen or ExactDifferenceMethod");
 static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal or Kolmogorov (spectral forces are out of scope)");

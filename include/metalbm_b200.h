@@ -51,8 +51,8 @@ typedef enum mlbm_lattice {
  * inherited Collision<ELBM>::calculateRelaxationTime (:227-241) never calls: they compile and run bit-identically to
  * ELBM (checked against the compiled reference, tests/test_oracle_vs_reference.py) and share its kernel here.
  * ForcedNR_ELBM_Forcing (:727-857) is a different algorithm (alpha solved on the FORCED populations f + S with the
- * mirror functor EntropicStep.h:65-108, no small-deviation shortcut): restated in the oracle and pinned by golden
- * vectors; its device kernel is not built yet and mlbm_create refuses it. */
+ * mirror functor EntropicStep.h:65-108, no small-deviation shortcut) with its own kernel variant, pinned by golden
+ * vectors of the reference. */
 typedef enum mlbm_collision {
   MLBM_BGK = 0, MLBM_ELBM = 1, MLBM_FORCED_NR_ELBM = 2, MLBM_APPROACHED_ELBM = 3, MLBM_MALASPINAS_ELBM = 4,
   MLBM_ESSENTIALLY1_ELBM = 5, MLBM_ESSENTIALLY2_ELBM = 6, MLBM_FORCED_BNR_ELBM = 7, MLBM_FORCED_NR_ELBM_FORCING = 8

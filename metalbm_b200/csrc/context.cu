@@ -684,8 +684,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
     // identical to ELBM in the reference snapshot: their calculateAlpha overrides are dead code (Collision.h:239, 705-723)
     case MLBM_ELBM: case MLBM_FORCED_NR_ELBM: case MLBM_APPROACHED_ELBM: case MLBM_MALASPINAS_ELBM:
     case MLBM_ESSENTIALLY1_ELBM: case MLBM_ESSENTIALLY2_ELBM: case MLBM_FORCED_BNR_ELBM: collision = kELBM; break;
-    case MLBM_FORCED_NR_ELBM_FORCING:
-      return fail(MLBM_ERR_INVALID, "ForcedNR_ELBM_Forcing (Collision.h:727-857) has an oracle and golden vectors but no device kernel yet");
+    case MLBM_FORCED_NR_ELBM_FORCING: collision = kELBMForcing; break;  // alpha solved on the forced populations (Collision.h:727-857)
     default: return fail(MLBM_ERR_INVALID, "unknown collision %d", config->collision);
   }
   if (!schemeOf(config->forcing_scheme, &scheme, &hydroShift)) return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
@@ -722,7 +721,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   ctx->partialBlocks = (long long)ctx->gridR * ctx->NM * ctx->LX;
   ctx->kernel = kernel;
   ctx->hydroShift = hydroShift;
-  if (collision == kELBM) {
+  if (collision != kBGK) {
     ctx->sharedBytes = entropicSharedBytes(Q, logTableInShared(Q));
     cudaError_t attributeError = cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->sharedBytes);
     if (attributeError != cudaSuccess) {
@@ -754,7 +753,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
     MLBM_CREATE_CUDA(cudaMalloc(&ctx->populations[i], bufferBytes));
     MLBM_CREATE_CUDA(cudaMemsetAsync(ctx->populations[i], 0, bufferBytes, ctx->computeStream));
   }
-  if (collision == kELBM) {
+  if (collision != kBGK) {
     // initAlpha: the alpha field starts at 2 (Initialize.h:82-88)
     MLBM_CREATE_CUDA(cudaMalloc(&ctx->alpha, (size_t)ctx->nodes * ctx->elementSize));
     const unsigned grid = (unsigned)((ctx->nodes + 255) / 256);

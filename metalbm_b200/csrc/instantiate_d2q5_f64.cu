@@ -27,6 +27,7 @@ static StepKernel pickEquilibrium(int equilibrium, int scheme) {
 StepKernel lookupStepKernel_d2q5_f64(int collision, int equilibrium, int scheme) {
   if (collision == kBGK) return pickEquilibrium<kBGK>(equilibrium, scheme);
   if (collision == kELBM) return pickEquilibrium<kELBM>(equilibrium, scheme);
+  if (collision == kELBMForcing) return pickEquilibrium<kELBMForcing>(equilibrium, scheme);
   return nullptr;
 }
 

@@ -29,6 +29,7 @@ static StepKernel pickEquilibrium(int equilibrium, int scheme) {
 StepKernel lookupStepKernel_d3q27_f32(int collision, int equilibrium, int scheme) {
   if (collision == kBGK) return pickEquilibrium<kBGK>(equilibrium, scheme);
   if (collision == kELBM) return pickEquilibrium<kELBM>(equilibrium, scheme);
+  if (collision == kELBMForcing) return pickEquilibrium<kELBMForcing>(equilibrium, scheme);
   return nullptr;
 }
 

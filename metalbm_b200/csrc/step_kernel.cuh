@@ -25,7 +25,8 @@
 
 namespace mlbm {
 
-enum CollisionKind { kBGK = 0, kELBM = 1 };
+// kELBMForcing = Collision<ForcedNR_ELBM_Forcing> (Collision.h:727-857): the entropic solve on the FORCED populations
+enum CollisionKind { kBGK = 0, kELBM = 1, kELBMForcing = 2 };
 enum EquilibriumKind { kTruncationMa3 = 0, kExact = 1 };
 // ShanChen has a zero collision source (ForcingScheme.h:141-151) and therefore shares the kernel of
 // "None"; the two only differ in the stored hydrodynamic velocity (hydroShift below).
@@ -600,7 +601,13 @@ __device__ __forceinline__ void reduceBlockObservables(const StepParams& p, int 
 // Entropic body: Collision<ELBM> (Collision.h:182-376); see the banner above entropicNewton.
 // grid = (ceil(NR / kStepBlock), NM, ceil(planes / planesPerBlock)); the block walks planesPerBlock planes.
 // ------------------------------------------------------------------------------------------------
-template <class L, int EQ, int SCHEME, typename StoreT>
+//
+// FORCED selects Collision<ForcedNR_ELBM_Forcing> (Collision.h:727-857): the populations handed to the solve are the
+// forced ones, ff_q = f_q + S_q(feq_q) (calculateRelaxationTime :757-778), alphaMax is min |ff_q / fNeq_q| over
+// fNeq_q > 0 (:810-832), there is no small-deviation shortcut (:792-808), the entropy condition is the mirror functor
+// EntropicStepFunctor<T, true> (EntropicStep.h:65-108; the same F and F' with ff in place of f) and the collide is
+// next = ff_q - alpha beta fNeq_q (:780-789).
+template <class L, int EQ, int SCHEME, typename StoreT, bool FORCED>
 __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
   constexpr int Q = L::Q;
   using C = SpeedClasses<L>;
@@ -661,13 +668,17 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       // two cheap screens of calculateAlpha run on the register values:
       //   isDeviationSmall (Collision.h:284-303): no |fNeq_q| / f_q above 1e-3
       //   calculateAlphaMax (Collision.h:305-326): min(2.5, min over fNeq_q > 0 of |f_q| / fNeq_q), tracked as a fraction
-      bool small = true;
+      bool small = !FORCED;  // the forced variant has no isDeviationSmall shortcut
       double num = 2.5, den = 1.0;
+      SourceTerm<L, EQ, SCHEME> forcedSource;
+      if (FORCED) forcedSource.set(p, rho, invRho, u, F);
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         constexpr double scale = C::scale(L::norm2(q));
-        const double fq = f[q];
-        const double nq = fq - rho * L::w(q) * eq.template shape<q>();
+        const double feq = rho * L::w(q) * eq.template shape<q>();
+        const double nq = f[q] - feq;
+        // the population the entropy condition is written for: f_q, or f_q + S_q for the forced variant
+        const double fq = FORCED ? f[q] + forcedSource.template value<q>(feq) : f[q];
         myF[C::row(q) * kStepBlock] = fq * scale;  // exact
         myN[C::row(q) * kStepBlock] = nq * scale;
         const double a = fabs(nq);
@@ -679,7 +690,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
         }
       });
       if (!small) {
-        // Collision<ELBM>::calculateAlpha (Collision.h:351-375)
+        // Collision<ELBM>::calculateAlpha (Collision.h:351-375) / Collision<ForcedNR_ELBM_Forcing>::calculateAlpha (:792-808)
         const double alphaMax = num / den;
         if (alphaMax < 2.0) alpha = 0.95 * alphaMax;
         else { needsNewton = true; s.alpha[t] = alphaMax; }
@@ -718,13 +729,15 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       alphaField[node] = (StoreT)alpha;
       const double omega = alpha * p.beta;  // 1 / tau_eff (Collision.h:240)
       SourceTerm<L, EQ, SCHEME> source;
-      source.set(p, rho, invRho, u, F);
-      // Collision<ELBM>::collideAndStream (Collision.h:243-258); the 2^k scaling of the stored values is undone exactly
+      if (!FORCED) source.set(p, rho, invRho, u, F);
+      // Collision<ELBM>::collideAndStream (Collision.h:243-258) / Collision<ForcedNR_ELBM_Forcing>::collideAndStream (:780-789,
+      // the source is already inside the stored populations); the 2^k scaling of the stored values is undone exactly
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         constexpr double inverse = C::inverseScale(L::norm2(q));
         const double f2 = myF[C::row(q) * kStepBlock], n2 = myN[C::row(q) * kStepBlock];
-        const double value = (f2 - omega * n2) * inverse + source.template value<q>((f2 - n2) * inverse);
+        double value = (f2 - omega * n2) * inverse;
+        if (!FORCED) value += source.template value<q>((f2 - n2) * inverse);
         storePopulation(next + q * p.stride + out, value);
         if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
         if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
@@ -740,10 +753,10 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
 // grid = (ceil(NR / kStepBlock), NM, number of x planes [/ planesPerBlock]), block = kStepBlock threads along r.
 // ------------------------------------------------------------------------------------------------
 template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
-__global__ void __launch_bounds__(kStepBlock, COLLISION == kELBM ? entropicBlocksPerSM(L::Q) : 1)
+__global__ void __launch_bounds__(kStepBlock, COLLISION != kBGK ? entropicBlocksPerSM(L::Q) : 1)
 fusedStepKernel(const __grid_constant__ StepParams p) {
-  if constexpr (COLLISION == kELBM) {
-    entropicStepBody<L, EQ, SCHEME, StoreT>(p);
+  if constexpr (COLLISION != kBGK) {
+    entropicStepBody<L, EQ, SCHEME, StoreT, COLLISION == kELBMForcing>(p);
   } else {
     constexpr int Q = L::Q;
     const int r = blockIdx.x * kStepBlock + threadIdx.x;

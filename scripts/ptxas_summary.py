@@ -13,6 +13,6 @@ for log in sorted(build.glob("instantiate_*.ptxas.log")):
                          r"ptxas info\s*: Function properties for \S+\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n"
                          r"ptxas info\s*: Used (\d+) registers(.*)", text):
         lattice, collision, eq, scheme, dtype, stack, sst, sld, regs, rest = m.groups()
-        label = f"{names[lattice]} {'ELBM' if collision == '1' else 'BGK '} {'Exact' if eq == '1' else 'Ma3  '} {['None', 'Guo ', 'EDM '][int(scheme)]} {'f64' if dtype == 'd' else 'f32'}"
+        label = f"{names[lattice]} { {'0': 'BGK ', '1': 'ELBM', '2': 'ELBF'}[collision] } {'Exact' if eq == '1' else 'Ma3  '} {['None', 'Guo ', 'EDM '][int(scheme)]} {'f64' if dtype == 'd' else 'f32'}"
         if pattern in label:
             print(f"{label}: {regs:>3} regs, stack {stack}, spill st/ld {sst}/{sld}{rest}")

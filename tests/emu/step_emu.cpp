@@ -33,7 +33,7 @@ static int run(const EmuLaunch& e) {
   p.beta = e.beta; p.guoFactor = e.guoFactor;
   const int gridR = (e.NR + kStepBlock - 1) / kStepBlock;
   const dim3 grid((unsigned)gridR, (unsigned)e.NM, (unsigned)((e.planeCount + e.planesPerBlock - 1) / e.planesPerBlock));
-  const size_t shared = COLLISION == kELBM ? (size_t)entropicSharedBytes(L::Q, logTableInShared(L::Q)) : 0;
+  const size_t shared = COLLISION != kBGK ? (size_t)entropicSharedBytes(L::Q, logTableInShared(L::Q)) : 0;
   cuda_emu::launch<StepParams>(fusedStepKernel<L, COLLISION, EQ, SCHEME, StoreT>, grid, kStepBlock, shared, p);
   return 0;
 }
@@ -51,11 +51,13 @@ static int runScheme(const EmuLaunch& e) {
 template <class L, bool HAS_EXACT, typename StoreT>
 static int runLattice(const EmuLaunch& e) {
   if (e.equilibrium == kTruncationMa3) {
-    return e.collision == kBGK ? runScheme<L, kBGK, kTruncationMa3, StoreT>(e) : runScheme<L, kELBM, kTruncationMa3, StoreT>(e);
+    return e.collision == kBGK ? runScheme<L, kBGK, kTruncationMa3, StoreT>(e)
+         : e.collision == kELBM ? runScheme<L, kELBM, kTruncationMa3, StoreT>(e) : runScheme<L, kELBMForcing, kTruncationMa3, StoreT>(e);
   }
   if constexpr (HAS_EXACT) {
     if (e.equilibrium == kExact)
-      return e.collision == kBGK ? runScheme<L, kBGK, kExact, StoreT>(e) : runScheme<L, kELBM, kExact, StoreT>(e);
+      return e.collision == kBGK ? runScheme<L, kBGK, kExact, StoreT>(e)
+           : e.collision == kELBM ? runScheme<L, kELBM, kExact, StoreT>(e) : runScheme<L, kELBMForcing, kExact, StoreT>(e);
   }
   return -1;
 }

@@ -11,8 +11,6 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_reproduces_reference_outputs(name):
     meta, cfg, data = load_golden(name)
-    if meta["collision"] == "ForcedNR_ELBM_Forcing":
-        pytest.skip("oracle and golden vectors only: the device kernel of ForcedNR_ELBM_Forcing is not built yet")
     got = run_cuda(cfg, data["f0"], meta["steps"])
     entropic = meta["collision"] != "BGK"
     if entropic:

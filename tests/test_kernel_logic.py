@@ -110,7 +110,8 @@ class Slab:
     def launch(self, x0, x1, is_stored, plane_step=1, planes_per_block=None, peer_low=None, peer_high=None):
         plan = capi.launch_plan(self.cfg, x0, x1, is_stored, plane_step)
         e = EmuLaunch()
-        e.lattice, e.collision = int(self.cfg.lattice), 1 if self.entropic else 0
+        e.lattice = int(self.cfg.lattice)
+        e.collision = 0 if not self.entropic else (2 if self.cfg.collision == capi.Collision.ForcedNR_ELBM_Forcing else 1)
         e.equilibrium, e.scheme = int(self.cfg.equilibrium), SCHEME_KERNEL[int(self.cfg.forcing_scheme)]
         e.f32 = 1 if self.dtype == np.float32 else 0
         e.prev = self.populations[self.current].ctypes.data
@@ -172,17 +173,23 @@ def _config(lattice, shape, collision, equilibrium="TruncationMa3", scheme="Guo"
 
 
 def _compare(cfg, got, ref, steps, entropic):
+    inherited = 0.0
     if entropic:
-        check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3)
+        # ill-conditioned Newton solves (tiny fNeq) make alpha, and with it the populations of the NEXT step, uncertain by the
+        # amount helpers.entropic_tolerances derives from the oracle's own rounding noise; moments inherit Q times that
+        _, population_tolerance = check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3)
+        inherited = ref.q * population_tolerance if steps > 1 else 0.0
     else:
         assert relative_error(got["f"], ref.f) <= 1e-12
         assert np.all(got["alpha"] == 2.0)      # untouched initial field: BGK never stores alpha
-    assert relative_error(got["density"], ref.density) <= 1e-12
-    assert np.abs(got["velocity"] - ref.velocity).max() <= 1e-13
+    assert np.abs(got["density"] - ref.density).max() <= 1e-12 * np.abs(ref.density).max() + inherited
+    assert np.abs(got["velocity"] - ref.velocity).max() <= 1e-13 + 2.0 * inherited
     assert np.array_equal(got["force"], ref.force)
     obs = ref.observables()
     energy, mass, mach = got["observables"]
-    assert abs(energy - obs[0]) <= 1e-9 * abs(obs[0]) and abs(mass - obs[3]) <= 1e-12 * abs(obs[3]) and abs(mach - obs[2]) <= 1e-12 * obs[2] + 1e-13
+    assert abs(energy - obs[0]) <= 1e-9 * abs(obs[0]) + inherited * inherited
+    assert abs(mass - obs[3]) <= 1e-12 * abs(obs[3]) + inherited * ref.f[0].size
+    assert abs(mach - obs[2]) <= 1e-12 * obs[2] + 1e-13 + 4.0 * inherited
 
 
 SINGLE_CASES = [
@@ -203,6 +210,13 @@ SINGLE_CASES = [
     ("D3Q19", (4, 3, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 2),      # every alpha branch
     ("D3Q27", (4, 3, 4), "ForcedNR_ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 2),
     ("D3Q27", (3, 2, 3), "Malaspinas_ELBM", "Exact", "ExactDifferenceMethod", "Kolmogorov", 0.50000032, 2e-2, 2),
+    # Collision<ForcedNR_ELBM_Forcing>: alpha solved on the forced populations, no small-deviation shortcut
+    ("D2Q9", (8, 12, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 3),
+    ("D2Q9", (6, 130, 1), "ForcedNR_ELBM_Forcing", "Exact", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 2),
+    ("D2Q9", (8, 12, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ShanChen", "Kolmogorov", 0.55, 4e-4, 2),
+    ("D3Q19", (4, 3, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 2),
+    ("D3Q27", (4, 3, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 2),
+    ("D3Q15", (4, 3, 5), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Constant", 0.6, 1e-1, 2),
 ]
 
 

@@ -67,6 +67,10 @@ ELBM_CASES = [
     ("D2Q9", (16, 12, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 4e-4),
     ("D3Q19", (8, 6, 4), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 3e-1),
     ("D3Q15", (8, 6, 4), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ELBM", 1e-1),
+    # Collision<ForcedNR_ELBM_Forcing> (Collision.h:727-857): alpha solved on the forced populations f + S
+    ("D2Q9", (16, 12, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.51, "ForcedNR_ELBM_Forcing", 2e-2),
+    ("D3Q27", (8, 6, 4), "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, "ForcedNR_ELBM_Forcing", 2e-2),
+    ("D3Q19", (8, 6, 4), "TruncationMa3", "Guo", "Kolmogorov", 0.55, "ForcedNR_ELBM_Forcing", 3e-1),
 ]
 
 
