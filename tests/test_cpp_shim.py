@@ -153,16 +153,49 @@ def test_template_api_reproduces_the_oracle(tmp_path, cuda_lib, world, case):
         assert node_error[alpha_ok].max() <= 1e-12 * np.abs(ref.f).max() + 2e-10 * ref.fneq_max.max()
 
 
+def test_observables_file_format_equals_the_reference(tmp_path):
+    """`../output/<prefix>/observables_<startIteration>.dat` as the drop-in ScalarAnalysisWriter writes it against the
+    committed bytes of the reference's own writer (Writer.h:140-190) and, where /root/reference is present, against the
+    reference class compiled on the spot."""
+    golden = (ROOT / "tests" / "golden" / "observables_reference_format.dat").read_bytes()
+    run = tmp_path / "ours" / "run"
+    run.mkdir(parents=True)
+    binary = compile_example(tmp_path, "observables_writer.cpp", "observables_writer", "D2Q9", (8, 6, 1), link=False)
+    assert subprocess.run([str(binary)], cwd=run).returncode == 0          # creates ../output/test/ itself
+    mine = (tmp_path / "ours" / "output" / "test" / "observables_7.dat").read_bytes()
+    assert mine == golden
+    from oracle import refbuild
+    if not refbuild.reference_available():
+        return
+    build = tmp_path / "reference"
+    (build / "run").mkdir(parents=True)
+    (build / "output" / "test").mkdir(parents=True)                         # the reference does not create it
+    (build / "Input.in").write_text(refbuild.input_in(refbuild.RefConfig(lattice="D2Q9", nx=8, ny=6, nz=1)).replace(
+        'constexpr auto prefix = "oracle";', 'constexpr auto prefix = "test";'))
+    command = ["g++", "-std=c++14", "-O1", "-w", "-DUSE_FFTW", "-DNPROCS=1", "-DNTHREADS=1", "-DGLOBAL_LENGTH_X=8",
+               "-DGLOBAL_LENGTH_Y=6", "-DGLOBAL_LENGTH_Z=1", '-DLBM_POSTFIX="test"', "-DOBSERVABLES_WRITER_REFERENCE",
+               f"-I{ROOT / 'oracle' / 'shim'}", f"-I{build}", f"-I{refbuild.REFERENCE_ROOT / 'include'}",
+               str(ROOT / "examples" / "observables_writer.cpp"), "-o", str(build / "writer")]
+    result = subprocess.run(command, capture_output=True, text=True)
+    assert result.returncode == 0, result.stderr[-3000:]
+    assert subprocess.run([str(build / "writer")], cwd=build / "run").returncode == 0
+    assert (build / "output" / "test" / "observables_7.dat").read_bytes() == golden
+
+
 @pytest.mark.gpu
 def test_reference_style_routine_runs(tmp_path, cuda_lib):
     """src/main.cu with Architecture::GPU: Routine::compute from a density peak, observables against the oracle."""
     shape = (64, 48, 1)
     binary = compile_example(tmp_path, "main_gpu.cpp", "main_gpu", "D2Q9", shape, scheme="Guo", force="Kolmogorov", tau=0.55,
                              steps=100)
-    result = subprocess.run([str(binary)], capture_output=True, text=True, cwd=tmp_path, timeout=300)
+    run = tmp_path / "run"
+    run.mkdir()
+    result = subprocess.run([str(binary)], capture_output=True, text=True, cwd=run, timeout=300)
     assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
-    table = np.loadtxt(tmp_path / "observables_test.dat", skiprows=1)
-    assert table.shape == (2, 5) and table[:, 0].tolist() == [50, 100]
+    # the reference's file (../output/<prefix>/observables_<startIteration>.dat, three columns) and the B200 extras next to it
+    table = np.loadtxt(tmp_path / "output" / "test" / "observables_0.dat", skiprows=1)
+    extras = np.loadtxt(tmp_path / "output" / "test" / "observables_b200_0.dat", skiprows=1)
+    assert table.shape == (2, 3) and extras.shape == (2, 3) and table[:, 0].tolist() == [50, 100] == extras[:, 0].tolist()
     # the same run on the oracle: rho = 1 with a 3x peak at (0.4, 0.3)(L - 1) (Initialize.h:30-46), u = 0, f = feq
     cfg = make_config(lattice="D2Q9", shape=shape, collision="BGK", forcing_scheme="Guo", force="Kolmogorov", tau=0.55,
                       amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0))
@@ -175,4 +208,5 @@ def test_reference_style_routine_runs(tmp_path, cuda_lib):
             obs = state.observables()
             row = table[iteration // 50 - 1]
             assert abs(row[1] - obs[0]) <= 1e-9 * abs(obs[0])
-            assert abs(row[4] - obs[3]) <= 1e-12 * abs(obs[3])
+            assert abs(row[2] - obs[1]) <= 1e-9 * abs(obs[1])
+            assert abs(extras[iteration // 50 - 1][2] - obs[3]) <= 1e-12 * abs(obs[3])
