@@ -64,6 +64,30 @@ WORKLOADS = {
 }
 
 
+# Secondary measurements carried in the same JSON line under "also" (device-resident throughput only, measured after
+# the headline numbers are final and under a watchdog, so that they can never change or lose the headline): the other
+# BASELINE configs at this GPU count.  (workload, dtype, eps, stored mode, timed steps)
+ALSO_SINGLE = [
+    ("d3q19_bgk_256", "F32", None, 1, 100),
+    ("d3q19_bgk_guo_256", "F64", None, 1, 100),
+    ("d3q27_elbm_512", "F64", 2e-2, 1, 20),
+    ("d3q27_elbm_512", "F64", 1e-5, 1, 20),
+    ("d2q9_elbm_shanchen_8192", "F64", 2e-2, 1, 50),
+    ("d2q9_elbm_shanchen_8192", "F64", 1e-5, 1, 50),
+    ("d2q9_elbm_edm_8192", "F32", 2e-2, 1, 50),
+    ("d3q19_bgk_512", "F64", None, 1, 100),
+]
+ALSO_MULTI = [
+    ("d3q19_bgk_1024", "F64", None, 2, 100),   # energy / mass / Mach reductions every 50 steps, no field arrays
+    ("d3q19_bgk_512", "F64", None, 1, 100),    # stored fields + spectral enstrophy every 50 steps
+    ("d3q27_elbm_512", "F64", 2e-2, 1, 20),
+    ("d3q27_elbm_512", "F64", 1e-5, 1, 20),
+    ("d2q9_elbm_shanchen_8192", "F64", 2e-2, 1, 50),
+    ("d2q9_elbm_edm_8192", "F32", 2e-2, 1, 50),
+    ("d3q19_bgk_1024", "F64", None, 1, 100),   # BASELINE configs[4] in full: + fields and the spectral enstrophy
+]
+
+
 def measured_peak():
     path = ROOT / "MEASURED_PEAKS.json"
     if path.is_file():
@@ -199,6 +223,170 @@ def cpu_baseline_leg() -> dict:
 
 
 # --------------------------------------------------------------------------------------------------
+# secondary workloads ("also")
+# --------------------------------------------------------------------------------------------------
+def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, min_over_ranks, peak) -> dict:
+    """Device-resident throughput of one named workload at this GPU count: fresh context, synthetic field made on
+    the device, 5 warm-up steps, `steps` timed steps between barriers (CUDA events, max over ranks)."""
+    import torch
+    from metalbm_b200.algorithm import Algorithm, Communication
+    from metalbm_b200.capi import make_config
+
+    name, dtype, eps, stored_mode, steps = entry
+    work = dict(WORKLOADS[name])
+    if eps is not None:
+        work["eps"] = eps
+    element = 8 if dtype == "F64" else 4
+    q_count = work["q"]
+    entropic = work["collision"] != "BGK"
+    shape = (work["shape"][0] * world,) + tuple(work["shape"][1:]) if work["scaling"] == "weak" else tuple(work["shape"])
+    result = {"name": name, "dtype": dtype.lower(), "eps": work["eps"], "scaling": work["scaling"], "n_gpus": world,
+              "global_length": list(shape), "store_every": int(work["store_every"]),
+              "stored_mode": stored_mode if work["store_every"] else None}
+    if shape[0] % world:
+        result["skipped"] = "number of GPUs does not divide the x extent"
+        return result
+    nodes_global = shape[0] * shape[1] * shape[2]
+    nodes_local = nodes_global // world
+    lx = shape[0] // world
+    dim = 3 if shape[2] > 1 else 2
+    # device memory this workload needs (populations with halo planes, alpha, and on fully stored steps the fields
+    # plus the spectra of the enstrophy), agreed over the ranks before anybody allocates
+    need = 2 * q_count * (nodes_local // lx) * (lx + 2) * element + (nodes_local * element if entropic else 0)
+    if work["store_every"] and stored_mode == 1:
+        need += (1 + 2 * dim) * nodes_local * element + 3 * dim * nodes_local * 8
+    free = torch.cuda.mem_get_info()[0]
+    fits = min_over_ranks(1.0 if need + (3 << 30) < free else 0.0)
+    result["device_bytes_needed"] = need
+    if not fits:
+        result["skipped"] = f"needs {need / 1e9:.1f} GB of the {free / 1e9:.1f} GB free per GPU"
+        return result
+    bytes_per_node = 2 * q_count * element + (2 * element if entropic else 0)
+    cfg = make_config(lattice=work["lattice"], shape=shape, collision=work["collision"], equilibrium=work["equilibrium"],
+                      forcing_scheme=work["scheme"], force=work["force"], tau=work["tau"], dtype=dtype,
+                      amplitude=(1e-5, 1e-5, 1e-5), wavelength=(32.0, 32.0, 32.0),
+                      overlap=args.overlap, rank=rank, nranks=world, device=local_rank, variant=args.variant)
+    algorithm = Algorithm(cfg, communication=Communication(rank, world), host_distribution=False, host_fields=False,
+                          peer_halos=(args.halo == "peer" and args.overlap == "On") if world > 1 else False)
+    try:
+        algorithm.init_synthetic(0.05, 0.05)
+        if work["eps"]:
+            algorithm.perturb(work["eps"])
+        store_every = int(work["store_every"])
+        warmup = 5
+        if store_every:
+            algorithm.run(0, 1, 1, stored_mode=stored_mode)      # first stored step: allocations, transform plans
+        algorithm.run(1, warmup, store_every, stored_mode=stored_mode)
+        algorithm.kernel_time()
+        barrier()
+        algorithm.mark(0)
+        algorithm.run(warmup + 1, steps, store_every, sync=False, stored_mode=stored_mode)
+        algorithm.mark(1)
+        algorithm.synchronize()
+        barrier()
+        device_ms = max_over_ranks(algorithm.elapsed_ms(0, 1))
+        kernel_ms, kernel_launches = algorithm.kernel_time()
+        stored_ms = None
+        if store_every:
+            barrier()
+            algorithm.mark(2)
+            algorithm.run(store_every, 1, store_every, sync=False, stored_mode=stored_mode)
+            algorithm.mark(3)
+            algorithm.synchronize()
+            stored_ms = max_over_ranks(algorithm.elapsed_ms(2, 3))
+        # liveness of the state that was timed: one more step reducing energy / mass / Mach only
+        algorithm.run(0, 1, 1, stored_mode=2)
+        observables = algorithm.observables()
+        overlapped = world > 1 and args.overlap == "On" and lx >= 3
+        kernel_nodes = nodes_local // lx * (lx - 2) if overlapped else nodes_local
+        achieved = bytes_per_node * kernel_nodes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else None
+        result.update({
+            "value": nodes_global * steps / (device_ms * 1e-3) / 1e6, "unit": UNIT, "steps": steps, "warmup": warmup,
+            "ms_per_step": device_ms / steps, "stored_step_ms": stored_ms,
+            "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_launches,
+            "roofline_achieved_GBps": achieved, "roofline_frac": achieved / peak if achieved else None,
+            "roofline_mlups_per_gpu": peak * 1e9 / bytes_per_node / 1e6,
+            "halo": ("peer" if algorithm.peer_halos else "nccl") if world > 1 else "none",
+            "energy": float(observables[0]), "mach": float(observables[2]),
+            "mass_per_node": float(observables[3]) / nodes_global,
+        })
+    finally:
+        algorithm.close()
+    return result
+
+
+def run_secondary(entries, measure, line, rank, world, max_over_ranks, sum_over_ranks, timeout, stream=None) -> None:
+    """Run the secondary workloads and print THE JSON line (rank 0) exactly once, whatever happens to them.
+
+    `line` (rank 0: the finished headline dict, other ranks: None) is printed with the results under "also":
+      * every entry is measured inside try/except, its failure is an {"error": ...} entry;
+      * with several ranks, a SUM all-reduce after every entry returns only when all ranks are done with it, so the ranks
+        stay in step after symmetric failures (not enough memory, a missing library);
+      * a rank that never comes back (a neighbour died inside a collective) is ended by a watchdog thread after `timeout`
+        seconds: it prints the line with what was measured so far and leaves with exit code 0;
+      * a rank on which the bench's own collectives fail publishes the line at once and leaves when the watchdogs of the
+        other ranks fire, so that no process disappears under a running neighbour.
+    Pure host logic (tests/test_bench_host.py drives it with fake workloads)."""
+    stream = stream or sys.stdout
+    also = []
+    printed = threading.Lock()
+
+    def emit(note=None):
+        if not printed.acquire(blocking=False):
+            return
+        if rank == 0:
+            if also or note:
+                line["also"] = list(also)
+            if note:
+                line["also_note"] = note
+            stream.write(json.dumps(line) + "\n")
+            stream.flush()
+
+    if not entries:
+        emit()
+        return
+
+    def bail():
+        emit(f"secondary workloads cut off by the {timeout} s watchdog")
+        os._exit(0)
+
+    watchdog = threading.Timer(timeout, bail)
+    watchdog.daemon = True
+    watchdog.start()
+    started = time.time()
+    in_step = True   # the ranks still take the same decisions
+    try:
+        for entry in entries:
+            # every rank takes the same decision: the elapsed time is agreed first
+            if max_over_ranks(time.time() - started) > timeout - min(60.0, 0.2 * timeout):
+                also.append({"name": entry[0], "skipped": "time budget of the secondary workloads used up"})
+                continue
+            ok = 1.0
+            try:
+                also.append(measure(entry))
+            except Exception as error:  # noqa: BLE001 -- reported in the line, the headline stands
+                ok = 0.0
+                also.append({"name": entry[0], "dtype": str(entry[1]).lower(), "eps": entry[2], "n_gpus": world,
+                             "error": str(error)[:300]})
+            if world > 1:
+                # returns once every rank is done with this entry, whatever its outcome: the ranks are in step again
+                ranks_ok = sum_over_ranks(ok)
+                if ranks_ok != world:
+                    also[-1]["ranks_ok"] = int(ranks_ok)
+    except Exception as error:  # noqa: BLE001 -- a collective of the bench itself failed (e.g. a poisoned CUDA context)
+        in_step = False
+        also.append({"error": f"secondary workloads stopped: {str(error)[:300]}"})
+    if in_step:
+        watchdog.cancel()
+        emit()
+        return
+    emit("secondary workloads stopped after an error on this rank")
+    if world > 1:
+        time.sleep(max(0.0, started + timeout - time.time()) + 5.0)   # the watchdog ends this process
+    os._exit(0)
+
+
+# --------------------------------------------------------------------------------------------------
 # this repository's arm
 # --------------------------------------------------------------------------------------------------
 def run_ours(args) -> int:
@@ -224,6 +412,16 @@ def run_ours(args) -> int:
             return value
         tensor = torch.tensor([value], dtype=torch.float64, device="cuda")
         dist.all_reduce(tensor, op=dist.ReduceOp.MAX)
+        return float(tensor.item())
+
+    def min_over_ranks(value: float) -> float:
+        return -max_over_ranks(-value)
+
+    def sum_over_ranks(value: float) -> float:
+        if world == 1:
+            return value
+        tensor = torch.tensor([value], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
         return float(tensor.item())
 
     work = dict(WORKLOADS[args.workload])
@@ -363,10 +561,8 @@ def run_ours(args) -> int:
                                  and args.workload == "d3q19_bgk_256") else None
     algorithm_peer = algorithm.peer_halos
     algorithm.close()
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
 
+    line = None
     if rank == 0:
         buffer_gb = q_count * nodes_local * element / 1e9
         metric = METRIC if args.workload == "d3q19_bgk_256" and dtype == "F64" else \
@@ -388,7 +584,20 @@ def run_ours(args) -> int:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+
+    # ---- the other BASELINE configs at this GPU count.  The headline line above is final; whatever happens below
+    # (an exception, a rank that stops answering) it is printed, by the watchdog if need be.
+    run_also = args.also == "on" or (args.also == "auto" and args.workload == "d3q19_bgk_256" and dtype == "F64"
+                                     and args.edge == EDGE)
+    entries = (ALSO_SINGLE if world == 1 else ALSO_MULTI) if run_also else []
+
+    def measure(entry):
+        return measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, min_over_ranks, peak)
+
+    run_secondary(entries, measure, line, rank, world, max_over_ranks, sum_over_ranks, args.also_timeout)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 
@@ -409,6 +618,10 @@ def main() -> int:
     parser.add_argument("--store-every", type=int, default=None, help="override the workload's observable cadence")
     parser.add_argument("--no-e2e", action="store_true", help="skip the host-buffer end-to-end leg (large workloads)")
     parser.add_argument("--no-cpu-baseline", action="store_true")
+    parser.add_argument("--also", default="auto", choices=["auto", "on", "off"],
+                        help="secondary workloads (the other BASELINE configs at this GPU count) under \"also\" in the "
+                             "JSON line; auto = with the default headline workload only")
+    parser.add_argument("--also-timeout", type=int, default=300, help="watchdog of the secondary workloads, seconds")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

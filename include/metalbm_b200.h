@@ -176,6 +176,12 @@ int mlbm_download_distribution(mlbm_ctx* ctx, void* host, size_t component_strid
 int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* velocity,
                           size_t component_stride, size_t padded_y, size_t padded_z);
 
+/* The synthetic initial field of the benchmarks (no reference counterpart; SURVEY.md 8d "Init B") evaluated on the
+ * device at global coordinates, f = feq(rho, u) (initDistribution, Initialize.h:106-117), without host field arrays:
+ *   3-D: rho = 1 + a sin X cos Y cos Z,  u = b (sin X cos Y cos Z, -cos X sin Y cos Z, cos X cos Y sin Z / 2)
+ *   2-D: rho = 1 + a sin X cos Y,        u = b (sin Y, cos X)            with X = 2 pi x / globalLengthX etc. */
+int mlbm_init_synthetic(mlbm_ctx* ctx, double density_amplitude, double velocity_amplitude);
+
 /* Synthetic non-equilibrium state for benchmarks and size-independent property tests (no reference counterpart;
  * SURVEY.md 8d "Init B"): multiplies every population by 1 + eps * n, n uniform with unit variance from a
  * counter-based hash of (seed, iQ, global node index) -- the same field whatever the number of ranks. */
@@ -195,6 +201,8 @@ int mlbm_step(mlbm_ctx* ctx, unsigned iteration, int is_stored);
 /* `count` calls of iterate for iterations first..first+count-1 with isStored = (iteration % store_every == 0)
  * (store_every == 0: never), enqueued without host synchronisation in between; returns immediately. */
 int mlbm_run_async(mlbm_ctx* ctx, unsigned first_iteration, unsigned count, unsigned store_every);
+/* The same with the `is_stored` value of the stored steps chosen by the caller (1 or 2, see mlbm_step). */
+int mlbm_run_async_stored(mlbm_ctx* ctx, unsigned first_iteration, unsigned count, unsigned store_every, int stored_mode);
 int mlbm_sync(mlbm_ctx* ctx);
 
 /* FieldList arrays as of the last stored step (Algorithm::storeFields): any pointer may be NULL.

@@ -74,8 +74,11 @@ class Distribution:
 class FieldList:
     """density, velocity, alpha, force (FieldList.h:22-63) in the reference's local padded layout."""
 
-    def __init__(self, domain: Domain):
+    def __init__(self, domain: Domain, allocate: bool = True):
         self.domain = domain
+        if not allocate:   # slabs that fill the GPU: the host never sees the fields
+            self.density = self.velocity = self.alpha = self.force = None
+            return
         self.density = domain.allocate(1)
         self.velocity = domain.allocate(domain.dim)
         self.alpha = domain.allocate(1)
@@ -138,11 +141,11 @@ class Algorithm:
 
     def __init__(self, config: MlbmConfig, field_list: FieldList | None = None,
                  distribution: Distribution | None = None, communication: Communication | None = None,
-                 host_distribution: bool = True, peer_halos: bool | None = None):
+                 host_distribution: bool = True, peer_halos: bool | None = None, host_fields: bool = True):
         self._lib = load_library()
         self.config = config
         self.domain = Domain(config)
-        self.fieldList = field_list if field_list is not None else FieldList(self.domain)
+        self.fieldList = field_list if field_list is not None else FieldList(self.domain, allocate=host_fields)
         self.distribution = (distribution if distribution is not None
                              else Distribution(self.domain, allocate=host_distribution))
         self.communication = communication or Communication(int(config.rank), int(config.nranks))
@@ -210,6 +213,10 @@ class Algorithm:
         check(self._lib.mlbm_init_equilibrium(self._ctx, self.fieldList.density.ctypes.data,
                                               self.fieldList.velocity.ctypes.data, stride, py, pz))
 
+    def init_synthetic(self, density_amplitude: float = 0.05, velocity_amplitude: float = 0.05) -> None:
+        """The benchmark's synthetic initial field (SURVEY 8d "Init B") evaluated on the device, no host arrays."""
+        check(self._lib.mlbm_init_synthetic(self._ctx, float(density_amplitude), float(velocity_amplitude)))
+
     def perturb(self, eps: float, seed: int = 20261017) -> None:
         """f *= 1 + eps * noise on the device (synthetic non-equilibrium fields, decomposition independent)."""
         check(self._lib.mlbm_perturb_distribution(self._ctx, float(eps), int(seed)))
@@ -221,11 +228,11 @@ class Algorithm:
     # -- Algorithm::iterate -----------------------------------------------------------------------
     def iterate(self, iteration: int) -> None:
         check(self._lib.mlbm_step(self._ctx, iteration, 1 if self.isStored else 0))
-        if self.isStored:
+        if self.isStored and self.fieldList.density is not None:
             self.fetch_fields()
 
-    def run(self, first_iteration: int, count: int, store_every: int = 0, sync: bool = True) -> None:
-        check(self._lib.mlbm_run_async(self._ctx, first_iteration, count, store_every))
+    def run(self, first_iteration: int, count: int, store_every: int = 0, sync: bool = True, stored_mode: int = 1) -> None:
+        check(self._lib.mlbm_run_async_stored(self._ctx, first_iteration, count, store_every, stored_mode))
         if sync:
             self.synchronize()
 

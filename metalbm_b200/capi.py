@@ -191,10 +191,12 @@ PROTOTYPES = {
     "mlbm_upload_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_download_distribution": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_init_equilibrium": (ctypes.c_int, [_P, _P, _P, _SZ, _SZ, _SZ]),
+    "mlbm_init_synthetic": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double]),
     "mlbm_perturb_distribution": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_uint64]),
     "mlbm_set_alpha": (ctypes.c_int, [_P, _P, _SZ, _SZ]),
     "mlbm_step": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_int]),
     "mlbm_run_async": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
+    "mlbm_run_async_stored": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_int]),
     "mlbm_sync": (ctypes.c_int, [_P]),
     "mlbm_download_fields": (ctypes.c_int, [_P, _P, _P, _P, _P, _SZ, _SZ, _SZ]),
     "mlbm_observables": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),

@@ -193,6 +193,43 @@ __global__ void initEquilibriumKernel(StoreT* __restrict__ populations, const St
   });
 }
 
+// The synthetic initial field of the benchmark (SURVEY.md 8d "Init B": density ripple + Taylor-Green-like velocity)
+// evaluated on the device at GLOBAL coordinates and written as f = feq(rho, u): no host field arrays, which is what
+// the slabs that fill a GPU (1024^3 on two GPUs) need.
+template <class L, int EQ, typename StoreT>
+__global__ void initSyntheticKernel(StoreT* __restrict__ populations, long long stride, long long plane, long long nodes,
+                                    int NR, int xOffset, int globalX, int globalY, int globalZ, double densityAmplitude,
+                                    double velocityAmplitude) {
+  const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (node >= nodes) return;
+  const int x = (int)(node / plane);
+  const long long inPlane = node - (long long)x * plane;
+  const int m = (int)(inPlane / NR), r = (int)(inPlane - (long long)m * NR);
+  double sx, cx, sy, cy, sz = 0.0, cz = 1.0;
+  sincospi(2.0 * (x + xOffset) / globalX, &sx, &cx);
+  sincospi(2.0 * (L::D == 3 ? m : r) / globalY, &sy, &cy);
+  if (L::D == 3) sincospi(2.0 * r / globalZ, &sz, &cz);
+  const double rho = 1.0 + densityAmplitude * sx * cy * cz;
+  double u[3] = {0.0, 0.0, 0.0};
+  if (L::D == 3) {
+    u[0] = velocityAmplitude * sx * cy * cz;
+    u[1] = -velocityAmplitude * cx * sy * cz;
+    u[2] = 0.5 * velocityAmplitude * cx * cy * sz;
+  } else {
+    u[0] = velocityAmplitude * sy;
+    u[1] = velocityAmplitude * cx;
+  }
+  double u2 = 0.0;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) u2 += u[d] * u[d];
+  EquilibriumCoefficients<L, EQ> eq;
+  eq.set(u, u2);
+  staticFor<0, L::Q>([&](auto qc) {
+    constexpr int q = decltype(qc)::value;
+    populations[q * stride + plane + node] = (StoreT)(rho * L::w(q) * eq.template shape<q>());
+  });
+}
+
 // f *= 1 + eps * n, n uniform with unit variance from a counter-based hash of (seed, population, GLOBAL node):
 // the synthetic non-equilibrium initial fields of the benchmark, independent of the decomposition.
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
@@ -243,6 +280,25 @@ static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* popu
       break;
     case kD3Q27: initEquilibriumKernel<Lattice<kD3Q27>, EQ, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes); break;
   }
+}
+
+template <int EQ, typename StoreT>
+static void launchInitSynthetic(int lattice, cudaStream_t stream, StoreT* populations, long long stride, long long plane,
+                                long long nodes, int NR, int xOffset, const int* global, double densityAmplitude,
+                                double velocityAmplitude) {
+  const int block = 128;
+  const unsigned grid = (unsigned)((nodes + block - 1) / block);
+#define MLBM_INIT_SYNTHETIC(LATTICE, EQUILIBRIUM)                                                                      \
+  initSyntheticKernel<Lattice<LATTICE>, EQUILIBRIUM, StoreT><<<grid, block, 0, stream>>>(                                \
+      populations, stride, plane, nodes, NR, xOffset, global[0], global[1], global[2], densityAmplitude, velocityAmplitude)
+  switch (lattice) {
+    case kD2Q5: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD2Q5, kTruncationMa3); break;
+    case kD2Q9: MLBM_INIT_SYNTHETIC(kD2Q9, EQ); break;
+    case kD3Q15: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD3Q15, kTruncationMa3); break;
+    case kD3Q19: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD3Q19, kTruncationMa3); break;
+    case kD3Q27: MLBM_INIT_SYNTHETIC(kD3Q27, EQ); break;
+  }
+#undef MLBM_INIT_SYNTHETIC
 }
 
 }  // namespace mlbm
@@ -1019,6 +1075,27 @@ int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* veloci
   return MLBM_OK;
 }
 
+int mlbm_init_synthetic(mlbm_ctx* ctx, double densityAmplitude, double velocityAmplitude) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  void* target = ctx->populations[ctx->current];
+  const int xOffset = ctx->config.rank * ctx->LX;  // gSD::sOffset (Domain.h:155-162)
+  const int* global = ctx->config.global_length;
+  const bool exact = ctx->config.equilibrium == MLBM_EXACT;
+  if (ctx->config.dtype == MLBM_F64) {
+    if (exact) launchInitSynthetic<kExact, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+    else launchInitSynthetic<kTruncationMa3, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+  } else {
+    if (exact) launchInitSynthetic<kExact, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+    else launchInitSynthetic<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+  }
+  MLBM_CUDA(cudaGetLastError());
+  ctx->launches += 1;
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  ctx->halosValid = false;
+  return MLBM_OK;
+}
+
 int mlbm_perturb_distribution(mlbm_ctx* ctx, double eps, uint64_t seed) {
   if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
   MLBM_CUDA(cudaSetDevice(ctx->device));
@@ -1060,16 +1137,21 @@ int mlbm_step(mlbm_ctx* ctx, unsigned iteration, int isStored) {
   return MLBM_OK;
 }
 
-int mlbm_run_async(mlbm_ctx* ctx, unsigned firstIteration, unsigned count, unsigned storeEvery) {
+int mlbm_run_async_stored(mlbm_ctx* ctx, unsigned firstIteration, unsigned count, unsigned storeEvery, int storedMode) {
   if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  if (storedMode != 1 && storedMode != 2) return fail(MLBM_ERR_INVALID, "stored mode %d (1 = fields + all observables, 2 = energy / mass / Mach only)", storedMode);
   MLBM_CUDA(cudaSetDevice(ctx->device));
   const bool profile = ctx->profiling;
   for (unsigned i = 0; i < count; ++i) {
     const unsigned iteration = firstIteration + i;
-    const int isStored = (storeEvery && iteration % storeEvery == 0) ? 1 : 0;
+    const int isStored = (storeEvery && iteration % storeEvery == 0) ? storedMode : 0;
     if (int status = enqueueStep(ctx, isStored, false, profile)) return status;
   }
   return MLBM_OK;
+}
+
+int mlbm_run_async(mlbm_ctx* ctx, unsigned firstIteration, unsigned count, unsigned storeEvery) {
+  return mlbm_run_async_stored(ctx, firstIteration, count, storeEvery, 1);
 }
 
 int mlbm_sync(mlbm_ctx* ctx) {
