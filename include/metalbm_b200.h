@@ -68,9 +68,13 @@ typedef enum mlbm_forcing_scheme {
   MLBM_SCHEME_NONE = 0, MLBM_GUO = 1, MLBM_SHAN_CHEN = 2, MLBM_EXACT_DIFFERENCE = 3
 } mlbm_forcing_scheme;
 
-/* ForceType (Options.h:41-43; Force.h:104-292) */
+/* ForceType (Options.h:41-43; Force.h:104-292).
+ * MLBM_FORCE_FIELD is the generic array read Force<T, ForceType::Generic>::setForce (Force.h:39-48): the force of a node
+ * is component iD of the force FIELD at the node's local index.  It is what every array-type force of the reference
+ * runs through on the step path (ConstantShell, EnergyRemoval, Turbulent2D, Force.h:296-623, fill that array with FFTs
+ * outside the step); here the caller supplies the array with mlbm_set_force_field. */
 typedef enum mlbm_force {
-  MLBM_FORCE_NONE = 0, MLBM_FORCE_CONSTANT = 1, MLBM_FORCE_SINUSOIDAL = 2, MLBM_FORCE_KOLMOGOROV = 3
+  MLBM_FORCE_NONE = 0, MLBM_FORCE_CONSTANT = 1, MLBM_FORCE_SINUSOIDAL = 2, MLBM_FORCE_KOLMOGOROV = 3, MLBM_FORCE_FIELD = 4
 } mlbm_force;
 
 /* `dataT` (Input_prod.in:10).  F32 is FP32 storage of populations and fields with the moments,
@@ -128,7 +132,8 @@ typedef struct mlbm_launch_plan {
   int32_t x0, plane_step, plane_count, planes_per_block;
   int32_t local_length[3];      /* LX, NM, NR: extents on the kernel axes (slab, middle, unit stride) */
   int32_t wrap_x;               /* 1: single rank, x wraps inside the slab; 0: halo planes hold the neighbours' data */
-  int32_t is_stored, hydro_shift, has_force;
+  int32_t is_stored, hydro_shift;
+  int32_t has_force;            /* 0: none, 1: per-axis profiles of the analytic forces, 2: read from the force field */
   uint64_t stride, plane;       /* elements between populations / between x planes */
   double beta;                  /* 1 / (2 tau)                 (Collision.h:122) */
   double guo_factor;            /* (1 - 1/(2 tau)) * inv_cs2   (ForcingScheme.h:115) */
@@ -189,6 +194,13 @@ int mlbm_perturb_distribution(mlbm_ctx* ctx, double eps, uint64_t seed);
 
 /* The alpha field the entropic solve warm-starts from (Algorithm.h:103-106; initAlpha, Initialize.h:82-88). */
 int mlbm_set_alpha(mlbm_ctx* ctx, const void* host, size_t padded_y, size_t padded_z);
+
+/* The force FIELD of a context created with MLBM_FORCE_FIELD (zero until set): [D] components laid out like the
+ * FieldList arrays (component iD at host + iD*component_stride, element (x, y, z) at (x*padded_y + y)*padded_z + z), this
+ * rank's slab.  Replaces the `forcePtr` that Force<Generic>::setForce reads (Force.h:39-48) and that
+ * Force::update / setForceArray fill (Force.h:51-54, 323-331, 452-560); may be called between steps (time-dependent
+ * forces).  On stored steps the step writes the same values back into the stored force field (Algorithm.h:186-190). */
+int mlbm_set_force_field(mlbm_ctx* ctx, const void* host, size_t component_stride, size_t padded_y, size_t padded_z);
 
 /* Algorithm::iterate (Algorithm.h:326-358 / 392-447): swap, halo exchange, periodic boundaries, fused node
  * update; synchronous like the reference (returns after the device finished).  `is_stored` is

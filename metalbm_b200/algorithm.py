@@ -225,6 +225,12 @@ class Algorithm:
         _, py, pz = self._layout()
         check(self._lib.mlbm_set_alpha(self._ctx, self.fieldList.alpha.ctypes.data, py, pz))
 
+    def set_force(self) -> None:
+        """Force::update / setForceArray (Force.h:51-54, 323-331): hand ``fieldList.force`` to the device as the array the
+        generic force read uses (contexts created with force="Field")."""
+        stride, py, pz = self._layout()
+        check(self._lib.mlbm_set_force_field(self._ctx, self.fieldList.force.ctypes.data, stride, py, pz))
+
     # -- Algorithm::iterate -----------------------------------------------------------------------
     def iterate(self, iteration: int) -> None:
         check(self._lib.mlbm_step(self._ctx, iteration, 1 if self.isStored else 0))

@@ -55,6 +55,7 @@ class Force(enum.IntEnum):
     Constant = 1
     Sinusoidal = 2
     Kolmogorov = 3
+    Field = 4          # generic array read (Force.h:39-48); the array comes from mlbm_set_force_field
 
 
 class DType(enum.IntEnum):
@@ -194,6 +195,7 @@ PROTOTYPES = {
     "mlbm_init_synthetic": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_double]),
     "mlbm_perturb_distribution": (ctypes.c_int, [_P, ctypes.c_double, ctypes.c_uint64]),
     "mlbm_set_alpha": (ctypes.c_int, [_P, _P, _SZ, _SZ]),
+    "mlbm_set_force_field": (ctypes.c_int, [_P, _P, _SZ, _SZ, _SZ]),
     "mlbm_step": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_int]),
     "mlbm_run_async": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
     "mlbm_run_async_stored": (ctypes.c_int, [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_int]),

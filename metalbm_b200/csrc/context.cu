@@ -447,7 +447,7 @@ static void fillLaunchScalars(const mlbm_config& config, const SlabGeometry& g, 
   p->wrapX = config.nranks == 1 ? 1 : 0;
   p->isStored = isStored;
   p->hydroShift = hydroShift;
-  p->hasForce = config.force != MLBM_FORCE_NONE;
+  p->hasForce = config.force == MLBM_FORCE_NONE ? 0 : (config.force == MLBM_FORCE_FIELD ? 2 : 1);
   p->beta = 1.0 / (2.0 * config.tau);
   p->guoFactor = (1.0 - 1.0 / (2.0 * config.tau)) * 3.0;
   // entropic kernels stage their logarithm table and constants once per block: let a block walk up to 16 planes
@@ -744,7 +744,7 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
     default: return fail(MLBM_ERR_INVALID, "unknown collision %d", config->collision);
   }
   if (!schemeOf(config->forcing_scheme, &scheme, &hydroShift)) return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
-  if (config->force < MLBM_FORCE_NONE || config->force > MLBM_FORCE_KOLMOGOROV) return fail(MLBM_ERR_INVALID, "unknown force %d", config->force);
+  if (config->force < MLBM_FORCE_NONE || config->force > MLBM_FORCE_FIELD) return fail(MLBM_ERR_INVALID, "unknown force %d", config->force);
   if (config->equilibrium != MLBM_TRUNCATION_MA3 && config->equilibrium != MLBM_EXACT) return fail(MLBM_ERR_INVALID, "unknown equilibrium %d", config->equilibrium);
   StepKernel kernel = lookupStepKernel(config->lattice, collision, config->equilibrium, scheme, config->dtype);
   if (!kernel) return fail(MLBM_ERR_INVALID, "no kernel for this lattice/equilibrium combination (the exact equilibrium exists for D2Q9 and D3Q27 only, Equilibrium.h:36-126)");
@@ -822,7 +822,10 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
 
   // Force profiles, evaluated on the host with libm exactly like Force::setForce does per node
   // (Force.h:154-159 Constant, :208-215 Sinusoidal, :262-267 Kolmogorov) at LOCAL coordinates (Collision.h:86).
-  if (config->force != MLBM_FORCE_NONE) {
+  if (config->force == MLBM_FORCE_FIELD) {
+    // the kernel reads the force field from the first step on: it exists (zero) before mlbm_set_force_field fills it
+    if (int status = ensureFields(ctx)) return cleanup(status);
+  } else if (config->force != MLBM_FORCE_NONE) {
     const int extent[3] = {ctx->LX, D == 3 ? config->global_length[1] : config->global_length[1], D == 3 ? config->global_length[2] : 1};
     const int kernelAxisOf[3] = {0, D == 3 ? 1 : 2, 2};  // physical axis -> kernel axis
     for (int d = 0; d < D; ++d) {
@@ -1118,6 +1121,15 @@ int mlbm_set_alpha(mlbm_ctx* ctx, const void* host, size_t paddedY, size_t padde
   if (!ctx->alpha) return fail(MLBM_ERR_STATE, "the BGK alpha field is the constant 2 (Collision.h:121)");
   MLBM_CUDA(cudaSetDevice(ctx->device));
   if (int status = copyField(ctx, const_cast<void*>(host), ctx->alpha, 1, 0, paddedY, paddedZ, true)) return status;
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  return MLBM_OK;
+}
+
+int mlbm_set_force_field(mlbm_ctx* ctx, const void* host, size_t componentStride, size_t paddedY, size_t paddedZ) {
+  if (!ctx || !host) return fail(MLBM_ERR_INVALID, "null argument");
+  if (ctx->config.force != MLBM_FORCE_FIELD) return fail(MLBM_ERR_STATE, "the context was not created with MLBM_FORCE_FIELD");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (int status = copyField(ctx, const_cast<void*>(host), ctx->force, ctx->D, componentStride, paddedY, paddedZ, true)) return status;
   MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
   return MLBM_OK;
 }

@@ -61,7 +61,8 @@ struct StepParams {
   int wrapX;               // 1: single rank, x is periodic inside the slab; 0: halo planes hold the neighbours' data
   int isStored;            // Algorithm::isStored (Routine.h:122-124): bit 0 = store fields, bit 1 = reduce observables
   int hydroShift;          // 1: stored velocity = u + F/(2 rho) (ForcingScheme.h:26-33); 0: u (scheme None, :50-57)
-  int hasForce;            // 0: force is identically zero
+  int hasForce;            // 0: force is identically zero; 1: per-axis profiles (forceTable); 2: read from the force FIELD
+                           // (`force`, the generic array read of Force.h:39-48 that the spectral forces of Force.h:296-623 use)
   double beta;             // 1 / (2 tau)                      (Collision.h:122)
   double guoFactor;        // (1 - 1/(2 tau)) * inv_cs2        (ForcingScheme.h:115)
 };
@@ -492,16 +493,22 @@ __device__ __forceinline__ void moments(const double (&f)[L::Q], double& rho, do
   }
 }
 
-// Force::setForce at local interior coordinates (Collision.h:81-88); profiles precomputed on the host
-template <class L>
+// Force::setForce at local interior coordinates (Collision.h:81-88): profiles precomputed on the host for the analytic
+// forces, or Force<Generic>::setForce (Force.h:39-48) for the array-type forces: component iD of the force FIELD at the
+// node's local index.  storeNodeFields writes the same values back on stored steps, like Algorithm::storeFields does.
+template <class L, typename StoreT>
 __device__ __forceinline__ void bodyForce(const StepParams& p, int x, int m, int r, double (&F)[3]) {
   F[0] = F[1] = F[2] = 0.0;
-  if (p.hasForce) {
+  if (p.hasForce == 1) {
 #pragma unroll
     for (int d = 0; d < L::D; ++d) {
       const int axis = p.forceAxis[d];
       if (axis >= 0) F[d] = __ldg(p.forceTable[d] + (axis == 0 ? x : (axis == 1 ? m : r)));
     }
+  } else if (p.hasForce == 2) {
+    const StoreT* field = static_cast<const StoreT*>(p.force) + ((long long)x * p.plane + (long long)m * p.NR + r);
+#pragma unroll
+    for (int d = 0; d < L::D; ++d) F[d] = (double)field[d * p.fieldStride];
   }
 }
 
@@ -661,7 +668,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
       double u2;
       moments<L>(f, rho, invRho, u, u2);
-      bodyForce<L>(p, x, m, r, F);
+      bodyForce<L, StoreT>(p, x, m, r, F);
       EquilibriumCoefficients<L, EQ> eq;
       eq.set(u, u2);
       // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241): fNeq, then alpha.  While fNeq is formed the
@@ -771,7 +778,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
       pullPopulations<L, StoreT>(p, n, f);
       double invRho, u2, u[3], F[3];
       moments<L>(f, rho, invRho, u, u2);
-      bodyForce<L>(p, x, m, r, F);
+      bodyForce<L, StoreT>(p, x, m, r, F);
       EquilibriumCoefficients<L, EQ> eq;
       eq.set(u, u2);
       SourceTerm<L, EQ, SCHEME> source;

@@ -269,7 +269,8 @@ static size_t wrap(long i, long n) { return (size_t)((i % n + n) % n); }
 /* One Algorithm::iterate (Algorithm.h:326-358) over the global domain = the per-node functor
  * Algorithm::operator() (Algorithm.h:97-126) at every node.
  *   prev, next : [Q][nx][ny][nz]      alpha : [nx][ny][nz] read (warm start) and written every step
- *   density, velocity[D], force[D] : written when is_stored (Algorithm::storeFields, Algorithm.h:150-194)
+ *   density, velocity[D], force[D] : written when is_stored (Algorithm::storeFields, Algorithm.h:150-194);
+ *   force[D] is also READ, every step, when cfg->force == MLBM_FORCE_FIELD
  *   branch, iterations (optional, [nx][ny][nz] int32): which alpha branch each node took. */
 int mlbm_oracle_step_ex(const mlbm_config* cfg, const double* prev, double* next, double* alpha, double* density,
                         double* velocity, double* force, int is_stored, int* branchOut, int* iterationsOut,
@@ -306,6 +307,12 @@ int mlbm_oracle_step_ex(const mlbm_config* cfg, const double* prev, double* next
         unsigned p[3] = {(unsigned)(x % lx), (unsigned)y, (unsigned)z};
         double F[3];
         body_force(&L, cfg, p, F);
+        if (cfg->force == MLBM_FORCE_FIELD) {
+          /* Force<T, ForceType::Generic>::setForce (Force.h:39-48): component iD of the force array at the node's index
+           * (the array-type forces ConstantShell / EnergyRemoval / Turbulent2D, Force.h:296-623, fill it outside the step) */
+          if (!force) return -1;
+          for (int d = 0; d < L.D; ++d) F[d] = force[(size_t)d * V + idx];
+        }
 
         double a = 2.0;
         if (cfg->collision == MLBM_FORCED_NR_ELBM_FORCING) {

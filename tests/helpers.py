@@ -57,14 +57,30 @@ def check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3):
     return mismatched, population_tolerance
 
 
-def run_oracle(cfg, f0, steps, alpha0=None):
+def force_field(cfg, seed=5, amplitude=2e-4):
+    """A smooth, non-separable body-force array [D, nx, ny, nz] for Force "Field" (the generic array read, Force.h:39-48)."""
+    shape = O.shape_of(cfg)
+    dim = capi.LATTICE_DQ[capi.Lattice(cfg.lattice)][0]
+    rng = np.random.default_rng(seed)
+    x, y, z = np.meshgrid(*[2 * np.pi * np.arange(n) / n for n in shape], indexing="ij")
+    field = np.zeros((dim,) + shape)
+    for d in range(dim):
+        kx, ky, kz = rng.integers(1, 3, size=3)
+        field[d] = amplitude * (np.sin(kx * x + 0.3 * d) * np.cos(ky * y) * np.cos(kz * z if dim == 3 else 0 * z)
+                                + 0.1 * rng.standard_normal(shape))
+    return field
+
+
+def run_oracle(cfg, f0, steps, alpha0=None, force=None):
     state = O.OracleState(cfg, f0, alpha0)
+    if force is not None:
+        state.force[...] = force
     for _ in range(steps):
         state.step(True)
     return state
 
 
-def run_cuda(cfg, f0, steps, alpha0=None, store_last=True):
+def run_cuda(cfg, f0, steps, alpha0=None, store_last=True, force=None):
     """unpack -> iterate x steps (isStored on the last) -> pack; returns dict of global arrays (single rank)."""
     algorithm = Algorithm(cfg)
     try:
@@ -74,6 +90,9 @@ def run_cuda(cfg, f0, steps, alpha0=None, store_last=True):
         if alpha0 is not None:
             domain.interior(algorithm.fieldList.alpha)[0] = alpha0
             algorithm.set_alpha()
+        if force is not None:
+            domain.interior(algorithm.fieldList.force)[...] = force
+            algorithm.set_force()
         for iteration in range(1, steps + 1):
             algorithm.isStored = store_last and iteration == steps
             algorithm.iterate(iteration)

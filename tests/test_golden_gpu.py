@@ -11,12 +11,13 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name", golden_names())
 def test_cuda_reproduces_reference_outputs(name):
     meta, cfg, data = load_golden(name)
-    got = run_cuda(cfg, data["f0"], meta["steps"])
+    force = data["force"] if meta["force"] == "Field" else None   # the array the reference's spectral force filled
+    got = run_cuda(cfg, data["f0"], meta["steps"], force=force)
     entropic = meta["collision"] != "BGK"
     if entropic:
         # the oracle (bit-identical to the reference: tests/test_oracle_golden.py) supplies the conditioning of the
         # Newton solve at every node; the values compared are the reference's own (the golden file)
-        ref = run_oracle(cfg, data["f0"], meta["steps"])
+        ref = run_oracle(cfg, data["f0"], meta["steps"], force=force)
         assert np.array_equal(ref.alpha, data["alpha"]) and np.array_equal(ref.f, data["f"])
         _, population_tolerance = check_entropic(got, ref, cfg, meta["steps"], mismatch_budget=5e-3)
         # density = sum of Q populations that each carry the alpha-inherited uncertainty of the previous step

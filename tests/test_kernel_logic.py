@@ -15,7 +15,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from helpers import check_entropic, relative_error, run_oracle
+from helpers import check_entropic, force_field, relative_error, run_oracle
 from metalbm_b200 import capi
 from metalbm_b200.capi import LATTICE_DQ, Lattice, make_config
 from oracle import oracle as O
@@ -107,6 +107,11 @@ class Slab:
     def download(self):
         return self.view(self.current)[:, 1:self.lx + 1].astype(np.float64).copy()
 
+    def set_force(self, field):
+        """mlbm_set_force_field: [D, LX, NM, NR] into the dense force field, components field_stride apart."""
+        for d in range(self.dim):
+            self.force[d * self.field_stride:d * self.field_stride + self.nodes] = field[d].reshape(-1)
+
     def launch(self, x0, x1, is_stored, plane_step=1, planes_per_block=None, peer_low=None, peer_high=None):
         plan = capi.launch_plan(self.cfg, x0, x1, is_stored, plane_step)
         e = EmuLaunch()
@@ -153,9 +158,11 @@ def kernel_shape(cfg, array):
     return array.reshape(lead + ((nx, ny, nz) if dim == 3 else (nx, 1, ny)))
 
 
-def run_single(emu, cfg, f0, steps, planes_per_block=None, dtype=np.float64):
+def run_single(emu, cfg, f0, steps, planes_per_block=None, dtype=np.float64, force=None):
     slab = Slab(emu, cfg, dtype)
     slab.upload(kernel_shape(cfg, f0).astype(dtype))
+    if force is not None:
+        slab.set_force(kernel_shape(cfg, force).astype(dtype))
     for step in range(1, steps + 1):
         slab.launch(0, slab.lx, 1 if step == steps else 0, planes_per_block=planes_per_block)
         slab.current ^= 1
@@ -232,6 +239,56 @@ def test_kernel_source_reproduces_the_oracle(emu, case):
     got = run_single(emu, cfg, f0, steps)
     ref = run_oracle(cfg, f0, steps)
     _compare(cfg, got, ref, steps, collision != "BGK")
+
+
+FIELD_FORCE_CASES = [
+    # lattice, shape, collision, equilibrium, scheme, tau, eps, steps
+    ("D2Q9", (12, 10, 1), "BGK", "TruncationMa3", "Guo", 0.7, 1e-2, 3),
+    ("D3Q19", (5, 4, 6), "BGK", "TruncationMa3", "ExactDifferenceMethod", 0.6, 1e-2, 2),
+    ("D3Q27", (3, 4, 3), "BGK", "Exact", "ShanChen", 0.55, 1e-2, 2),
+    ("D2Q9", (6, 131, 1), "ELBM", "TruncationMa3", "Guo", 0.55, 2e-2, 2),
+    ("D3Q19", (4, 3, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", 0.55, 2e-2, 2),
+]
+
+
+@pytest.mark.parametrize("case", FIELD_FORCE_CASES, ids=lambda c: "-".join(map(str, (c[0], c[2], c[3], c[4]))))
+def test_force_read_from_the_force_field(emu, case):
+    """Force "Field": the generic array read of Force.h:39-48 (what the reference's spectral forces run through)."""
+    lattice, shape, collision, equilibrium, scheme, tau, eps, steps = case
+    cfg = _config(lattice, shape, collision, equilibrium, scheme, "Field", tau)
+    assert capi.launch_plan(cfg, 0, shape[0]).has_force == 2
+    f0 = O.synthetic_populations(cfg, eps=eps, **_flow(eps))
+    field = force_field(cfg)
+    got = run_single(emu, cfg, f0, steps, force=field)
+    ref = run_oracle(cfg, f0, steps, force=field)
+    assert np.abs(ref.force).max() > 0 and np.array_equal(ref.force, field)   # storeFields writes the same values back
+    _compare(cfg, got, ref, steps, collision != "BGK")
+
+
+@pytest.mark.parametrize("name", ["d2q9_bgk_guo_constantshell", "d2q9_elbm_edm_constantshell", "d2q9_bgk_shanchen_turbulent2d"])
+def test_field_force_against_the_reference_spectral_forces(emu, name):
+    """Golden vectors of the reference run with ConstantShell / Turbulent2D: the kernel source, fed the force array the
+    reference filled, reproduces the reference's populations."""
+    from golden_util import load_golden
+    meta, cfg, data = load_golden(name)
+    assert meta["force"] == "Field" and meta["reference_force"] in ("ConstantShell", "Turbulent2D")
+    got = run_single(emu, cfg, data["f0"], meta["steps"], force=data["force"])
+    ref = run_oracle(cfg, data["f0"], meta["steps"], force=data["force"])
+    assert np.array_equal(ref.f, data["f"])                       # the oracle is the reference, bit for bit
+    _compare(cfg, got, ref, meta["steps"], meta["collision"] != "BGK")
+    assert np.array_equal(got["force"], data["force"])
+
+
+def test_field_force_holding_the_kolmogorov_profile_equals_the_analytic_force(emu):
+    """The same doubles through either route: bit-identical populations."""
+    analytic = _config("D3Q19", (4, 6, 5), "BGK", scheme="Guo", force="Kolmogorov", tau=0.6)
+    f0 = O.synthetic_populations(analytic, eps=1e-2)
+    reference = run_oracle(analytic, f0, 1)
+    array = _config("D3Q19", (4, 6, 5), "BGK", scheme="Guo", force="Field", tau=0.6)
+    got = run_single(emu, array, f0, 2, force=reference.force)
+    want = run_single(emu, analytic, f0, 2)
+    assert np.array_equal(got["f"], want["f"]) and np.array_equal(got["velocity"], want["velocity"])
+    assert np.array_equal(run_oracle(array, f0, 2, force=reference.force).f, run_oracle(analytic, f0, 2).f)
 
 
 @pytest.mark.parametrize("planes_per_block", [2, 3, 16])

@@ -6,7 +6,7 @@ energy <= 1e-9 relative after 100 steps."""
 import numpy as np
 import pytest
 
-from helpers import check_entropic, relative_error, run_cuda, run_oracle
+from helpers import check_entropic, force_field, relative_error, run_cuda, run_oracle
 from metalbm_b200.capi import check, make_config
 from oracle import oracle as O
 
@@ -90,6 +90,53 @@ def test_elbm_alpha_and_populations(case):
         ref = run_oracle(cfg, f0, steps)
         # threshold flips between branches are possible in principle (device log vs libm): budget of 0.1 % of nodes
         check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3)
+
+
+FIELD_FORCE_CASES = [
+    # lattice, shape, equilibrium, scheme, tau, collision, eps
+    ("D2Q9", (33, 130, 1), "TruncationMa3", "Guo", 0.7, "BGK", 1e-2),
+    ("D3Q19", (12, 10, 9), "TruncationMa3", "ExactDifferenceMethod", 0.6, "BGK", 1e-2),
+    ("D3Q27", (8, 6, 4), "Exact", "ShanChen", 0.55, "BGK", 1e-2),
+    ("D2Q9", (16, 140, 1), "TruncationMa3", "Guo", 0.55, "ELBM", 2e-2),
+    ("D3Q19", (8, 6, 4), "TruncationMa3", "Guo", 0.55, "ForcedNR_ELBM_Forcing", 2e-2),
+]
+
+
+@pytest.mark.parametrize("case", FIELD_FORCE_CASES, ids=lambda c: "-".join(map(str, c[:1] + c[2:4] + c[5:6])))
+def test_force_read_from_the_force_field(case):
+    """Force "Field" (mlbm_set_force_field): the generic array read Force<Generic>::setForce (Force.h:39-48) that the
+    reference's spectral forces run through; pinned to the reference by tests/golden/*constantshell*.npz."""
+    lattice, shape, equilibrium, scheme, tau, collision, eps = case
+    cfg = _config(lattice, shape, equilibrium, scheme, "Field", tau, collision)
+    f0 = O.synthetic_populations(cfg, eps=eps, **_flow(eps))
+    field = force_field(cfg)
+    for steps in (1, 3):
+        got = run_cuda(cfg, f0, steps, force=field)
+        ref = run_oracle(cfg, f0, steps, force=field)
+        if collision == "BGK":
+            assert relative_error(got["f"], ref.f) <= POPULATION_TOLERANCE
+            assert np.abs(got["velocity"] - ref.velocity).max() <= 1e-13
+        else:
+            check_entropic(got, ref, cfg, steps, mismatch_budget=1e-3)
+        assert np.array_equal(got["force"], field)      # storeFields writes the values it read back (Algorithm.h:186-190)
+
+
+def test_field_force_equals_the_analytic_force_bit_for_bit():
+    """The Kolmogorov profile handed over as an array: the same doubles through the other route."""
+    analytic = _config("D3Q19", (12, 10, 130), "TruncationMa3", "Guo", "Kolmogorov", 0.55)
+    f0 = O.synthetic_populations(analytic, eps=1e-2)
+    want = run_cuda(analytic, f0, 3)
+    array = _config("D3Q19", (12, 10, 130), "TruncationMa3", "Guo", "Field", 0.55)
+    got = run_cuda(array, f0, 3, force=want["force"])
+    assert np.array_equal(got["f"], want["f"]) and np.array_equal(got["velocity"], want["velocity"])
+
+
+def test_force_field_needs_a_field_force_context():
+    from metalbm_b200.algorithm import Algorithm
+    from metalbm_b200.capi import MlbmError
+    with Algorithm(_config("D2Q9", (8, 8, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.7)) as algorithm:
+        with pytest.raises(MlbmError):
+            algorithm.set_force()
 
 
 def test_elbm_branches_are_exercised():
