@@ -43,6 +43,8 @@ struct StepParams {
   void* velocity;          // [D] components, fieldStride apart
   void* force;             // [D] components, fieldStride apart
   double* partials;        // [LX * NM * ceil(NR / kStepBlock)][kObservableSlots] block partial sums (only when isStored)
+  unsigned char* hints;    // [LX * NM * ceil(NR / kStepBlock)] entropic kernels built with MLBM_ELBM_FASTPATH: 1 = this block's
+                           // plane had a node off the small-deviation shortcut in the previous step (else unused)
   const double* forceTable[3];  // per force component: amplitude * profile along forceAxis (host libm values)
   int forceAxis[3];        // 0 = x, 1 = m, 2 = r, -1 = component is identically zero
   long long stride;        // elements between populations
@@ -469,6 +471,25 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
   }
 }
 
+// EXPERIMENT (MLBM_PREFETCH_NEXT_PLANE): the entropic blocks walk several planes and spend most of a plane computing, so
+// too few loads are in flight per SM to keep HBM busy; ask L2 for the populations of the block's NEXT plane while this one
+// is being solved.  One request per 32-byte sector.
+template <class L, typename StoreT>
+__device__ __forceinline__ void prefetchPopulations(const StepParams& p, const NodeIndex& n) {
+#if defined(__CUDA_ARCH__)
+  if ((threadIdx.x & (32 / (int)sizeof(StoreT) - 1)) != 0) return;
+  const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
+#pragma unroll
+  for (int q = 0; q < L::Q; ++q) {
+    const int xs = L::cx(q) == 1 ? n.xPrev : (L::cx(q) == -1 ? n.xNext : n.xh);
+    const int ms = L::cm(q) == 1 ? n.mPrev : (L::cm(q) == -1 ? n.mNext : n.m);
+    const int rs = L::cr(q) == 1 ? n.rPrev : (L::cr(q) == -1 ? n.rNext : n.r);
+    const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(source));
+  }
+#endif
+}
+
 // Moment::calculateDensity / calculateVelocity (Moment.h:14-47)
 template <class L>
 __device__ __forceinline__ void moments(const double (&f)[L::Q], double& rho, double& invRho, double (&u)[3], double& u2) {
@@ -659,13 +680,74 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
     const long long rowNode = (long long)x * p.plane + (long long)m * p.NR;  // field / alpha index of r = 0
     __syncthreads();  // constants staged (first plane) / shared columns of the previous plane no longer read
 
+#ifdef MLBM_ELBM_FASTPATH
+    // EXPERIMENT.  Where the flow is resolved every node of a block takes the small-deviation shortcut alpha = 2
+    // (Collision.h:284-303, 357-359) and the shared-memory staging, the compaction and three of the four barriers below
+    // buy nothing.  A one-byte hint per block and plane remembers whether the previous step found a node off the
+    // shortcut; if not, the block finishes the plane OPTIMISTICALLY from registers (exactly the BGK data flow) and votes
+    // afterwards.  The decision stays exact: a block in which some node turns out to be off the shortcut runs the general
+    // path after all, which overwrites everything the optimistic pass stored (same threads, same addresses), and raises
+    // the hint.
+    unsigned char* const hint = (!FORCED && p.hints) ? p.hints + (((long long)x * p.NM + m) * gridDim.x + blockIdx.x) : nullptr;
+    if (hint && *hint == 0) {  // block-uniform
+      bool large = false;
+      double rhoFast = 0.0, energyFast = 0.0, speed2Fast = 0.0;
+      if (active) {
+        const NodeIndex n = nodeIndex(p, x, m, r);
+        double f[Q];
+        pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
+        double invRhoFast, u2, uFast[3], forceFast[3];
+        moments<L>(f, rhoFast, invRhoFast, uFast, u2);
+        bodyForce<L, StoreT>(p, x, m, r, forceFast);
+        EquilibriumCoefficients<L, EQ> eqFast;
+        eqFast.set(uFast, u2);
+        const long long node = rowNode + r;
+        const long long out = (long long)(x + 1) * p.plane + (long long)m * p.NR + r;
+        StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
+        StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
+        alphaField[node] = (StoreT)2.0;
+        const double omega = 2.0 * p.beta;
+        SourceTerm<L, EQ, SCHEME> source;
+        source.set(p, rhoFast, invRhoFast, uFast, forceFast);
+        staticFor<0, Q>([&](auto qc) {
+          constexpr int q = decltype(qc)::value;
+          const double feq = rhoFast * L::w(q) * eqFast.template shape<q>();
+          const double nq = f[q] - feq;
+          const double a = fabs(nq);
+          large = large || (f[q] > 0.0 ? (a > 1.0e-3 * f[q]) : (f[q] == 0.0 ? a > 0.0 : false));
+          // the general path's (F2 - omega N2) 2^-k + S with F2 = 2^k f, N2 = 2^k fNeq: the power of two commutes with the rounding
+          const double value = fma(-omega, nq, f[q]) + source.template value<q>(f[q] - nq);
+          storePopulation(next + q * p.stride + out, value);
+          if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
+          if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
+        });
+        if (p.isStored) storeNodeFields<L, StoreT>(p, node, rhoFast, invRhoFast, uFast, forceFast, energyFast, speed2Fast);
+      }
+      if (p.isStored) reduceBlockObservables(p, x, energyFast, active ? rhoFast : 0.0, speed2Fast);
+      const unsigned largeBallot = __ballot_sync(0xffffffffu, large);
+      if ((t & 31) == 0) s.warpCount[t >> 5] = largeBallot != 0u;
+      __syncthreads();
+      int anyLarge = 0;
+#pragma unroll
+      for (int w = 0; w < kStepBlock / 32; ++w) anyLarge |= s.warpCount[w];
+      if (!anyLarge) continue;  // block-uniform: the plane is done
+      __syncthreads();          // the compaction below writes the warp counters again
+    }
+#endif
+
     double rho = 0.0, invRho = 0.0, energy = 0.0, speed2 = 0.0, alpha = 2.0;
     double u[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
     bool needsNewton = false;
+#ifdef MLBM_ELBM_FASTPATH
+    bool offShortcut = false;
+#endif
     if (active) {
       const NodeIndex n = nodeIndex(p, x, m, r);
       double f[Q];
       pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
+#ifdef MLBM_PREFETCH_NEXT_PLANE
+      if (i + 1 < p.planesPerBlock && planeIndex + 1 < p.planeCount) prefetchPopulations<L, StoreT>(p, nodeIndex(p, x + p.planeStep, m, r));
+#endif
       double u2;
       moments<L>(f, rho, invRho, u, u2);
       bodyForce<L, StoreT>(p, x, m, r, F);
@@ -696,6 +778,9 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
           if (af * den < num * nq) { num = af; den = nq; }
         }
       });
+#ifdef MLBM_ELBM_FASTPATH
+      offShortcut = !small;
+#endif
       if (!small) {
         // Collision<ELBM>::calculateAlpha (Collision.h:351-375) / Collision<ForcedNR_ELBM_Forcing>::calculateAlpha (:792-808)
         const double alphaMax = num / den;
@@ -707,15 +792,31 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
     // compaction: the i-th node (in thread order) that needs the Newton solve is solved by thread i
     const unsigned ballot = __ballot_sync(0xffffffffu, needsNewton);
     const int warp = t >> 5, lane = t & 31;
+#ifdef MLBM_ELBM_FASTPATH
+    const unsigned offBallot = __ballot_sync(0xffffffffu, offShortcut);
+    if (lane == 0) s.warpCount[warp] = __popc(ballot) | (offBallot != 0u ? 0x10000 : 0);
+#else
     if (lane == 0) s.warpCount[warp] = __popc(ballot);
+#endif
     __syncthreads();
     int before = 0, total = 0;
+#ifdef MLBM_ELBM_FASTPATH
+    int anyOff = 0;
+#endif
 #pragma unroll
     for (int w = 0; w < kStepBlock / 32; ++w) {
+#ifdef MLBM_ELBM_FASTPATH
+      const int count = s.warpCount[w] & 0xffff;
+      anyOff |= s.warpCount[w] >> 16;
+#else
       const int count = s.warpCount[w];
+#endif
       if (w < warp) before += count;
       total += count;
     }
+#ifdef MLBM_ELBM_FASTPATH
+    if (hint && t == 0) *hint = anyOff ? 1 : 0;  // the next step of this block and plane starts from what this one saw
+#endif
     if (total > 0) {  // block-uniform
       if (needsNewton) s.list[before + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)t;
       __syncthreads();

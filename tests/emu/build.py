@@ -17,8 +17,10 @@ LIBRARY = BUILD / "libstep_emu.so"
 DYNAMIC_SHARED = "extern __shared__ __align__(16) unsigned char dynamicShared[];"
 
 
-def build() -> Path:
+def build(flags: tuple = ()) -> Path:
+    """``flags``: extra -D switches (the experimental kernel variants); every set of flags is its own library."""
     BUILD.mkdir(exist_ok=True)
+    LIBRARY = BUILD / ("libstep_emu" + "".join("_" + f.lstrip("-D").lower() for f in flags) + ".so")
     sources = [CSRC / "step_kernel.cuh", CSRC / "lattice.cuh", CSRC / "log_table.inc", HERE / "cuda_emu.h", HERE / "step_emu.cpp",
                HERE / "include" / "cuda_runtime.h", Path(__file__)]
     if LIBRARY.is_file() and all(s.stat().st_mtime <= LIBRARY.stat().st_mtime for s in sources):
@@ -31,7 +33,7 @@ def build() -> Path:
     # hidden visibility + -Bsymbolic: libmetalbm_b200.so (loaded RTLD_GLOBAL by the tests) exports host stubs with the very
     # same mangled kernel names; the emulator must bind to its own definitions
     cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-shared", "-ffp-contract=off", "-fno-strict-aliasing", "-w",
-           "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic",
+           "-fvisibility=hidden", "-fvisibility-inlines-hidden", "-Wl,-Bsymbolic", *flags,
            f"-I{HERE / 'include'}", f"-I{BUILD}", f"-I{CSRC}", str(HERE / "step_emu.cpp"), "-o", str(LIBRARY)]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
