@@ -528,6 +528,20 @@ def run_ours(args) -> int:
         t3 = time.perf_counter()
         barrier()
         e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+        # outside the timed region: what the same bytes cost as ONE contiguous copy each way (the upload / download above
+        # move 2 KB rows of a padded host array with cudaMemcpy2DAsync); tells whether a staged contiguous copy would pay
+        contiguous = {}
+        try:
+            device_copy = torch.empty(pinned.shape, dtype=pinned.dtype, device="cuda")
+            for name, source, target in (("h2d", pinned, device_copy), ("d2h", device_copy, pinned)):
+                torch.cuda.synchronize()
+                c0 = time.perf_counter()
+                target.copy_(source, non_blocking=True)
+                torch.cuda.synchronize()
+                contiguous[name + "_contiguous_GBps"] = pinned.numel() * element / (time.perf_counter() - c0) / 1e9
+            del device_copy
+        except Exception as error:  # noqa: BLE001 -- a diagnostic, never fatal
+            contiguous = {"contiguous_probe_error": str(error)[:200]}
         e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
         distribution_bytes = q_count * nodes_local * element
         e2e = {"value": e2e_value, "unit": UNIT,
@@ -538,7 +552,7 @@ def run_ours(args) -> int:
                        "amortised over K", "last_energy": energy,
                "unpack_ms": (t1 - t0) * 1e3, "steps_ms": (t2 - t1) * 1e3, "pack_ms": (t3 - t2) * 1e3,
                "h2d_GBps": q_count * nodes_local * element / (t1 - t0) / 1e9,
-               "d2h_GBps": q_count * nodes_local * element / (t3 - t2) / 1e9}
+               "d2h_GBps": q_count * nodes_local * element / (t3 - t2) / 1e9, **contiguous}
 
     peak, peak_source = measured_peak()
     # the dominant kernel is the bulk launch of the fused step: all local planes at N = 1, all but the two boundary
