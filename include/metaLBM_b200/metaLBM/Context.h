@@ -39,13 +39,14 @@ constexpr int abiScheme(ForcingSchemeType s) {
 }
 constexpr int abiForce(ForceType f) {
   return f == ForceType::None ? (int)MLBM_FORCE_NONE : f == ForceType::Constant ? (int)MLBM_FORCE_CONSTANT
-       : f == ForceType::Sinusoidal ? (int)MLBM_FORCE_SINUSOIDAL : f == ForceType::Kolmogorov ? (int)MLBM_FORCE_KOLMOGOROV : -1;
+       : f == ForceType::Sinusoidal ? (int)MLBM_FORCE_SINUSOIDAL : f == ForceType::Kolmogorov ? (int)MLBM_FORCE_KOLMOGOROV
+       : (f == ForceType::ConstantShell && L::dimD == 2) ? (int)MLBM_FORCE_CONSTANT_SHELL : -1;
 }
 
 static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or one of the entropic variants that behave like ELBM in the reference (Approached_, Malaspinas_, Essentially1_, Essentially2_, ForcedNR_, ForcedBNR_ELBM) or ForcedNR_ELBM_Forcing");
 static_assert(abiEquilibrium(equilibriumT) >= 0, "metalbm_b200: equilibriumT must be TruncationMa3 or Exact");
 static_assert(abiScheme(forcingSchemeT) >= 0, "metalbm_b200: forcingSchemeT must be None, Guo, ShanChen or ExactDifferenceMethod");
-static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal or Kolmogorov (spectral forces are out of scope)");
+static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal, Kolmogorov or (2-D lattices) ConstantShell; the other spectral forces go through the C-ABI's MLBM_FORCE_FIELD");
 static_assert(algorithmT == AlgorithmType::Pull && memoryL == MemoryLayout::SoA && partitionningT == PartitionningType::OneD,
               "metalbm_b200 implements the Pull / SoA / OneD step (Algorithm.h:300-452)");
 static_assert(sizeof(dataT) == 8 || sizeof(dataT) == 4, "dataT must be double or float");
@@ -71,6 +72,8 @@ class Context {
     config.nranks = numProcs;
     config.device = -1;  // rank % device count, CUDAInitializer.h:23-26
     config.tau = (double)relaxationTime;
+    config.force_k_min = (int)forcekMin;  // Algorithm.h:90-91
+    config.force_k_max = (int)forcekMax;
     LBM_B200_CALL(mlbm_create(&config, &handle));
     if (numProcs > 1) {
       unsigned char id[128] = {0};

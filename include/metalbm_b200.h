@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MLBM_ABI_VERSION 1
+#define MLBM_ABI_VERSION 2
 
 typedef struct mlbm_ctx mlbm_ctx;
 
@@ -72,9 +72,16 @@ typedef enum mlbm_forcing_scheme {
  * MLBM_FORCE_FIELD is the generic array read Force<T, ForceType::Generic>::setForce (Force.h:39-48): the force of a node
  * is component iD of the force FIELD at the node's local index.  It is what every array-type force of the reference
  * runs through on the step path (ConstantShell, EnergyRemoval, Turbulent2D, Force.h:296-623, fill that array with FFTs
- * outside the step); here the caller supplies the array with mlbm_set_force_field. */
+ * outside the step); here the caller supplies the array with mlbm_set_force_field.
+ * MLBM_FORCE_CONSTANT_SHELL is Force<double, ForceType::ConstantShell> (Force.h:296-420) for 2-D lattices: the stream
+ * function psi^(k) = force_amplitude[0] on the shell force_k_min^2 <= |k|^2 <= force_k_max^2 (integer wave numbers),
+ * made solenoidal by MakeIncompressible (Transformer.h:300-384: F^ = (i k_y psi^, -i k_x psi^)), transformed back and
+ * divided by the volume; the array is synthesised once on the device when the context is created and then read like
+ * MLBM_FORCE_FIELD.  (The reference's 3-D variant corrupts its heap -- Force.h:341-355 writes mirrored indices of a
+ * padded local array -- and is not rebuilt; a 3-D shell force goes through MLBM_FORCE_FIELD.) */
 typedef enum mlbm_force {
-  MLBM_FORCE_NONE = 0, MLBM_FORCE_CONSTANT = 1, MLBM_FORCE_SINUSOIDAL = 2, MLBM_FORCE_KOLMOGOROV = 3, MLBM_FORCE_FIELD = 4
+  MLBM_FORCE_NONE = 0, MLBM_FORCE_CONSTANT = 1, MLBM_FORCE_SINUSOIDAL = 2, MLBM_FORCE_KOLMOGOROV = 3, MLBM_FORCE_FIELD = 4,
+  MLBM_FORCE_CONSTANT_SHELL = 5
 } mlbm_force;
 
 /* `dataT` (Input_prod.in:10).  F32 is FP32 storage of populations and fields with the moments,
@@ -104,6 +111,8 @@ typedef struct mlbm_config {
   double tau;                 /* relaxationTime  */
   double force_amplitude[3];  /* forceAmplitude  */
   double force_wavelength[3]; /* forceWaveLength */
+  int32_t force_k_min;        /* forcekMin (shell forces, Force.h:303, 315) */
+  int32_t force_k_max;        /* forcekMax */
 } mlbm_config;
 
 const char* mlbm_last_error(void);

@@ -14,7 +14,7 @@ from pathlib import Path
 PACKAGE_DIR = Path(__file__).resolve().parent
 # MLBM_VARIANT selects an experimental build (metalbm_b200/build.py); the product library otherwise
 LIBRARY_PATH = PACKAGE_DIR / ("libmetalbm_b200" + ("_" + os.environ["MLBM_VARIANT"] if os.environ.get("MLBM_VARIANT") else "") + ".so")
-ABI_VERSION = 1
+ABI_VERSION = 2
 PEER_HANDLE_BYTES = 256
 
 
@@ -56,6 +56,7 @@ class Force(enum.IntEnum):
     Sinusoidal = 2
     Kolmogorov = 3
     Field = 4          # generic array read (Force.h:39-48); the array comes from mlbm_set_force_field
+    ConstantShell = 5  # Force.h:296-420, 2-D lattices: synthesised on the device at mlbm_create
 
 
 class DType(enum.IntEnum):
@@ -91,6 +92,8 @@ class MlbmConfig(ctypes.Structure):
         ("tau", ctypes.c_double),
         ("force_amplitude", ctypes.c_double * 3),
         ("force_wavelength", ctypes.c_double * 3),
+        ("force_k_min", ctypes.c_int32),
+        ("force_k_max", ctypes.c_int32),
     ]
 
 
@@ -152,7 +155,7 @@ def _lookup(enum_cls, value):
 def make_config(lattice="D2Q9", shape=(16, 16, 1), collision="BGK", equilibrium="TruncationMa3",
                 forcing_scheme="None", force="None", tau=0.7, amplitude=(0.0, 0.0, 0.0),
                 wavelength=(32.0, 32.0, 32.0), dtype="F64", overlap="Off", rank=0, nranks=1,
-                device=-1, variant=0) -> MlbmConfig:
+                device=-1, variant=0, k_min=1, k_max=2) -> MlbmConfig:
     cfg = MlbmConfig()
     cfg.abi_version = ABI_VERSION
     cfg.lattice = _lookup(Lattice, lattice)
@@ -170,6 +173,7 @@ def make_config(lattice="D2Q9", shape=(16, 16, 1), collision="BGK", equilibrium=
         cfg.force_wavelength[i] = float(wavelength[i])
     cfg.rank, cfg.nranks, cfg.device, cfg.variant = int(rank), int(nranks), int(device), int(variant)
     cfg.tau = float(tau)
+    cfg.force_k_min, cfg.force_k_max = int(k_min), int(k_max)
     return cfg
 
 

@@ -84,6 +84,8 @@ class OracleState:
         self.density = np.zeros(self.shape)
         self.velocity = np.zeros((self.dim,) + self.shape)
         self.force = np.zeros((self.dim,) + self.shape)
+        if int(cfg.force) == 5:   # ConstantShell: the array setForceArray makes in the Collision ctor (Collision.h:51-54)
+            self.force[...] = constant_shell_force(cfg)
         self.branch = np.zeros(self.shape, dtype=np.int32)
         self.iterations = np.zeros(self.shape, dtype=np.int32)
         # checker-side diagnostics of the last step: rounding-noise floor of the Newton iterate and max_q |fNeq_q|
@@ -105,6 +107,26 @@ class OracleState:
         lib().mlbm_oracle_observables(ctypes.byref(self.cfg), _dp(self.density), _dp(self.velocity), _dp(out))
         out[1] = spectral_enstrophy(self.velocity, self.dim)
         return out
+
+
+def constant_shell_force(cfg: MlbmConfig) -> np.ndarray:
+    """Force<double, ForceType::ConstantShell> for 2-D lattices, step by step as the reference does it:
+    initTempArray (Force.h:333-420): psi^ = amplitude[0] (real) on the shell kMin^2 <= |k|^2 <= kMax^2 of the r2c half
+    spectrum [Nx][Ny/2+1], integer wave numbers k = i <= N/2 ? i : i - N (the mirrored writes of :353-372, :394-414 set the
+    same values); MakeIncompressible<2>::executeFourier (Transformer.h:318-381): F^x = (-ky Im psi^, ky Re psi^),
+    F^y = (kx Im psi^, -kx Re psi^); BackwardFFT::execute (Transformer.h:101-108): c2r, divided by the volume.
+    numpy's irfft2 is that c2r (it drops the non-Hermitian part of the self-conjugate columns like FFTW) already divided
+    by the volume.  Pinned against the arrays the reference itself produced (tests/golden/*constantshell*.npz)."""
+    nx, ny, nz = shape_of(cfg)
+    assert nz == 1 and LATTICE_DQ[Lattice(cfg.lattice)][0] == 2, "the 3-D variant corrupts the reference's heap; not restated"
+    kx = np.array([i if i <= nx // 2 else i - nx for i in range(nx)], dtype=np.float64)[:, None]
+    ky = np.arange(ny // 2 + 1, dtype=np.float64)[None, :]
+    k2 = kx * kx + ky * ky
+    psi = np.where((k2 >= cfg.force_k_min ** 2) & (k2 <= cfg.force_k_max ** 2), float(cfg.force_amplitude[0]), 0.0).astype(np.complex128)
+    fx_hat = (-ky * psi.imag) + 1j * (ky * psi.real)
+    fy_hat = (kx * psi.imag) + 1j * (-kx * psi.real)
+    force = np.stack([np.fft.irfft2(fx_hat, s=(nx, ny)), np.fft.irfft2(fy_hat, s=(nx, ny))])
+    return force.reshape(2, nx, ny, 1)
 
 
 def init_equilibrium(cfg: MlbmConfig, density: np.ndarray, velocity: np.ndarray) -> np.ndarray:

@@ -71,6 +71,33 @@ def force_field(cfg, seed=5, amplitude=2e-4):
     return field
 
 
+def shell_force_direct(cfg):
+    """The sum shellForceKernel (csrc/context.cu) evaluates, mode list and integer angle reduction included, in numpy."""
+    nx, ny, _ = O.shape_of(cfg)
+    scale = cfg.force_amplitude[0] / (nx * ny)
+    x, y = np.arange(nx)[:, None], np.arange(ny)[None, :]
+    field = np.zeros((2, nx, ny, 1))
+    for ix in range(nx):
+        kx = ix if ix <= nx // 2 else ix - nx
+        for iy in range(ny // 2 + 1):
+            k2 = kx * kx + iy * iy
+            if k2 < cfg.force_k_min ** 2 or k2 > cfg.force_k_max ** 2:
+                continue
+            weight = 1.0 if (iy == 0 or (ny % 2 == 0 and iy == ny // 2)) else 2.0
+            s = np.sin(np.pi * (2.0 * ((kx * x) % nx) / nx + 2.0 * ((iy * y) % ny) / ny)) * (weight * scale)
+            field[0, :, :, 0] -= iy * s
+            field[1, :, :, 0] += kx * s
+    return field
+
+
+def native_shell_config(meta, **extra):
+    """The golden cases recorded with the reference's ConstantShell (forcekMin = 1, forcekMax = 2, oracle/refbuild.py) as a
+    configuration of this repository's own ConstantShell."""
+    return capi.make_config(lattice=meta["lattice"], shape=meta["shape"], collision=meta["collision"],
+                            equilibrium=meta["equilibrium"], forcing_scheme=meta["forcing_scheme"], force="ConstantShell",
+                            tau=meta["tau"], amplitude=meta["amplitude"], wavelength=meta["wavelength"], k_min=1, k_max=2, **extra)
+
+
 def run_oracle(cfg, f0, steps, alpha0=None, force=None):
     state = O.OracleState(cfg, f0, alpha0)
     if force is not None:

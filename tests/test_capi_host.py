@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
 
 
 def test_struct_layout_matches_header(cuda_lib):
-    assert ctypes.sizeof(capi.MlbmConfig) == 8 * 4 + 3 * 4 + 4 * 4 + 4 + 8 + 24 + 24  # includes 4 bytes of padding before tau
+    assert ctypes.sizeof(capi.MlbmConfig) == 8 * 4 + 3 * 4 + 4 * 4 + 4 + 8 + 24 + 24 + 2 * 4  # includes 4 bytes of padding before tau
     assert ctypes.sizeof(capi.MlbmHaloMessage) == 32
 
 
@@ -54,7 +54,9 @@ def test_create_rejects_bad_configurations(cuda_lib):
     ctx = ctypes.c_void_p()
     bad = [capi.make_config("D3Q19", (8, 8, 8), equilibrium="Exact"),      # Exact exists for D2Q9 / D3Q27 only
            capi.make_config("D3Q19", (9, 8, 8), nranks=2),                 # numProcs must divide globalLengthX
-           capi.make_config("D2Q9", (8, 8, 1), tau=0.5)]
+           capi.make_config("D2Q9", (8, 8, 1), tau=0.5),
+           capi.make_config("D3Q19", (8, 8, 8), force="ConstantShell"),    # the shell force is rebuilt for 2-D lattices only
+           capi.make_config("D2Q9", (8, 8, 1), force="ConstantShell", k_min=3, k_max=2)]
     for cfg in bad:
         assert cuda_lib.mlbm_create(ctypes.byref(cfg), ctypes.byref(ctx)) == -1
     cfg = capi.make_config("D2Q9", (8, 8, 1))
@@ -184,6 +186,8 @@ def test_halo_plan_over_gloo(cuda_lib, oracle_lib, tmp_path, world):
     ("D3Q27", (512, 512, 512), "ELBM", "Guo", "Kolmogorov", 0.50000032, 1),
     ("D2Q9", (8192, 8192, 1), "ELBM", "ShanChen", "Kolmogorov", 0.7, 8),
     ("D2Q9", (24, 130, 1), "ForcedNR_ELBM", "ExactDifferenceMethod", "Constant", 0.9, 2),
+    ("D3Q27", (16, 12, 10), "BGK", "Guo", "Field", 0.6, 2),            # array-type forces read the force field
+    ("D2Q9", (64, 48, 1), "ELBM", "Guo", "ConstantShell", 0.6, 4),
 ])
 def test_launch_plan_scalars_follow_the_configuration(cuda_lib, lattice, shape, collision, scheme, force, tau, nranks):
     cfg = capi.make_config(lattice=lattice, shape=shape, collision=collision, forcing_scheme=scheme, force=force, tau=tau,
@@ -198,7 +202,7 @@ def test_launch_plan_scalars_follow_the_configuration(cuda_lib, lattice, shape, 
         assert plan.wrap_x == (1 if nranks == 1 else 0)
         assert plan.is_stored == is_stored
         assert plan.hydro_shift == (0 if scheme == "None" else 1)              # ForcingScheme.h:26-33 / :50-57
-        assert plan.has_force == (0 if force == "None" else 1)
+        assert plan.has_force == (0 if force == "None" else (2 if force in ("Field", "ConstantShell") else 1))
         assert list(plan.local_length) == [lx, nm, nr]
         assert plan.plane == nm * nr and plan.stride >= plan.plane * (lx + 2) and plan.stride % 32 == 0
         assert plan.block == 128 and plan.grid[0] == -(-nr // 128) and plan.grid[1] == nm

@@ -70,6 +70,9 @@ def test_reference_style_main_compiles_and_links(tmp_path, cuda_lib):
 
 
 def test_unsupported_choices_fail_at_compile_time(tmp_path):
+    compile_example(tmp_path, "shim_check.cpp", "shell", "D2Q9", (24, 20, 1), force="ConstantShell", link=False)
+    with pytest.raises(AssertionError):   # the shell force exists for 2-D lattices only
+        compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), force="ConstantShell", link=False)
     with pytest.raises(AssertionError):
         compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), equilibrium="Exact", link=False)
     with pytest.raises(AssertionError):
@@ -104,6 +107,7 @@ SHIM_CASES = [
     ("D3Q19", (16, 12, 10), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 3),
     ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 3),
     ("D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 1),
+    ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "ConstantShell", 3),   # forcekMin / forcekMax of examples/Input_generic.in
 ]
 
 

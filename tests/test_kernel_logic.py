@@ -81,6 +81,11 @@ class Slab:
         grid_r = -(-self.nr // 128)
         self.partials = np.full(grid_r * self.nm * self.lx * 3, np.nan)
         self.hints = np.zeros(grid_r * self.nm * self.lx, dtype=np.uint8)   # context.cu: one byte per block and plane
+        if cfg.force == capi.Force.ConstantShell:
+            # mlbm_create synthesises the shell force into the force field (shellForceKernel); this rank's slab of it
+            from helpers import shell_force_direct
+            lo = int(cfg.rank) * self.lx
+            self.set_force(shell_force_direct(cfg)[:, lo:lo + self.lx].reshape(2, self.lx, 1, self.nr).astype(dtype))
         self.entropic = cfg.collision != capi.Collision.BGK
         # force profiles exactly as mlbm_create evaluates them (context.cu), at LOCAL coordinates (Collision.h:86)
         extent = [self.lx, cfg.global_length[1], cfg.global_length[2] if self.dim == 3 else 1]
@@ -254,6 +259,21 @@ def test_kernel_source_reproduces_the_oracle(emu, case):
     got = run_single(emu, cfg, f0, steps)
     ref = run_oracle(cfg, f0, steps)
     _compare(cfg, got, ref, steps, collision != "BGK")
+
+
+@pytest.mark.parametrize("collision,scheme,shell", [("BGK", "Guo", (1, 2)), ("ELBM", "ExactDifferenceMethod", (1, 2)),
+                                                    ("BGK", "ShanChen", (0, 5))])
+def test_constant_shell_force(emu, collision, scheme, shell):
+    """Force "ConstantShell" (2-D): the kernel reads the array made at create time; the oracle holds the reference's own
+    construction of it (FFT route), the slab the device's mode sum."""
+    cfg = make_config(lattice="D2Q9", shape=(10, 9, 1), collision=collision, forcing_scheme=scheme, force="ConstantShell", tau=0.6,
+                      amplitude=(2e-3, 0.0, 0.0), k_min=shell[0], k_max=shell[1])
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    got = run_single(emu, cfg, f0, 2)
+    ref = run_oracle(cfg, f0, 2)
+    assert np.abs(ref.force).max() > 1e-5 and np.abs(got["force"] - ref.force).max() <= 4e-15 * np.abs(ref.force).max()
+    got["force"] = ref.force          # _compare asks for bit-equal force arrays: compared above at the synthesis tolerance
+    _compare(cfg, got, ref, 2, collision != "BGK")
 
 
 FIELD_FORCE_CASES = [

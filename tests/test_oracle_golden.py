@@ -4,6 +4,8 @@ import numpy as np
 import pytest
 
 from golden_util import golden_names, load_golden
+from helpers import native_shell_config, shell_force_direct
+from metalbm_b200.capi import make_config
 from oracle import oracle as O
 
 
@@ -45,3 +47,33 @@ def test_every_alpha_branch_is_covered_by_the_golden_set(oracle_lib):
         state.step(True)
         seen |= set(np.unique(state.branch).tolist())
     assert {0, 1, 2, 3} <= seen
+
+
+SHELL_GOLDEN = ["d2q9_bgk_guo_constantshell", "d2q9_elbm_edm_constantshell", "d2q9_bgk_shanchen_turbulent2d"]
+
+
+@pytest.mark.parametrize("name", SHELL_GOLDEN)
+def test_constant_shell_restatement_against_the_reference_arrays(name, oracle_lib):
+    """oracle.constant_shell_force (Force.h:296-420 + Transformer.h:300-384 restated) against the force array the reference
+    itself made, and the oracle run from the NATIVE ConstantShell configuration against the reference's populations."""
+    meta, _, data = load_golden(name)
+    cfg = native_shell_config(meta)
+    scale = np.abs(data["force"]).max()
+    assert np.abs(O.constant_shell_force(cfg) - data["force"]).max() <= 2e-15 * scale
+    assert np.abs(shell_force_direct(cfg) - data["force"]).max() <= 4e-15 * scale       # the device kernel's formula
+    state = O.OracleState(cfg, data["f0"])
+    for _ in range(meta["steps"]):
+        state.step(True)
+    assert np.abs(state.f - data["f"]).max() <= 1e-14 * np.abs(data["f"]).max()
+    assert np.abs(state.alpha - data["alpha"]).max() <= 1e-10
+
+
+@pytest.mark.parametrize("shape", [(8, 6, 1), (7, 5, 1), (8, 5, 1), (9, 8, 1)])
+@pytest.mark.parametrize("shell", [(1, 2), (0, 4), (2, 6), (3, 3)])
+def test_constant_shell_direct_sum_equals_the_transform(shape, shell):
+    """The device synthesises the shell force as a sum over the shell's modes instead of a c2r transform: equal for even and
+    odd extents and for shells that reach the Nyquist wave numbers (where the transform drops non-Hermitian parts)."""
+    cfg = make_config("D2Q9", shape, force="ConstantShell", amplitude=(1e-4, 0.0, 0.0), k_min=shell[0], k_max=shell[1])
+    transform = O.constant_shell_force(cfg)
+    assert np.abs(transform).max() > 0
+    assert np.abs(shell_force_direct(cfg) - transform).max() <= 4e-15 * np.abs(transform).max()

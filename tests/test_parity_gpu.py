@@ -6,7 +6,7 @@ energy <= 1e-9 relative after 100 steps."""
 import numpy as np
 import pytest
 
-from helpers import check_entropic, force_field, relative_error, run_cuda, run_oracle
+from helpers import check_entropic, force_field, native_shell_config, relative_error, run_cuda, run_oracle
 from metalbm_b200.capi import check, make_config
 from oracle import oracle as O
 
@@ -137,6 +137,36 @@ def test_force_field_needs_a_field_force_context():
     with Algorithm(_config("D2Q9", (8, 8, 1), "TruncationMa3", "Guo", "Kolmogorov", 0.7)) as algorithm:
         with pytest.raises(MlbmError):
             algorithm.set_force()
+
+
+@pytest.mark.parametrize("name", ["d2q9_bgk_guo_constantshell", "d2q9_elbm_edm_constantshell", "d2q9_bgk_shanchen_turbulent2d"])
+def test_native_constant_shell_against_the_reference(name):
+    """Force "ConstantShell" synthesised on the device at mlbm_create (csrc/context.cu: shellForceKernel) against golden
+    vectors of the reference run with its own ConstantShell / Turbulent2D force: the force array and the populations."""
+    from golden_util import load_golden
+    meta, _, data = load_golden(name)
+    cfg = native_shell_config(meta)
+    got = run_cuda(cfg, data["f0"], meta["steps"])
+    assert np.abs(got["force"] - data["force"]).max() <= 4e-15 * np.abs(data["force"]).max()
+    if meta["collision"] == "BGK":
+        assert relative_error(got["f"], data["f"]) <= POPULATION_TOLERANCE
+    else:
+        ref = run_oracle(cfg, data["f0"], meta["steps"])
+        check_entropic(got, ref, cfg, meta["steps"], mismatch_budget=5e-3)
+    energy = data["observables"][-1][1]
+    assert abs(got["observables"][0] - energy) <= ENERGY_TOLERANCE * abs(energy)
+
+
+@pytest.mark.parametrize("shape,shell,dtype", [((33, 20, 1), (1, 2), "F64"), ((16, 15, 1), (0, 9), "F64"), ((24, 130, 1), (2, 3), "F32")])
+def test_native_constant_shell_odd_sizes_and_nyquist_shells(shape, shell, dtype):
+    cfg = make_config(lattice="D2Q9", shape=shape, collision="BGK", forcing_scheme="Guo", force="ConstantShell", tau=0.7,
+                      amplitude=(2e-3, 0.0, 0.0), k_min=shell[0], k_max=shell[1], dtype=dtype)
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    got = run_cuda(cfg, f0, 2)
+    ref = run_oracle(cfg, f0, 2)
+    scale = np.abs(ref.force).max()
+    assert scale > 0 and np.abs(got["force"] - ref.force).max() <= (4e-15 if dtype == "F64" else 1e-7) * scale
+    assert relative_error(got["f"], ref.f) <= (POPULATION_TOLERANCE if dtype == "F64" else 1e-5)
 
 
 def test_elbm_branches_are_exercised():
