@@ -45,6 +45,8 @@ constexpr int abiForce(ForceType f) {
 
 static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or one of the entropic variants that behave like ELBM in the reference (Approached_, Malaspinas_, Essentially1_, Essentially2_, ForcedNR_, ForcedBNR_ELBM) or ForcedNR_ELBM_Forcing");
 static_assert(abiEquilibrium(equilibriumT) >= 0, "metalbm_b200: equilibriumT must be TruncationMa3 or Exact");
+static_assert(equilibriumT != EquilibriumType::Exact || latticeT == LatticeType::D2Q9 || latticeT == LatticeType::D3Q27,
+              "metalbm_b200: the exact equilibrium exists for D2Q9 and D3Q27 only (Equilibrium.h:36-126)");
 static_assert(abiScheme(forcingSchemeT) >= 0, "metalbm_b200: forcingSchemeT must be None, Guo, ShanChen or ExactDifferenceMethod");
 static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal, Kolmogorov or (2-D lattices) ConstantShell; the other spectral forces go through the C-ABI's MLBM_FORCE_FIELD");
 static_assert(algorithmT == AlgorithmType::Pull && memoryL == MemoryLayout::SoA && partitionningT == PartitionningType::OneD,

@@ -23,7 +23,8 @@ LIBDIR = ROOT / "metalbm_b200"
 
 
 def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equilibrium="TruncationMa3", scheme="Guo",
-                    force="Kolmogorov", tau=0.55, nprocs=1, overlap="Off", link=True, input_file="Input_generic.in", steps=100):
+                    force="Kolmogorov", tau=0.55, nprocs=1, overlap="Off", link=True, input_file="Input_generic.in", steps=100,
+                    compile_only=False):
     output = tmp_path / name
     command = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
                f"-DNPROCS={nprocs}", "-DNTHREADS=1", f"-DGLOBAL_LENGTH_X={shape[0]}", f"-DGLOBAL_LENGTH_Y={shape[1]}",
@@ -32,7 +33,9 @@ def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equ
                f"-DLBM_OVERLAP={overlap}", f"-DLBM_STEPS={steps}",
                "-include", str(ROOT / "examples" / input_file), "-I", str(INCLUDE), str(ROOT / "examples" / source),
                "-o", str(output)]
-    if link:
+    if compile_only:
+        command.insert(1, "-c")
+    elif link:
         command += ["-L", str(LIBDIR), "-lmetalbm_b200", f"-Wl,-rpath,{LIBDIR}"]
     result = subprocess.run(command, capture_output=True, text=True)
     assert result.returncode == 0, result.stderr[-4000:]
@@ -70,13 +73,16 @@ def test_reference_style_main_compiles_and_links(tmp_path, cuda_lib):
 
 
 def test_unsupported_choices_fail_at_compile_time(tmp_path):
-    compile_example(tmp_path, "shim_check.cpp", "shell", "D2Q9", (24, 20, 1), force="ConstantShell", link=False)
-    with pytest.raises(AssertionError):   # the shell force exists for 2-D lattices only
-        compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), force="ConstantShell", link=False)
-    with pytest.raises(AssertionError):
-        compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), equilibrium="Exact", link=False)
-    with pytest.raises(AssertionError):
-        compile_example(tmp_path, "shim_check.cpp", "bad", "D3Q19", (8, 6, 4), collision="Malaspinas_ELBM", link=False)
+    """static_asserts of the template layer, not link errors: compiled with -c."""
+    compile_example(tmp_path, "shim_check.cpp", "shell.o", "D2Q9", (24, 20, 1), force="ConstantShell", compile_only=True)
+    compile_example(tmp_path, "shim_check.cpp", "alpha.o", "D3Q19", (8, 6, 4), collision="Malaspinas_ELBM", compile_only=True)
+    rejected = [dict(lattice="D3Q19", shape=(8, 6, 4), equilibrium="Exact"),          # Exact: D2Q9 / D3Q27 only (Equilibrium.h:36-126)
+                dict(lattice="D3Q19", shape=(8, 6, 4), force="ConstantShell"),        # the shell force is rebuilt for 2-D lattices only
+                dict(lattice="D2Q9", shape=(8, 6, 1), force="EnergyRemoval"),         # FFT-per-step forces: MLBM_FORCE_FIELD
+                dict(lattice="D2Q9", shape=(8, 6, 1), force="Turbulent2D")]
+    for choice in rejected:
+        with pytest.raises(AssertionError, match="static assertion failed"):
+            compile_example(tmp_path, "shim_check.cpp", "bad.o", choice.pop("lattice"), choice.pop("shape"), compile_only=True, **choice)
 
 
 def _run_shim(tmp_path, binary, f0_slabs, steps, env_extra=None):
