@@ -40,7 +40,9 @@ constexpr int abiScheme(ForcingSchemeType s) {
 constexpr int abiForce(ForceType f) {
   return f == ForceType::None ? (int)MLBM_FORCE_NONE : f == ForceType::Constant ? (int)MLBM_FORCE_CONSTANT
        : f == ForceType::Sinusoidal ? (int)MLBM_FORCE_SINUSOIDAL : f == ForceType::Kolmogorov ? (int)MLBM_FORCE_KOLMOGOROV
-       : (f == ForceType::ConstantShell && L::dimD == 2) ? (int)MLBM_FORCE_CONSTANT_SHELL : -1;
+       : (f == ForceType::ConstantShell && L::dimD == 2) ? (int)MLBM_FORCE_CONSTANT_SHELL
+       : (f == ForceType::EnergyRemoval && L::dimD == 2) ? (int)MLBM_FORCE_ENERGY_REMOVAL
+       : (f == ForceType::Turbulent2D && L::dimD == 2) ? (int)MLBM_FORCE_TURBULENT_2D : -1;
 }
 
 static_assert(abiCollision(collisionT) >= 0, "metalbm_b200: collisionT must be BGK, ELBM or one of the entropic variants that behave like ELBM in the reference (Approached_, Malaspinas_, Essentially1_, Essentially2_, ForcedNR_, ForcedBNR_ELBM) or ForcedNR_ELBM_Forcing");
@@ -48,7 +50,7 @@ static_assert(abiEquilibrium(equilibriumT) >= 0, "metalbm_b200: equilibriumT mus
 static_assert(equilibriumT != EquilibriumType::Exact || latticeT == LatticeType::D2Q9 || latticeT == LatticeType::D3Q27,
               "metalbm_b200: the exact equilibrium exists for D2Q9 and D3Q27 only (Equilibrium.h:36-126)");
 static_assert(abiScheme(forcingSchemeT) >= 0, "metalbm_b200: forcingSchemeT must be None, Guo, ShanChen or ExactDifferenceMethod");
-static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal, Kolmogorov or (2-D lattices) ConstantShell; the other spectral forces go through the C-ABI's MLBM_FORCE_FIELD");
+static_assert(abiForce(forceT) >= 0, "metalbm_b200: forceT must be None, Constant, Sinusoidal, Kolmogorov or, on 2-D lattices, ConstantShell, EnergyRemoval, Turbulent2D (their 3-D variants go through the C-ABI's MLBM_FORCE_FIELD)");
 static_assert(algorithmT == AlgorithmType::Pull && memoryL == MemoryLayout::SoA && partitionningT == PartitionningType::OneD,
               "metalbm_b200 implements the Pull / SoA / OneD step (Algorithm.h:300-452)");
 static_assert(sizeof(dataT) == 8 || sizeof(dataT) == 4, "dataT must be double or float");
@@ -76,6 +78,9 @@ class Context {
     config.tau = (double)relaxationTime;
     config.force_k_min = (int)forcekMin;  // Algorithm.h:90-91
     config.force_k_max = (int)forcekMax;
+    config.removal_k_min = (int)removalForcekMin;  // Force.h:586-587
+    config.removal_k_max = (int)removalForcekMax;
+    for (int iD = 0; iD < 3; ++iD) config.removal_amplitude[iD] = (double)removalForceAmplitude[iD];
     LBM_B200_CALL(mlbm_create(&config, &handle));
     if (numProcs > 1) {
       unsigned char id[128] = {0};

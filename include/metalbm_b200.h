@@ -78,10 +78,17 @@ typedef enum mlbm_forcing_scheme {
  * made solenoidal by MakeIncompressible (Transformer.h:300-384: F^ = (i k_y psi^, -i k_x psi^)), transformed back and
  * divided by the volume; the array is synthesised once on the device when the context is created and then read like
  * MLBM_FORCE_FIELD.  (The reference's 3-D variant corrupts its heap -- Force.h:341-355 writes mirrored indices of a
- * padded local array -- and is not rebuilt; a 3-D shell force goes through MLBM_FORCE_FIELD.) */
+ * padded local array -- and is not rebuilt; a 3-D shell force goes through MLBM_FORCE_FIELD.)
+ * MLBM_FORCE_ENERGY_REMOVAL is Force<double, ForceType::EnergyRemoval> (Force.h:423-561), 2-D: F_d = -force_amplitude[d] x
+ * (the momentum rho u_d of the LAST STORED fields, band-passed to the shell force_k_min..force_k_max).  The reference
+ * recomputes it with two FFTs in every iterate from fieldList (Force.h:552-558), which only changes on stored steps; here
+ * it is recomputed after every step stored with bit 0 of is_stored, as a projection onto the shell's few modes (a
+ * reduction + one NCCL all-reduce of 4 doubles per mode) and a synthesis, with no distributed transform.
+ * MLBM_FORCE_TURBULENT_2D is Force<double, ForceType::Turbulent2D> (Force.h:564-616): ConstantShell(force_amplitude,
+ * force_k_min/max) + EnergyRemoval(removal_amplitude, removal_k_min/max). */
 typedef enum mlbm_force {
   MLBM_FORCE_NONE = 0, MLBM_FORCE_CONSTANT = 1, MLBM_FORCE_SINUSOIDAL = 2, MLBM_FORCE_KOLMOGOROV = 3, MLBM_FORCE_FIELD = 4,
-  MLBM_FORCE_CONSTANT_SHELL = 5
+  MLBM_FORCE_CONSTANT_SHELL = 5, MLBM_FORCE_ENERGY_REMOVAL = 6, MLBM_FORCE_TURBULENT_2D = 7
 } mlbm_force;
 
 /* `dataT` (Input_prod.in:10).  F32 is FP32 storage of populations and fields with the moments,
@@ -113,6 +120,9 @@ typedef struct mlbm_config {
   double force_wavelength[3]; /* forceWaveLength */
   int32_t force_k_min;        /* forcekMin (shell forces, Force.h:303, 315) */
   int32_t force_k_max;        /* forcekMax */
+  int32_t removal_k_min;      /* removalForcekMin (Turbulent2D, Force.h:575-577) */
+  int32_t removal_k_max;      /* removalForcekMax */
+  double removal_amplitude[3];/* removalForceAmplitude */
 } mlbm_config;
 
 const char* mlbm_last_error(void);

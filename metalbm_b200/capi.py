@@ -57,6 +57,8 @@ class Force(enum.IntEnum):
     Kolmogorov = 3
     Field = 4          # generic array read (Force.h:39-48); the array comes from mlbm_set_force_field
     ConstantShell = 5  # Force.h:296-420, 2-D lattices: synthesised on the device at mlbm_create
+    EnergyRemoval = 6  # Force.h:423-561, 2-D: -amplitude x band-passed momentum of the last stored fields
+    Turbulent2D = 7    # Force.h:564-616: ConstantShell + EnergyRemoval(removal_*)
 
 
 class DType(enum.IntEnum):
@@ -94,6 +96,9 @@ class MlbmConfig(ctypes.Structure):
         ("force_wavelength", ctypes.c_double * 3),
         ("force_k_min", ctypes.c_int32),
         ("force_k_max", ctypes.c_int32),
+        ("removal_k_min", ctypes.c_int32),
+        ("removal_k_max", ctypes.c_int32),
+        ("removal_amplitude", ctypes.c_double * 3),
     ]
 
 
@@ -155,7 +160,8 @@ def _lookup(enum_cls, value):
 def make_config(lattice="D2Q9", shape=(16, 16, 1), collision="BGK", equilibrium="TruncationMa3",
                 forcing_scheme="None", force="None", tau=0.7, amplitude=(0.0, 0.0, 0.0),
                 wavelength=(32.0, 32.0, 32.0), dtype="F64", overlap="Off", rank=0, nranks=1,
-                device=-1, variant=0, k_min=1, k_max=2) -> MlbmConfig:
+                device=-1, variant=0, k_min=1, k_max=2, removal_amplitude=(0.0, 0.0, 0.0), removal_k_min=1,
+                removal_k_max=2) -> MlbmConfig:
     cfg = MlbmConfig()
     cfg.abi_version = ABI_VERSION
     cfg.lattice = _lookup(Lattice, lattice)
@@ -174,6 +180,9 @@ def make_config(lattice="D2Q9", shape=(16, 16, 1), collision="BGK", equilibrium=
     cfg.rank, cfg.nranks, cfg.device, cfg.variant = int(rank), int(nranks), int(device), int(variant)
     cfg.tau = float(tau)
     cfg.force_k_min, cfg.force_k_max = int(k_min), int(k_max)
+    cfg.removal_k_min, cfg.removal_k_max = int(removal_k_min), int(removal_k_max)
+    for i in range(3):
+        cfg.removal_amplitude[i] = float(removal_amplitude[i])
     return cfg
 
 

@@ -15,6 +15,7 @@
 
 #include "../../include/metalbm_b200.h"
 #include "nccl_loader.h"
+#include "shell_force.h"
 #include "spectral.h"
 #include "step_kernel.cuh"
 
@@ -230,31 +231,6 @@ __global__ void initSyntheticKernel(StoreT* __restrict__ populations, long long 
   });
 }
 
-// Force<double, ForceType::ConstantShell> in 2-D (Force.h:296-420 + MakeIncompressible, Transformer.h:300-384 + BackwardFFT,
-// Transformer.h:101-108) written as the sum the c2r transform evaluates: with psi^(k) = A on the shell of the stored half
-// spectrum (k_y >= 0), F^ = (i k_y A, -i k_x A), and the transform's Hermitian completion,
-//     F(x, y) = (1 / V) sum_{k in shell} w_k A (-k_y, k_x) sin(2 pi (k_x x / N_x + k_y y / N_y)),
-// w_k = 2 for 0 < k_y < N_y / 2 and 1 on the two self-conjugate columns (whose non-Hermitian parts the transform drops; their
-// sine terms cancel in pairs).  modes[i] = (k_x, k_y, w_k A / V).  The angle is reduced in integers, so the field is the same
-// on any decomposition.  Pinned against the reference's own arrays in tests/golden/*constantshell*.npz.
-template <typename StoreT>
-__global__ void shellForceKernel(StoreT* __restrict__ force, long long fieldStride, long long nodes, int NR, int xOffset,
-                                 int globalX, int globalY, const double* __restrict__ modes, int modeCount) {
-  const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (node >= nodes) return;
-  const long long x = node / NR + xOffset, y = node % NR;
-  double fx = 0.0, fy = 0.0;
-  for (int i = 0; i < modeCount; ++i) {
-    const long long kx = (long long)modes[3 * i], ky = (long long)modes[3 * i + 1];
-    const long long px = ((kx * x) % globalX + globalX) % globalX, py = (ky * y) % globalY;
-    const double s = sinpi(2.0 * (double)px / globalX + 2.0 * (double)py / globalY) * modes[3 * i + 2];
-    fx -= (double)ky * s;
-    fy += (double)kx * s;
-  }
-  force[node] = (StoreT)fx;
-  force[fieldStride + node] = (StoreT)fy;
-}
-
 // f *= 1 + eps * n, n uniform with unit variance from a counter-based hash of (seed, population, GLOBAL node):
 // the synthetic non-equilibrium initial fields of the benchmark, independent of the decomposition.
 __device__ __forceinline__ unsigned long long splitmix64(unsigned long long z) {
@@ -387,6 +363,8 @@ struct mlbm_ctx {
   unsigned* reduceTicket = nullptr;
   double* deviceObservables = nullptr;   // [energy sum, mass, max speed^2, enstrophy sum]
   SpectralEnstrophy* spectral = nullptr; // created on the first step that stores the fields
+  ShellForce* shell = nullptr;           // ConstantShell / EnergyRemoval / Turbulent2D (2-D): maker of the force field
+  bool forceStale = false;               // the fields changed since the force field was made (Force::update is due)
   bool enstrophyValid = false;           // the last stored step stored the velocity field (bit 0 of isStored)
   double* forceTables[3] = {nullptr, nullptr, nullptr};
   int forceAxis[3] = {-1, -1, -1};
@@ -473,7 +451,7 @@ static void fillLaunchScalars(const mlbm_config& config, const SlabGeometry& g, 
   p->wrapX = config.nranks == 1 ? 1 : 0;
   p->isStored = isStored;
   p->hydroShift = hydroShift;
-  p->hasForce = config.force == MLBM_FORCE_NONE ? 0 : (config.force == MLBM_FORCE_FIELD || config.force == MLBM_FORCE_CONSTANT_SHELL ? 2 : 1);
+  p->hasForce = config.force == MLBM_FORCE_NONE ? 0 : (config.force >= MLBM_FORCE_FIELD ? 2 : 1);  // array-type forces read the field
   p->beta = 1.0 / (2.0 * config.tau);
   p->guoFactor = (1.0 - 1.0 / (2.0 * config.tau)) * 3.0;
   // entropic kernels stage their logarithm table and constants once per block: let a block walk up to 16 planes
@@ -623,6 +601,13 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
   if (isStored & 1) { if (int status = ensureFields(ctx)) return status; }
   if (isStored) { if (int status = ensurePartials(ctx)) return status; }
   cudaStream_t compute = ctx->computeStream;
+  if (ctx->shell && ctx->forceStale) {
+    // Collision::update -> Force::update at the top of iterate (Algorithm.h:338, Collision.h:97-100, Force.h:552-558)
+    std::string error;
+    if (shellForceUpdate(ctx->shell, ctx->density, ctx->velocity, ctx->force, ctx->fieldStride, ctx->nccl, ctx->comm, compute, &ctx->launches, &error))
+      return fail(MLBM_ERR_CUDA, "spectral force: %s", error.c_str());
+    ctx->forceStale = false;
+  }
   if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeStart, compute));
 
   if (!multi) {
@@ -700,6 +685,7 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
         return fail(MLBM_ERR_CUDA, "spectral enstrophy: %s", error.c_str());
       ctx->fieldsStored = true;
       ctx->enstrophyValid = true;
+      if (ctx->shell && shellForceIsTimeDependent(ctx->shell)) ctx->forceStale = true;  // fieldList changed
     }
     MLBM_CUDA(cudaGetLastError());
     ctx->observablesValid = true;
@@ -732,6 +718,7 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   if (ctx->peerFlags) cudaFree(ctx->peerFlags);
   if (ctx->peerTimedOut) cudaFreeHost(ctx->peerTimedOut);
   if (ctx->spectral) spectralDestroy(ctx->spectral);
+  if (ctx->shell) shellForceDestroy(ctx->shell);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
                         (void*)ctx->partials, (void*)ctx->hints, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
@@ -771,10 +758,12 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
     default: return fail(MLBM_ERR_INVALID, "unknown collision %d", config->collision);
   }
   if (!schemeOf(config->forcing_scheme, &scheme, &hydroShift)) return fail(MLBM_ERR_INVALID, "unknown forcing scheme %d", config->forcing_scheme);
-  if (config->force < MLBM_FORCE_NONE || config->force > MLBM_FORCE_CONSTANT_SHELL) return fail(MLBM_ERR_INVALID, "unknown force %d", config->force);
-  if (config->force == MLBM_FORCE_CONSTANT_SHELL) {
-    if (D != 2) return fail(MLBM_ERR_INVALID, "the shell force is rebuilt for 2-D lattices only (the reference's 3-D variant corrupts its heap, Force.h:341-355); use MLBM_FORCE_FIELD");
+  if (config->force < MLBM_FORCE_NONE || config->force > MLBM_FORCE_TURBULENT_2D) return fail(MLBM_ERR_INVALID, "unknown force %d", config->force);
+  if (config->force >= MLBM_FORCE_CONSTANT_SHELL) {
+    if (D != 2) return fail(MLBM_ERR_INVALID, "the spectral forces are rebuilt for 2-D lattices only (the reference's 3-D variants corrupt its heap, Force.h:341-355); use MLBM_FORCE_FIELD");
     if (config->force_k_min < 0 || config->force_k_max < config->force_k_min) return fail(MLBM_ERR_INVALID, "bad shell [%d, %d]", config->force_k_min, config->force_k_max);
+    if (config->force == MLBM_FORCE_TURBULENT_2D && (config->removal_k_min < 0 || config->removal_k_max < config->removal_k_min))
+      return fail(MLBM_ERR_INVALID, "bad removal shell [%d, %d]", config->removal_k_min, config->removal_k_max);
   }
   if (config->equilibrium != MLBM_TRUNCATION_MA3 && config->equilibrium != MLBM_EXACT) return fail(MLBM_ERR_INVALID, "unknown equilibrium %d", config->equilibrium);
   StepKernel kernel = lookupStepKernel(config->lattice, collision, config->equilibrium, scheme, config->dtype);
@@ -858,37 +847,26 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   if (config->force == MLBM_FORCE_FIELD) {
     // the kernel reads the force field from the first step on: it exists (zero) before mlbm_set_force_field fills it
     if (int status = ensureFields(ctx)) return cleanup(status);
-  } else if (config->force == MLBM_FORCE_CONSTANT_SHELL) {
-    // setForceArray in the Collision ctor (Collision.h:51-54): the time-independent array is made once
+  } else if (config->force >= MLBM_FORCE_CONSTANT_SHELL) {
+    // setForceArray in the Collision ctor (Collision.h:51-54): the array exists from the start; its time-dependent part is
+    // remade from the stored fields at the top of the step that follows a change of them (Force::update, Algorithm.h:338)
     if (int status = ensureFields(ctx)) return cleanup(status);
-    const int GX = config->global_length[0], GY = config->global_length[1];
-    const double scale = config->force_amplitude[0] / ((double)GX * GY);
-    std::vector<double> modes;
-    for (int ix = 0; ix < GX; ++ix) {
-      const int kx = ix <= GX / 2 ? ix : ix - GX;  // Force.h:349-350
-      for (int iy = 0; iy <= GY / 2; ++iy) {       // the stored half spectrum: k_y = iy
-        const long long k2 = (long long)kx * kx + (long long)iy * iy;
-        if (k2 < (long long)config->force_k_min * config->force_k_min || k2 > (long long)config->force_k_max * config->force_k_max) continue;  // Force.h:385-386
-        const bool selfConjugate = iy == 0 || (GY % 2 == 0 && iy == GY / 2);
-        modes.push_back(kx); modes.push_back(iy); modes.push_back((selfConjugate ? 1.0 : 2.0) * scale);
-      }
-    }
-    double* deviceModes = nullptr;
-    const int modeCount = (int)(modes.size() / 3);
-    MLBM_CREATE_CUDA(cudaMalloc(&deviceModes, sizeof(double) * (modes.size() + 1)));
-    cudaError_t shellError = cudaMemcpyAsync(deviceModes, modes.data(), sizeof(double) * modes.size(), cudaMemcpyHostToDevice, ctx->computeStream);
-    if (shellError == cudaSuccess) {
-      const unsigned grid = (unsigned)((ctx->nodes + 127) / 128);
-      if (config->dtype == MLBM_F64)
-        shellForceKernel<double><<<grid, 128, 0, ctx->computeStream>>>(static_cast<double*>(ctx->force), ctx->fieldStride, ctx->nodes, ctx->NR, config->rank * ctx->LX, GX, GY, deviceModes, modeCount);
-      else
-        shellForceKernel<float><<<grid, 128, 0, ctx->computeStream>>>(static_cast<float*>(ctx->force), ctx->fieldStride, ctx->nodes, ctx->NR, config->rank * ctx->LX, GX, GY, deviceModes, modeCount);
-      shellError = cudaGetLastError();
-      ctx->launches += 1;
-    }
-    if (shellError == cudaSuccess) shellError = cudaStreamSynchronize(ctx->computeStream);  // `modes` and deviceModes are released below
-    cudaFree(deviceModes);
-    MLBM_CREATE_CUDA(shellError);
+    ShellForceGeometry shellGeometry = {ctx->LX, ctx->NR, config->rank, config->nranks, config->global_length[0], config->global_length[1], (int)ctx->elementSize};
+    ShellForceSpec spec = {};
+    spec.injection = config->force == MLBM_FORCE_CONSTANT_SHELL || config->force == MLBM_FORCE_TURBULENT_2D;
+    spec.injectionAmplitude = config->force_amplitude[0];
+    spec.injectionKMin = config->force_k_min;
+    spec.injectionKMax = config->force_k_max;
+    spec.removal = config->force != MLBM_FORCE_CONSTANT_SHELL;
+    const bool turbulent = config->force == MLBM_FORCE_TURBULENT_2D;
+    for (int d = 0; d < 2; ++d) spec.removalAmplitude[d] = turbulent ? config->removal_amplitude[d] : config->force_amplitude[d];
+    spec.removalKMin = turbulent ? config->removal_k_min : config->force_k_min;
+    spec.removalKMax = turbulent ? config->removal_k_max : config->force_k_max;
+    std::string shellError;
+    ctx->shell = shellForceCreate(shellGeometry, spec, &shellError);
+    if (!ctx->shell) return cleanup(fail(MLBM_ERR_CUDA, "spectral force: %s", shellError.c_str()));
+    if (shellForceInitial(ctx->shell, ctx->force, ctx->fieldStride, ctx->computeStream, &ctx->launches, &shellError))
+      return cleanup(fail(MLBM_ERR_CUDA, "spectral force: %s", shellError.c_str()));
     ctx->fieldsStored = true;  // the force array is meaningful from the start (writeForce, Collision.h:51-54)
   } else if (config->force != MLBM_FORCE_NONE) {
     const int extent[3] = {ctx->LX, D == 3 ? config->global_length[1] : config->global_length[1], D == 3 ? config->global_length[2] : 1};
@@ -1140,6 +1118,7 @@ int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* veloci
   ctx->launches += 1;
   MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
   ctx->halosValid = false;
+  if (ctx->shell && shellForceIsTimeDependent(ctx->shell)) ctx->forceStale = true;  // fieldList holds the initial fields (Initialize.h)
   return MLBM_OK;
 }
 

@@ -307,7 +307,7 @@ int mlbm_oracle_step_ex(const mlbm_config* cfg, const double* prev, double* next
         unsigned p[3] = {(unsigned)(x % lx), (unsigned)y, (unsigned)z};
         double F[3];
         body_force(&L, cfg, p, F);
-        if (cfg->force == MLBM_FORCE_FIELD || cfg->force == MLBM_FORCE_CONSTANT_SHELL) {  /* the shell array: oracle.py */
+        if (cfg->force >= MLBM_FORCE_FIELD) {  /* array-type forces; the spectral ones are made by oracle.py */
           /* Force<T, ForceType::Generic>::setForce (Force.h:39-48): component iD of the force array at the node's index
            * (the array-type forces ConstantShell / EnergyRemoval / Turbulent2D, Force.h:296-623, fill it outside the step) */
           if (!force) return -1;

@@ -84,7 +84,7 @@ class OracleState:
         self.density = np.zeros(self.shape)
         self.velocity = np.zeros((self.dim,) + self.shape)
         self.force = np.zeros((self.dim,) + self.shape)
-        if int(cfg.force) == 5:   # ConstantShell: the array setForceArray makes in the Collision ctor (Collision.h:51-54)
+        if int(cfg.force) in (5, 7):   # ConstantShell / Turbulent2D: the array setForceArray makes in the Collision ctor (Collision.h:51-54)
             self.force[...] = constant_shell_force(cfg)
         self.branch = np.zeros(self.shape, dtype=np.int32)
         self.iterations = np.zeros(self.shape, dtype=np.int32)
@@ -93,6 +93,10 @@ class OracleState:
         self.fneq_max = np.zeros(self.shape)
 
     def step(self, is_stored: bool = True) -> None:
+        if int(self.cfg.force) in (6, 7):
+            # Collision::update -> Force::update (Collision.h:97-100, Force.h:552-558, 605-609) at the top of every iterate
+            # (Algorithm.h:338): the array is rebuilt from fieldList, i.e. from the fields of the LAST STORED step
+            self.force[...] = time_dependent_force(self.cfg, self.density, self.velocity)
         status = lib().mlbm_oracle_step_ex(ctypes.byref(self.cfg), _dp(self.f), _dp(self.next), _dp(self.alpha),
                                            _dp(self.density), _dp(self.velocity), _dp(self.force),
                                            1 if is_stored else 0, _ip(self.branch), _ip(self.iterations),
@@ -127,6 +131,34 @@ def constant_shell_force(cfg: MlbmConfig) -> np.ndarray:
     fy_hat = (kx * psi.imag) + 1j * (-kx * psi.real)
     force = np.stack([np.fft.irfft2(fx_hat, s=(nx, ny)), np.fft.irfft2(fy_hat, s=(nx, ny))])
     return force.reshape(2, nx, ny, 1)
+
+
+def energy_removal_force(cfg: MlbmConfig, density: np.ndarray, velocity: np.ndarray, amplitude, k_min: int, k_max: int) -> np.ndarray:
+    """Force<double, ForceType::EnergyRemoval>::setForceArray (Force.h:452-550) for 2-D lattices: momentum = density *
+    velocity of fieldList (:466-474), r2c (:478-480), F^_d = -amplitude[d] * momentum^_d on the shell
+    kMin^2 <= |k|^2 <= kMax^2 and zero elsewhere (:485-545, integer wave numbers of the half-spectrum indices),
+    c2r divided by the volume (:547-549, Transformer.h:101-108)."""
+    nx, ny, nz = shape_of(cfg)
+    assert nz == 1
+    kx = np.array([i if i <= nx // 2 else i - nx for i in range(nx)], dtype=np.float64)[:, None]
+    ky = np.arange(ny // 2 + 1, dtype=np.float64)[None, :]
+    k2 = kx * kx + ky * ky
+    shell = (k2 >= k_min ** 2) & (k2 <= k_max ** 2)
+    force = np.zeros((2, nx, ny, 1))
+    for d in range(2):
+        momentum = (density * velocity[d]).reshape(nx, ny)
+        spectrum = np.where(shell, -float(amplitude[d]) * np.fft.rfft2(momentum), 0.0)
+        force[d, :, :, 0] = np.fft.irfft2(spectrum, s=(nx, ny))
+    return force
+
+
+def time_dependent_force(cfg: MlbmConfig, density: np.ndarray, velocity: np.ndarray) -> np.ndarray:
+    """EnergyRemoval (Force.h:423-561) or Turbulent2D = ConstantShell injection + EnergyRemoval with the removal* constants
+    (Force.h:564-616: setForceArray adds the two arrays, :583-603)."""
+    if int(cfg.force) == 6:
+        return energy_removal_force(cfg, density, velocity, cfg.force_amplitude, cfg.force_k_min, cfg.force_k_max)
+    return constant_shell_force(cfg) + energy_removal_force(cfg, density, velocity, cfg.removal_amplitude,
+                                                            cfg.removal_k_min, cfg.removal_k_max)
 
 
 def init_equilibrium(cfg: MlbmConfig, density: np.ndarray, velocity: np.ndarray) -> np.ndarray:

@@ -46,6 +46,11 @@ class RefConfig:
     amplitude: tuple = (1e-5, 1e-5, 1e-5)
     wavelength: tuple = (32.0, 32.0, 32.0)
     init_density: str = "Homogeneous"   # Homogeneous | Peak
+    k_min: int = 1                      # forcekMin / forcekMax: shell of the spectral forces (Force.h:296-623)
+    k_max: int = 2
+    removal_amplitude: tuple = (0.0, 0.0, 0.0)   # removalForce*: the EnergyRemoval half of Turbulent2D (Force.h:566-577)
+    removal_k_min: int = 1
+    removal_k_max: int = 2
     nprocs: int = 1
     optimize: str = "-O2"               # "-O2" = parity build (no FMA contraction); TIMING_FLAGS = timing build
 
@@ -115,12 +120,12 @@ namespace lbm {{
   constexpr ForceType forceT = ForceType::{cfg.force};
   constexpr Vector forceAmplitude = {_vector(cfg.amplitude)};
   constexpr Vector forceWaveLength = {_vector(cfg.wavelength)};
-  constexpr int forcekMin = 1;
-  constexpr int forcekMax = 2;
-  constexpr Vector removalForceAmplitude = {{ {{0.0, 0.0, 0.0}} }};
+  constexpr int forcekMin = {int(cfg.k_min)};
+  constexpr int forcekMax = {int(cfg.k_max)};
+  constexpr Vector removalForceAmplitude = {_vector(cfg.removal_amplitude)};
   constexpr Vector removalForceWaveLength = {{ {{32.0, 32.0, 32.0}} }};
-  constexpr int removalForcekMin = 1;
-  constexpr int removalForcekMax = 2;
+  constexpr int removalForcekMin = {int(cfg.removal_k_min)};
+  constexpr int removalForcekMax = {int(cfg.removal_k_max)};
   constexpr BoundaryType boundaryT = BoundaryType::Generic;
   constexpr InputOutputFormat inputOutputFormatT = InputOutputFormat::ascii;
   constexpr auto prefix = LBM_POSTFIX;

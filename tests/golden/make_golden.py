@@ -58,6 +58,18 @@ CASES = [
     # mirrored index of a padded local array -- so the 3-D array read is pinned by the oracle and by identities only)
 ]
 ARRAY_FORCES = {"ConstantShell", "EnergyRemoval", "Turbulent2D"}
+# time-dependent spectral forces (Force.h:423-616): the force array changes with the stored fields, so these are replayed
+# natively (force "EnergyRemoval" / "Turbulent2D" of this repository), not through a recorded array
+SPECTRAL_CASES = [
+    dict(name="d2q9_bgk_guo_energyremoval", lattice="D2Q9", shape=(16, 12, 1), collision="BGK", scheme="Guo", force="EnergyRemoval",
+         tau=0.7, eps=1e-2, steps=4, amplitude=(2e-3, 3e-3, 0.0), k_min=1, k_max=3),
+    dict(name="d2q9_elbm_guo_turbulent2d_removal", lattice="D2Q9", shape=(16, 12, 1), collision="ELBM", scheme="Guo", force="Turbulent2D",
+         tau=0.51, eps=2e-2, steps=3, amplitude=(1e-4, 0.0, 0.0), k_min=1, k_max=2, removal_amplitude=(2e-3, 3e-3, 0.0),
+         removal_k_min=2, removal_k_max=4),
+    dict(name="d2q9_bgk_edm_turbulent2d_removal_odd", lattice="D2Q9", shape=(15, 10, 1), collision="BGK", scheme="ExactDifferenceMethod",
+         force="Turbulent2D", tau=0.6, eps=1e-2, steps=4, amplitude=(2e-4, 0.0, 0.0), k_min=2, k_max=3,
+         removal_amplitude=(5e-3, 1e-3, 0.0), removal_k_min=0, removal_k_max=5),
+]
 ONLY = set(sys.argv[1:])   # optional: names of the cases to (re)generate; default all
 AMPLITUDE = (1e-4, 2e-4, 3e-4)
 WAVELENGTH = (8.0, 4.0, 16.0)
@@ -85,5 +97,30 @@ def main():
         print(name, out["f"].shape, out["observables"][-1])
 
 
+def spectral():
+    for case in SPECTRAL_CASES:
+        if ONLY and case["name"] not in ONLY:
+            continue
+        shape = case["shape"]
+        shell = {k: case[k] for k in ("k_min", "k_max", "removal_amplitude", "removal_k_min", "removal_k_max") if k in case}
+        ref_cfg = RefConfig(lattice=case["lattice"], nx=shape[0], ny=shape[1], nz=shape[2], collision=case["collision"],
+                            forcing_scheme=case["scheme"], force=case["force"], tau=case["tau"], amplitude=case["amplitude"],
+                            wavelength=WAVELENGTH, **shell)
+        cfg = make_config(lattice=case["lattice"], shape=shape, collision=case["collision"], forcing_scheme=case["scheme"],
+                          tau=case["tau"])
+        f0 = O.synthetic_populations(cfg, eps=case["eps"], amplitude=0.05, ripple=0.05)
+        out = run_ref(ref_cfg, f0, case["steps"], store_every=1)
+        meta = dict(name=case["name"], lattice=case["lattice"], shape=list(shape), collision=case["collision"],
+                    equilibrium="TruncationMa3", forcing_scheme=case["scheme"], force=case["force"], tau=case["tau"],
+                    amplitude=list(case["amplitude"]), wavelength=list(WAVELENGTH), steps=case["steps"], ranks=1, eps=case["eps"],
+                    reference_force=case["force"], native_spectral=True, shell={k: (list(v) if isinstance(v, tuple) else v) for k, v in shell.items()},
+                    source="oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off), oracle/ref_driver.cpp")
+        np.savez_compressed(HERE / f"{case['name']}.npz", meta=json.dumps(meta), f0=f0, f=out["f"], alpha=out["alpha"],
+                            density=out["density"], velocity=out["velocity"], force=out["force"],
+                            observables=np.array(out["observables"], dtype=np.float64))
+        print(case["name"], out["f"].shape, out["observables"][-1], "max |F|", np.abs(out["force"]).max())
+
+
 if __name__ == "__main__":
     main()
+    spectral()

@@ -90,6 +90,30 @@ def shell_force_direct(cfg):
     return field
 
 
+def energy_removal_direct(cfg, density, velocity, amplitude, k_min, k_max, constant=None):
+    """What projectKernel / reduceKernel / synthesisKernel (csrc/shell_force.cu) evaluate, in numpy: the momentum of the stored
+    fields projected onto the shell's modes and synthesised back, times -amplitude / V (+ the injection array)."""
+    nx, ny, _ = O.shape_of(cfg)
+    x, y = np.arange(nx)[:, None], np.arange(ny)[None, :]
+    field = np.zeros((2, nx, ny, 1))
+    momentum = [(density * velocity[d]).reshape(nx, ny) for d in range(2)]
+    for ix in range(nx):
+        kx = ix if ix <= nx // 2 else ix - nx
+        for iy in range(ny // 2 + 1):
+            k2 = kx * kx + iy * iy
+            if k2 < k_min ** 2 or k2 > k_max ** 2:
+                continue
+            weight = 1.0 if (iy == 0 or (ny % 2 == 0 and iy == ny // 2)) else 2.0
+            theta = np.pi * (2.0 * ((kx * x) % nx) / nx + 2.0 * ((iy * y) % ny) / ny)
+            cosine, sine = np.cos(theta), np.sin(theta)
+            for d in range(2):
+                real, imaginary = (momentum[d] * cosine).sum(), -(momentum[d] * sine).sum()
+                field[d, :, :, 0] += weight * (real * cosine - imaginary * sine)
+    for d in range(2):
+        field[d] *= -float(amplitude[d]) / (nx * ny)
+    return field if constant is None else constant + field
+
+
 def native_shell_config(meta, **extra):
     """The golden cases recorded with the reference's ConstantShell (forcekMin = 1, forcekMax = 2, oracle/refbuild.py) as a
     configuration of this repository's own ConstantShell."""
@@ -98,17 +122,19 @@ def native_shell_config(meta, **extra):
                             tau=meta["tau"], amplitude=meta["amplitude"], wavelength=meta["wavelength"], k_min=1, k_max=2, **extra)
 
 
-def run_oracle(cfg, f0, steps, alpha0=None, force=None):
+def run_oracle(cfg, f0, steps, alpha0=None, force=None, store_last_only=False):
+    """`store_last_only`: isStored on the last step alone (what run_cuda and the C++ example do); it only matters for the
+    forces that follow the stored fields (EnergyRemoval, Turbulent2D)."""
     state = O.OracleState(cfg, f0, alpha0)
     if force is not None:
         state.force[...] = force
-    for _ in range(steps):
-        state.step(True)
+    for step in range(1, steps + 1):
+        state.step(step == steps or not store_last_only)
     return state
 
 
-def run_cuda(cfg, f0, steps, alpha0=None, store_last=True, force=None):
-    """unpack -> iterate x steps (isStored on the last) -> pack; returns dict of global arrays (single rank)."""
+def run_cuda(cfg, f0, steps, alpha0=None, store_last=True, force=None, store_every_step=False):
+    """unpack -> iterate x steps (isStored on the last, or on every step) -> pack; returns dict of global arrays (single rank)."""
     algorithm = Algorithm(cfg)
     try:
         domain = algorithm.domain
@@ -121,7 +147,7 @@ def run_cuda(cfg, f0, steps, alpha0=None, store_last=True, force=None):
             domain.interior(algorithm.fieldList.force)[...] = force
             algorithm.set_force()
         for iteration in range(1, steps + 1):
-            algorithm.isStored = store_last and iteration == steps
+            algorithm.isStored = store_every_step or (store_last and iteration == steps)
             algorithm.iterate(iteration)
         algorithm.pack()
         fields = algorithm.fieldList

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(cuda_lib):
 
 
 def test_struct_layout_matches_header(cuda_lib):
-    assert ctypes.sizeof(capi.MlbmConfig) == 8 * 4 + 3 * 4 + 4 * 4 + 4 + 8 + 24 + 24 + 2 * 4  # includes 4 bytes of padding before tau
+    assert ctypes.sizeof(capi.MlbmConfig) == 8 * 4 + 3 * 4 + 4 * 4 + 4 + 8 + 24 + 24 + 4 * 4 + 24  # includes 4 bytes of padding before tau
     assert ctypes.sizeof(capi.MlbmHaloMessage) == 32
 
 

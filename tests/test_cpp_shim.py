@@ -74,12 +74,13 @@ def test_reference_style_main_compiles_and_links(tmp_path, cuda_lib):
 
 def test_unsupported_choices_fail_at_compile_time(tmp_path):
     """static_asserts of the template layer, not link errors: compiled with -c."""
-    compile_example(tmp_path, "shim_check.cpp", "shell.o", "D2Q9", (24, 20, 1), force="ConstantShell", compile_only=True)
+    for force in ("ConstantShell", "EnergyRemoval", "Turbulent2D"):
+        compile_example(tmp_path, "shim_check.cpp", "shell.o", "D2Q9", (24, 20, 1), force=force, compile_only=True)
     compile_example(tmp_path, "shim_check.cpp", "alpha.o", "D3Q19", (8, 6, 4), collision="Malaspinas_ELBM", compile_only=True)
     rejected = [dict(lattice="D3Q19", shape=(8, 6, 4), equilibrium="Exact"),          # Exact: D2Q9 / D3Q27 only (Equilibrium.h:36-126)
                 dict(lattice="D3Q19", shape=(8, 6, 4), force="ConstantShell"),        # the shell force is rebuilt for 2-D lattices only
-                dict(lattice="D2Q9", shape=(8, 6, 1), force="EnergyRemoval"),         # FFT-per-step forces: MLBM_FORCE_FIELD
-                dict(lattice="D2Q9", shape=(8, 6, 1), force="Turbulent2D")]
+                dict(lattice="D3Q27", shape=(8, 6, 4), force="EnergyRemoval"),
+                dict(lattice="D3Q15", shape=(8, 6, 4), force="Turbulent2D")]
     for choice in rejected:
         with pytest.raises(AssertionError, match="static assertion failed"):
             compile_example(tmp_path, "shim_check.cpp", "bad.o", choice.pop("lattice"), choice.pop("shape"), compile_only=True, **choice)
@@ -114,6 +115,7 @@ SHIM_CASES = [
     ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 3),
     ("D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 1),
     ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "ConstantShell", 3),   # forcekMin / forcekMax of examples/Input_generic.in
+    ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "Turbulent2D", 3),     # + removalForce* of examples/Input_generic.in
 ]
 
 
@@ -128,11 +130,12 @@ def test_template_api_reproduces_the_oracle(tmp_path, cuda_lib, world, case):
     binary = compile_example(tmp_path, "shim_check.cpp", "shim_check", lattice, shape, collision, equilibrium, scheme, force,
                              tau=0.55, nprocs=world, overlap="On" if world > 1 else "Off")
     cfg = make_config(lattice=lattice, shape=shape, collision=collision, equilibrium=equilibrium, forcing_scheme=scheme,
-                      force=force, tau=0.55, amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0))
+                      force=force, tau=0.55, amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0), k_min=1, k_max=2,
+                      removal_amplitude=(5e-3, 2e-3, 0.0), removal_k_min=2, removal_k_max=4)   # examples/Input_generic.in
     f0 = O.synthetic_populations(cfg, eps=1e-2)
     lx = shape[0] // world
     outputs = _run_shim(tmp_path, binary, [np.ascontiguousarray(f0[:, r * lx:(r + 1) * lx]) for r in range(world)], steps)
-    ref = run_oracle(cfg, f0, steps)
+    ref = run_oracle(cfg, f0, steps, store_last_only=True)   # examples/shim_check.cpp stores the last step only
     dim, q = ref.dim, ref.q
     got = np.concatenate([np.fromfile(tmp_path / f"out{r}.bin").reshape((q, lx) + tuple(shape[1:])) for r in range(world)], axis=1)
     if collision == "BGK":

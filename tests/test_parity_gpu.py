@@ -169,6 +169,69 @@ def test_native_constant_shell_odd_sizes_and_nyquist_shells(shape, shell, dtype)
     assert relative_error(got["f"], ref.f) <= (POPULATION_TOLERANCE if dtype == "F64" else 1e-5)
 
 
+SPECTRAL_FORCE_CASES = [
+    # force, shape, collision, scheme, dtype, shell keywords
+    ("EnergyRemoval", (33, 20, 1), "BGK", "Guo", "F64", dict(amplitude=(2e-3, 3e-3, 0.0), k_min=1, k_max=3)),
+    ("EnergyRemoval", (16, 15, 1), "ELBM", "ExactDifferenceMethod", "F64", dict(amplitude=(4e-3, 1e-3, 0.0), k_min=0, k_max=9)),
+    ("Turbulent2D", (24, 130, 1), "BGK", "Guo", "F64", dict(amplitude=(2e-4, 0.0, 0.0), k_min=1, k_max=2,
+                                                             removal_amplitude=(5e-3, 2e-3, 0.0), removal_k_min=2, removal_k_max=4)),
+    ("Turbulent2D", (24, 20, 1), "BGK", "ShanChen", "F32", dict(amplitude=(2e-4, 0.0, 0.0), k_min=1, k_max=2,
+                                                                removal_amplitude=(5e-3, 2e-3, 0.0), removal_k_min=1, removal_k_max=3)),
+]
+
+
+@pytest.mark.parametrize("case", SPECTRAL_FORCE_CASES, ids=lambda c: "-".join(map(str, (c[0], "x".join(map(str, c[1])), c[2], c[3], c[4]))))
+def test_time_dependent_spectral_forces(case):
+    """EnergyRemoval / Turbulent2D (Force.h:423-616) on the device: the force follows the fields of the last STORED step.
+    Every step is stored here (the array changes every step); pinned to the reference by tests/golden/*energyremoval*,
+    *turbulent2d_removal*."""
+    force, shape, collision, scheme, dtype, shell = case
+    cfg = make_config(lattice="D2Q9", shape=shape, collision=collision, forcing_scheme=scheme, force=force, tau=0.6, dtype=dtype, **shell)
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    from metalbm_b200.algorithm import Algorithm
+    with Algorithm(cfg) as algorithm:
+        domain = algorithm.domain
+        algorithm.distribution.set_interior(f0.astype(domain.dtype))
+        algorithm.unpack()
+        state = O.OracleState(cfg, f0)
+        for iteration in range(1, 5):
+            algorithm.isStored = True
+            algorithm.iterate(iteration)
+            state.step(True)
+            got_force = domain.interior(algorithm.fieldList.force).astype(np.float64)
+            scale = max(np.abs(state.force).max(), 1e-30)
+            assert np.abs(got_force - state.force).max() <= (1e-11 if dtype == "F64" else 1e-6) * scale, f"step {iteration}"
+        algorithm.pack()
+        got = algorithm.distribution.get_interior().astype(np.float64)
+    assert np.abs(state.force).max() > 1e-6
+    if collision == "BGK":
+        assert relative_error(got, state.f) <= (4 * POPULATION_TOLERANCE if dtype == "F64" else 1e-5)
+    else:
+        alpha = domain.interior(algorithm.fieldList.alpha)[0].astype(np.float64)
+        check_entropic({"f": got, "alpha": alpha}, state, cfg, 4, mismatch_budget=5e-3)
+
+
+def test_spectral_force_follows_the_stored_fields_only():
+    """Between stored steps fieldList does not change, so neither does the reference's EnergyRemoval array (Force.h:552-558
+    recomputes it from the same fields): steps 1-3 unstored, step 4 stored, steps 5-6 unstored."""
+    cfg = make_config(lattice="D2Q9", shape=(20, 18, 1), collision="BGK", forcing_scheme="Guo", force="EnergyRemoval", tau=0.7,
+                      amplitude=(3e-3, 3e-3, 0.0), k_min=1, k_max=3)
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    from metalbm_b200.algorithm import Algorithm
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.set_interior(f0)
+        algorithm.unpack()
+        state = O.OracleState(cfg, f0)
+        for iteration in range(1, 7):
+            algorithm.isStored = iteration == 4
+            algorithm.iterate(iteration)
+            state.step(iteration == 4)
+        algorithm.pack()
+        got = algorithm.distribution.get_interior()
+    assert np.abs(state.force).max() > 1e-6          # the force switched on after the stored step
+    assert relative_error(got, state.f) <= 6 * POPULATION_TOLERANCE
+
+
 def test_elbm_branches_are_exercised():
     """The synthetic inputs above reach every alpha branch of Collision<ELBM>::calculateAlpha (Collision.h:351-375)."""
     seen = set()
