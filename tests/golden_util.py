@@ -9,11 +9,16 @@ from metalbm_b200.capi import make_config
 GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 
 
-def golden_names():
-    """Alphabetical, the array-type / spectral force cases last (newest code paths: a failure there must not hide the rest
-    of the set from a run that stops at the first failure)."""
-    spectral = ("constantshell", "turbulent2d", "energyremoval")
-    return sorted((p.stem for p in GOLDEN_DIR.glob("*.npz")), key=lambda name: (any(s in name for s in spectral), name))
+SPECTRAL_MARKERS = ("constantshell", "turbulent2d", "energyremoval")
+
+
+def golden_names(spectral=None):
+    """Names of the committed golden vectors; `spectral` = True / False selects / excludes the cases recorded with the
+    reference's array-type spectral forces (Force.h:296-616), whose GPU tests live in tests/test_spectral_forces_gpu.py."""
+    names = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz"))
+    if spectral is None:
+        return names
+    return [n for n in names if any(m in n for m in SPECTRAL_MARKERS) == spectral]
 
 
 def load_golden(name):

@@ -114,6 +114,9 @@ SHIM_CASES = [
     ("D3Q19", (16, 12, 10), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 3),
     ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 3),
     ("D3Q27", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 1),
+]
+# the spectral force types run in tests/test_spectral_forces_gpu.py (same check, later in the order)
+SPECTRAL_SHIM_CASES = [
     ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "ConstantShell", 3),   # forcekMin / forcekMax of examples/Input_generic.in
     ("D2Q9", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "Turbulent2D", 3),     # + removalForce* of examples/Input_generic.in
 ]
@@ -123,6 +126,10 @@ SHIM_CASES = [
 @pytest.mark.parametrize("world", [1, 2])
 @pytest.mark.parametrize("case", SHIM_CASES, ids=lambda c: "-".join(map(str, c[:1] + c[2:6])))
 def test_template_api_reproduces_the_oracle(tmp_path, cuda_lib, world, case):
+    check_template_api(tmp_path, world, case)
+
+
+def check_template_api(tmp_path, world, case):
     import torch
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")

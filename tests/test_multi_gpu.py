@@ -152,27 +152,3 @@ def test_slabs_reproduce_the_single_rank_result(tmp_path, world, case):
         assert abs(rank_observables[3] - obs[3]) <= 1e-12 * abs(obs[3])
         assert abs(rank_observables[2] - obs[2]) <= 1e-12 * abs(obs[2])
         assert np.array_equal(rank_observables, got["observables"][0])
-
-
-@pytest.mark.parametrize("peer", [True, False], ids=["peer", "nccl"])
-@pytest.mark.parametrize("world", [2, 4, 8])
-@pytest.mark.parametrize("force", ["ConstantShell", "Turbulent2D"])
-def test_spectral_forces_on_slabs(tmp_path, world, force, peer):
-    """ConstantShell / Turbulent2D on x-slabs: the synthesis uses global coordinates, the projection of the stored momentum
-    onto the shell's modes is all-reduced over the ranks (csrc/shell_force.cu).  ConstantShell must be bit-identical to the
-    single-GPU run; with the removal part the summation order of the projection differs, so the oracle's tolerance applies."""
-    if _device_count() < world:
-        pytest.skip(f"needs {world} GPUs")
-    shape, steps = (24, 20, 1), 4
-    config = dict(lattice="D2Q9", shape=list(shape), collision="BGK", forcing_scheme="Guo", force=force, tau=0.6,
-                  amplitude=[2e-4, 0.0, 0.0], overlap="On", k_min=1, k_max=2, removal_amplitude=[5e-3, 2e-3, 0.0],
-                  removal_k_min=2, removal_k_max=4)
-    single = make_config(**config)
-    f0 = O.synthetic_populations(single, eps=1e-2)
-    got = _run_ranks(tmp_path, world, config, f0, steps, "stored", peer)
-    if force == "ConstantShell":
-        one = run_cuda(single, f0, steps, store_every_step=True)
-        assert np.array_equal(got["f"], one["f"])
-    ref = run_oracle(single, f0, steps)
-    assert relative_error(got["f"], ref.f) <= 1e-12 * steps
-    assert abs(got["observables"][0][0] - ref.observables()[0]) <= 1e-9 * abs(ref.observables()[0])
