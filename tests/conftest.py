@@ -28,3 +28,24 @@ def cuda_lib():
         from metalbm_b200 import build
         build.build()
     return capi.load_library()
+
+
+def _gpu_order(item) -> int:
+    """0: the BGK paths (validated on hardware longest), 1: the entropic kernels, 2: the array-type / spectral forces."""
+    node = item.nodeid
+    if "test_spectral_forces_gpu" in node:
+        return 2
+    lowered = node.lower()
+    if any(word in lowered for word in ("elbm", "entropic", "alpha", "logarithm")):
+        return 1
+    return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """GPU runs stop at the first failure (-x): keep the order within each group, but run the groups oldest code first, so
+    that a defect in a newer kernel cannot hide the verdict on the older ones."""
+    gpu = [item for item in items if item.get_closest_marker("gpu")]
+    if not gpu:
+        return
+    ordered = iter(sorted(gpu, key=_gpu_order))   # stable
+    items[:] = [next(ordered) if item.get_closest_marker("gpu") else item for item in items]
