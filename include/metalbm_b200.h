@@ -252,6 +252,15 @@ int mlbm_download_fields(mlbm_ctx* ctx, void* density, void* velocity, void* alp
  *   out[3] total mass       sum of density (PerformanceAnalysisList mass, Routine.h:117-118) */
 int mlbm_observables(mlbm_ctx* ctx, double out[4]);
 
+/* SpectralAnalysisList::writeAnalyses (AnalysisList.h:132-170) of the fields of the last stored step (bit 0 of is_stored):
+ * the energy spectrum of the stored velocity and the forcing spectrum of the force array (PowerSpectra, Analysis.h:122-177),
+ * summed over ranks (Communication::reduce, AnalysisList.h:184-187).  Bin k collects the stored half-spectrum modes with
+ * floor(|k|) == k, each with sum_d |a^_d|^2 of the unnormalised transform, halved where the last wave number is 0; only the
+ * energy spectrum is divided by the global volume (AnalysisList.h:189).  *count = gFD::maxWaveNumber()
+ * = max(Lx, min(Ly, Lz)) / 2 (FourierDomain.h:77-79 with Helpers.h:37-39); either array may be NULL; `capacity` is the
+ * length of the arrays given.  Unlike the reference, the fields are left untouched (its transforms run in place). */
+int mlbm_power_spectra(mlbm_ctx* ctx, double* energy_spectrum, double* forcing_spectrum, int capacity, int* count);
+
 /* Communication::reduce(T* localSumPtr, numberComponents) (Communication.h:76-89): element-wise sum of `count` host
  * doubles over all ranks, result on EVERY rank (the reference leaves it on rank 0 only); a no-op for one rank. */
 int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count);

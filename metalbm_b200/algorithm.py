@@ -259,6 +259,15 @@ class Algorithm:
         check(self._lib.mlbm_observables(self._ctx, out))
         return np.array(list(out))
 
+    def power_spectra(self) -> np.ndarray:
+        """[K, 2]: energy spectrum of the stored velocity and forcing spectrum of the force array of the last stored step
+        (SpectralAnalysisList::writeAnalyses, AnalysisList.h:132-170), reduced over ranks; K = gFD::maxWaveNumber()."""
+        count = ctypes.c_int()
+        check(self._lib.mlbm_power_spectra(self._ctx, None, None, 0, ctypes.byref(count)))
+        energy, forcing = (ctypes.c_double * max(count.value, 1))(), (ctypes.c_double * max(count.value, 1))()
+        check(self._lib.mlbm_power_spectra(self._ctx, energy, forcing, count.value, ctypes.byref(count)))
+        return np.stack([np.array(energy[:count.value]), np.array(forcing[:count.value])], axis=1)
+
     def getCommunicationTime(self) -> float:
         c, _ = ctypes.c_double(), ctypes.c_double()
         check(self._lib.mlbm_timers(self._ctx, ctypes.byref(c), None))

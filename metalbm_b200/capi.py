@@ -215,6 +215,8 @@ PROTOTYPES = {
     "mlbm_sync": (ctypes.c_int, [_P]),
     "mlbm_download_fields": (ctypes.c_int, [_P, _P, _P, _P, _P, _SZ, _SZ, _SZ]),
     "mlbm_observables": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
+    "mlbm_power_spectra": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
+                                          ctypes.POINTER(ctypes.c_int)]),
     "mlbm_reduce_sum": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "mlbm_selftest_log": (ctypes.c_int, [_P, _P, _SZ]),
     "mlbm_alloc_pinned": (ctypes.c_int, [_SZ, ctypes.POINTER(_P)]),

@@ -1273,6 +1273,52 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
   return MLBM_OK;
 }
 
+int mlbm_power_spectra(mlbm_ctx* ctx, double* energySpectrum, double* forcingSpectrum, int capacity, int* count) {
+  if (!ctx || !count) return fail(MLBM_ERR_INVALID, "null argument");
+  const int* L = ctx->config.global_length;
+  const int rest = L[1] < L[2] ? L[1] : L[2];                     // unused dimensions are 1
+  const int bins = (L[0] > rest ? L[0] : rest) / 2;               // gFD::maxWaveNumber(): arrayMax is max(first, MIN of the rest)
+  *count = bins;
+  if (!energySpectrum && !forcingSpectrum) return MLBM_OK;
+  if (capacity < bins) return fail(MLBM_ERR_INVALID, "capacity %d < %d wave numbers", capacity, bins);
+  if (!ctx->fieldsStored || !ctx->velocity) return fail(MLBM_ERR_STATE, "no stored step yet (Algorithm::isStored was never set)");
+  if (bins == 0) return MLBM_OK;
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->config.nranks > 1 && !ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
+  std::string error;
+  if (!ctx->spectral) {
+    SpectralGeometry geometry = {ctx->D, ctx->LX, ctx->NM, ctx->NR, ctx->config.rank, ctx->config.nranks, (int)ctx->elementSize};
+    ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->comm, &error);
+    if (!ctx->spectral) return fail(MLBM_ERR_CUDA, "power spectra: %s", error.c_str());
+  }
+  double* device = nullptr;
+  MLBM_CUDA(cudaMalloc(&device, sizeof(double) * 2 * (size_t)bins));
+  int status = MLBM_OK;
+  cudaStream_t stream = ctx->computeStream;
+  if (spectralPowerSpectrum(ctx->spectral, ctx->velocity, ctx->fieldStride, bins, device, stream, &ctx->launches, &error) ||
+      spectralPowerSpectrum(ctx->spectral, ctx->force, ctx->fieldStride, bins, device + bins, stream, &ctx->launches, &error))
+    status = fail(MLBM_ERR_CUDA, "power spectra: %s", error.c_str());
+  if (status == MLBM_OK && ctx->config.nranks > 1) {
+    const ncclResult_t result = ctx->nccl->AllReduce(device, device, 2 * (size_t)bins, ncclDouble, ncclSum, ctx->comm, stream);
+    if (result != ncclSuccess) status = fail(MLBM_ERR_COMM, "ncclAllReduce: %s", ctx->nccl->GetErrorString(result));
+  }
+  std::vector<double> host(2 * (size_t)bins);
+  cudaError_t copyError = cudaSuccess;
+  if (status == MLBM_OK) copyError = cudaMemcpyAsync(host.data(), device, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, stream);
+  const cudaError_t syncError = cudaStreamSynchronize(stream);
+  cudaFree(device);
+  if (status != MLBM_OK) return status;
+  if (copyError != cudaSuccess || syncError != cudaSuccess)
+    return fail(MLBM_ERR_CUDA, "power spectra: %s", cudaGetErrorString(copyError != cudaSuccess ? copyError : syncError));
+  double volume = 1.0;
+  for (int d = 0; d < ctx->D; ++d) volume *= L[d];
+  for (int k = 0; k < bins; ++k) {
+    if (energySpectrum) energySpectrum[k] = host[k] / volume;      // normalizeAnalyses: the energy spectrum only (AnalysisList.h:189)
+    if (forcingSpectrum) forcingSpectrum[k] = host[bins + k];
+  }
+  return MLBM_OK;
+}
+
 int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count) {
   if (!ctx || !values || count < 0) return fail(MLBM_ERR_INVALID, "null argument");
   if (ctx->config.nranks == 1 || count == 0) return MLBM_OK;

@@ -159,6 +159,40 @@ __global__ void finishKernel(const double* __restrict__ blockSums, long long cou
   if (threadIdx.x == 0) *out = scratch[0] * invVolume * invVolume * invVolume * 0.5;
 }
 
+// PowerSpectra::operator() (Analysis.h:148-168) over this rank's part of the half spectrum: sum_d |a^_d|^2, halved where the
+// wave number of the last (halved) dimension is 0, into bin floor(|k|) when that is below `bins`.  Shared-memory bins per
+// block, then one partial row per block (summed in block order by binSumKernel).
+template <int D>
+__global__ void powerBinKernel(const double2* __restrict__ ax, const double2* __restrict__ ay, const double2* __restrict__ az, int NX, int NM,
+                               int NR, long long myColumns, long long firstColumn, int bins, double* __restrict__ blockBins) {
+  extern __shared__ double shared[];
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) shared[b] = 0.0;
+  __syncthreads();
+  const int NRc = NR / 2 + 1;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)NX * myColumns; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = (int)(i / myColumns);
+    const long long column = firstColumn + i % myColumns;
+    const int im = (int)(column / NRc), ir = (int)(column % NRc);
+    const long long kx = ix <= NX / 2 ? ix : ix - NX, ky = D == 3 ? (im <= NM / 2 ? im : im - NM) : 0, kr = ir;  // AnalysisList.h:141-149
+    const unsigned kNorm = (unsigned)sqrt((double)(kx * kx + ky * ky + kr * kr));
+    if (kNorm >= (unsigned)bins) continue;
+    const double2 a = ax[i], b = ay[i];
+    double energy = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+    if (D == 3) { const double2 c = az[i]; energy += c.x * c.x + c.y * c.y; }
+    atomicAdd(shared + kNorm, (ir == 0 ? 0.5 : 1.0) * energy);
+  }
+  __syncthreads();
+  for (int b = threadIdx.x; b < bins; b += blockDim.x) blockBins[(long long)blockIdx.x * bins + b] = shared[b];
+}
+
+__global__ void binSumKernel(const double* __restrict__ blockBins, int blocks, int bins, double* __restrict__ out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= bins) return;
+  double total = 0.0;
+  for (int block = 0; block < blocks; ++block) total += blockBins[(long long)block * bins + b];
+  out[b] = total;
+}
+
 }  // namespace
 
 class SpectralEnstrophy {
@@ -177,12 +211,14 @@ class SpectralEnstrophy {
   double2* spectrum[3] = {nullptr, nullptr, nullptr};  // [NX][myColumns] per component
   double* blockSums = nullptr;
   long long blocks = 0;
+  double* blockBins = nullptr;     // power spectra: [blocks][bins] partial bins, made on first use
+  int blockBinsCapacity = 0;
 
   ~SpectralEnstrophy() {
     if (havePlanes) fft->Destroy(planPlanes);
     if (haveX) fft->Destroy(planX);
     for (void* pointer : {(void*)realStage, (void*)local, (void*)packed, (void*)spectrum[0], (void*)spectrum[1],
-                          (void*)spectrum[2], (void*)blockSums})
+                          (void*)spectrum[2], (void*)blockSums, (void*)blockBins})
       if (pointer) cudaFree(pointer);
   }
 };
@@ -259,12 +295,12 @@ SpectralEnstrophy* spectralCreate(const SpectralGeometry& geometry, const NcclAp
 
 void spectralDestroy(SpectralEnstrophy* plan) { delete plan; }
 
-int spectralEnqueue(SpectralEnstrophy* s, const void* velocity, long long fieldStride, double* out, cudaStream_t stream,
-                    unsigned long long* launches, std::string* error) {
+// forward transform of the D components of a dense field into s->spectrum[d] ([NX][myColumns], this rank's columns)
+static int transformComponents(SpectralEnstrophy* s, const void* velocity, long long fieldStride, cudaStream_t stream,
+                               unsigned long long& count, std::string* error) {
   const SpectralGeometry& g = s->g;
   const long long localNodes = (long long)g.LX * g.NM * g.NR;
   const long long localSpectrum = (long long)g.LX * s->columns;
-  unsigned long long count = 0;
   if (!checkFft(s->fft->SetStream(s->planPlanes, stream), "cufftSetStream", error)) return -1;
   if (s->haveX && !checkFft(s->fft->SetStream(s->planX, stream), "cufftSetStream", error)) return -1;
 
@@ -307,6 +343,14 @@ int spectralEnqueue(SpectralEnstrophy* s, const void* velocity, long long fieldS
       ++count;
     }
   }
+  return 0;
+}
+
+int spectralEnqueue(SpectralEnstrophy* s, const void* velocity, long long fieldStride, double* out, cudaStream_t stream,
+                    unsigned long long* launches, std::string* error) {
+  const SpectralGeometry& g = s->g;
+  unsigned long long count = 0;
+  if (transformComponents(s, velocity, fieldStride, stream, count, error)) return -1;
   if (s->blocks > 0 && s->myColumns > 0) {
     if (g.D == 3)
       vorticityNormKernel<3><<<(unsigned)s->blocks, kBlock, 0, stream>>>(s->spectrum[0], s->spectrum[1], s->spectrum[2], s->NX, g.NM, g.NR,
@@ -320,6 +364,41 @@ int spectralEnqueue(SpectralEnstrophy* s, const void* velocity, long long fieldS
   finishKernel<<<1, kBlock, 0, stream>>>(s->blockSums, s->myColumns > 0 ? s->blocks : 0, 1.0 / volume, out);
   ++count;
   if (!check(cudaGetLastError(), "spectral enstrophy kernels", error)) return -1;
+  if (launches) *launches += count;
+  return 0;
+}
+
+int spectralPowerSpectrum(SpectralEnstrophy* s, const void* field, long long fieldStride, int bins, double* out, cudaStream_t stream,
+                          unsigned long long* launches, std::string* error) {
+  const SpectralGeometry& g = s->g;
+  unsigned long long count = 0;
+  if (bins <= 0) return 0;
+  if ((size_t)bins * sizeof(double) > 48 * 1024) {
+    if (error) *error = "power spectra: more than 6144 wave-number bins";
+    return -1;
+  }
+  const int blocks = (int)std::max<long long>(1, s->blocks);
+  if (s->blockBinsCapacity < blocks * bins) {
+    if (s->blockBins) cudaFree(s->blockBins);
+    s->blockBins = nullptr;
+    s->blockBinsCapacity = 0;
+    if (!check(cudaMalloc(&s->blockBins, sizeof(double) * (size_t)blocks * bins), "cudaMalloc", error)) return -1;
+    s->blockBinsCapacity = blocks * bins;
+  }
+  if (transformComponents(s, field, fieldStride, stream, count, error)) return -1;
+  if (s->myColumns > 0) {
+    if (g.D == 3)
+      powerBinKernel<3><<<(unsigned)blocks, kBlock, bins * sizeof(double), stream>>>(s->spectrum[0], s->spectrum[1], s->spectrum[2], s->NX, g.NM, g.NR,
+                                                                                    s->myColumns, s->firstColumn, bins, s->blockBins);
+    else
+      powerBinKernel<2><<<(unsigned)blocks, kBlock, bins * sizeof(double), stream>>>(s->spectrum[0], s->spectrum[1], nullptr, s->NX, g.NM, g.NR,
+                                                                                    s->myColumns, s->firstColumn, bins, s->blockBins);
+    binSumKernel<<<(unsigned)((bins + 127) / 128), 128, 0, stream>>>(s->blockBins, blocks, bins, out);
+    count += 2;
+  } else if (!check(cudaMemsetAsync(out, 0, sizeof(double) * bins, stream), "cudaMemsetAsync", error)) {
+    return -1;
+  }
+  if (!check(cudaGetLastError(), "power spectra kernels", error)) return -1;
   if (launches) *launches += count;
   return 0;
 }

@@ -31,4 +31,11 @@ void spectralDestroy(SpectralEnstrophy* plan);
 int spectralEnqueue(SpectralEnstrophy* plan, const void* velocity, long long fieldStride, double* out, cudaStream_t stream,
                     unsigned long long* launches, std::string* error);
 
+// Enqueues on `stream`: out[0 .. bins) = this rank's share of the reference's power spectrum of a dense field of D components
+// (PowerSpectra, Analysis.h:122-177, as driven by SpectralAnalysisList::writeAnalyses, AnalysisList.h:132-170): per stored
+// half-spectrum mode of the unnormalised transform, sum_d |a^_d|^2 (halved where the last wave number is 0) into bin
+// floor(|k|).  The sum over ranks is the reference's spectrum before AnalysisSpectral::normalize.
+int spectralPowerSpectrum(SpectralEnstrophy* plan, const void* field, long long fieldStride, int bins, double* out,
+                          cudaStream_t stream, unsigned long long* launches, std::string* error);
+
 }  // namespace mlbm

@@ -113,6 +113,43 @@ class OracleState:
         return out
 
 
+def max_wave_number(cfg: MlbmConfig) -> int:
+    """gFD::maxWaveNumber() = arrayMax(globalLengthInt) / 2 (FourierDomain.h:77-79), where arrayMax_impl is
+    Max(first, arrayMIN of the rest) (Helpers.h:37-39): max(Lx, min(Ly, Lz)) / 2 with the unused dimensions equal to 1."""
+    nx, ny, nz = shape_of(cfg)
+    return max(nx, min(ny, nz)) // 2
+
+
+def power_spectra(cfg: MlbmConfig, velocity: np.ndarray, force: np.ndarray) -> np.ndarray:
+    """SpectralAnalysisList::writeAnalyses (AnalysisList.h:132-170) with PowerSpectra (Analysis.h:122-177): [K, 2] energy and
+    forcing spectra, K = max_wave_number (FourierDomain.h:77-79).  Per stored half-spectrum mode of the
+    UNNORMALISED r2c transform: sum_d |a^_d|^2, halved where the wave number of the last dimension is 0 (:151-154, so the
+    Nyquist column counts in full), added to bin floor(|k|) when that is below K (:166-167; integer wave numbers
+    k = i <= N/2 ? i : i - N, kNorm = (unsigned)norm).  Only the energy spectrum is divided by the volume (normalizeAnalyses,
+    AnalysisList.h:189)."""
+    shape = shape_of(cfg)
+    dim = LATTICE_DQ[Lattice(cfg.lattice)][0]
+    lengths = shape[:dim]
+    bins = max_wave_number(cfg)
+    wave = [np.array([i if i <= n // 2 else i - n for i in range(n)], dtype=np.float64) for n in lengths]
+    wave[-1] = np.arange(lengths[-1] // 2 + 1, dtype=np.float64)      # the halved dimension: 0 .. N/2
+    grids = np.meshgrid(*wave, indexing="ij")
+    k_norm = np.floor(np.sqrt(sum(g * g for g in grids))).astype(np.int64)
+    coefficient = np.where(grids[-1] == 0, 0.5, 1.0)
+    out = np.zeros((bins, 2))
+    for column, field in enumerate((velocity, force)):
+        energy = np.zeros(k_norm.shape)
+        for d in range(dim):
+            spectrum = np.fft.rfftn(np.asarray(field[d], dtype=np.float64).reshape(lengths))
+            energy += spectrum.real ** 2 + spectrum.imag ** 2
+        weighted = (coefficient * energy).ravel()
+        index = k_norm.ravel()
+        keep = index < bins
+        out[:, column] = np.bincount(index[keep], weights=weighted[keep], minlength=bins)[:bins]
+    out[:, 0] /= float(np.prod(lengths))
+    return out
+
+
 def constant_shell_force(cfg: MlbmConfig) -> np.ndarray:
     """Force<double, ForceType::ConstantShell> for 2-D lattices, step by step as the reference does it:
     initTempArray (Force.h:333-420): psi^ = amplitude[0] (real) on the shell kMin^2 <= |k|^2 <= kMax^2 of the r2c half

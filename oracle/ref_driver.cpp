@@ -10,7 +10,7 @@
 // fields and scalar observables dumped as raw float64 for the parity tests.
 // Everything physical is done by reference code: Algorithm::iterate (Algorithm.h:326-358),
 // TotalEnergy / TotalEnstrophy (Analysis.h:33-98), Curl (Transformer.h:118-295),
-// Communication::reduce (Communication.h:76-89).
+// Communication::reduce (Communication.h:76-89), SpectralAnalysisList (AnalysisList.h:99-202).
 //
 // usage: ref_driver <populations.bin | -> <output prefix> <steps> <store every> [observables 0|1] [dump 0|1] [warm-up steps]
 //   populations.bin : float64 [Q][GX][GY][GZ] global interior populations ("-" = the
@@ -166,6 +166,21 @@ int main(int argc, char* argv[]) {
   for (int iD = 0; iD < 2 * L::dimD - 3; ++iD) gather(fieldList.vorticity.getData(numberElements, iD));
   if (withDump) writeRaw(outputPrefix + ".r" + std::to_string(rank) + ".bin", out);
 
+  // SpectralAnalysisList::writeAnalyses (AnalysisList.h:132-170) on the fields of the last stored step: energy spectrum of
+  // the stored velocity, forcing spectrum of the force array.  Done after the dump: its transforms run in place on the
+  // fields (forward, then backward / V).  The writer's file goes to ../output/ (Writer.h:37), which need not exist.
+  std::string spectra;
+  if (withDump && withObservables && numProcs == 1) {
+    SpectralAnalysisList<dataT, arch> spectralAnalysisList(fieldList, communication, 1, 0);
+    spectralAnalysisList.writeAnalyses(steps);
+    for (unsigned int k = 0; k < gFD::maxWaveNumber(); ++k) {
+      char line[256];
+      snprintf(line, sizeof(line), "spec %u %.17g %.17g\n", k, spectralAnalysisList.energySpectra.spectra[k],
+               spectralAnalysisList.forcingSpectra.spectra[k]);
+      spectra += line;
+    }
+  }
+
   communication.reduce(&computationTime, 1);
   communication.reduce(&communicationTime, 1);
   if (rank == 0) {
@@ -174,6 +189,7 @@ int main(int argc, char* argv[]) {
             L::dimQ, numProcs, local[d::X], local[d::Y], local[d::Z], global[d::X], global[d::Y],
             global[d::Z], steps);
     fprintf(file, "%s", observables.c_str());
+    fprintf(file, "%s", spectra.c_str());
     // per-rank averages of the reference's own timers (Algorithm.h:340-357)
     fprintf(file, "time_computation %.9g\ntime_communication %.9g\ntime_wall %.9g\n",
             computationTime / numProcs, communicationTime / numProcs,

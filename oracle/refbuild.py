@@ -156,7 +156,10 @@ def binary_path(cfg: RefConfig) -> Path:
 def build_ref(cfg: RefConfig, force: bool = False) -> Path:
     """Compile (or reuse) the reference binary for ``cfg``; returns its path."""
     out = binary_path(cfg)
-    if out.is_file() and not force:
+    driver = ORACLE_DIR / "ref_driver.cpp"
+    # a binary older than the driver is stale -- but only where it can be rebuilt (the GPU box has no reference sources)
+    stale = out.is_file() and reference_available() and driver.stat().st_mtime > out.stat().st_mtime
+    if out.is_file() and not force and not stale:
         return out
     if not reference_available():
         raise FileNotFoundError(f"{out} is not prebuilt and {REFERENCE_ROOT} is absent")
@@ -203,6 +206,8 @@ def run_ref(cfg: RefConfig, populations: np.ndarray | None, steps: int, store_ev
             parts = line.split()
             if parts[0] == "obs":
                 result["observables"].append((int(parts[1]), float(parts[2]), float(parts[3])))
+            elif parts[0] == "spec":   # wave number, energy spectrum, forcing spectrum of the last step's fields
+                result.setdefault("spectra", []).append((float(parts[2]), float(parts[3])))
             elif parts[0].startswith("time_"):
                 result[parts[0]] = float(parts[1])
         if not dump:

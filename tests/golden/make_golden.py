@@ -75,6 +75,12 @@ AMPLITUDE = (1e-4, 2e-4, 3e-4)
 WAVELENGTH = (8.0, 4.0, 16.0)
 
 
+def _spectra(out):
+    """[K, 2] energy / forcing spectra of the last step's stored fields (SpectralAnalysisList, AnalysisList.h:99-202);
+    single-rank runs only (the FFT stub is single-rank)."""
+    return {"spectra": np.array(out["spectra"], dtype=np.float64)} if "spectra" in out else {}
+
+
 def main():
     for name, lattice, shape, collision, equilibrium, scheme, force, tau, eps, flow, ripple, steps, ranks in CASES:
         if ONLY and name not in ONLY:
@@ -93,7 +99,7 @@ def main():
                     source="oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off), oracle/ref_driver.cpp")
         np.savez_compressed(HERE / f"{name}.npz", meta=json.dumps(meta), f0=f0, f=out["f"], alpha=out["alpha"],
                             density=out["density"], velocity=out["velocity"], force=out["force"],
-                            observables=np.array(out["observables"], dtype=np.float64))
+                            observables=np.array(out["observables"], dtype=np.float64), **_spectra(out))
         print(name, out["f"].shape, out["observables"][-1])
 
 
@@ -117,7 +123,7 @@ def spectral():
                     source="oracle/_ref (unmodified reference, g++ -O2 -ffp-contract=off), oracle/ref_driver.cpp")
         np.savez_compressed(HERE / f"{case['name']}.npz", meta=json.dumps(meta), f0=f0, f=out["f"], alpha=out["alpha"],
                             density=out["density"], velocity=out["velocity"], force=out["force"],
-                            observables=np.array(out["observables"], dtype=np.float64))
+                            observables=np.array(out["observables"], dtype=np.float64), **_spectra(out))
         print(case["name"], out["f"].shape, out["observables"][-1], "max |F|", np.abs(out["force"]).max())
 
 

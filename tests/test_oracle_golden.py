@@ -100,3 +100,24 @@ def test_energy_removal_mode_sums_equal_the_transforms(shape, shell, oracle_lib)
     direct = energy_removal_direct(cfg, density, velocity, cfg.force_amplitude, shell[0], shell[1])
     assert np.abs(transform).max() > 0
     assert np.abs(direct - transform).max() <= 1e-13 * np.abs(transform).max()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names()])
+def test_power_spectra_restatement_against_the_reference(name, oracle_lib):
+    """oracle.power_spectra (SpectralAnalysisList / PowerSpectra restated, maxWaveNumber quirk included) against the spectra
+    the reference computed from the very fields stored in the golden file."""
+    meta, cfg, data = load_golden(name)
+    if "spectra" not in data.files:
+        pytest.skip("recorded on several ranks: the reference's FFT stub is single-rank")
+    spectra = data["spectra"]
+    assert spectra.shape == (O.max_wave_number(cfg), 2)
+    mine = O.power_spectra(cfg, data["velocity"], data["force"])
+    assert np.abs(mine[:, 0] - spectra[:, 0]).max() <= 1e-13 * np.abs(spectra[:, 0]).max()
+    assert np.abs(mine[:, 1] - spectra[:, 1]).max() <= 1e-13 * max(np.abs(spectra[:, 1]).max(), 1e-300)
+
+
+def test_max_wave_number_follows_the_reference_quirk():
+    """arrayMax is Max(first, arrayMIN of the rest) (Helpers.h:37-39)."""
+    assert O.max_wave_number(make_config("D3Q19", (8, 6, 10))) == 4
+    assert O.max_wave_number(make_config("D3Q19", (6, 8, 10))) == 4
+    assert O.max_wave_number(make_config("D2Q9", (12, 16, 1))) == 6

@@ -163,6 +163,53 @@ def test_spectral_force_follows_the_stored_fields_only():
     assert relative_error(got, state.f) <= 6 * POPULATION_TOLERANCE
 
 
+POWER_SPECTRA_GOLDEN = ["d2q9_bgk_guo_kolmogorov", "d2q9_bgk_none", "d3q15_bgk_edm", "d3q19_bgk_none", "d3q19_bgk_guo_kolmogorov",
+                        "d3q27_elbm_guo", "d2q9_bgk_guo_constantshell"]
+
+
+@pytest.mark.parametrize("name", POWER_SPECTRA_GOLDEN)
+def test_power_spectra_against_the_reference(name):
+    """mlbm_power_spectra (energy spectrum of the stored velocity, forcing spectrum of the force array; distributed cuFFT
+    transform + binning kernel) against the spectra the reference's SpectralAnalysisList computed (golden vectors)."""
+    from golden_util import load_golden
+    from metalbm_b200.algorithm import Algorithm
+    meta, cfg, data = load_golden(name)
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.set_interior(data["f0"])
+        algorithm.unpack()
+        if meta["force"] == "Field":
+            algorithm.domain.interior(algorithm.fieldList.force)[...] = data["force"]
+            algorithm.set_force()
+        for iteration in range(1, meta["steps"] + 1):
+            algorithm.isStored = iteration == meta["steps"]
+            algorithm.iterate(iteration)
+        got = algorithm.power_spectra()
+    spectra = data["spectra"]
+    assert got.shape == spectra.shape
+    assert np.abs(got[:, 0] - spectra[:, 0]).max() <= 1e-9 * np.abs(spectra[:, 0]).max()
+    assert np.abs(got[:, 1] - spectra[:, 1]).max() <= 1e-9 * max(np.abs(spectra[:, 1]).max(), 1e-300)
+
+
+@pytest.mark.parametrize("lattice,shape", [("D2Q9", (33, 20, 1)), ("D2Q9", (16, 131, 1)), ("D3Q19", (9, 8, 7)), ("D3Q27", (6, 8, 10))])
+def test_power_spectra_odd_sizes_against_the_oracle(lattice, shape):
+    from metalbm_b200.algorithm import Algorithm
+    cfg = _config(lattice, shape, "TruncationMa3", "Guo", "Sinusoidal", 0.6)
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.set_interior(f0)
+        algorithm.unpack()
+        algorithm.isStored = True
+        algorithm.iterate(1)
+        got = algorithm.power_spectra()
+        again = algorithm.power_spectra()               # the fields are left untouched
+    ref = run_oracle(cfg, f0, 1)
+    want = O.power_spectra(cfg, ref.velocity, ref.force)
+    assert got.shape == want.shape and np.array_equal(got.shape, again.shape)
+    assert np.abs(got - want).max(axis=0)[0] <= 1e-10 * np.abs(want[:, 0]).max()
+    assert np.abs(got - want).max(axis=0)[1] <= 1e-10 * np.abs(want[:, 1]).max()
+    assert np.abs(got - again).max() <= 1e-12 * np.abs(got).max()
+
+
 @pytest.mark.parametrize("world", [1, 2])
 @pytest.mark.parametrize("case", SPECTRAL_SHIM_CASES, ids=lambda c: "-".join(map(str, c[:1] + c[2:6])))
 def test_template_api_with_spectral_forces(tmp_path, cuda_lib, world, case):
