@@ -230,3 +230,66 @@ def test_measure_also_bookkeeping_with_a_fake_context(monkeypatch, world):
         assert fake.calls[-1] == ("run", 0, 1, 1, 2)   # the liveness step reduces energy / mass / Mach only
         if world > 1:
             assert out["halo"] == "peer" and tuple(fake.cfg.global_length)[0] == shape[0]
+
+
+class _FakeLib:
+    def mlbm_step(self, ctx, iteration, stored):
+        return 0
+
+    def mlbm_run_async(self, ctx, first, count, store_every):
+        return 0
+
+
+class _FakeBenchAlgorithm(_FakeAlgorithm):
+    """The part of Algorithm that bench.run_ours uses around the headline measurement."""
+
+    def __init__(self, cfg, communication=None, host_distribution=True, peer_halos=None, host_fields=True):
+        from metalbm_b200.algorithm import Distribution, Domain, FieldList
+        self.cfg, self.peer_halos, self.calls, self.closed = cfg, bool(peer_halos), [], False
+        self.domain = Domain(cfg)
+        self.fieldList = FieldList(self.domain, allocate=host_fields)
+        self.distribution = Distribution(self.domain, allocate=host_distribution)
+        self._lib, self._ctx = _FakeLib(), None
+        _FakeAlgorithm.created.append(self)
+
+    def init_equilibrium(self): self.calls.append(("init_equilibrium",))
+    def launch_count(self): return 7 * len(self.calls)
+    def pack(self): self.calls.append(("pack",))
+    def unpack(self): self.calls.append(("unpack",))
+
+
+def test_run_ours_prints_one_complete_line_with_a_fake_context(monkeypatch, capsys):
+    """The whole of bench.run_ours on the CPU with the device faked away: every key of the contract is there, the secondary
+    workloads follow, exactly one line is printed."""
+    import types
+    import torch
+    import metalbm_b200.algorithm as A
+    import metalbm_b200.capi as capi
+    monkeypatch.setattr(A, "Algorithm", _FakeBenchAlgorithm)
+    monkeypatch.setattr(capi, "check", lambda status: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (190 * 10**9, 192 * 10**9))
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{key: v for key, v in k.items() if key not in ("pin_memory", "device")}))
+    monkeypatch.setattr(bench, "cpu_baseline_leg", lambda: {"value": 50.0, "unit": "MLUPS", "cores": 4, "kind": "reference", "sample": "fake"})
+    monkeypatch.setattr(bench, "EDGE", 8)
+    monkeypatch.setitem(bench.WORKLOADS["d3q19_bgk_256"], "shape", (8, 8, 8))
+    args = types.SimpleNamespace(gpus=1, steps=5, warmup=3, impl="ours", edge=8, variant=0, workload="d3q19_bgk_256", dtype="f64",
+                                 overlap="On", halo="peer", eps=None, store_every=None, no_e2e=False, no_cpu_baseline=False,
+                                 also="auto", also_timeout=120)
+    _FakeAlgorithm.created.clear()
+    assert bench.run_ours(args) == 0
+    out = capsys.readouterr().out
+    line = _only_line(out)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "also"):
+        assert key in line, key
+    assert line["metric"] == "MLUPS (D3Q19, FP64)" and line["unit"] == "MLUPS" and line["n_gpus"] == 1 and line["steps"] == 5
+    assert line["value"] == pytest.approx(8 ** 3 * 5 / 0.050 / 1e6)
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["algorithmic_bytes_per_node"] == 304
+    assert line["e2e"]["h2d_bytes_per_step"] == pytest.approx(19 * 8 ** 3 * 8 / 5)
+    assert line["cpu_baseline"]["kind"] == "reference" and line["vs_baseline"] is None and line["dtype"] == "f64"
+    assert [e["name"] for e in line["also"]] == [e[0] for e in bench.ALSO_SINGLE]
+    assert all("value" in e or "skipped" in e for e in line["also"])
+    assert all(a.closed for a in _FakeAlgorithm.created)
