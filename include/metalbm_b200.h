@@ -40,9 +40,13 @@ typedef enum mlbm_status {
   MLBM_ERR_NOMEM = -5
 } mlbm_status;
 
-/* LatticeType (Options.h:13-14, descriptors Lattice.h:80,145,460,535,614) */
+/* LatticeType (Options.h:13-14, descriptors Lattice.h:80,145,460,535,614).  The multi-speed lattices D2Q13 (:213),
+ * D2Q17 (:290), D2Q21 (:372) and D3Q33 (:706) -- jumps of up to 3 nodes, their own sound speeds, TruncationMa3 only --
+ * run on ONE GPU (nranks == 1): every coordinate wraps by index arithmetic.  D1Q3 (:22) does not compile in the reference
+ * (Force.h:329) and is not rebuilt. */
 typedef enum mlbm_lattice {
-  MLBM_D2Q5 = 0, MLBM_D2Q9 = 1, MLBM_D3Q15 = 2, MLBM_D3Q19 = 3, MLBM_D3Q27 = 4
+  MLBM_D2Q5 = 0, MLBM_D2Q9 = 1, MLBM_D3Q15 = 2, MLBM_D3Q19 = 3, MLBM_D3Q27 = 4,
+  MLBM_D2Q13 = 5, MLBM_D2Q17 = 6, MLBM_D2Q21 = 7, MLBM_D3Q33 = 8
 } mlbm_lattice;
 
 /* CollisionType (Options.h:35-38; Collision.h:103-180 BGK, :182-376 ELBM).
@@ -155,7 +159,7 @@ typedef struct mlbm_launch_plan {
   int32_t has_force;            /* 0: none, 1: per-axis profiles of the analytic forces, 2: read from the force field */
   uint64_t stride, plane;       /* elements between populations / between x planes */
   double beta;                  /* 1 / (2 tau)                 (Collision.h:122) */
-  double guo_factor;            /* (1 - 1/(2 tau)) * inv_cs2   (ForcingScheme.h:115) */
+  double guo_factor;            /* (1 - 1/(2 tau)) * inv_cs2   (ForcingScheme.h:115; inv_cs2 of the lattice) */
 } mlbm_launch_plan;
 int mlbm_launch_plan_for(const mlbm_config* config, int x0, int x1, int is_stored, int plane_step, mlbm_launch_plan* out);
 

@@ -24,6 +24,10 @@ class Lattice(enum.IntEnum):
     D3Q15 = 2
     D3Q19 = 3
     D3Q27 = 4
+    D2Q13 = 5   # multi-speed lattices (halo 2-3): one GPU
+    D2Q17 = 6
+    D2Q21 = 7
+    D3Q33 = 8
 
 
 class Collision(enum.IntEnum):
@@ -72,7 +76,9 @@ class Overlapping(enum.IntEnum):
 
 
 LATTICE_DQ = {Lattice.D2Q5: (2, 5), Lattice.D2Q9: (2, 9), Lattice.D3Q15: (3, 15),
-              Lattice.D3Q19: (3, 19), Lattice.D3Q27: (3, 27)}
+              Lattice.D3Q19: (3, 19), Lattice.D3Q27: (3, 27), Lattice.D2Q13: (2, 13), Lattice.D2Q17: (2, 17),
+              Lattice.D2Q21: (2, 21), Lattice.D3Q33: (3, 33)}
+LATTICE_INV_CS2 = {Lattice.D2Q17: 2.0 / 3.0, Lattice.D2Q21: 1.0 / (2.0 / 3.0), Lattice.D3Q33: 1.0 / 0.4156023517935171}   # else 3
 
 
 class MlbmConfig(ctypes.Structure):

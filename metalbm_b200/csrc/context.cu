@@ -31,6 +31,14 @@ StepKernel lookupStepKernel_d3q19_f64(int, int, int);
 StepKernel lookupStepKernel_d3q19_f32(int, int, int);
 StepKernel lookupStepKernel_d3q27_f64(int, int, int);
 StepKernel lookupStepKernel_d3q27_f32(int, int, int);
+StepKernel lookupStepKernel_d2q13_f64(int, int, int);
+StepKernel lookupStepKernel_d2q13_f32(int, int, int);
+StepKernel lookupStepKernel_d2q17_f64(int, int, int);
+StepKernel lookupStepKernel_d2q17_f32(int, int, int);
+StepKernel lookupStepKernel_d2q21_f64(int, int, int);
+StepKernel lookupStepKernel_d2q21_f32(int, int, int);
+StepKernel lookupStepKernel_d3q33_f64(int, int, int);
+StepKernel lookupStepKernel_d3q33_f32(int, int, int);
 
 StepKernel lookupStepKernel(int lattice, int collision, int equilibrium, int scheme, int dtype) {
   const bool f64 = dtype == MLBM_F64;
@@ -40,6 +48,10 @@ StepKernel lookupStepKernel(int lattice, int collision, int equilibrium, int sch
     case kD3Q15: return f64 ? lookupStepKernel_d3q15_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q15_f32(collision, equilibrium, scheme);
     case kD3Q19: return f64 ? lookupStepKernel_d3q19_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q19_f32(collision, equilibrium, scheme);
     case kD3Q27: return f64 ? lookupStepKernel_d3q27_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q27_f32(collision, equilibrium, scheme);
+    case kD2Q13: return f64 ? lookupStepKernel_d2q13_f64(collision, equilibrium, scheme) : lookupStepKernel_d2q13_f32(collision, equilibrium, scheme);
+    case kD2Q17: return f64 ? lookupStepKernel_d2q17_f64(collision, equilibrium, scheme) : lookupStepKernel_d2q17_f32(collision, equilibrium, scheme);
+    case kD2Q21: return f64 ? lookupStepKernel_d2q21_f64(collision, equilibrium, scheme) : lookupStepKernel_d2q21_f32(collision, equilibrium, scheme);
+    case kD3Q33: return f64 ? lookupStepKernel_d3q33_f64(collision, equilibrium, scheme) : lookupStepKernel_d3q33_f32(collision, equilibrium, scheme);
     default: return nullptr;
   }
 }
@@ -280,6 +292,12 @@ static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* popu
       if (EQ == kTruncationMa3) initEquilibriumKernel<Lattice<kD3Q19>, kTruncationMa3, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes);
       break;
     case kD3Q27: initEquilibriumKernel<Lattice<kD3Q27>, EQ, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes); break;
+#define MLBM_INIT_WIDE(LATTICE)                                                                                        \
+    case LATTICE:                                                                                                        \
+      if (EQ == kTruncationMa3) initEquilibriumKernel<Lattice<LATTICE>, kTruncationMa3, StoreT><<<grid, block, 0, stream>>>(populations, density, velocity, stride, plane, fieldStride, nodes); \
+      break;
+    MLBM_INIT_WIDE(kD2Q13) MLBM_INIT_WIDE(kD2Q17) MLBM_INIT_WIDE(kD2Q21) MLBM_INIT_WIDE(kD3Q33)
+#undef MLBM_INIT_WIDE
   }
 }
 
@@ -298,6 +316,10 @@ static void launchInitSynthetic(int lattice, cudaStream_t stream, StoreT* popula
     case kD3Q15: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD3Q15, kTruncationMa3); break;
     case kD3Q19: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD3Q19, kTruncationMa3); break;
     case kD3Q27: MLBM_INIT_SYNTHETIC(kD3Q27, EQ); break;
+    case kD2Q13: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD2Q13, kTruncationMa3); break;
+    case kD2Q17: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD2Q17, kTruncationMa3); break;
+    case kD2Q21: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD2Q21, kTruncationMa3); break;
+    case kD3Q33: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD3Q33, kTruncationMa3); break;
   }
 #undef MLBM_INIT_SYNTHETIC
 }
@@ -426,6 +448,7 @@ struct SlabGeometry {
 static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
   g->Q = latticeQ(config->lattice);
   if (!g->Q || config->nranks < 1 || config->global_length[0] % config->nranks) return false;
+  if (latticeHalo(config->lattice) > 1 && config->nranks > 1) return false;  // one halo plane per side
   g->D = latticeDim(config->lattice);
   g->faceQ = latticeFaceQ(config->lattice);
   g->LX = config->global_length[0] / config->nranks;
@@ -453,7 +476,7 @@ static void fillLaunchScalars(const mlbm_config& config, const SlabGeometry& g, 
   p->hydroShift = hydroShift;
   p->hasForce = config.force == MLBM_FORCE_NONE ? 0 : (config.force >= MLBM_FORCE_FIELD ? 2 : 1);  // array-type forces read the field
   p->beta = 1.0 / (2.0 * config.tau);
-  p->guoFactor = (1.0 - 1.0 / (2.0 * config.tau)) * 3.0;
+  p->guoFactor = (1.0 - 1.0 / (2.0 * config.tau)) * latticeInvCs2(config.lattice);
   // entropic kernels stage their logarithm table and constants once per block: let a block walk up to 16 planes
   // (measured: +30 % on D2Q9 8192^2, +11 % on D3Q27 512^3 against one plane per block) while the grid keeps >= ~20 waves
   static const int planesOverride = getenv("MLBM_PLANES_PER_BLOCK") ? atoi(getenv("MLBM_PLANES_PER_BLOCK")) : 0;  // experiments
@@ -747,6 +770,8 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   for (int d = 0; d < D; ++d)
     if (config->global_length[d] < 1) return fail(MLBM_ERR_INVALID, "global_length[%d] = %d", d, config->global_length[d]);
   if (config->global_length[0] % config->nranks) return fail(MLBM_ERR_INVALID, "nranks %d does not divide globalLengthX %d (Domain.h:22-24)", config->nranks, config->global_length[0]);
+  if (latticeHalo(config->lattice) > 1 && config->nranks > 1)
+    return fail(MLBM_ERR_INVALID, "the multi-speed lattices (halo %d) run on one GPU in this build: the x-slab exchange moves one plane per side", latticeHalo(config->lattice));
 
   int collision, scheme, hydroShift;
   switch (config->collision) {
@@ -1268,7 +1293,7 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
   for (int d = 0; d < ctx->D; ++d) globalVolume *= ctx->config.global_length[d];
   out[0] = local[0] / globalVolume;          // AnalysisScalar::normalize (Analysis.h:30)
   out[1] = ctx->enstrophyValid ? local[3] / globalVolume : NAN;  // Analysis.h:85-93; needs the stored velocity field
-  out[2] = sqrt(local[2] * 3.0);             // |u| / c_s, c_s^2 = 1/3
+  out[2] = sqrt(local[2] * latticeInvCs2(ctx->config.lattice));  // |u| / c_s, c_s^2 = 1 / inv_cs2 (1/3 but for the multi-speed lattices)
   out[3] = local[1];
   return MLBM_OK;
 }

@@ -84,32 +84,43 @@ template <typename StoreT> __device__ __forceinline__ void storePopulation(Store
 // ------------------------------------------------------------------------------------------------
 // Equilibrium, evaluated for all Q populations from q-independent coefficients.
 //   TruncationMa3 (Equilibrium.h:17-34): the reference's 9-term polynomial regrouped by powers of c.u
-//     P = A0 + cu (A1 + cu (A2 + cu (A3 + cu A4))),  s = inv_cs2 = 3
+//     P = A0 + cu (A1 + cu (A2 + cu (A3 + cu A4))),  s = inv_cs2 (3 but for the multi-speed lattices)
 //     A0 = 1 - s/2 u2 + s^2/8 u2^2, A1 = s - s^2/2 u2, A2 = s^2/2 - s^3/4 u2, A3 = s^3/6, A4 = s^4/24
 //   Exact (Equilibrium.h:60-81, 106-126): product form, three factors per dimension precomputed.
 // ------------------------------------------------------------------------------------------------
 template <class L, int EQ> struct EquilibriumCoefficients;
 
+// c_q . v for a compile-time celerity: additions and subtractions for the unit components, one multiply for the others
+template <class L, int q> __device__ __forceinline__ double celerityDot(const double* v) {
+  double r = 0.0;
+#pragma unroll
+  for (int d = 0; d < L::D; ++d) {
+    if (L::c(q, d) == 1) r += v[d];
+    else if (L::c(q, d) == -1) r -= v[d];
+    else if (L::c(q, d) != 0) r += (double)L::c(q, d) * v[d];
+  }
+  return r;
+}
+
 template <class L> struct EquilibriumCoefficients<L, kTruncationMa3> {
+  // s = L::inv_cs2: 3 for the single-speed lattices, where these constants are exactly 1.5, 1.125, 3, 4.5, 4.5, 6.75, 4.5, 3.375
+  static constexpr double s = L::inv_cs2;
+  static constexpr double kA0u2 = 0.5 * s, kA0u4 = 0.125 * s * s, kA1 = s, kA1u2 = 0.5 * s * s, kA2 = 0.5 * s * s,
+                          kA2u2 = 0.25 * s * s * s, kA3 = s * s * s / 6.0, kA4 = s * s * s * s / 24.0;
   double a0, a1, a2;
   double u[3];
   __device__ __forceinline__ void set(const double* velocity, double u2) {
-    a0 = 1.0 - 1.5 * u2 + 1.125 * u2 * u2;
-    a1 = 3.0 - 4.5 * u2;
-    a2 = 4.5 - 6.75 * u2;
+    a0 = 1.0 - kA0u2 * u2 + kA0u4 * u2 * u2;
+    a1 = kA1 - kA1u2 * u2;
+    a2 = kA2 - kA2u2 * u2;
 #pragma unroll
     for (int d = 0; d < 3; ++d) u[d] = d < L::D ? velocity[d] : 0.0;
   }
   // returns feq / (rho * w_q)
   template <int q> __device__ __forceinline__ double shape() const {
-    double cu = 0.0;
-#pragma unroll
-    for (int d = 0; d < L::D; ++d) {
-      if (L::c(q, d) == 1) cu += u[d];
-      if (L::c(q, d) == -1) cu -= u[d];
-    }
+    const double cu = celerityDot<L, q>(u);
     if (L::norm2(q) == 0) return a0;
-    return a0 + cu * (a1 + cu * (a2 + cu * (4.5 + cu * 3.375)));
+    return a0 + cu * (a1 + cu * (a2 + cu * (kA3 + cu * kA4)));
   }
 };
 
@@ -279,23 +290,24 @@ struct EntropicShared {
   double* f;             // [Q][kStepBlock]  F2, rows sorted by speed class
   double* fNeq;          // [Q][kStepBlock]  N2
   double* alpha;         // [kStepBlock]     in: alphaMax of the nodes to solve, out: their alpha
-  double* rowOffset;     // [32]  C_c of the row's class          (library fallback only)
-  double* rowInverse;    // [32]  2^-k_c of the row's class       (library fallback only)
+  double* rowOffset;     // [kRowSlots]  C_c of the row's class       (library fallback only)
+  double* rowInverse;    // [kRowSlots]  2^-k_c of the row's class    (library fallback only)
   int* warpCount;        // [kStepBlock / 32]
   unsigned char* list;   // [kStepBlock]     nodes (thread indices) that need the Newton solve, ascending
   const double2* table;  // fastLog table (shared or global memory)
 };
 
 constexpr int kLogTableBytes = kLogTableEntries * 16;
+constexpr int rowSlots(int Q) { return Q <= 32 ? 32 : 40; }  // D3Q33 has 33 rows
 constexpr int entropicSharedBytes(int Q, bool tableInShared) {
-  return 2 * Q * kStepBlock * 8 + kStepBlock * 8 + 2 * 32 * 8 + 16 + kStepBlock + (tableInShared ? kLogTableBytes : 0);
+  return 2 * Q * kStepBlock * 8 + kStepBlock * 8 + 2 * rowSlots(Q) * 8 + 16 + kStepBlock + (tableInShared ? kLogTableBytes : 0);
 }
 // blocks per SM the entropic kernels are compiled for (registers) and sized for (shared memory)
 // (measured, D3Q27 512^3: three blocks with the table in shared memory beat four blocks with the table in L1 by 10-14 %)
 #ifndef MLBM_ENTROPIC_BLOCKS_Q9
 #define MLBM_ENTROPIC_BLOCKS_Q9 5
 #endif
-constexpr int entropicBlocksPerSM(int Q) { return Q <= 9 ? MLBM_ENTROPIC_BLOCKS_Q9 : (Q == 27 ? 3 : 4); }
+constexpr int entropicBlocksPerSM(int Q) { return Q <= 9 ? MLBM_ENTROPIC_BLOCKS_Q9 : (Q >= 27 ? 3 : 4); }
 // the fastLog table is staged in shared memory whenever those blocks still fit (228 KB, 1 KB reserved per block)
 constexpr bool logTableInShared(int Q) { return entropicBlocksPerSM(Q) * (entropicSharedBytes(Q, true) + 1024) <= 233472; }
 
@@ -396,7 +408,7 @@ __device__ __forceinline__ double entropicNewton(const EntropicShared& s, int co
   const double* nColumn = s.fNeq + column;
   unsigned range = 0;
   double hoisted = 0.0, offsetF = 0.0, offsetN = 0.0, sumN = 0.0;
-  staticFor<0, 4>([&](auto nc) {
+  staticFor<0, L::maxNorm2() + 1>([&](auto nc) {
     constexpr int n2 = decltype(nc)::value;
     if constexpr (C::count(n2) > 0) {
       double hC, sF, sN;
@@ -416,7 +428,7 @@ __device__ __forceinline__ double entropicNewton(const EntropicShared& s, int co
   for (int iteration = 1; iteration <= 50; ++iteration) {
     x = x - step;
     double total = 0.0, slope = 0.0;
-    staticFor<0, 4>([&](auto nc) {
+    staticFor<0, L::maxNorm2() + 1>([&](auto nc) {
       constexpr int n2 = decltype(nc)::value;
       if constexpr (C::count(n2) > 0) {
         double sC, dC;
@@ -458,9 +470,29 @@ __device__ __forceinline__ NodeIndex nodeIndex(const StepParams& p, int x, int m
   return n;
 }
 
+// periodic image of coordinate v - c in [0, n) for |c| up to 3 and any n >= 1
+__device__ __forceinline__ int wrapCoordinate(int v, int n) {
+  v %= n;
+  return v < 0 ? v + n : v;
+}
+
 template <class L, typename StoreT, bool STREAMING = false>
 __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeIndex& n, double (&f)[L::Q]) {
   const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
+  if constexpr (L::H > 1) {
+    // multi-speed lattices (one GPU: x is periodic inside the slab, mlbm_create enforces it): every coordinate wraps by
+    // index arithmetic, whatever the length of the jump (Lattice.h:213-458, 706-803)
+    const int x = n.xh - 1;
+#pragma unroll
+    for (int q = 0; q < L::Q; ++q) {
+      const int xs = L::cx(q) == 0 ? n.xh : wrapCoordinate(x - L::cx(q), p.LX) + 1;
+      const int ms = L::cm(q) == 0 ? n.m : wrapCoordinate(n.m - L::cm(q), p.NM);
+      const int rs = L::cr(q) == 0 ? n.r : wrapCoordinate(n.r - L::cr(q), p.NR);
+      const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
+      f[q] = STREAMING ? loadPopulationStreaming(source) : loadPopulation(source);
+    }
+    return;
+  }
 #pragma unroll
   for (int q = 0; q < L::Q; ++q) {
     const int xs = L::cx(q) == 1 ? n.xPrev : (L::cx(q) == -1 ? n.xNext : n.xh);
@@ -477,6 +509,7 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
 template <class L, typename StoreT>
 __device__ __forceinline__ void prefetchPopulations(const StepParams& p, const NodeIndex& n) {
 #if defined(__CUDA_ARCH__)
+  if (L::H > 1) return;
   if ((threadIdx.x & (32 / (int)sizeof(StoreT) - 1)) != 0) return;
   const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
 #pragma unroll
@@ -502,7 +535,8 @@ __device__ __forceinline__ void moments(const double (&f)[L::Q], double& rho, do
 #pragma unroll
     for (int d = 0; d < L::D; ++d) {
       if (L::c(q, d) == 1) u[d] += f[q];
-      if (L::c(q, d) == -1) u[d] -= f[q];
+      else if (L::c(q, d) == -1) u[d] -= f[q];
+      else if (L::c(q, d) != 0) u[d] += (double)L::c(q, d) * f[q];
     }
   }
   invRho = 1.0 / rho;
@@ -565,9 +599,10 @@ template <class L, int EQ, int SCHEME> struct SourceTerm {
 #pragma unroll
       for (int d = 0; d < L::D; ++d) {
         if (L::c(q, d) == 1) { cF += F[d]; cu += u[d]; }
-        if (L::c(q, d) == -1) { cF -= F[d]; cu -= u[d]; }
+        else if (L::c(q, d) == -1) { cF -= F[d]; cu -= u[d]; }
+        else if (L::c(q, d) != 0) { cF += (double)L::c(q, d) * F[d]; cu += (double)L::c(q, d) * u[d]; }
       }
-      return guoFactor * L::w(q) * (cF - uF + 3.0 * cu * cF);
+      return guoFactor * L::w(q) * (cF - uF + L::inv_cs2 * cu * cF);
     }
     if (SCHEME == kSchemeEDM) return rho * L::w(q) * shifted.template shape<q>() - feq;
     return 0.0;
@@ -645,8 +680,8 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
   s.fNeq = s.f + Q * kStepBlock;
   s.alpha = s.fNeq + Q * kStepBlock;
   s.rowOffset = s.alpha + kStepBlock;
-  s.rowInverse = s.rowOffset + 32;
-  s.warpCount = reinterpret_cast<int*>(s.rowInverse + 32);
+  s.rowInverse = s.rowOffset + rowSlots(Q);
+  s.warpCount = reinterpret_cast<int*>(s.rowInverse + rowSlots(Q));
   s.list = reinterpret_cast<unsigned char*>(s.warpCount + 4);
   s.table = kLogTable;
   staticFor<0, Q>([&](auto qc) {

@@ -23,12 +23,13 @@
 
 #include "../include/metalbm_b200.h"
 
-#define MAXQ 27
+#define MAXQ 33
 
 typedef struct {
   int D, Q;
   int c[MAXQ][3];
   double w[MAXQ];
+  double inv_cs2;   /* L::inv_cs2 */
 } lattice_t;
 
 /* Lattice.h:80-143 (D2Q5), :145-210 (D2Q9), :460-532 (D3Q15), :535-612 (D3Q19), :614-703 (D3Q27) */
@@ -42,8 +43,24 @@ static int lattice_table(int lattice, lattice_t* L) {
   static const int c_d3q27[27][3] = {{0,0,0},{-1,0,0},{-1,-1,0},{-1,1,0},{-1,0,-1},{-1,0,1},{-1,-1,-1},{-1,-1,1},{-1,1,-1},
                                      {-1,1,1},{1,0,0},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{1,1,1},{1,1,-1},{1,-1,1},{1,-1,-1},
                                      {0,-1,0},{0,0,-1},{0,-1,-1},{0,-1,1},{0,1,0},{0,0,1},{0,1,1},{0,1,-1}};
+  /* multi-speed lattices: Lattice.h:213-288 (D2Q13), :290-370 (D2Q17), :372-458 (D2Q21), :706-803 (D3Q33) */
+  static const int c_d2q13[13][3] = {{0,0,0},{-1,0,0},{-1,-1,0},{-1,1,0},{-2,0,0},{1,0,0},{1,-1,0},{1,1,0},{2,0,0},{0,-1,0},
+                                     {0,1,0},{0,-2,0},{0,2,0}};
+  static const int c_d2q17[17][3] = {{0,0,0},{-1,-1,0},{-1,1,0},{-2,-2,0},{-2,2,0},{-3,0,0},{-3,-3,0},{-3,3,0},{1,-1,0},{1,1,0},
+                                     {2,-2,0},{2,2,0},{3,0,0},{3,-3,0},{3,3,0},{0,-3,0},{0,3,0}};
+  static const int c_d2q21[21][3] = {{0,0,0},{-1,0,0},{-1,-1,0},{-1,1,0},{-2,0,0},{-2,2,0},{-2,-2,0},{-3,0,0},{1,0,0},{1,-1,0},
+                                     {1,1,0},{2,0,0},{2,-2,0},{2,2,0},{3,0,0},{0,-1,0},{0,1,0},{0,-2,0},{0,2,0},{0,-3,0},{0,3,0}};
+  static const int c_d3q33[33][3] = {{0,0,0},{-1,0,0},{-1,-1,0},{-1,1,0},{-1,0,-1},{-1,0,1},{-1,-1,-1},{-1,-1,1},{-1,1,-1},
+                                     {-1,1,1},{-2,0,0},{1,0,0},{1,1,0},{1,-1,0},{1,0,1},{1,0,-1},{1,1,1},{1,1,-1},{1,-1,1},
+                                     {1,-1,-1},{2,0,0},{0,-1,0},{0,0,-1},{0,-1,-1},{0,-1,1},{0,1,0},{0,0,1},{0,1,1},{0,1,-1},
+                                     {0,2,0},{0,-2,0},{0,0,2},{0,0,-2}};
   const int (*c)[3] = NULL;
+  L->inv_cs2 = 3.0;   /* Lattice.h:86,151,218,466,541,620 */
   switch (lattice) {
+    case MLBM_D2Q13: L->D = 2; L->Q = 13; c = c_d2q13; break;
+    case MLBM_D2Q17: L->D = 2; L->Q = 17; c = c_d2q17; L->inv_cs2 = 2.0 / 3.0; break;                 /* Lattice.h:294 */
+    case MLBM_D2Q21: L->D = 2; L->Q = 21; c = c_d2q21; L->inv_cs2 = 1.0 / (2.0 / 3.0); break;         /* Lattice.h:377-378 */
+    case MLBM_D3Q33: L->D = 3; L->Q = 33; c = c_d3q33; L->inv_cs2 = 1.0 / 0.4156023517935171; break;  /* Lattice.h:710-711 */
     case MLBM_D2Q5: L->D = 2; L->Q = 5; c = c_d2q5; break;
     case MLBM_D2Q9: L->D = 2; L->Q = 9; c = c_d2q9; break;
     case MLBM_D3Q15: L->D = 3; L->Q = 15; c = c_d3q15; break;
@@ -60,6 +77,13 @@ static int lattice_table(int lattice, lattice_t* L) {
       case MLBM_D2Q9: w = n2 == 0 ? 4.0 / 9.0 : (n2 == 1 ? 1.0 / 9.0 : 1.0 / 36.0); break;
       case MLBM_D3Q15: w = n2 == 0 ? 2.0 / 9.0 : (n2 == 1 ? 1.0 / 9.0 : 1.0 / 72.0); break;
       case MLBM_D3Q19: w = n2 == 0 ? 1.0 / 3.0 : (n2 == 1 ? 1.0 / 18.0 : 1.0 / 36.0); break;
+      case MLBM_D2Q13: w = n2 == 0 ? 1.0 / 2.0 : (n2 == 1 ? 4.0 / 45.0 : (n2 == 2 ? 1.0 / 30.0 : 1.0 / 360.0)); break;
+      case MLBM_D2Q17: w = n2 == 0 ? 0.121527777777777777777778 : (n2 == 2 ? 0.175781250000000000000000 :
+                           (n2 == 8 ? 0.014062500000000000000000 : (n2 == 9 ? 0.027777777777777777777778 : 0.001996527777777777777778))); break;
+      case MLBM_D2Q21: w = n2 == 0 ? 91. / 324. : (n2 == 1 ? 1. / 12. : (n2 == 2 ? 2. / 27. : (n2 == 4 ? 7. / 360. :
+                           (n2 == 8 ? 1. / 432. : 1. / 1620.)))); break;
+      case MLBM_D3Q33: w = n2 == 0 ? 0.177627658370520295649084 : (n2 == 1 ? 0.103315974899246818673111 :
+                           (n2 == 2 ? 0.000513472406731114352456 : (n2 == 3 ? 0.021333928148672240120078 : 0.004273899693974583187026))); break;
       default: w = n2 == 0 ? 8.0 / 27.0 : (n2 == 1 ? 2.0 / 27.0 : (n2 == 2 ? 1.0 / 54.0 : 1.0 / 216.0)); break;
     }
     L->w[q] = w;
@@ -99,7 +123,7 @@ static double power_base(double arg, int power) {
 
 /* Equilibrium::calculate -- TruncationMa3 (Equilibrium.h:17-34), Exact (Equilibrium.h:60-81, 106-126) */
 static double equilibrium(const lattice_t* L, int type, double density, const double* u, double u2, int q) {
-  const double s = 3.0; /* L::inv_cs2, every supported lattice (Lattice.h:86,151,466,541,620) */
+  const double s = L->inv_cs2;
   if (type == MLBM_TRUNCATION_MA3) {
     const double cu = cdot(L, q, u);
     const double s2 = s * s, s3 = s * s * s, s4 = s * s * s * s;
@@ -123,7 +147,7 @@ static double collision_source(const lattice_t* L, const mlbm_config* cfg, const
   (void)u2;
   switch (cfg->forcing_scheme) {
     case MLBM_GUO: {
-      const double s = 3.0;
+      const double s = L->inv_cs2;
       const double cu = cdot(L, q, u);
       double t[3];
       for (int d = 0; d < L->D; ++d) t[d] = ((double)L->c[q][d] - u[d]) + (double)L->c[q][d] * (s * cu);
@@ -419,7 +443,7 @@ int mlbm_oracle_observables(const mlbm_config* cfg, const double* density, const
   }
   out[0] = energy / (double)V;
   out[1] = 0.0;
-  out[2] = sqrt(mach2 * 3.0);
+  out[2] = sqrt(mach2 * L.inv_cs2);
   out[3] = mass;
   return 0;
 }

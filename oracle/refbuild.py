@@ -28,6 +28,7 @@ REF_DIR = ORACLE_DIR / "_ref"
 
 LATTICES = {
     "D1Q3": (1, 3), "D2Q5": (2, 5), "D2Q9": (2, 9), "D3Q15": (3, 15), "D3Q19": (3, 19), "D3Q27": (3, 27),
+    "D2Q13": (2, 13), "D2Q17": (2, 17), "D2Q21": (2, 21), "D3Q33": (3, 33),   # multi-speed (Lattice.h:213-458, 706-803)
 }
 
 

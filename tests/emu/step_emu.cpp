@@ -72,6 +72,10 @@ static int runType(const EmuLaunch& e) {
     case kD3Q15: return runLattice<Lattice<kD3Q15>, false, StoreT>(e);
     case kD3Q19: return runLattice<Lattice<kD3Q19>, false, StoreT>(e);
     case kD3Q27: return runLattice<Lattice<kD3Q27>, true, StoreT>(e);
+    case kD2Q13: return runLattice<Lattice<kD2Q13>, false, StoreT>(e);
+    case kD2Q17: return runLattice<Lattice<kD2Q17>, false, StoreT>(e);
+    case kD2Q21: return runLattice<Lattice<kD2Q21>, false, StoreT>(e);
+    case kD3Q33: return runLattice<Lattice<kD3Q33>, false, StoreT>(e);
     default: return -1;
   }
 }

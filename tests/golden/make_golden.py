@@ -48,6 +48,12 @@ CASES = [
     ("d2q9_forcednr_elbm_forcing", "D2Q9", (12, 10, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 0.05, 0.05, 3, 1),
     ("d3q19_forcednr_elbm_forcing", "D3Q19", (6, 4, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 0.05, 0.05, 2, 1),
     ("d3q27_forcednr_elbm_forcing_edm", "D3Q27", (6, 6, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+    # multi-speed lattices (Lattice.h:213-458, 706-803): jumps of up to 3 nodes, their own sound speeds
+    ("d2q13_bgk_guo", "D2Q13", (14, 10, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.7, 1e-2, 0.05, 0.05, 3, 1),
+    ("d2q17_bgk_edm", "D2Q17", (12, 10, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.7, 1e-2, 0.05, 0.05, 3, 1),
+    ("d2q21_elbm_guo", "D2Q21", (12, 10, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
+    ("d3q33_bgk_guo", "D3Q33", (6, 5, 4), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.6, 1e-2, 0.05, 0.05, 3, 1),
+    ("d3q33_elbm_shanchen", "D3Q33", (6, 5, 4), "ELBM", "TruncationMa3", "ShanChen", "Kolmogorov", 0.55, 2e-2, 0.05, 0.05, 2, 1),
     # array-type forces (Force.h:296-623): the reference fills fieldList.force spectrally (its FFTs run on the oracle's DFT
     # stub of FFTW) and the step reads it through Force<Generic>::setForce (Force.h:39-48).  The golden file carries that
     # array; this repository's configuration is force "Field" fed with it

@@ -10,15 +10,19 @@ GOLDEN_DIR = Path(__file__).resolve().parent / "golden"
 
 
 SPECTRAL_MARKERS = ("constantshell", "turbulent2d", "energyremoval")
+WIDE_MARKERS = ("d2q13", "d2q17", "d2q21", "d3q33")   # multi-speed lattices: GPU tests in tests/test_wide_lattices_gpu.py
 
 
-def golden_names(spectral=None):
-    """Names of the committed golden vectors; `spectral` = True / False selects / excludes the cases recorded with the
-    reference's array-type spectral forces (Force.h:296-616), whose GPU tests live in tests/test_spectral_forces_gpu.py."""
+def golden_names(spectral=None, wide=None):
+    """Names of the committed golden vectors; `spectral` / `wide` = True / False select / exclude the cases recorded with the
+    reference's array-type spectral forces (Force.h:296-616) and with its multi-speed lattices, whose GPU tests live in files
+    of their own (tests/test_spectral_forces_gpu.py, tests/test_wide_lattices_gpu.py)."""
     names = sorted(p.stem for p in GOLDEN_DIR.glob("*.npz"))
-    if spectral is None:
-        return names
-    return [n for n in names if any(m in n for m in SPECTRAL_MARKERS) == spectral]
+    if spectral is not None:
+        names = [n for n in names if any(m in n for m in SPECTRAL_MARKERS) == spectral]
+    if wide is not None:
+        names = [n for n in names if any(m in n for m in WIDE_MARKERS) == wide]
+    return names
 
 
 def load_golden(name):

@@ -55,6 +55,8 @@ def test_create_rejects_bad_configurations(cuda_lib):
     bad = [capi.make_config("D3Q19", (8, 8, 8), equilibrium="Exact"),      # Exact exists for D2Q9 / D3Q27 only
            capi.make_config("D3Q19", (9, 8, 8), nranks=2),                 # numProcs must divide globalLengthX
            capi.make_config("D2Q9", (8, 8, 1), tau=0.5),
+           capi.make_config("D2Q13", (8, 8, 1), nranks=2),                 # multi-speed lattices: one GPU
+           capi.make_config("D3Q33", (8, 8, 8), equilibrium="Exact"),
            capi.make_config("D3Q19", (8, 8, 8), force="ConstantShell"),    # the shell force is rebuilt for 2-D lattices only
            capi.make_config("D2Q9", (8, 8, 1), force="ConstantShell", k_min=3, k_max=2)]
     for cfg in bad:
@@ -187,6 +189,8 @@ def test_halo_plan_over_gloo(cuda_lib, oracle_lib, tmp_path, world):
     ("D2Q9", (8192, 8192, 1), "ELBM", "ShanChen", "Kolmogorov", 0.7, 8),
     ("D2Q9", (24, 130, 1), "ForcedNR_ELBM", "ExactDifferenceMethod", "Constant", 0.9, 2),
     ("D3Q27", (16, 12, 10), "BGK", "Guo", "Field", 0.6, 2),            # array-type forces read the force field
+    ("D2Q17", (64, 48, 1), "ELBM", "Guo", "Kolmogorov", 0.6, 1),       # multi-speed: inv_cs2 = 2/3 in Guo's prefactor
+    ("D3Q33", (16, 12, 10), "BGK", "Guo", "Kolmogorov", 0.6, 1),
     ("D2Q9", (64, 48, 1), "ELBM", "Guo", "ConstantShell", 0.6, 4),
 ])
 def test_launch_plan_scalars_follow_the_configuration(cuda_lib, lattice, shape, collision, scheme, force, tau, nranks):
@@ -198,7 +202,8 @@ def test_launch_plan_scalars_follow_the_configuration(cuda_lib, lattice, shape, 
     for is_stored in (0, 1, 2):
         plan = capi.launch_plan(cfg, 0, lx, is_stored)
         assert plan.beta == 1.0 / (2.0 * tau)                                  # Collision.h:122
-        assert plan.guo_factor == (1.0 - 1.0 / (2.0 * tau)) * 3.0              # ForcingScheme.h:115
+        inv_cs2 = capi.LATTICE_INV_CS2.get(capi.Lattice(cfg.lattice), 3.0)
+        assert plan.guo_factor == (1.0 - 1.0 / (2.0 * tau)) * inv_cs2          # ForcingScheme.h:115
         assert plan.wrap_x == (1 if nranks == 1 else 0)
         assert plan.is_stored == is_stored
         assert plan.hydro_shift == (0 if scheme == "None" else 1)              # ForcingScheme.h:26-33 / :50-57

@@ -8,7 +8,7 @@ from helpers import check_entropic, relative_error, run_cuda, run_oracle
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", golden_names(spectral=False))
+@pytest.mark.parametrize("name", golden_names(spectral=False, wide=False))
 def test_cuda_reproduces_reference_outputs(name):
     check_cuda_against_golden(name)
 

@@ -165,7 +165,8 @@ class Slab:
 
     def observables(self, global_volume):
         partials = self.partials.reshape(-1, 3)
-        return partials[:, 0].sum() / global_volume, partials[:, 1].sum(), math.sqrt(partials[:, 2].max() * 3.0)
+        inv_cs2 = capi.LATTICE_INV_CS2.get(Lattice(self.cfg.lattice), 3.0)   # mlbm_observables: |u| / c_s
+        return partials[:, 0].sum() / global_volume, partials[:, 1].sum(), math.sqrt(partials[:, 2].max() * inv_cs2)
 
 
 def kernel_shape(cfg, array):
@@ -244,6 +245,15 @@ SINGLE_CASES = [
     ("D3Q19", (4, 3, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 2),
     ("D3Q27", (4, 3, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 2),
     ("D3Q15", (4, 3, 5), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Constant", 0.6, 1e-1, 2),
+    # multi-speed lattices: jumps of up to 3 nodes wrap by index arithmetic in all three axes (extents down to 2 < |c|)
+    ("D2Q13", (7, 9, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.7, 1e-2, 3),
+    ("D2Q17", (5, 131, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Sinusoidal", 0.7, 1e-2, 2),
+    ("D2Q21", (2, 4, 1), "BGK", "TruncationMa3", "ShanChen", "Kolmogorov", 0.7, 1e-2, 2),
+    ("D3Q33", (3, 2, 5), "BGK", "TruncationMa3", "Guo", "Constant", 0.6, 1e-2, 2),
+    ("D2Q13", (6, 12, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 2),
+    ("D2Q17", (6, 12, 1), "ELBM", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 2),
+    ("D2Q21", (6, 12, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 2),
+    ("D3Q33", (4, 3, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 2),
 ]
 
 

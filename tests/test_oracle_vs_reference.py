@@ -23,6 +23,15 @@ CASES = [
     ("D2Q9", (12, 10, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.51, 2e-2, 1),
     ("D3Q27", (6, 6, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 1),
     ("D3Q19", (6, 4, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 3e-1, 1),
+    # multi-speed lattices (halos of 2-3 nodes, their own sound speeds)
+    ("D2Q13", (12, 10, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.7, 1e-2, 1),
+    ("D2Q17", (12, 10, 1), "BGK", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.7, 1e-2, 1),
+    ("D2Q21", (12, 10, 1), "BGK", "TruncationMa3", "ShanChen", "Kolmogorov", 0.7, 1e-2, 1),
+    ("D3Q33", (6, 5, 4), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 0.6, 1e-2, 1),
+    ("D2Q13", (12, 10, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 1),
+    ("D2Q21", (12, 10, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 1),
+    ("D3Q33", (6, 5, 4), "ELBM", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 2e-2, 1),
+    ("D2Q17", (12, 10, 1), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 1),
 ]
 
 

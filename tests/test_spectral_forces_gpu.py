@@ -18,7 +18,7 @@ from test_parity_gpu import ENERGY_TOLERANCE, POPULATION_TOLERANCE, _config, _fl
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", golden_names(spectral=True))
+@pytest.mark.parametrize("name", golden_names(spectral=True, wide=False))
 def test_cuda_reproduces_reference_outputs_with_spectral_forces(name):
     check_cuda_against_golden(name)
 
