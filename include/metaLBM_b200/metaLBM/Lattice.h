@@ -67,6 +67,65 @@ template <> struct Stencil<LatticeType::D3Q27> {
   }
 };
 
+// multi-speed lattices (Lattice.h:213-458, 706-803): jumps of up to dimH nodes, their own sound speeds; one GPU
+template <> struct Stencil<LatticeType::D2Q13> {
+  static constexpr int dimD = 2, dimQ = 13, faceQ = 4, abi = MLBM_D2Q13, dimH = 2;
+  static constexpr double invCs2() { return 3.0; }
+  static constexpr int c(int q, int d) {
+    constexpr int t[13][3] = {{0, 0, 0}, {-1, 0, 0}, {-1, -1, 0}, {-1, 1, 0}, {-2, 0, 0}, {1, 0, 0}, {1, -1, 0},
+                              {1, 1, 0}, {2, 0, 0},  {0, -1, 0},  {0, 1, 0},  {0, -2, 0}, {0, 2, 0}};
+    return t[q][d];
+  }
+  static constexpr double weightOfNorm2(int n) { return n == 0 ? 1.0 / 2.0 : (n == 1 ? 4.0 / 45.0 : (n == 2 ? 1.0 / 30.0 : 1.0 / 360.0)); }
+};
+template <> struct Stencil<LatticeType::D2Q17> {
+  static constexpr int dimD = 2, dimQ = 17, faceQ = 7, abi = MLBM_D2Q17, dimH = 3;
+  static constexpr double invCs2() { return 2.0 / 3.0; }
+  static constexpr int c(int q, int d) {
+    constexpr int t[17][3] = {{0, 0, 0}, {-1, -1, 0}, {-1, 1, 0}, {-2, -2, 0}, {-2, 2, 0}, {-3, 0, 0}, {-3, -3, 0}, {-3, 3, 0}, {1, -1, 0},
+                              {1, 1, 0}, {2, -2, 0},  {2, 2, 0},  {3, 0, 0},   {3, -3, 0}, {3, 3, 0},  {0, -3, 0},  {0, 3, 0}};
+    return t[q][d];
+  }
+  static constexpr double weightOfNorm2(int n) {
+    return n == 0 ? 0.121527777777777777777778
+                  : (n == 2 ? 0.175781250000000000000000
+                            : (n == 8 ? 0.014062500000000000000000 : (n == 9 ? 0.027777777777777777777778 : 0.001996527777777777777778)));
+  }
+};
+template <> struct Stencil<LatticeType::D2Q21> {
+  static constexpr int dimD = 2, dimQ = 21, faceQ = 7, abi = MLBM_D2Q21, dimH = 3;
+  static constexpr double invCs2() { return 1.0 / (2.0 / 3.0); }
+  static constexpr int c(int q, int d) {
+    constexpr int t[21][3] = {{0, 0, 0}, {-1, 0, 0}, {-1, -1, 0}, {-1, 1, 0}, {-2, 0, 0}, {-2, 2, 0}, {-2, -2, 0}, {-3, 0, 0}, {1, 0, 0},
+                              {1, -1, 0}, {1, 1, 0}, {2, 0, 0},   {2, -2, 0}, {2, 2, 0},  {3, 0, 0},  {0, -1, 0},  {0, 1, 0},  {0, -2, 0},
+                              {0, 2, 0},  {0, -3, 0}, {0, 3, 0}};
+    return t[q][d];
+  }
+  static constexpr double weightOfNorm2(int n) {
+    return n == 0 ? 91. / 324. : (n == 1 ? 1. / 12. : (n == 2 ? 2. / 27. : (n == 4 ? 7. / 360. : (n == 8 ? 1. / 432. : 1. / 1620.))));
+  }
+};
+template <> struct Stencil<LatticeType::D3Q33> {
+  static constexpr int dimD = 3, dimQ = 33, faceQ = 10, abi = MLBM_D3Q33, dimH = 2;
+  static constexpr double invCs2() { return 1.0 / 0.4156023517935171; }
+  static constexpr int c(int q, int d) {
+    constexpr int t[33][3] = {{0, 0, 0},   {-1, 0, 0},  {-1, -1, 0}, {-1, 1, 0}, {-1, 0, -1}, {-1, 0, 1}, {-1, -1, -1}, {-1, -1, 1}, {-1, 1, -1},
+                              {-1, 1, 1},  {-2, 0, 0},  {1, 0, 0},   {1, 1, 0},  {1, -1, 0},  {1, 0, 1},  {1, 0, -1},   {1, 1, 1},   {1, 1, -1},
+                              {1, -1, 1},  {1, -1, -1}, {2, 0, 0},   {0, -1, 0}, {0, 0, -1},  {0, -1, -1}, {0, -1, 1},  {0, 1, 0},   {0, 0, 1},
+                              {0, 1, 1},   {0, 1, -1},  {0, 2, 0},   {0, -2, 0}, {0, 0, 2},   {0, 0, -2}};
+    return t[q][d];
+  }
+  static constexpr double weightOfNorm2(int n) {
+    return n == 0 ? 0.177627658370520295649084
+                  : (n == 1 ? 0.103315974899246818673111
+                            : (n == 2 ? 0.000513472406731114352456 : (n == 3 ? 0.021333928148672240120078 : 0.004273899693974583187026)));
+  }
+};
+
+// dimH and inv_cs2 of a stencil: 1 and 3 unless it says otherwise
+template <class S, class = void> struct StencilHalo { static constexpr int value = 1; static constexpr double invCs2() { return 3.0; } };
+template <class S> struct StencilHalo<S, decltype((void)S::dimH)> { static constexpr int value = S::dimH; static constexpr double invCs2() { return S::invCs2(); } };
+
 }  // namespace b200
 
 template <class T, LatticeType LatticeT>
@@ -79,7 +138,7 @@ struct Lattice {
     MathVector<unsigned int, Count> r = {};
     unsigned int n = 0;
     for (int q = 0; q < S::dimQ; ++q)
-      if (axis < S::dimD && S::c(q, axis) == sign && n < Count) r.sArray[n++] = (unsigned int)q;
+      if (axis < S::dimD && S::c(q, axis) * sign > 0 && n < Count) r.sArray[n++] = (unsigned int)q;
     return r;
   }
 
@@ -87,12 +146,12 @@ struct Lattice {
   static constexpr LatticeType Type = LatticeT;
   static constexpr int abi = S::abi;  // the mlbm_lattice value of the C-ABI
 
-  static constexpr T inv_cs2 = (T)3;
+  static constexpr T inv_cs2 = (T)b200::StencilHalo<S>::invCs2();
   static constexpr T cs2 = (T)1 / inv_cs2;
 
   static constexpr int dimD = S::dimD;
   static constexpr int dimQ = S::dimQ;
-  static constexpr int dimH = 1;
+  static constexpr int dimH = b200::StencilHalo<S>::value;
   static constexpr int faceQ = S::faceQ;
 
   static constexpr Position halo() { return Position{{dimH, dimD > 1 ? dimH : 0u, dimD > 2 ? dimH : 0u}}; }

@@ -59,8 +59,8 @@ def lattice(name) -> tuple:
     """(D, Q, celerity[Q,3] int, weight[Q])."""
     lat = Lattice[name] if isinstance(name, str) else Lattice(int(name))
     d, q = ctypes.c_int(), ctypes.c_int()
-    c = np.zeros((27, 3), dtype=np.int32)
-    w = np.zeros(27, dtype=np.float64)
+    c = np.zeros((40, 3), dtype=np.int32)      # MAXQ of lbm_oracle.c is 33 (D3Q33)
+    w = np.zeros(40, dtype=np.float64)
     assert lib().mlbm_oracle_lattice(int(lat), ctypes.byref(d), ctypes.byref(q), _ip(c), _dp(w)) == 0
     return d.value, q.value, c[:q.value].copy(), w[:q.value].copy()
 

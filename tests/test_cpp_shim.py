@@ -43,27 +43,29 @@ def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equ
 
 
 @pytest.mark.parametrize("lattice,shape", [("D2Q5", (8, 6, 1)), ("D2Q9", (8, 6, 1)), ("D3Q15", (8, 6, 4)),
-                                           ("D3Q19", (8, 6, 4)), ("D3Q27", (8, 6, 5))])
+                                           ("D3Q19", (8, 6, 4)), ("D3Q27", (8, 6, 5)), ("D2Q13", (8, 6, 1)), ("D2Q17", (8, 6, 1)),
+                                           ("D2Q21", (8, 6, 1)), ("D3Q33", (8, 6, 5))])
 def test_lattice_descriptor_equals_reference_tables(tmp_path, oracle_lib, lattice, shape):
     binary = compile_example(tmp_path, "lattice_dump.cpp", "lattice_dump", lattice, shape, link=False)
     lines = subprocess.run([str(binary)], capture_output=True, text=True, check=True).stdout.strip().splitlines()
     dim, q, c, w = O.lattice(lattice)
     head = list(map(int, lines[0].split()))
-    face = {"D2Q5": 1, "D2Q9": 3, "D3Q15": 5, "D3Q19": 5, "D3Q27": 9}[lattice]
-    assert head == [dim, q, 1, face]
+    face = {"D2Q5": 1, "D2Q9": 3, "D3Q15": 5, "D3Q19": 5, "D3Q27": 9, "D2Q13": 4, "D2Q17": 7, "D2Q21": 7, "D3Q33": 10}[lattice]
+    halo = int(np.abs(c).max())                      # dimH = the longest jump (Lattice.h:223, 300, 382, 716)
+    assert head == [dim, q, halo, face]
     for iq in range(q):
         parts = lines[1 + iq].split()
         assert list(map(int, parts[:3])) == c[iq].tolist()
         assert float(parts[3]) == w[iq]
     faces = [list(map(int, part.split())) for part in lines[1 + q].split("|")]
-    expect = [[i for i in range(q) if c[i, axis] == sign] if axis < dim else [] for axis, sign in ((1, -1), (1, 1), (2, -1), (2, 1))]
+    expect = [[i for i in range(q) if c[i, axis] * sign > 0] if axis < dim else [] for axis, sign in ((1, -1), (1, 1), (2, -1), (2, 1))]
     assert faces == expect
     # lSD::pLength pads the last used dimension to 2 (n / 2 + 1) (Domain.h:53-57); hSD::volume has a halo of 1 per used side
     px, py, pz, pvolume, hvolume = map(int, lines[2 + q].split())
     padded = list(shape)
     padded[dim - 1] = 2 * (shape[dim - 1] // 2 + 1)
     assert [px, py, pz] == padded and pvolume == int(np.prod(padded))
-    assert hvolume == int(np.prod([n + 2 if i < dim else n for i, n in enumerate(shape)]))
+    assert hvolume == int(np.prod([n + 2 * halo if i < dim else n for i, n in enumerate(shape)]))
     assert int(lines[3 + q]) == 2 ** 32 - 1
 
 

@@ -9,6 +9,7 @@ from golden_util import golden_names
 from helpers import check_entropic, relative_error, run_cuda, run_oracle
 from metalbm_b200.capi import make_config
 from oracle import oracle as O
+from test_cpp_shim import check_template_api
 from test_golden_gpu import check_cuda_against_golden
 
 pytestmark = pytest.mark.gpu
@@ -55,3 +56,11 @@ def test_multi_speed_lattices_against_the_oracle(case):
         assert abs(got["observables"][0] - obs[0]) <= 1e-9 * abs(obs[0])
         assert abs(got["observables"][2] - obs[2]) <= 1e-12 * abs(obs[2]) + (0 if collision == "BGK" else 1e-9)   # Mach with the lattice's c_s
         assert abs(got["observables"][3] - obs[3]) <= 1e-12 * abs(obs[3]) + (0 if collision == "BGK" else 1e-9)
+
+
+@pytest.mark.parametrize("case", [("D2Q13", (24, 20, 1), "BGK", "TruncationMa3", "Guo", "Kolmogorov", 3),
+                                  ("D3Q33", (8, 6, 4), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 1)],
+                         ids=lambda c: "-".join(map(str, c[:1] + c[2:6])))
+def test_template_api_on_multi_speed_lattices(tmp_path, cuda_lib, case):
+    """latticeT = D2Q13 / D3Q33 through the reference's template spellings (one rank)."""
+    check_template_api(tmp_path, 1, case)
