@@ -4,7 +4,7 @@ mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 : > gpurun_out/elbm.jsonl
-run() { echo "== $*" >> gpurun_out/elbm.err; timeout 600 python bench.py --no-cpu-baseline --no-e2e "$@" >> gpurun_out/elbm.jsonl 2>> gpurun_out/elbm.err; }
+run() { echo "== $*" >> gpurun_out/elbm.err; timeout 600 python bench.py --no-cpu-baseline --also off --no-e2e "$@" >> gpurun_out/elbm.jsonl 2>> gpurun_out/elbm.err; }
 run --workload d3q27_elbm_512 --steps 20
 run --workload d3q27_elbm_512 --steps 20 --eps 2e-3
 run --workload d3q27_elbm_512 --steps 20 --eps 1e-5

@@ -3,7 +3,7 @@
 set -u
 mkdir -p gpurun_out
 : > gpurun_out/elbm_quick.jsonl
-run() { timeout 600 python bench.py --no-cpu-baseline --no-e2e "$@" >> gpurun_out/elbm_quick.jsonl 2>> gpurun_out/elbm_quick.err; }
+run() { timeout 600 python bench.py --no-cpu-baseline --also off --no-e2e "$@" >> gpurun_out/elbm_quick.jsonl 2>> gpurun_out/elbm_quick.err; }
 run --workload d3q27_elbm_512 --steps 20
 run --workload d3q27_elbm_512 --steps 20 --eps 1e-5
 run --workload d2q9_elbm_shanchen_8192 --steps 50

@@ -8,8 +8,8 @@ timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_n$N.log 2>
 tail -15 gpurun_out/pytest_gpu_n$N.log
 : > gpurun_out/multi_n$N.jsonl
 run() { local n=$1; shift; echo "== n=$n $*" >> gpurun_out/multi_n$N.err
-  if [ "$n" = 1 ]; then timeout 600 python bench.py --gpus 1 --no-cpu-baseline --no-e2e "$@" >> gpurun_out/multi_n$N.jsonl 2>> gpurun_out/multi_n$N.err
-  else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $n --no-cpu-baseline --no-e2e "$@" >> gpurun_out/multi_n$N.jsonl 2>> gpurun_out/multi_n$N.err; fi; }
+  if [ "$n" = 1 ]; then timeout 600 python bench.py --gpus 1 --no-cpu-baseline --also off --no-e2e "$@" >> gpurun_out/multi_n$N.jsonl 2>> gpurun_out/multi_n$N.err
+  else timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $n --no-cpu-baseline --also off --no-e2e "$@" >> gpurun_out/multi_n$N.jsonl 2>> gpurun_out/multi_n$N.err; fi; }
 run 1 --workload d3q19_bgk_256 --steps 100
 run $N --workload d3q19_bgk_256 --steps 100
 run $N --workload d3q19_bgk_256 --steps 100 --halo nccl

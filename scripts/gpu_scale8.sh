@@ -8,8 +8,8 @@ timeout 600 python -m pytest tests/test_multi_gpu.py -q -k "peer-8 or sync-8 or 
 tail -4 gpurun_out/pytest_gpu_n8.log
 : > gpurun_out/scale8.jsonl
 run() { local n=$1; shift; echo "== n=$n $*" >> gpurun_out/scale8.err
-  if [ "$n" = 1 ]; then timeout 400 python bench.py --gpus 1 --no-cpu-baseline --no-e2e "$@" >> gpurun_out/scale8.jsonl 2>> gpurun_out/scale8.err
-  else timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n --no-cpu-baseline --no-e2e "$@" >> gpurun_out/scale8.jsonl 2>> gpurun_out/scale8.err; fi; }
+  if [ "$n" = 1 ]; then timeout 400 python bench.py --gpus 1 --no-cpu-baseline --no-e2e --also off "$@" >> gpurun_out/scale8.jsonl 2>> gpurun_out/scale8.err
+  else timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $n --no-cpu-baseline --no-e2e --also off "$@" >> gpurun_out/scale8.jsonl 2>> gpurun_out/scale8.err; fi; }
 # config 5: D3Q19 BGK 1024^3 strong-scaled, observables every 50 steps
 run 8 --workload d3q19_bgk_1024 --steps 100
 run 8 --workload d3q19_bgk_1024 --steps 100 --halo nccl

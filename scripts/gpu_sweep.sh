@@ -5,7 +5,7 @@ mkdir -p gpurun_out
 free -g > gpurun_out/host.txt; nproc >> gpurun_out/host.txt
 timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 : > gpurun_out/sweep.jsonl
-run() { echo "== $*" >> gpurun_out/sweep.err; timeout 600 python bench.py --no-cpu-baseline --no-e2e "$@" >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err; }
+run() { echo "== $*" >> gpurun_out/sweep.err; timeout 600 python bench.py --no-cpu-baseline --also off --no-e2e "$@" >> gpurun_out/sweep.jsonl 2>> gpurun_out/sweep.err; }
 run --workload d3q19_bgk_256 --steps 100
 run --workload d3q19_bgk_256 --steps 100 --dtype f32
 run --workload d3q19_bgk_guo_256 --steps 100
