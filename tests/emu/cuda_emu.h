@@ -19,6 +19,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <tuple>
+#include <type_traits>
+#include <utility>
 #include <vector>
 
 #define __global__
@@ -121,29 +125,21 @@ inline void blockBarrier() {
   while (s.barrierGeneration == generation) yield();
 }
 
-template <class Kernel, class Params>
-struct Entry {
-  static Kernel kernel;
-  static const Params* params;
-  static void run() {
-    kernel(*params);
-    State& s = state();
-    s.fibers[s.current].done = true;
-    ++s.progress;
-    swapcontext(&s.fibers[s.current].context, &s.scheduler);
-  }
-};
-template <class Kernel, class Params> Kernel Entry<Kernel, Params>::kernel = nullptr;
-template <class Kernel, class Params> const Params* Entry<Kernel, Params>::params = nullptr;
+// what every fiber of the running launch executes (set by the launch functions below)
+inline std::function<void()>& thunk() { static std::function<void()> f; return f; }
 
-// kernel<<<grid, block, sharedBytes>>>(params), one block after the other
-template <class Params>
-inline void launch(void (*kernel)(const Params), dim3 grid, unsigned block, size_t sharedBytes, const Params& params) {
+inline void fiberEntry() {
+  thunk()();
+  State& s = state();
+  s.fibers[s.current].done = true;
+  ++s.progress;
+  swapcontext(&s.fibers[s.current].context, &s.scheduler);
+}
+
+// one block after the other; every thread of a block is a fiber
+inline void runGrid(dim3 grid, unsigned block, size_t sharedBytes) {
   State& s = state();
   if (block > (unsigned)kMaxThreads || sharedBytes > kSharedBytes) { std::fprintf(stderr, "cuda_emu: launch too large\n"); std::abort(); }
-  using E = Entry<void (*)(const Params), Params>;
-  E::kernel = kernel;
-  E::params = &params;
   gridDim = grid;
   blockDim = dim3(block, 1, 1);
   s.blockThreads = (int)block;
@@ -163,7 +159,7 @@ inline void launch(void (*kernel)(const Params), dim3 grid, unsigned block, size
           f.context.uc_stack.ss_sp = f.stack.data();
           f.context.uc_stack.ss_size = f.stack.size();
           f.context.uc_link = &s.scheduler;
-          makecontext(&f.context, (void (*)())E::run, 0);
+          makecontext(&f.context, (void (*)())fiberEntry, 0);
         }
         unsigned remaining = block;
         while (remaining > 0) {
@@ -184,6 +180,22 @@ inline void launch(void (*kernel)(const Params), dim3 grid, unsigned block, size
           }
         }
       }
+}
+
+// kernel<<<grid, block, sharedBytes>>>(params) for the one-struct step kernels
+template <class Params>
+inline void launch(void (*kernel)(const Params), dim3 grid, unsigned block, size_t sharedBytes, const Params& params) {
+  thunk() = [kernel, &params]() { kernel(params); };
+  runGrid(grid, block, sharedBytes);
+}
+
+// kernel<<<grid, block, sharedBytes, stream>>>(args...) for any kernel (tests/emu/build_context.py rewrites the launches of
+// csrc/context.cu, shell_force.cu and spectral.cu into calls of this); streams are synchronous here
+template <class... Params, class... Args>
+inline void launchKernel(void (*kernel)(Params...), dim3 grid, dim3 block, size_t sharedBytes, Args&&... args) {
+  std::tuple<std::decay_t<Params>...> stored(std::forward<Args>(args)...);
+  thunk() = [kernel, &stored]() { std::apply(kernel, stored); };
+  runGrid(grid, block.x * block.y * block.z, sharedBytes);
 }
 
 }  // namespace cuda_emu
@@ -225,3 +237,13 @@ using std::log;
 using std::max;
 using std::min;
 using std::sqrt;
+
+// ---- intrinsics used by the kernels of csrc/context.cu, shell_force.cu and spectral.cu -----------------------------
+inline unsigned atomicAdd(unsigned* address, unsigned value) { const unsigned old = *address; *address = old + value; return old; }
+inline double atomicAdd(double* address, double value) { const double old = *address; *address = old + value; return old; }
+inline void __threadfence() {}
+inline void __threadfence_system() {}
+inline long long clock64() { static long long ticks = 0; return ticks += 1000; }
+inline void __nanosleep(unsigned) { cuda_emu::yield(); }
+inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
+inline double sinpi(double x) { return std::sin(M_PI * x); }

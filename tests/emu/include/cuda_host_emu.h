@@ -1,0 +1,70 @@
+// tests/emu/include/cuda_host_emu.h -- TEST INFRASTRUCTURE ONLY.
+//
+// The slice of the CUDA runtime API that csrc/context.cu, shell_force.cu and spectral.cu call, implemented on the host so
+// that the library's HOST logic (allocation, pitched copies, the per-step orchestration, the observables pipeline) can be
+// executed by the CPU test-suite around the emulated kernels (tests/emu/cuda_emu.h): device memory is host memory, streams
+// execute immediately, events are time stamps, there is one device and no peer access.  See tests/emu/build_context.py.
+#pragma once
+
+#include <chrono>
+#include <cstdlib>
+#include <cstring>
+
+typedef int cudaError_t;
+enum { cudaSuccess = 0, cudaErrorMemoryAllocation = 2, cudaErrorInvalidValue = 1, cudaErrorNotSupported = 801 };
+typedef struct CUevent_emu { double stamp; }* cudaEvent_t;
+enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3 };
+enum { cudaStreamNonBlocking = 1, cudaEventDisableTiming = 2, cudaHostAllocMapped = 2, cudaIpcMemLazyEnablePeerAccess = 1 };
+enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
+struct cudaIpcMemHandle_t { char reserved[64]; };
+
+namespace cuda_emu {
+inline cudaError_t& lastError() { static cudaError_t e = cudaSuccess; return e; }
+inline double now() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+}  // namespace cuda_emu
+
+inline const char* cudaGetErrorString(cudaError_t e) { return e == cudaSuccess ? "no error" : (e == cudaErrorMemoryAllocation ? "out of memory" : "emulated CUDA error"); }
+inline cudaError_t cudaGetLastError() { const cudaError_t e = cuda_emu::lastError(); cuda_emu::lastError() = cudaSuccess; return e; }
+inline cudaError_t cudaGetDeviceCount(int* count) { *count = 1; return cudaSuccess; }
+inline cudaError_t cudaSetDevice(int device) { return device == 0 ? cudaSuccess : cudaErrorInvalidValue; }
+inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
+inline cudaError_t cudaDeviceGetStreamPriorityRange(int* least, int* greatest) { *least = 0; *greatest = -5; return cudaSuccess; }
+
+template <class T> inline cudaError_t cudaMalloc(T** pointer, size_t bytes) {
+  // poisoned like fresh device memory is not: reads of bytes nobody wrote show up as NaNs / huge integers
+  void* p = std::malloc(bytes ? bytes : 1);
+  if (!p) return cudaErrorMemoryAllocation;
+  std::memset(p, 0xFF, bytes);
+  *pointer = static_cast<T*>(p);
+  return cudaSuccess;
+}
+inline cudaError_t cudaFree(void* pointer) { std::free(pointer); return cudaSuccess; }
+template <class T> inline cudaError_t cudaMallocHost(T** pointer, size_t bytes) { *pointer = static_cast<T*>(std::malloc(bytes ? bytes : 1)); return *pointer ? cudaSuccess : cudaErrorMemoryAllocation; }
+template <class T> inline cudaError_t cudaHostAlloc(T** pointer, size_t bytes, unsigned) { return cudaMallocHost(pointer, bytes); }
+inline cudaError_t cudaFreeHost(void* pointer) { std::free(pointer); return cudaSuccess; }
+inline cudaError_t cudaMemset(void* p, int value, size_t bytes) { std::memset(p, value, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemsetAsync(void* p, int value, size_t bytes, cudaStream_t = nullptr) { std::memset(p, value, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemcpy(void* dst, const void* src, size_t bytes, cudaMemcpyKind) { std::memmove(dst, src, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t bytes, cudaMemcpyKind, cudaStream_t = nullptr) { std::memmove(dst, src, bytes); return cudaSuccess; }
+inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind,
+                                     cudaStream_t = nullptr) {
+  if (width > dpitch || width > spitch) return cudaErrorInvalidValue;   // what the runtime rejects as "invalid pitch"
+  for (size_t row = 0; row < height; ++row) std::memcpy(static_cast<char*>(dst) + row * dpitch, static_cast<const char*>(src) + row * spitch, width);
+  return cudaSuccess;
+}
+
+inline cudaError_t cudaStreamCreateWithPriority(cudaStream_t* stream, unsigned, int) { *stream = std::malloc(1); return cudaSuccess; }
+inline cudaError_t cudaStreamDestroy(cudaStream_t stream) { std::free(stream); return cudaSuccess; }
+inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
+inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, unsigned) { return cudaSuccess; }
+inline cudaError_t cudaEventCreate(cudaEvent_t* event) { *event = new CUevent_emu{0.0}; return cudaSuccess; }
+inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* event, unsigned) { return cudaEventCreate(event); }
+inline cudaError_t cudaEventDestroy(cudaEvent_t event) { delete event; return cudaSuccess; }
+inline cudaError_t cudaEventRecord(cudaEvent_t event, cudaStream_t = nullptr) { event->stamp = cuda_emu::now(); return cudaSuccess; }
+inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
+inline cudaError_t cudaEventElapsedTime(float* ms, cudaEvent_t start, cudaEvent_t stop) { *ms = (float)(stop->stamp - start->stamp); return cudaSuccess; }
+inline cudaError_t cudaFuncSetAttribute(const void*, cudaFuncAttribute, int bytes) { return bytes <= 227 * 1024 ? cudaSuccess : cudaErrorInvalidValue; }
+// one process, one device: no peer mappings
+inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* handle, void*) { std::memset(handle, 0, sizeof(*handle)); return cudaSuccess; }
+inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

@@ -19,7 +19,7 @@ from oracle import oracle as O
 
 ROOT = Path(__file__).resolve().parent.parent
 INCLUDE = ROOT / "include" / "metaLBM_b200"
-LIBDIR = ROOT / "metalbm_b200"
+LIBDIR = Path(os.environ.get("MLBM_SHIM_LIBDIR", ROOT / "metalbm_b200"))   # tests/conftest.py re-points it for emulated runs
 
 
 def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equilibrium="TruncationMa3", scheme="Guo",
