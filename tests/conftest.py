@@ -55,7 +55,7 @@ def _gpu_order(item) -> int:
     """0: the BGK paths (validated on hardware longest), 1: the entropic kernels, 2: the array-type / spectral forces and
     the multi-speed lattices."""
     node = item.nodeid
-    if "test_spectral_forces_gpu" in node or "test_wide_lattices_gpu" in node:
+    if "test_spectral_forces_gpu" in node or "test_wide_lattices_gpu" in node or "test_bench_support_gpu" in node:
         return 2
     lowered = node.lower()
     if any(word in lowered for word in ("elbm", "entropic", "alpha", "logarithm")):
