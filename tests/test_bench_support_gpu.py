@@ -57,3 +57,54 @@ def test_run_async_with_energy_only_stored_steps():
     with pytest.raises(Exception):
         with Algorithm(cfg) as algorithm:
             algorithm.run(1, 2, 1, stored_mode=3)
+
+
+def test_secondary_workloads_of_the_bench_at_toy_sizes(monkeypatch):
+    """bench.measure_also with the real context on every single-GPU secondary workload, the grids shrunk to toys: the calls it
+    makes exist and agree with the library (device-side init, perturbation, stored modes, kernel timing, observables)."""
+    import types
+
+    import torch
+
+    import bench
+    if not torch.cuda.is_available():          # the emulated library: there is no device memory to ask about
+        monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (10 ** 11, 10 ** 11))
+    for name, work in bench.WORKLOADS.items():
+        monkeypatch.setitem(work, "shape", (8, 6, 5) if work["shape"][2] > 1 else (12, 10, 1))
+        if work["store_every"]:
+            monkeypatch.setitem(work, "store_every", 2)
+    args = types.SimpleNamespace(overlap="On", halo="peer", variant=0)
+    identity = lambda v: v  # noqa: E731
+    for entry in bench.ALSO_SINGLE:
+        name, dtype, eps, mode, steps = entry
+        out = bench.measure_also((name, dtype, eps, mode, 4), args, 0, 1, 0, lambda: None, identity, identity, 6500.0)
+        assert "skipped" not in out and out["value"] > 0 and out["kernel_launches_timed"] == 4, out
+        assert abs(out["mass_per_node"] - 1.0) < 1e-3 and out["energy"] > 0 and 0 < out["mach"] < 0.5, out
+        if bench.WORKLOADS[name]["store_every"]:
+            assert out["stored_step_ms"] is not None and out["stored_step_ms"] >= 0
+
+
+def test_bench_prints_one_contract_line_on_a_small_cube():
+    """`python bench.py --edge 32`: the whole driver on a real device at a size that takes a second; every key of the contract,
+    the e2e leg through host buffers, the roofline of the fused kernel."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (bench.py drives torch.cuda directly)")
+    root = Path(__file__).resolve().parent.parent
+    result = subprocess.run([sys.executable, str(root / "bench.py"), "--edge", "32", "--steps", "20", "--warmup", "3", "--no-cpu-baseline"],
+                            capture_output=True, text=True, timeout=600, cwd=root)
+    assert result.returncode == 0, result.stderr[-3000:]
+    lines = [l for l in result.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, result.stdout[-2000:]
+    line = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline"):
+        assert key in line, key
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] >= 20
+    assert line["roofline"]["bound"] == "hbm" and line["roofline"]["achieved"] > 0
+    assert "also" not in line            # secondary workloads only ride along with the default headline workload
