@@ -21,7 +21,7 @@ def pytest_configure(config):
         sys.path.insert(0, str(ROOT / "tests" / "emu"))
         import build_context
         from metalbm_b200 import capi
-        library = build_context.build()
+        library = build_context.build(tuple(os.environ.get("MLBM_EMULATED_FLAGS", "").split()))   # e.g. -DMLBM_ELBM_FASTPATH
         capi._library = capi.load_library(library)
         shim_dir = library.parent / "shim_lib"
         shim_dir.mkdir(exist_ok=True)

@@ -114,7 +114,12 @@ def transform(name: str) -> str:
     return text
 
 
-def build() -> Path:
+def build(flags: tuple = ()) -> Path:
+    """``flags``: extra -D switches (the experimental kernel variants); every set of flags is its own library."""
+    global BUILD, LIBRARY
+    suffix = "".join("_" + f.lstrip("-D").lower() for f in flags)
+    BUILD = HERE / "_build" / ("context" + suffix)
+    LIBRARY = HERE / "_build" / ("libmetalbm_emu" + suffix + ".so")
     BUILD.mkdir(parents=True, exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
     inputs = [*sources, *CSRC.glob("*.cuh"), *CSRC.glob("*.h"), *CSRC.glob("*.inc"), HERE / "cuda_emu.h", Path(__file__),
@@ -128,7 +133,7 @@ def build() -> Path:
         translated = BUILD / (source.stem + ".cpp")
         translated.write_text(transform(source.name))
         obj = BUILD / (source.stem + ".o")
-        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-c", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-DMLBM_EMU_HOST",
+        cmd = ["g++", "-std=c++17", "-O1", "-g", "-fPIC", "-c", "-ffp-contract=off", "-fno-strict-aliasing", "-w", "-DMLBM_EMU_HOST", *flags,
                f"-I{HERE / 'include'}", f"-I{BUILD}", str(translated), "-o", str(obj)]
         proc = subprocess.run(cmd, capture_output=True, text=True)
         if proc.returncode != 0:
