@@ -20,6 +20,12 @@ def pytest_configure(config):
         # logic, never of hardware behaviour.  The binding is re-pointed from here; the product knows nothing about it.
         sys.path.insert(0, str(ROOT / "tests" / "emu"))
         import build_context
+        if not os.environ.get("PYTEST_XDIST_WORKER"):
+            for stale in Path("/dev/shm").glob("mlbm_emu_*"):     # segments of emulated ranks that were killed
+                try:
+                    stale.unlink()
+                except OSError:
+                    pass
         from metalbm_b200 import capi
         library = build_context.build(tuple(os.environ.get("MLBM_EMULATED_FLAGS", "").split()))   # e.g. -DMLBM_ELBM_FASTPATH
         capi._library = capi.load_library(library)
@@ -31,7 +37,10 @@ def pytest_configure(config):
         link.symlink_to(library)
         os.environ["MLBM_SHIM_LIBDIR"] = str(shim_dir)
         import torch
-        torch.cuda.device_count = lambda: 1      # the emulated device; multi-rank cases skip themselves
+        # emulated devices: one process per rank, NCCL and CUDA IPC over shared memory (MLBM_EMULATED_RANKS=1: single-rank cases only)
+        ranks = int(os.environ.get("MLBM_EMULATED_RANKS", "8"))
+        torch.cuda.device_count = lambda: ranks
+        os.environ["MLBM_EMULATED_LIBRARY"] = str(library)   # for the rank processes the multi-GPU tests start
 
 
 @pytest.fixture(scope="session")

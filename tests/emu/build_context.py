@@ -10,7 +10,8 @@ The sources are taken from ``metalbm_b200/csrc`` at build time.  Edits, all mech
   * ``kernel<<<grid, block[, shared[, stream]]>>>(args)``  ->  ``cuda_emu::launchKernel(kernel, grid, block, shared, args)``;
   * the one ``extern __shared__`` declaration of each file -> the emulator's shared-memory buffer;
   * ``asm volatile("trap;")`` -> ``abort()``;
-  * spectral.cu resolves its cuFFT entry points from the naive host transforms of ``include/cufft.h`` instead of dlopen.
+  * spectral.cu resolves its cuFFT entry points from the naive host transforms of ``include/cufft.h`` instead of dlopen,
+    context.cu its NCCL entry points from the shared-memory NCCL of ``include/nccl.h`` (one process per rank).
 ``cuda_runtime.h``, ``nccl.h`` and ``cufft.h`` resolve to the stand-ins under ``tests/emu/include``: device memory is host
 memory (poisoned at allocation), streams run immediately, there is one device and one rank.  Nothing under
 ``metalbm_b200/`` can reach this library; it says nothing about hardware behaviour or speed.
@@ -105,6 +106,12 @@ def transform(name: str) -> str:
     text = DYNAMIC_SHARED.sub(lambda m: f"{m.group(1)}* const {m.group(2)} = reinterpret_cast<{m.group(1)}*>(cuda_emu::dynamicSharedBase());", text)
     text = text.replace('asm volatile("trap;");', "abort();")
     text = text.replace('#include "../../include/metalbm_b200.h"', f'#include "{ROOT / "include" / "metalbm_b200.h"}"')
+    if name == "context.cu":
+        start = text.index("const NcclApi* loadNccl(const char** error) {")
+        end = _matching(text, text.index("{", start), "{", "}")
+        text = (text[:start] + "const NcclApi* loadNccl(const char** error) {\n  (void)error;\n"
+                "  static NcclApi api = {ncclGetUniqueId, ncclCommInitRank, ncclCommDestroy, ncclSend, ncclRecv, ncclGroupStart, ncclGroupEnd,\n"
+                "                        ncclAllReduce, ncclGetErrorString};\n  return &api;\n}" + text[end:])
     if name == "spectral.cu":
         start = text.index("const CufftApi* loadCufft(std::string* error) {")
         end = _matching(text, text.index("{", start), "{", "}")
@@ -143,7 +150,7 @@ def build(flags: tuple = ()) -> Path:
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
         objects = list(pool.map(compile_one, sources))
     # -Bsymbolic: the tests load libmetalbm_b200.so as well, with the very same exported names
-    cmd = ["g++", "-shared", "-Wl,-Bsymbolic", "-o", str(LIBRARY), *map(str, objects), "-ldl"]
+    cmd = ["g++", "-shared", "-Wl,-Bsymbolic", "-o", str(LIBRARY), *map(str, objects), "-ldl", "-lrt", "-pthread"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("emulated link failed:\n" + proc.stderr[-4000:])

@@ -11,9 +11,11 @@
 // Shared memory is poisoned with NaN bit patterns before every block so that reads of unwritten shared memory show.
 #pragma once
 
+#include <sched.h>
 #include <ucontext.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -243,7 +245,9 @@ inline unsigned atomicAdd(unsigned* address, unsigned value) { const unsigned ol
 inline double atomicAdd(double* address, double value) { const double old = *address; *address = old + value; return old; }
 inline void __threadfence() {}
 inline void __threadfence_system() {}
-inline long long clock64() { static long long ticks = 0; return ticks += 1000; }
-inline void __nanosleep(unsigned) { cuda_emu::yield(); }
+inline long long clock64() {   // nanoseconds ~ cycles at 1 GHz: the peer-flag wait gives up after tens of seconds, as on the box
+  return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+inline void __nanosleep(unsigned) { ++cuda_emu::state().progress; sched_yield(); cuda_emu::yield(); }   // waits on another rank (process): not a deadlock
 inline void sincospi(double x, double* s, double* c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 inline double sinpi(double x) { return std::sin(M_PI * x); }

@@ -28,6 +28,10 @@ import torch
 import torch.distributed as dist
 root, rank, world, port, out = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4], sys.argv[5]
 sys.path.insert(0, root)
+import os
+from metalbm_b200 import capi
+if os.environ.get("MLBM_EMULATED") == "1":   # tests/conftest.py: the library compiled for the host, NCCL over shared memory
+    capi._library = capi.load_library(os.environ["MLBM_EMULATED_LIBRARY"])
 from metalbm_b200.algorithm import Algorithm, Communication, slab_of
 from metalbm_b200.capi import make_config
 
