@@ -108,3 +108,81 @@ def test_bench_prints_one_contract_line_on_a_small_cube():
     assert line["value"] > 0 and line["e2e"]["value"] > 0 and line["gpu_launches"] >= 20
     assert line["roofline"]["bound"] == "hbm" and line["roofline"]["achieved"] > 0
     assert "also" not in line            # secondary workloads only ride along with the default headline workload
+
+
+_RANK_WORKER = r'''
+import os, sys, types, json
+root, rank, world, port = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+sys.path.insert(0, root)
+import torch
+import torch.distributed as dist
+from metalbm_b200 import capi
+if os.environ.get("MLBM_EMULATED") == "1":   # tests/conftest.py: the library compiled for the host
+    capi._library = capi.load_library(os.environ["MLBM_EMULATED_LIBRARY"])
+    torch.cuda.mem_get_info = lambda *a: (10 ** 11, 10 ** 11)
+import bench
+dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+def reduce(op):
+    def f(value):
+        t = torch.tensor([float(value)], dtype=torch.float64)
+        dist.all_reduce(t, op=op)
+        return float(t.item())
+    return f
+for name, work in bench.WORKLOADS.items():
+    work["shape"] = (8, 6, 5) if work["shape"][2] > 1 else (16, 10, 1)
+    if work["store_every"]:
+        work["store_every"] = 2
+args = types.SimpleNamespace(overlap="On", halo="peer", variant=0)
+maximum, minimum = reduce(dist.ReduceOp.MAX), (lambda v: -reduce(dist.ReduceOp.MAX)(-v))
+results = []
+for entry in bench.ALSO_MULTI:
+    name, dtype, eps, mode, steps = entry
+    results.append(bench.measure_also((name, dtype, eps, mode, 4), args, rank, world, rank, dist.barrier, maximum, minimum, 6500.0))
+if rank == 0:
+    print("RESULTS " + json.dumps(results))
+dist.barrier()
+dist.destroy_process_group()
+print("ok", rank)
+'''
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_secondary_workloads_of_the_bench_on_several_ranks(tmp_path, world):
+    """bench.measure_also for every multi-GPU secondary workload (toy grids), one process per rank: a fresh context per entry --
+    NCCL communicator, peer mappings, spectral plans made and torn down again and again -- which is what the driver's 1 -> 8 GPU
+    scaling run does."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "worker.py"
+    script.write_text(_RANK_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, str(script), str(root), str(r), str(world), str(port)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")) for r in range(world)]
+    outputs = []
+    for r, p in enumerate(procs):
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            out, _ = p.communicate()
+        assert p.returncode == 0 and f"ok {r}" in out, out[-3000:]
+        outputs.append(out)
+    results = json.loads([l for l in outputs[0].splitlines() if l.startswith("RESULTS ")][0][len("RESULTS "):])
+    import bench
+    assert [r["name"] for r in results] == [e[0] for e in bench.ALSO_MULTI]
+    for r in results:
+        if "skipped" in r:      # x extent of the toy grid not divisible by the rank count
+            continue
+        assert r["value"] > 0 and r["halo"] == "peer" and abs(r["mass_per_node"] - 1.0) < 1e-3 and r["energy"] > 0, r
