@@ -178,6 +178,24 @@ __global__ void signalPeersKernel(unsigned long long* leftNeighbourFlags, unsign
   __threadfence_system();
 }
 
+// Staged pack / unpack (EXPERIMENT, MLBM_STAGED_COPY=1): the host keeps every population as rows of NR values with a pitch of
+// `pitch` >= NR values (the FFTW padding of lSD, Domain.h:53-57).  Instead of one pitched DMA per population (2 KB rows),
+// the padded block crosses PCIe as ONE contiguous copy and the padding is stripped / added on the device at HBM speed.
+template <typename StoreT>
+__global__ void stripPaddingKernel(const StoreT* __restrict__ padded, StoreT* __restrict__ dense, long long rows, int NR, long long pitch) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * NR) return;
+  const long long row = i / NR;
+  dense[i] = padded[row * pitch + (i - row * NR)];
+}
+template <typename StoreT>
+__global__ void addPaddingKernel(const StoreT* __restrict__ dense, StoreT* __restrict__ padded, long long rows, int NR, long long pitch) {
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= rows * pitch) return;
+  const long long row = j / pitch, r = j - row * pitch;
+  padded[j] = r < NR ? dense[row * NR + r] : (StoreT)0;   // the padding values arrive as zeros (they are scratch: Domain.h:53-57)
+}
+
 template <typename StoreT> __global__ void fillKernel(StoreT* data, long long count, StoreT value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) data[i] = value;
@@ -381,6 +399,8 @@ struct mlbm_ctx {
   bool fieldsStored = false;
   double* partials = nullptr;
   unsigned char* hints = nullptr;        // entropic contexts: one byte per block and plane (StepParams::hints)
+  void* staging = nullptr;               // staged pack / unpack: one padded population block
+  size_t stagingBytes = 0;
   double* reduceStage = nullptr;         // [kReduceBlocks][kObservableSlots] second-stage partials
   unsigned* reduceTicket = nullptr;
   double* deviceObservables = nullptr;   // [energy sum, mass, max speed^2, enstrophy sum]
@@ -744,7 +764,7 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   if (ctx->shell) shellForceDestroy(ctx->shell);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
-                        (void*)ctx->partials, (void*)ctx->hints, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
+                        (void*)ctx->partials, (void*)ctx->hints, ctx->staging, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
                         (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
     if (pointer) cudaFree(pointer);
   for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->stepStart, ctx->timeStart, ctx->timeMid, ctx->timeStop})
@@ -1074,6 +1094,37 @@ static int copyDistribution(mlbm_ctx* ctx, void* host, size_t componentStride, s
   const size_t hostPitch = threeD ? paddedZ : paddedY;  // elements between consecutive host rows
   if (hostPitch < (size_t)ctx->NR || (threeD && paddedY < (size_t)ctx->NM)) return fail(MLBM_ERR_INVALID, "padded lengths smaller than the local lengths");
   const bool uniform = !threeD || paddedY == (size_t)ctx->NM;
+  static const bool stagedCopy = getenv("MLBM_STAGED_COPY") && atoi(getenv("MLBM_STAGED_COPY")) != 0;   // experiment, see stripPaddingKernel
+  if (stagedCopy && uniform) {
+    const long long rows = (long long)ctx->LX * ctx->NM;
+    const size_t blockBytes = (size_t)rows * hostPitch * es;
+    if (ctx->stagingBytes < blockBytes) {
+      if (ctx->staging) MLBM_CUDA(cudaFree(ctx->staging));
+      ctx->staging = nullptr;
+      ctx->stagingBytes = 0;
+      MLBM_CUDA(cudaMalloc(&ctx->staging, blockBytes));
+      ctx->stagingBytes = blockBytes;
+    }
+    const unsigned denseGrid = (unsigned)((rows * ctx->NR + 255) / 256), paddedGrid = (unsigned)((rows * (long long)hostPitch + 255) / 256);
+    for (int q = 0; q < ctx->Q; ++q) {
+      void* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->plane) * es;
+      char* hostQ = static_cast<char*>(host) + (size_t)q * componentStride * es;
+      if (upload) {
+        MLBM_CUDA(cudaMemcpyAsync(ctx->staging, hostQ, blockBytes, cudaMemcpyHostToDevice, ctx->computeStream));
+        if (es == 8) stripPaddingKernel<double><<<denseGrid, 256, 0, ctx->computeStream>>>(static_cast<const double*>(ctx->staging), static_cast<double*>(device), rows, ctx->NR, (long long)hostPitch);
+        else stripPaddingKernel<float><<<denseGrid, 256, 0, ctx->computeStream>>>(static_cast<const float*>(ctx->staging), static_cast<float*>(device), rows, ctx->NR, (long long)hostPitch);
+      } else {
+        if (es == 8) addPaddingKernel<double><<<paddedGrid, 256, 0, ctx->computeStream>>>(static_cast<const double*>(device), static_cast<double*>(ctx->staging), rows, ctx->NR, (long long)hostPitch);
+        else addPaddingKernel<float><<<paddedGrid, 256, 0, ctx->computeStream>>>(static_cast<const float*>(device), static_cast<float*>(ctx->staging), rows, ctx->NR, (long long)hostPitch);
+        MLBM_CUDA(cudaMemcpyAsync(hostQ, ctx->staging, blockBytes, cudaMemcpyDeviceToHost, ctx->computeStream));
+      }
+      ctx->launches += 1;
+    }
+    MLBM_CUDA(cudaGetLastError());
+    MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+    if (upload) ctx->halosValid = false;
+    return MLBM_OK;
+  }
   for (int q = 0; q < ctx->Q; ++q) {
     char* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->plane) * es;
     char* hostQ = static_cast<char*>(host) + (size_t)q * componentStride * es;

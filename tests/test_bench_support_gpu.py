@@ -186,3 +186,62 @@ def test_secondary_workloads_of_the_bench_on_several_ranks(tmp_path, world):
         if "skipped" in r:      # x extent of the toy grid not divisible by the rank count
             continue
         assert r["value"] > 0 and r["halo"] == "peer" and abs(r["mass_per_node"] - 1.0) < 1e-3 and r["energy"] > 0, r
+
+
+_STAGED_WORKER = r'''
+import os, sys
+root, out = sys.argv[1], sys.argv[2]
+sys.path.insert(0, root); sys.path.insert(0, root + "/tests")
+import numpy as np
+from metalbm_b200 import capi
+if os.environ.get("MLBM_EMULATED") == "1":
+    capi._library = capi.load_library(os.environ["MLBM_EMULATED_LIBRARY"])
+from metalbm_b200.algorithm import Algorithm
+from metalbm_b200.capi import make_config
+from oracle import oracle as O
+results = {}
+for key, lattice, shape, dtype in (("a", "D2Q9", (9, 11, 1), "F64"), ("b", "D3Q19", (5, 4, 7), "F64"), ("c", "D3Q27", (3, 4, 130), "F32")):
+    cfg = make_config(lattice=lattice, shape=shape, forcing_scheme="Guo", force="Kolmogorov", tau=0.6, dtype=dtype,
+                      amplitude=(1e-4, 1e-4, 1e-4), wavelength=(4.0, 4.0, 4.0))
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.array[...] = 7.0           # padding included
+        algorithm.distribution.set_interior(f0.astype(algorithm.domain.dtype))
+        algorithm.unpack()
+        algorithm.distribution.array[...] = -1.0
+        algorithm.pack()
+        results[key + "_roundtrip"] = algorithm.distribution.array.copy()
+        for iteration in (1, 2):
+            algorithm.iterate(iteration)
+        algorithm.pack()
+        results[key + "_stepped"] = algorithm.distribution.get_interior()
+np.savez(out, **results)
+print("ok")
+'''
+
+
+def test_staged_pack_and_unpack_equal_the_pitched_copies(tmp_path):
+    """MLBM_STAGED_COPY=1 (experiment, off by default): every population crosses PCIe as one contiguous padded block and the
+    padding is stripped / added by a kernel.  Same interior values as the pitched cudaMemcpy2DAsync route, bit for bit; the
+    padding comes back as zeros where the pitched route leaves the host's values alone."""
+    import os
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "worker.py"
+    script.write_text(_STAGED_WORKER)
+    outputs = {}
+    for mode in ("0", "1"):
+        out = tmp_path / f"staged{mode}.npz"
+        result = subprocess.run([sys.executable, str(script), str(root), str(out)], capture_output=True, text=True, timeout=600,
+                                env=dict(os.environ, MLBM_STAGED_COPY=mode, OMP_NUM_THREADS="1"))
+        assert result.returncode == 0 and "ok" in result.stdout, result.stdout[-2000:] + result.stderr[-2000:]
+        outputs[mode] = np.load(out)
+    for key in ("a", "b", "c"):
+        pitched, staged = outputs["0"][key + "_roundtrip"], outputs["1"][key + "_roundtrip"]
+        assert np.array_equal(outputs["0"][key + "_stepped"], outputs["1"][key + "_stepped"])
+        interior = pitched != -1.0                              # the pitched route writes the interior only
+        assert interior.any() and not interior.all()
+        assert np.array_equal(staged[interior], pitched[interior])
+        assert np.all(staged[~interior] == 0.0)
