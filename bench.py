@@ -510,49 +510,53 @@ def run_ours(args) -> int:
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        algorithm.pack()                         # current state -> host array (also first-touches the host pages)
-        host = algorithm.distribution.array
-        pinned = torch.empty(host.shape, dtype=torch.float64 if element == 8 else torch.float32, pin_memory=True)
-        pinned.numpy()[...] = host
-        algorithm.distribution.array = pinned.numpy()
-        barrier()
-        t0 = time.perf_counter()
-        algorithm.unpack()                       # H2D of the whole SoA distribution from pinned host memory
-        t1 = time.perf_counter()
-        energy = 0.0
-        for iteration in range(1, args.steps + 1):
-            algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
-            energy = algorithm.observables()[0]  # D2H read of the step's scalar results
-        t2 = time.perf_counter()
-        algorithm.pack()                         # D2H of the whole distribution
-        t3 = time.perf_counter()
-        barrier()
-        e2e_seconds = max_over_ranks(time.perf_counter() - t0)
-        # outside the timed region: what the same bytes cost as ONE contiguous copy each way (the upload / download above
-        # move 2 KB rows of a padded host array with cudaMemcpy2DAsync); tells whether a staged contiguous copy would pay
-        contiguous = {}
         try:
-            device_copy = torch.empty(pinned.shape, dtype=pinned.dtype, device="cuda")
-            for name, source, target in (("h2d", pinned, device_copy), ("d2h", device_copy, pinned)):
-                torch.cuda.synchronize()
-                c0 = time.perf_counter()
-                target.copy_(source, non_blocking=True)
-                torch.cuda.synchronize()
-                contiguous[name + "_contiguous_GBps"] = pinned.numel() * element / (time.perf_counter() - c0) / 1e9
-            del device_copy
-        except Exception as error:  # noqa: BLE001 -- a diagnostic, never fatal
-            contiguous = {"contiguous_probe_error": str(error)[:200]}
-        e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
-        distribution_bytes = q_count * nodes_local * element
-        e2e = {"value": e2e_value, "unit": UNIT,
-               "h2d_bytes_per_step": distribution_bytes / args.steps,
-               "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
-               "note": "timed region: unpack (H2D of all populations from pinned host memory) + K synchronous mlbm_step calls "
-                       "each followed by a D2H read of the observables + pack (D2H of all populations); population bytes "
-                       "amortised over K", "last_energy": energy,
-               "unpack_ms": (t1 - t0) * 1e3, "steps_ms": (t2 - t1) * 1e3, "pack_ms": (t3 - t2) * 1e3,
-               "h2d_GBps": q_count * nodes_local * element / (t1 - t0) / 1e9,
-               "d2h_GBps": q_count * nodes_local * element / (t3 - t2) / 1e9, **contiguous}
+            algorithm.pack()                         # current state -> host array (also first-touches the host pages)
+            host = algorithm.distribution.array
+            pinned = torch.empty(host.shape, dtype=torch.float64 if element == 8 else torch.float32, pin_memory=True)
+            pinned.numpy()[...] = host
+            algorithm.distribution.array = pinned.numpy()
+            barrier()
+            t0 = time.perf_counter()
+            algorithm.unpack()                       # H2D of the whole SoA distribution from pinned host memory
+            t1 = time.perf_counter()
+            energy = 0.0
+            for iteration in range(1, args.steps + 1):
+                algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
+                energy = algorithm.observables()[0]  # D2H read of the step's scalar results
+            t2 = time.perf_counter()
+            algorithm.pack()                         # D2H of the whole distribution
+            t3 = time.perf_counter()
+            barrier()
+            e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+            # outside the timed region: what the same bytes cost as ONE contiguous copy each way (the upload / download above
+            # move 2 KB rows of a padded host array with cudaMemcpy2DAsync); tells whether a staged contiguous copy would pay
+            contiguous = {}
+            try:
+                device_copy = torch.empty(pinned.shape, dtype=pinned.dtype, device="cuda")
+                for name, source, target in (("h2d", pinned, device_copy), ("d2h", device_copy, pinned)):
+                    torch.cuda.synchronize()
+                    c0 = time.perf_counter()
+                    target.copy_(source, non_blocking=True)
+                    torch.cuda.synchronize()
+                    contiguous[name + "_contiguous_GBps"] = pinned.numel() * element / (time.perf_counter() - c0) / 1e9
+                del device_copy
+            except Exception as error:  # noqa: BLE001 -- a diagnostic, never fatal
+                contiguous = {"contiguous_probe_error": str(error)[:200]}
+            e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
+            distribution_bytes = q_count * nodes_local * element
+            e2e = {"value": e2e_value, "unit": UNIT,
+                   "h2d_bytes_per_step": distribution_bytes / args.steps,
+                   "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
+                   "note": "timed region: unpack (H2D of all populations from pinned host memory) + K synchronous mlbm_step calls "
+                           "each followed by a D2H read of the observables + pack (D2H of all populations); population bytes "
+                           "amortised over K", "last_energy": energy,
+                   "unpack_ms": (t1 - t0) * 1e3, "steps_ms": (t2 - t1) * 1e3, "pack_ms": (t3 - t2) * 1e3,
+                   "h2d_GBps": q_count * nodes_local * element / (t1 - t0) / 1e9,
+                   "d2h_GBps": q_count * nodes_local * element / (t3 - t2) / 1e9, **contiguous}
+
+        except Exception as error:  # noqa: BLE001 -- the device-resident headline above stands; the line says what happened
+            e2e = {"value": None, "unit": UNIT, "error": str(error)[:300]}
 
     peak, peak_source = measured_peak()
     # the dominant kernel is the bulk launch of the fused step: all local planes at N = 1, all but the two boundary
