@@ -45,6 +45,9 @@ WORKLOADS = {
     "d3q19_bgk_guo_256": dict(config=1, lattice="D3Q19", q=19, shape=(256, 256, 256), scaling="weak", collision="BGK",
                               equilibrium="TruncationMa3", scheme="Guo", force="Kolmogorov", tau=0.55, eps=0.0, store_every=0,
                               text="D3Q19 SRT-BGK Guo-forced Kolmogorov periodic 256^3 per GPU (second row of BASELINE configs[1])"),
+    "d3q27_bgk_512": dict(config=2, lattice="D3Q27", q=27, shape=(512, 512, 512), scaling="strong", collision="BGK",
+                          equilibrium="TruncationMa3", scheme="Guo", force="Kolmogorov", tau=0.55, eps=0.0, store_every=0,
+                          text="D3Q27 SRT-BGK Guo Kolmogorov 512^3 (the HBM-bound counterpart of BASELINE configs[2])"),
     "d3q27_elbm_512": dict(config=2, lattice="D3Q27", q=27, shape=(512, 512, 512), scaling="strong", collision="ELBM",
                            equilibrium="TruncationMa3", scheme="Guo", force="Kolmogorov", tau=0.55, eps=2e-2, store_every=0,
                            text="D3Q27 SRT-Entropic (alpha Newton solve) Guo Kolmogorov 512^3, x-slab (BASELINE configs[2])"),
@@ -70,6 +73,7 @@ WORKLOADS = {
 ALSO_SINGLE = [
     ("d3q19_bgk_256", "F32", None, 1, 100),
     ("d3q19_bgk_guo_256", "F64", None, 1, 100),
+    ("d3q27_bgk_512", "F64", None, 1, 50),
     ("d3q27_elbm_512", "F64", 2e-2, 1, 20),
     ("d3q27_elbm_512", "F64", 1e-5, 1, 20),
     ("d2q9_elbm_shanchen_8192", "F64", 2e-2, 1, 50),
@@ -294,6 +298,8 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
             algorithm.mark(3)
             algorithm.synchronize()
             stored_ms = max_over_ranks(algorithm.elapsed_ms(2, 3))
+        # what the entropic collision was doing at the end of the timed region: share of nodes off the alpha = 2 shortcut
+        newton_fraction, alpha_min, alpha_max = algorithm.alpha_statistics() if entropic else (None, None, None)
         # liveness of the state that was timed: one more step reducing energy / mass / Mach only
         algorithm.run(0, 1, 1, stored_mode=2)
         observables = algorithm.observables()
@@ -310,6 +316,8 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
             "energy": float(observables[0]), "mach": float(observables[2]),
             "mass_per_node": float(observables[3]) / nodes_global,
         })
+        if entropic:
+            result.update({"alpha_off_shortcut_fraction_at_end": newton_fraction, "alpha_min": alpha_min, "alpha_max": alpha_max})
     finally:
         algorithm.close()
     return result

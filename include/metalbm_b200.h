@@ -265,6 +265,12 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]);
  * length of the arrays given.  Unlike the reference, the fields are left untouched (its transforms run in place). */
 int mlbm_power_spectra(mlbm_ctx* ctx, double* energy_spectrum, double* forcing_spectrum, int capacity, int* count);
 
+/* What the entropic collision did in the last step, from the alpha field (Algorithm.h:103-106), over all ranks:
+ *   out[0] fraction of nodes whose alpha differs from 2, i.e. that left the small-deviation shortcut (Collision.h:357-359)
+ *   out[1] smallest alpha, out[2] largest alpha.
+ * Characterises a benchmark state (how much of the grid pays for the Newton solve); BGK contexts report {0, 2, 2}. */
+int mlbm_alpha_statistics(mlbm_ctx* ctx, double out[3]);
+
 /* Communication::reduce(T* localSumPtr, numberComponents) (Communication.h:76-89): element-wise sum of `count` host
  * doubles over all ranks, result on EVERY rank (the reference leaves it on rank 0 only); a no-op for one rank. */
 int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count);

@@ -268,6 +268,12 @@ class Algorithm:
         check(self._lib.mlbm_power_spectra(self._ctx, energy, forcing, count.value, ctypes.byref(count)))
         return np.stack([np.array(energy[:count.value]), np.array(forcing[:count.value])], axis=1)
 
+    def alpha_statistics(self) -> tuple:
+        """(fraction of nodes whose alpha left the shortcut value 2, min alpha, max alpha) of the last step, over all ranks."""
+        out = (ctypes.c_double * 3)()
+        check(self._lib.mlbm_alpha_statistics(self._ctx, out))
+        return float(out[0]), float(out[1]), float(out[2])
+
     def getCommunicationTime(self) -> float:
         c, _ = ctypes.c_double(), ctypes.c_double()
         check(self._lib.mlbm_timers(self._ctx, ctypes.byref(c), None))

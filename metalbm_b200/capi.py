@@ -223,6 +223,7 @@ PROTOTYPES = {
     "mlbm_observables": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "mlbm_power_spectra": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_int)]),
+    "mlbm_alpha_statistics": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "mlbm_reduce_sum": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "mlbm_selftest_log": (ctypes.c_int, [_P, _P, _SZ]),
     "mlbm_alloc_pinned": (ctypes.c_int, [_SZ, ctypes.POINTER(_P)]),

@@ -196,6 +196,30 @@ __global__ void addPaddingKernel(const StoreT* __restrict__ dense, StoreT* __res
   padded[j] = r < NR ? dense[row * NR + r] : (StoreT)0;   // the padding values arrive as zeros (they are scratch: Domain.h:53-57)
 }
 
+// one block: count of alpha != 2, min and max of the alpha field (a diagnostic, not on the step path)
+template <typename StoreT>
+__global__ void __launch_bounds__(256) alphaStatisticsKernel(const StoreT* __restrict__ alpha, long long nodes, double* __restrict__ out) {
+  __shared__ double scratch[3][256];
+  double count = 0.0, low = 1e300, high = -1e300;
+  for (long long i = threadIdx.x; i < nodes; i += blockDim.x) {
+    const double a = (double)alpha[i];
+    count += a != 2.0 ? 1.0 : 0.0;
+    low = fmin(low, a);
+    high = fmax(high, a);
+  }
+  scratch[0][threadIdx.x] = count; scratch[1][threadIdx.x] = low; scratch[2][threadIdx.x] = high;
+  __syncthreads();
+  for (int width = 128; width > 0; width >>= 1) {
+    if ((int)threadIdx.x < width) {
+      scratch[0][threadIdx.x] += scratch[0][threadIdx.x + width];
+      scratch[1][threadIdx.x] = fmin(scratch[1][threadIdx.x], scratch[1][threadIdx.x + width]);
+      scratch[2][threadIdx.x] = fmax(scratch[2][threadIdx.x], scratch[2][threadIdx.x + width]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { out[0] = scratch[0][0]; out[1] = -scratch[1][0]; out[2] = scratch[2][0]; }   // -min: reduced with max over ranks
+}
+
 template <typename StoreT> __global__ void fillKernel(StoreT* data, long long count, StoreT value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) data[i] = value;
@@ -1392,6 +1416,41 @@ int mlbm_power_spectra(mlbm_ctx* ctx, double* energySpectrum, double* forcingSpe
     if (energySpectrum) energySpectrum[k] = host[k] / volume;      // normalizeAnalyses: the energy spectrum only (AnalysisList.h:189)
     if (forcingSpectrum) forcingSpectrum[k] = host[bins + k];
   }
+  return MLBM_OK;
+}
+
+int mlbm_alpha_statistics(mlbm_ctx* ctx, double out[3]) {
+  if (!ctx || !out) return fail(MLBM_ERR_INVALID, "null argument");
+  if (!ctx->alpha) { out[0] = 0.0; out[1] = 2.0; out[2] = 2.0; return MLBM_OK; }   // BGK: alpha == 2 (Collision.h:121)
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->config.nranks > 1 && !ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
+  double* device = nullptr;
+  MLBM_CUDA(cudaMalloc(&device, 3 * sizeof(double)));
+  cudaStream_t stream = ctx->computeStream;
+  if (ctx->config.dtype == MLBM_F64) alphaStatisticsKernel<double><<<1, 256, 0, stream>>>(static_cast<const double*>(ctx->alpha), ctx->nodes, device);
+  else alphaStatisticsKernel<float><<<1, 256, 0, stream>>>(static_cast<const float*>(ctx->alpha), ctx->nodes, device);
+  ctx->launches += 1;
+  int status = MLBM_OK;
+  if (ctx->config.nranks > 1) {
+    ncclResult_t result = ctx->nccl->GroupStart();
+    if (result == ncclSuccess) result = ctx->nccl->AllReduce(device, device, 1, ncclDouble, ncclSum, ctx->comm, stream);
+    if (result == ncclSuccess) result = ctx->nccl->AllReduce(device + 1, device + 1, 2, ncclDouble, ncclMax, ctx->comm, stream);
+    const ncclResult_t end = ctx->nccl->GroupEnd();
+    if (result == ncclSuccess) result = end;
+    if (result != ncclSuccess) status = fail(MLBM_ERR_COMM, "ncclAllReduce: %s", ctx->nccl->GetErrorString(result));
+  }
+  double host[3] = {0.0, 0.0, 0.0};
+  cudaError_t error = cudaGetLastError();
+  if (error == cudaSuccess && status == MLBM_OK) error = cudaMemcpyAsync(host, device, sizeof(host), cudaMemcpyDeviceToHost, stream);
+  const cudaError_t syncError = cudaStreamSynchronize(stream);
+  cudaFree(device);
+  if (status != MLBM_OK) return status;
+  if (error != cudaSuccess || syncError != cudaSuccess) return fail(MLBM_ERR_CUDA, "alpha statistics: %s", cudaGetErrorString(error != cudaSuccess ? error : syncError));
+  double globalNodes = 1.0;
+  for (int d = 0; d < ctx->D; ++d) globalNodes *= ctx->config.global_length[d];
+  out[0] = host[0] / globalNodes;
+  out[1] = -host[1];
+  out[2] = host[2];
   return MLBM_OK;
 }
 

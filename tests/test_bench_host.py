@@ -192,6 +192,7 @@ class _FakeAlgorithm:
         nodes = 1
         for n in self.cfg.global_length: nodes *= n
         return [1e-3, float("nan"), 0.1, float(nodes)]
+    def alpha_statistics(self): return 0.5, 1.2, 2.1
     def close(self): self.closed = True
 
 

@@ -245,3 +245,25 @@ def test_staged_pack_and_unpack_equal_the_pitched_copies(tmp_path):
         assert interior.any() and not interior.all()
         assert np.array_equal(staged[interior], pitched[interior])
         assert np.all(staged[~interior] == 0.0)
+
+
+def test_alpha_statistics_follow_the_alpha_field():
+    """mlbm_alpha_statistics: share of nodes off the alpha = 2 shortcut, min and max alpha, against the oracle's alpha field."""
+    from helpers import run_oracle
+    cfg = make_config(lattice="D2Q9", shape=(16, 140, 1), collision="ELBM", forcing_scheme="Guo", force="Kolmogorov", tau=0.55,
+                      amplitude=(1e-4, 1e-4, 1e-4), wavelength=(8.0, 8.0, 8.0))
+    f0 = O.synthetic_populations(cfg, eps=1e-5, amplitude=0.0, ripple=0.0)
+    rng = np.random.default_rng(5)
+    for _ in range(60):
+        f0[:, rng.integers(0, 16), rng.integers(0, 140), 0] *= 1.0 + 0.05 * rng.standard_normal(9)
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.set_interior(f0)
+        algorithm.unpack()
+        algorithm.iterate(1)
+        fraction, low, high = algorithm.alpha_statistics()
+    ref = run_oracle(cfg, f0, 1)
+    assert 0.0 < fraction < 0.5
+    assert abs(fraction - (ref.alpha != 2.0).mean()) <= 2.0 / ref.alpha.size
+    assert abs(low - ref.alpha.min()) <= 1e-9 and abs(high - ref.alpha.max()) <= 1e-9
+    with Algorithm(make_config(lattice="D2Q9", shape=(8, 8, 1))) as bgk:
+        assert bgk.alpha_statistics() == (0.0, 2.0, 2.0)
