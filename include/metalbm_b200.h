@@ -42,8 +42,8 @@ typedef enum mlbm_status {
 
 /* LatticeType (Options.h:13-14, descriptors Lattice.h:80,145,460,535,614).  The multi-speed lattices D2Q13 (:213),
  * D2Q17 (:290), D2Q21 (:372) and D3Q33 (:706) -- jumps of up to 3 nodes, their own sound speeds, TruncationMa3 only --
- * run on ONE GPU (nranks == 1): every coordinate wraps by index arithmetic.  D1Q3 (:22) does not compile in the reference
- * (Force.h:329) and is not rebuilt. */
+ * carry dimH halo planes per side and exchange them over NCCL (direct peer halos are for the single-speed lattices).
+ * D1Q3 (:22) does not compile in the reference (Force.h:329) and is not rebuilt. */
 typedef enum mlbm_lattice {
   MLBM_D2Q5 = 0, MLBM_D2Q9 = 1, MLBM_D3Q15 = 2, MLBM_D3Q19 = 3, MLBM_D3Q27 = 4,
   MLBM_D2Q13 = 5, MLBM_D2Q17 = 6, MLBM_D2Q21 = 7, MLBM_D3Q33 = 8

@@ -162,7 +162,8 @@ class Algorithm:
             # direct peer halos (boundary kernel stores into the neighbours' halo planes over NVLink): default on with
             # Overlapping::On; MLBM_PEER_HALOS=0 or peer_halos=False keeps the NCCL send/recv exchange
             if peer_halos is None:
-                peer_halos = int(config.overlap) == 1 and os.environ.get("MLBM_PEER_HALOS", "1") != "0"
+                single_speed = Lattice(config.lattice) in (Lattice.D2Q5, Lattice.D2Q9, Lattice.D3Q15, Lattice.D3Q19, Lattice.D3Q27)
+                peer_halos = int(config.overlap) == 1 and single_speed and os.environ.get("MLBM_PEER_HALOS", "1") != "0"
             self.peer_halos = False
             if peer_halos:
                 self._attach_peers()

@@ -252,7 +252,7 @@ __global__ void initEquilibriumKernel(StoreT* __restrict__ populations, const St
 // evaluated on the device at GLOBAL coordinates and written as f = feq(rho, u): no host field arrays, which is what
 // the slabs that fill a GPU (1024^3 on two GPUs) need.
 template <class L, int EQ, typename StoreT>
-__global__ void initSyntheticKernel(StoreT* __restrict__ populations, long long stride, long long plane, long long nodes,
+__global__ void initSyntheticKernel(StoreT* __restrict__ populations, long long stride, long long plane, long long interior, long long nodes,
                                     int NR, int xOffset, int globalX, int globalY, int globalZ, double densityAmplitude,
                                     double velocityAmplitude) {
   const long long node = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -281,7 +281,7 @@ __global__ void initSyntheticKernel(StoreT* __restrict__ populations, long long 
   eq.set(u, u2);
   staticFor<0, L::Q>([&](auto qc) {
     constexpr int q = decltype(qc)::value;
-    populations[q * stride + plane + node] = (StoreT)(rho * L::w(q) * eq.template shape<q>());
+    populations[q * stride + interior + node] = (StoreT)(rho * L::w(q) * eq.template shape<q>());
   });
 }
 
@@ -345,13 +345,13 @@ static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* popu
 
 template <int EQ, typename StoreT>
 static void launchInitSynthetic(int lattice, cudaStream_t stream, StoreT* populations, long long stride, long long plane,
-                                long long nodes, int NR, int xOffset, const int* global, double densityAmplitude,
+                                long long interior, long long nodes, int NR, int xOffset, const int* global, double densityAmplitude,
                                 double velocityAmplitude) {
   const int block = 128;
   const unsigned grid = (unsigned)((nodes + block - 1) / block);
 #define MLBM_INIT_SYNTHETIC(LATTICE, EQUILIBRIUM)                                                                      \
   initSyntheticKernel<Lattice<LATTICE>, EQUILIBRIUM, StoreT><<<grid, block, 0, stream>>>(                                \
-      populations, stride, plane, nodes, NR, xOffset, global[0], global[1], global[2], densityAmplitude, velocityAmplitude)
+      populations, stride, plane, interior, nodes, NR, xOffset, global[0], global[1], global[2], densityAmplitude, velocityAmplitude)
   switch (lattice) {
     case kD2Q5: if (EQ == kTruncationMa3) MLBM_INIT_SYNTHETIC(kD2Q5, kTruncationMa3); break;
     case kD2Q9: MLBM_INIT_SYNTHETIC(kD2Q9, EQ); break;
@@ -411,6 +411,8 @@ struct mlbm_ctx {
   int LX = 0, NM = 0, NR = 0;           // local extents on the kernel axes (x, m, r)
   size_t elementSize = 8;
   long long plane = 0, stride = 0, fieldStride = 0, nodes = 0;
+  int H = 1;                            // halo planes per side in x
+  long long interior = 0;               // elements from the start of a population to its first interior plane (H * plane)
   long long partialBlocks = 0;
   int gridR = 0;
 
@@ -486,20 +488,22 @@ static int collectProfile(mlbm_ctx* ctx) {
 // geometry shared by the context and the (device-free) halo plan
 struct SlabGeometry {
   int D, Q, faceQ, LX, NM, NR;
+  int H;                 // halo planes per side in x (Lattice dimH: 1 but for the multi-speed lattices)
   long long plane, stride;
 };
 
 static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
   g->Q = latticeQ(config->lattice);
   if (!g->Q || config->nranks < 1 || config->global_length[0] % config->nranks) return false;
-  if (latticeHalo(config->lattice) > 1 && config->nranks > 1) return false;  // one halo plane per side
+  g->H = latticeHalo(config->lattice);
+  if (config->nranks > 1 && config->global_length[0] / config->nranks < g->H) return false;  // a slab thinner than the halo
   g->D = latticeDim(config->lattice);
   g->faceQ = latticeFaceQ(config->lattice);
   g->LX = config->global_length[0] / config->nranks;
   g->NM = g->D == 3 ? config->global_length[1] : 1;
   g->NR = g->D == 3 ? config->global_length[2] : config->global_length[1];
   g->plane = (long long)g->NM * g->NR;
-  const long long perPopulation = g->plane * (g->LX + 2);
+  const long long perPopulation = g->plane * (g->LX + 2 * g->H);
   g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
   return true;
 }
@@ -611,16 +615,16 @@ static int haloPlan(const mlbm_config* config, std::vector<mlbm_halo_message>* p
     message.is_send = isSend;
     message.reserved = 0;
     message.offset = (uint64_t)(q * g.stride + xPlane * g.plane);
-    message.count = (uint64_t)g.plane;
+    message.count = (uint64_t)(g.H * g.plane);   // dimH adjacent planes travel together (Communication.h:145-150: sizeStripeX)
     plan->push_back(message);
   };
   for (int q = g.faceQ + 1; q < 2 * g.faceQ + 1; ++q) {
-    add(q, right, 1, g.LX);  // last interior plane
-    add(q, left, 0, 0);      // left halo plane
+    add(q, right, 1, g.LX);  // last H interior planes (interior planes are H .. LX + H - 1)
+    add(q, left, 0, 0);      // left halo planes
   }
   for (int q = 1; q < g.faceQ + 1; ++q) {
-    add(q, left, 1, 1);          // first interior plane
-    add(q, right, 0, g.LX + 1);  // right halo plane
+    add(q, left, 1, g.H);          // first H interior planes
+    add(q, right, 0, g.LX + g.H);  // right halo planes
   }
   return MLBM_OK;
 }
@@ -710,7 +714,7 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
     if (int status = launchStep(ctx, compute, 1, ctx->LX - 1, isStored, profile)) return status;
     MLBM_CUDA(cudaStreamWaitEvent(compute, ctx->boundaryDone, 0));
     ctx->halosValid = true;  // the neighbours deliver the halo planes of the buffer that becomes current; waited for next step
-  } else if (ctx->config.overlap == MLBM_OVERLAP_OFF || ctx->LX < 3) {
+  } else if (ctx->config.overlap == MLBM_OVERLAP_OFF || ctx->LX < 2 * ctx->H + 1) {
     // the reference's order (Algorithm.h:336-355): exchange the halos of the buffer about to be read, then compute
     if (!ctx->halosValid) { if (int status = exchangeHalos(ctx, ctx->current, compute)) return status; }
     if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
@@ -723,13 +727,13 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
       if (int status = exchangeHalos(ctx, ctx->current, compute)) return status;
     }
     if (timed) MLBM_CUDA(cudaEventRecord(ctx->timeMid, compute));
-    if (int status = launchStep(ctx, compute, 0, 1, isStored, false)) return status;
-    if (int status = launchStep(ctx, compute, ctx->LX - 1, ctx->LX, isStored, false)) return status;
+    if (int status = launchStep(ctx, compute, 0, ctx->H, isStored, false)) return status;
+    if (int status = launchStep(ctx, compute, ctx->LX - ctx->H, ctx->LX, isStored, false)) return status;
     MLBM_CUDA(cudaEventRecord(ctx->boundaryDone, compute));
     MLBM_CUDA(cudaStreamWaitEvent(ctx->commStream, ctx->boundaryDone, 0));
     if (int status = exchangeHalos(ctx, ctx->current ^ 1, ctx->commStream)) return status;
     MLBM_CUDA(cudaEventRecord(ctx->exchangeDone, ctx->commStream));
-    if (int status = launchStep(ctx, compute, 1, ctx->LX - 1, isStored, profile)) return status;
+    if (int status = launchStep(ctx, compute, ctx->H, ctx->LX - ctx->H, isStored, profile)) return status;
     MLBM_CUDA(cudaStreamWaitEvent(compute, ctx->exchangeDone, 0));
     ctx->halosValid = true;  // of the buffer that becomes current below
   }
@@ -814,8 +818,8 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   for (int d = 0; d < D; ++d)
     if (config->global_length[d] < 1) return fail(MLBM_ERR_INVALID, "global_length[%d] = %d", d, config->global_length[d]);
   if (config->global_length[0] % config->nranks) return fail(MLBM_ERR_INVALID, "nranks %d does not divide globalLengthX %d (Domain.h:22-24)", config->nranks, config->global_length[0]);
-  if (latticeHalo(config->lattice) > 1 && config->nranks > 1)
-    return fail(MLBM_ERR_INVALID, "the multi-speed lattices (halo %d) run on one GPU in this build: the x-slab exchange moves one plane per side", latticeHalo(config->lattice));
+  if (config->nranks > 1 && config->global_length[0] / config->nranks < latticeHalo(config->lattice))
+    return fail(MLBM_ERR_INVALID, "slabs of %d planes are thinner than the lattice's halo of %d", config->global_length[0] / config->nranks, latticeHalo(config->lattice));
 
   int collision, scheme, hydroShift;
   switch (config->collision) {
@@ -858,6 +862,8 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   ctx->NR = geometry.NR;
   ctx->elementSize = config->dtype == MLBM_F64 ? 8 : 4;
   ctx->plane = geometry.plane;
+  ctx->H = geometry.H;
+  ctx->interior = geometry.H * geometry.plane;
   ctx->nodes = ctx->plane * ctx->LX;
   ctx->fieldStride = (ctx->nodes + 31) / 32 * 32;  // every field component 128-byte aligned (cuFFT reads them as double2)
   ctx->stride = geometry.stride;
@@ -1069,6 +1075,7 @@ int mlbm_comm_peer_attach(mlbm_ctx* ctx, const void* leftHandle, const void* rig
   if (ctx->peerAttached) return fail(MLBM_ERR_STATE, "peer halos already attached");
   if (!ctx->peerFlags) return fail(MLBM_ERR_STATE, "mlbm_comm_peer_export has to be called first");
   if (!ctx->comm) return fail(MLBM_ERR_STATE, "mlbm_comm_init has to be called first (initial halo exchange and shutdown barrier)");
+  if (ctx->H > 1) return fail(MLBM_ERR_INVALID, "direct peer halos are built for the single-speed lattices (one halo plane); the multi-speed ones exchange over NCCL");
   MLBM_CUDA(cudaSetDevice(ctx->device));
   PeerBlob blobs[2];
   memcpy(&blobs[0], leftHandle, sizeof(PeerBlob));
@@ -1131,7 +1138,7 @@ static int copyDistribution(mlbm_ctx* ctx, void* host, size_t componentStride, s
     }
     const unsigned denseGrid = (unsigned)((rows * ctx->NR + 255) / 256), paddedGrid = (unsigned)((rows * (long long)hostPitch + 255) / 256);
     for (int q = 0; q < ctx->Q; ++q) {
-      void* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->plane) * es;
+      void* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->interior) * es;
       char* hostQ = static_cast<char*>(host) + (size_t)q * componentStride * es;
       if (upload) {
         MLBM_CUDA(cudaMemcpyAsync(ctx->staging, hostQ, blockBytes, cudaMemcpyHostToDevice, ctx->computeStream));
@@ -1150,7 +1157,7 @@ static int copyDistribution(mlbm_ctx* ctx, void* host, size_t componentStride, s
     return MLBM_OK;
   }
   for (int q = 0; q < ctx->Q; ++q) {
-    char* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->plane) * es;
+    char* device = static_cast<char*>(ctx->populations[ctx->current]) + ((size_t)q * ctx->stride + ctx->interior) * es;
     char* hostQ = static_cast<char*>(host) + (size_t)q * componentStride * es;
     const int chunks = uniform ? 1 : ctx->LX;
     const size_t rows = uniform ? (size_t)ctx->LX * ctx->NM : (size_t)ctx->NM;
@@ -1205,14 +1212,14 @@ int mlbm_init_equilibrium(mlbm_ctx* ctx, const void* density, const void* veloci
   void* target = ctx->populations[ctx->current];
   if (ctx->config.dtype == MLBM_F64) {
     if (ctx->config.equilibrium == MLBM_EXACT)
-      launchInitEquilibrium<kExact, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), static_cast<const double*>(ctx->density), static_cast<const double*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+      launchInitEquilibrium<kExact, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), static_cast<const double*>(ctx->density), static_cast<const double*>(ctx->velocity), ctx->stride, ctx->interior, ctx->fieldStride, ctx->nodes);
     else
-      launchInitEquilibrium<kTruncationMa3, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), static_cast<const double*>(ctx->density), static_cast<const double*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+      launchInitEquilibrium<kTruncationMa3, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), static_cast<const double*>(ctx->density), static_cast<const double*>(ctx->velocity), ctx->stride, ctx->interior, ctx->fieldStride, ctx->nodes);
   } else {
     if (ctx->config.equilibrium == MLBM_EXACT)
-      launchInitEquilibrium<kExact, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+      launchInitEquilibrium<kExact, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->interior, ctx->fieldStride, ctx->nodes);
     else
-      launchInitEquilibrium<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->plane, ctx->fieldStride, ctx->nodes);
+      launchInitEquilibrium<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), static_cast<const float*>(ctx->density), static_cast<const float*>(ctx->velocity), ctx->stride, ctx->interior, ctx->fieldStride, ctx->nodes);
   }
   MLBM_CUDA(cudaGetLastError());
   ctx->launches += 1;
@@ -1230,11 +1237,11 @@ int mlbm_init_synthetic(mlbm_ctx* ctx, double densityAmplitude, double velocityA
   const int* global = ctx->config.global_length;
   const bool exact = ctx->config.equilibrium == MLBM_EXACT;
   if (ctx->config.dtype == MLBM_F64) {
-    if (exact) launchInitSynthetic<kExact, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
-    else launchInitSynthetic<kTruncationMa3, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+    if (exact) launchInitSynthetic<kExact, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), ctx->stride, ctx->plane, ctx->interior, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+    else launchInitSynthetic<kTruncationMa3, double>(ctx->config.lattice, ctx->computeStream, static_cast<double*>(target), ctx->stride, ctx->plane, ctx->interior, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
   } else {
-    if (exact) launchInitSynthetic<kExact, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
-    else launchInitSynthetic<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), ctx->stride, ctx->plane, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+    if (exact) launchInitSynthetic<kExact, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), ctx->stride, ctx->plane, ctx->interior, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
+    else launchInitSynthetic<kTruncationMa3, float>(ctx->config.lattice, ctx->computeStream, static_cast<float*>(target), ctx->stride, ctx->plane, ctx->interior, ctx->nodes, ctx->NR, xOffset, global, densityAmplitude, velocityAmplitude);
   }
   MLBM_CUDA(cudaGetLastError());
   ctx->launches += 1;
@@ -1250,9 +1257,9 @@ int mlbm_perturb_distribution(mlbm_ctx* ctx, double eps, uint64_t seed) {
   const long long offset = (long long)ctx->config.rank * ctx->nodes;
   void* target = ctx->populations[ctx->current];
   if (ctx->config.dtype == MLBM_F64)
-    perturbKernel<double><<<grid, 256, 0, ctx->computeStream>>>(static_cast<double*>(target), ctx->stride, ctx->plane, ctx->nodes, offset, ctx->Q, eps, seed);
+    perturbKernel<double><<<grid, 256, 0, ctx->computeStream>>>(static_cast<double*>(target), ctx->stride, ctx->interior, ctx->nodes, offset, ctx->Q, eps, seed);
   else
-    perturbKernel<float><<<grid, 256, 0, ctx->computeStream>>>(static_cast<float*>(target), ctx->stride, ctx->plane, ctx->nodes, offset, ctx->Q, eps, seed);
+    perturbKernel<float><<<grid, 256, 0, ctx->computeStream>>>(static_cast<float*>(target), ctx->stride, ctx->interior, ctx->nodes, offset, ctx->Q, eps, seed);
   MLBM_CUDA(cudaGetLastError());
   ctx->launches += 1;
   MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
@@ -1522,7 +1529,7 @@ int mlbm_device_distribution(mlbm_ctx* ctx, mlbm_device_layout* out) {
   out->component_stride = (size_t)ctx->stride;
   out->plane = (size_t)ctx->plane;
   out->row = (size_t)ctx->NR;
-  out->halo_x = 1;
+  out->halo_x = ctx->H;
   out->local_length[0] = ctx->LX;
   out->local_length[1] = ctx->D == 3 ? ctx->NM : ctx->NR;
   out->local_length[2] = ctx->D == 3 ? ctx->NR : 1;

@@ -451,10 +451,11 @@ struct NodeIndex {
   int xPrev, xh, xNext, mPrev, m, mNext, rPrev, r, rNext;
 };
 
+template <class L>
 __device__ __forceinline__ NodeIndex nodeIndex(const StepParams& p, int x, int m, int r) {
   // upstream coordinates: pull from (x - cx, m - cm, r - cr) of the periodic image
   NodeIndex n;
-  n.xh = x + 1;  // halo plane 0 precedes the interior
+  n.xh = x + L::H;  // L::H halo planes (one but for the multi-speed lattices) precede the interior
   n.xPrev = n.xh - 1;
   n.xNext = n.xh + 1;
   if (p.wrapX) {
@@ -480,12 +481,12 @@ template <class L, typename StoreT, bool STREAMING = false>
 __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeIndex& n, double (&f)[L::Q]) {
   const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
   if constexpr (L::H > 1) {
-    // multi-speed lattices (one GPU: x is periodic inside the slab, mlbm_create enforces it): every coordinate wraps by
-    // index arithmetic, whatever the length of the jump (Lattice.h:213-458, 706-803)
-    const int x = n.xh - 1;
+    // multi-speed lattices (Lattice.h:213-458, 706-803): m and r wrap by index arithmetic whatever the length of the jump;
+    // x wraps the same way on one rank and reaches into the L::H halo planes per side otherwise
+    const int x = n.xh - L::H;
 #pragma unroll
     for (int q = 0; q < L::Q; ++q) {
-      const int xs = L::cx(q) == 0 ? n.xh : wrapCoordinate(x - L::cx(q), p.LX) + 1;
+      const int xs = L::cx(q) == 0 ? n.xh : (p.wrapX ? wrapCoordinate(x - L::cx(q), p.LX) : x - L::cx(q)) + L::H;
       const int ms = L::cm(q) == 0 ? n.m : wrapCoordinate(n.m - L::cm(q), p.NM);
       const int rs = L::cr(q) == 0 ? n.r : wrapCoordinate(n.r - L::cr(q), p.NR);
       const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
@@ -728,7 +729,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       bool large = false;
       double rhoFast = 0.0, energyFast = 0.0, speed2Fast = 0.0;
       if (active) {
-        const NodeIndex n = nodeIndex(p, x, m, r);
+        const NodeIndex n = nodeIndex<L>(p, x, m, r);
         double f[Q];
         pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
         double invRhoFast, u2, uFast[3], forceFast[3];
@@ -737,7 +738,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
         EquilibriumCoefficients<L, EQ> eqFast;
         eqFast.set(uFast, u2);
         const long long node = rowNode + r;
-        const long long out = (long long)(x + 1) * p.plane + (long long)m * p.NR + r;
+        const long long out = (long long)(x + L::H) * p.plane + (long long)m * p.NR + r;
         StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
         StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
         alphaField[node] = (StoreT)2.0;
@@ -777,11 +778,11 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
     bool offShortcut = false;
 #endif
     if (active) {
-      const NodeIndex n = nodeIndex(p, x, m, r);
+      const NodeIndex n = nodeIndex<L>(p, x, m, r);
       double f[Q];
       pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
 #ifdef MLBM_PREFETCH_NEXT_PLANE
-      if (i + 1 < p.planesPerBlock && planeIndex + 1 < p.planeCount) prefetchPopulations<L, StoreT>(p, nodeIndex(p, x + p.planeStep, m, r));
+      if (i + 1 < p.planesPerBlock && planeIndex + 1 < p.planeCount) prefetchPopulations<L, StoreT>(p, nodeIndex<L>(p, x + p.planeStep, m, r));
 #endif
       double u2;
       moments<L>(f, rho, invRho, u, u2);
@@ -866,7 +867,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
 
     if (active) {
       const long long node = rowNode + r;
-      const long long out = (long long)(x + 1) * p.plane + (long long)m * p.NR + r;
+      const long long out = (long long)(x + L::H) * p.plane + (long long)m * p.NR + r;
       StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
       StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
       alphaField[node] = (StoreT)alpha;
@@ -908,7 +909,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
     const bool active = r < p.NR;
     double rho = 0.0, energy = 0.0, speed2 = 0.0;
     if (active) {
-      const NodeIndex n = nodeIndex(p, x, m, r);
+      const NodeIndex n = nodeIndex<L>(p, x, m, r);
       StoreT* __restrict__ next = static_cast<StoreT*>(p.next);
       double f[Q];
       pullPopulations<L, StoreT>(p, n, f);

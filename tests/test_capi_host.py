@@ -55,7 +55,7 @@ def test_create_rejects_bad_configurations(cuda_lib):
     bad = [capi.make_config("D3Q19", (8, 8, 8), equilibrium="Exact"),      # Exact exists for D2Q9 / D3Q27 only
            capi.make_config("D3Q19", (9, 8, 8), nranks=2),                 # numProcs must divide globalLengthX
            capi.make_config("D2Q9", (8, 8, 1), tau=0.5),
-           capi.make_config("D2Q13", (8, 8, 1), nranks=2),                 # multi-speed lattices: one GPU
+           capi.make_config("D2Q17", (4, 8, 1), nranks=2),                 # slabs of 2 planes under a halo of 3
            capi.make_config("D3Q33", (8, 8, 8), equilibrium="Exact"),
            capi.make_config("D3Q19", (8, 8, 8), force="ConstantShell"),    # the shell force is rebuilt for 2-D lattices only
            capi.make_config("D2Q9", (8, 8, 1), force="ConstantShell", k_min=3, k_max=2)]
@@ -89,6 +89,25 @@ def test_halo_plan_messages(cuda_lib, lattice, shape, face):
         assert m.peer == (0 if m.population <= face else 2)   # c_x < 0 travels left, c_x > 0 right
     plane = shape[1] * shape[2]
     assert all(m.count == plane for m in plan)
+
+
+@pytest.mark.parametrize("lattice,shape,face,halo", [("D2Q13", (8, 6, 1), 4, 2), ("D2Q21", (12, 6, 1), 7, 3), ("D3Q33", (8, 6, 4), 10, 2)])
+def test_halo_plan_of_the_multi_speed_lattices(cuda_lib, lattice, shape, face, halo):
+    """dimH planes per side travel together (Communication.h:145-150, sizeStripeX): the last H interior planes of the c_x > 0
+    populations to the right neighbour's planes 0..H-1, the first H interior planes of the c_x < 0 ones to the left neighbour's
+    planes LX+H..LX+2H-1; interior planes are H..LX+H-1 of a population."""
+    cfg = capi.make_config(lattice, shape, nranks=2, rank=1)
+    plan = capi.halo_plan(cfg)
+    lx, plane = shape[0] // 2, shape[1] * shape[2]
+    stride = capi.launch_plan(cfg, 0, lx).stride
+    assert stride >= plane * (lx + 2 * halo) and len(plan) == 4 * face and all(m.count == halo * plane for m in plan)
+    for m in plan:
+        first_plane = (m.offset - m.population * stride) // plane
+        right_going = m.population > face
+        if m.is_send:
+            assert first_plane == (lx if right_going else halo)
+        else:
+            assert first_plane == (0 if right_going else lx + halo)
 
 
 WORKER = r'''

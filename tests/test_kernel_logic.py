@@ -70,6 +70,7 @@ class Slab:
         self.plan = capi.launch_plan(cfg, 0, cfg.global_length[0] // cfg.nranks)
         self.lx, self.nm, self.nr = self.plan.local_length
         self.stride, self.plane = int(self.plan.stride), int(self.plan.plane)
+        self.halo = int(np.abs(O.lattice(int(cfg.lattice))[2]).max())     # dimH halo planes per side in x (context.cu: slabGeometry)
         self.nodes = self.lx * self.plane
         self.field_stride = (self.nodes + 31) // 32 * 32
         self.populations = [np.zeros(self.q * self.stride, dtype=dtype) for _ in range(2)]
@@ -112,17 +113,17 @@ class Slab:
 
     # -- upload / download of the interior planes (Algorithm::unpack / pack) --
     def view(self, which):
-        """[Q, LX + 2, NM, NR] window (no copy) onto buffer `which`: population q starts at q * stride."""
+        """[Q, LX + 2 H, NM, NR] window (no copy) onto buffer `which`: population q starts at q * stride."""
         item = self.populations[which].itemsize
         return np.lib.stride_tricks.as_strided(
-            self.populations[which], shape=(self.q, self.lx + 2, self.nm, self.nr),
+            self.populations[which], shape=(self.q, self.lx + 2 * self.halo, self.nm, self.nr),
             strides=(self.stride * item, self.plane * item, self.nr * item, item))
 
     def upload(self, f):
-        self.view(self.current)[:, 1:self.lx + 1] = f.reshape(self.q, self.lx, self.nm, self.nr)
+        self.view(self.current)[:, self.halo:self.lx + self.halo] = f.reshape(self.q, self.lx, self.nm, self.nr)
 
     def download(self):
-        return self.view(self.current)[:, 1:self.lx + 1].astype(np.float64).copy()
+        return self.view(self.current)[:, self.halo:self.lx + self.halo].astype(np.float64).copy()
 
     def set_force(self, field):
         """mlbm_set_force_field: [D, LX, NM, NR] into the dense force field, components field_stride apart."""

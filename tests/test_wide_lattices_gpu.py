@@ -11,6 +11,7 @@ from metalbm_b200.capi import make_config
 from oracle import oracle as O
 from test_cpp_shim import check_template_api
 from test_golden_gpu import check_cuda_against_golden
+from test_multi_gpu import _device_count, _run_ranks
 
 pytestmark = pytest.mark.gpu
 
@@ -64,3 +65,25 @@ def test_multi_speed_lattices_against_the_oracle(case):
 def test_template_api_on_multi_speed_lattices(tmp_path, cuda_lib, case):
     """latticeT = D2Q13 / D3Q33 through the reference's template spellings (one rank)."""
     check_template_api(tmp_path, 1, case)
+
+
+@pytest.mark.parametrize("overlap", ["On", "Off"])
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("lattice,shape,collision", [("D2Q13", (16, 12, 1), "BGK"), ("D2Q17", (24, 12, 1), "ELBM"), ("D3Q33", (16, 5, 4), "BGK")])
+def test_multi_speed_lattices_on_slabs(tmp_path, world, lattice, shape, collision, overlap):
+    """x-slabs with dimH halo planes per side, exchanged over NCCL before the step (Off) or overlapped with the bulk planes
+    (On: the first and last dimH planes first).  Bit-identical to the single-GPU run."""
+    if _device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    steps = 3
+    config = dict(lattice=lattice, shape=list(shape), collision=collision, forcing_scheme="Guo", force="Kolmogorov", tau=0.6,
+                  amplitude=[1e-4, 2e-4, 3e-4], wavelength=[8.0, 4.0, 16.0], overlap=overlap)
+    single = make_config(**config)
+    f0 = O.synthetic_populations(single, eps=1e-2)
+    got = _run_ranks(tmp_path, world, config, f0, steps, "sync", False)
+    one = run_cuda(single, f0, steps)
+    assert np.array_equal(got["f"], one["f"]) and np.array_equal(got["alpha"], one["alpha"])
+    ref = run_oracle(single, f0, steps)
+    if collision == "BGK":
+        assert relative_error(got["f"], ref.f) <= 1e-12 * steps
+    assert abs(got["observables"][0][0] - ref.observables()[0]) <= 1e-9 * abs(ref.observables()[0])
