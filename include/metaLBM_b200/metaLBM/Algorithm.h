@@ -85,6 +85,12 @@ class Algorithm {
   // B200 additions (not in the reference): on-line observables of the last stored step, reduced over ranks
   //   out = {total energy, total enstrophy, max Mach, total mass}   (AnalysisList.h:55-73 as device reductions)
   void getObservables(double out[4]) { LBM_B200_CALL(mlbm_observables(context, out)); }
+  //   energy / forcing spectra of the last stored step (SpectralAnalysisList, AnalysisList.h:132-170); returns the number of bins
+  int getPowerSpectra(double* energySpectrum, double* forcingSpectrum, int capacity) {
+    int count = 0;
+    LBM_B200_CALL(mlbm_power_spectra(context, energySpectrum, forcingSpectrum, capacity, &count));
+    return count;
+  }
   mlbm_ctx* getContext() { return context; }
 
  private:

@@ -10,6 +10,7 @@
 #pragma once
 
 #include <string>
+#include <vector>
 
 #include "Algorithm.h"
 #include "Writer.h"
@@ -53,6 +54,44 @@ class ScalarAnalysisList {
       extraAnalysisWriter.openFile(iteration);
       extraAnalysisWriter.template writeAnalysis<2>(iteration, extraList);
       extraAnalysisWriter.closeFile();
+    }
+  }
+};
+
+// `SpectralAnalysisList<T, architecture>` (AnalysisList.h:99-202): energy spectrum of the stored velocity and forcing
+// spectrum of the force array, appended by rank 0 to `../output/<prefix>/spectra_<startIteration>.dat`.  The reference runs
+// two in-place FFTW-MPI transforms per field on the host; here the device transforms of csrc/spectral.cu and a binning
+// kernel do the work (mlbm_power_spectra) and the fields are left untouched.
+template <class T, Architecture architecture>
+class SpectralAnalysisList {
+  using Algorithm_t = Algorithm<T, algorithmT, architecture, memoryL, partitionningT, communicationT, overlappingT>;
+  Algorithm_t& algorithm;
+  const unsigned int startIteration;
+
+ public:
+  SpectralAnalysisWriter_ spectralAnalysisWriter;
+  std::vector<double> energySpectra, forcingSpectra;   // gFD::maxWaveNumber() bins each (FourierDomain.h:77-79)
+
+  SpectralAnalysisList(Algorithm_t& algorithm_in, const unsigned int spectralAnalysisStep_in, const unsigned int startIteration_in)
+      : algorithm(algorithm_in), startIteration(startIteration_in),
+        spectralAnalysisWriter(prefix, "spectra", startIteration_in, spectralAnalysisStep_in) {
+    if (MPIInit::rank[d::X] == 0 && spectralAnalysisStep_in != 0)
+      spectralAnalysisWriter.writeHeader("iteration wavenumber energy_spectra forcing_spectra");   // AnalysisList.h:194-199
+  }
+
+  inline bool getIsAnalyzed(const unsigned int iteration) { return spectralAnalysisWriter.getIsAnalyzed(iteration); }
+
+  inline void writeAnalyses(const unsigned int iteration) {
+    const int bins = algorithm.getPowerSpectra(nullptr, nullptr, 0);
+    energySpectra.assign((size_t)bins, 0.0);
+    forcingSpectra.assign((size_t)bins, 0.0);
+    algorithm.getPowerSpectra(energySpectra.data(), forcingSpectra.data(), bins);
+    if (MPIInit::rank[d::X] == 0) {
+      std::vector<T> energy(energySpectra.begin(), energySpectra.end()), forcing(forcingSpectra.begin(), forcingSpectra.end());
+      T* spectraList[2] = {energy.data(), forcing.data()};   // AnalysisList.h:163-168
+      spectralAnalysisWriter.openFile(iteration);
+      spectralAnalysisWriter.template writeAnalysis<2>(iteration, (unsigned int)bins, spectraList);
+      spectralAnalysisWriter.closeFile();
     }
   }
 };

@@ -33,6 +33,7 @@ class Routine {
   Distribution<T, architecture> distribution;
   Algorithm_ algorithm;
   ScalarAnalysisList<T, architecture> scalarAnalysisList;
+  SpectralAnalysisList<T, architecture> spectralAnalysisList;   // Routine.h:52, 78-79
   double computationTime = 0, communicationTime = 0, totalTime = 0;
 
  public:
@@ -41,20 +42,24 @@ class Routine {
         fieldList(defaultStream),
         distribution(initDistribution<T, architecture>(fieldList.density, fieldList.velocity, defaultStream)),
         algorithm(fieldList, distribution, communication),
-        scalarAnalysisList(algorithm, scalarAnalysisStep, startIteration) {}
+        scalarAnalysisList(algorithm, scalarAnalysisStep, startIteration),
+        spectralAnalysisList(algorithm, spectralAnalysisStep, startIteration) {}
 
   FieldList<T, architecture>& getFieldList() { return fieldList; }
   Distribution<T, architecture>& getDistribution() { return distribution; }
   Algorithm_& getAlgorithm() { return algorithm; }
   ScalarAnalysisList<T, architecture>& getScalarAnalysisList() { return scalarAnalysisList; }
+  SpectralAnalysisList<T, architecture>& getSpectralAnalysisList() { return spectralAnalysisList; }
 
   void compute() {
     algorithm.unpack(defaultStream);
     const auto t0 = Clock::now();
     for (unsigned int iteration = startIteration + 1; iteration <= endIteration; ++iteration) {
-      algorithm.isStored = scalarAnalysisList.getIsAnalyzed(iteration) || b200::isMultiple(iteration, writeStep);
+      algorithm.isStored = scalarAnalysisList.getIsAnalyzed(iteration) || spectralAnalysisList.getIsAnalyzed(iteration) ||
+                           b200::isMultiple(iteration, writeStep);   // Routine.h:122-124
       algorithm.iterate(iteration, defaultStream, bulkStream, leftStream, rightStream, leftEvent, rightEvent);
       if (algorithm.isStored) scalarAnalysisList.writeAnalyses(iteration);
+      if (spectralAnalysisList.getIsAnalyzed(iteration)) spectralAnalysisList.writeAnalyses(iteration);   // Routine.h:227-229
       communicationTime += algorithm.getCommunicationTime();
       computationTime += algorithm.getComputationTime();
     }

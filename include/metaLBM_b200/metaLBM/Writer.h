@@ -100,4 +100,49 @@ class ScalarAnalysisWriter : public Writer<T, InputOutput::Generic, inputOutputF
 
 typedef ScalarAnalysisWriter<dataT, InputOutputFormat::ascii> ScalarAnalysisWriter_;
 
+// SpectralAnalysisWriter (Writer.h:193-251): `../output/<prefix>/spectra_<startIteration>.dat`, one line per wave number and
+// analysed iteration: "iteration wavenumber energy_spectra forcing_spectra " (the same trailing blank).
+template <class T, InputOutputFormat inputOutputFormat>
+class SpectralAnalysisWriter : public Writer<T, InputOutput::Generic, inputOutputFormat> {
+  static_assert(inputOutputFormat == InputOutputFormat::ascii, "metalbm_b200 writes the spectral analyses as ascii (Writer.h:564-565)");
+  using Base = Writer<T, InputOutput::Generic, inputOutputFormat>;
+  unsigned int startIteration;
+  unsigned int analysisStep;
+
+ public:
+  SpectralAnalysisWriter(const std::string& writerFolder_in, const std::string& filePrefix_in, const unsigned int startIteration_in,
+                         const unsigned int analysisStep_in)
+      : Base(writerFolder_in, filePrefix_in, ".dat"), startIteration(startIteration_in), analysisStep(analysisStep_in) {}
+
+  // the reference divides by analysisStep unguarded (Writer.h:211-213); 0 means "never" here
+  inline bool getIsAnalyzed(const unsigned int iteration) { return analysisStep != 0 && (iteration % analysisStep) == 0; }
+
+  inline std::string fileName() { return Base::getFileName("_" + std::to_string(startIteration)); }
+  inline void openFile(const unsigned int) { Base::openAndAppend(fileName()); }
+  inline void closeFile() { Base::file.close(); }
+
+  template <unsigned int NumberSpectralAnalyses>
+  void writeAnalysis(const unsigned int iteration, const unsigned int maxWaveNumber, T* data[NumberSpectralAnalyses]) {
+    for (unsigned int kNorm = 0; kNorm < maxWaveNumber; ++kNorm) {   // Writer.h:226-238
+      Base::write(iteration);
+      Base::file << " ";
+      Base::write(kNorm);
+      Base::file << " ";
+      for (unsigned int iS = 0; iS < NumberSpectralAnalyses; ++iS) {
+        Base::write(data[iS][kNorm]);
+        Base::file << " ";
+      }
+      Base::file << std::endl;
+    }
+  }
+
+  void writeHeader(const std::string& header) {
+    Base::openAndTruncate(fileName());
+    Base::file << header << std::endl;
+    closeFile();
+  }
+};
+
+typedef SpectralAnalysisWriter<dataT, InputOutputFormat::ascii> SpectralAnalysisWriter_;
+
 }  // namespace lbm

@@ -24,13 +24,13 @@ LIBDIR = Path(os.environ.get("MLBM_SHIM_LIBDIR", ROOT / "metalbm_b200"))   # tes
 
 def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equilibrium="TruncationMa3", scheme="Guo",
                     force="Kolmogorov", tau=0.55, nprocs=1, overlap="Off", link=True, input_file="Input_generic.in", steps=100,
-                    compile_only=False):
+                    compile_only=False, spectral_step=0):
     output = tmp_path / name
     command = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
                f"-DNPROCS={nprocs}", "-DNTHREADS=1", f"-DGLOBAL_LENGTH_X={shape[0]}", f"-DGLOBAL_LENGTH_Y={shape[1]}",
                f"-DGLOBAL_LENGTH_Z={shape[2]}", '-DLBM_POSTFIX="test"', f"-DLBM_LATTICE={lattice}", f"-DLBM_COLLISION={collision}",
                f"-DLBM_EQUILIBRIUM={equilibrium}", f"-DLBM_SCHEME={scheme}", f"-DLBM_FORCE={force}", f"-DLBM_TAU={tau}",
-               f"-DLBM_OVERLAP={overlap}", f"-DLBM_STEPS={steps}",
+               f"-DLBM_OVERLAP={overlap}", f"-DLBM_STEPS={steps}", f"-DLBM_SPECTRAL_STEP={spectral_step}",
                "-include", str(ROOT / "examples" / input_file), "-I", str(INCLUDE), str(ROOT / "examples" / source),
                "-o", str(output)]
     if compile_only:

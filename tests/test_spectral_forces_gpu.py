@@ -10,7 +10,7 @@ from golden_util import golden_names
 from helpers import check_entropic, force_field, native_shell_config, relative_error, run_cuda, run_oracle
 from metalbm_b200.capi import make_config
 from oracle import oracle as O
-from test_cpp_shim import SPECTRAL_SHIM_CASES, check_template_api
+from test_cpp_shim import SPECTRAL_SHIM_CASES, check_template_api, compile_example
 from test_golden_gpu import check_cuda_against_golden
 from test_multi_gpu import _device_count, _run_ranks
 from test_parity_gpu import ENERGY_TOLERANCE, POPULATION_TOLERANCE, _config, _flow
@@ -238,3 +238,35 @@ def test_spectral_forces_on_slabs(tmp_path, world, force, peer):
     ref = run_oracle(single, f0, steps)
     assert relative_error(got["f"], ref.f) <= 1e-12 * steps
     assert abs(got["observables"][0][0] - ref.observables()[0]) <= 1e-9 * abs(ref.observables()[0])
+
+
+def test_reference_style_routine_writes_the_spectra_table(tmp_path, cuda_lib):
+    """src/main.cu with Architecture::GPU and spectralAnalysisStep = 50: Routine::compute appends the energy / forcing spectra
+    to ../output/<prefix>/spectra_<startIteration>.dat (SpectralAnalysisList, AnalysisList.h:99-202; SpectralAnalysisWriter,
+    Writer.h:193-251: "iteration wavenumber energy_spectra forcing_spectra"), against the oracle's restatement."""
+    import subprocess
+    shape = (32, 24, 1)
+    binary = compile_example(tmp_path, "main_gpu.cpp", "main_gpu", "D2Q9", shape, scheme="Guo", force="Kolmogorov", tau=0.55,
+                             steps=100, spectral_step=50)
+    run = tmp_path / "run"
+    run.mkdir()
+    result = subprocess.run([str(binary)], capture_output=True, text=True, cwd=run, timeout=300)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    lines = (tmp_path / "output" / "test" / "spectra_0.dat").read_text().splitlines()
+    assert lines[0] == "iteration wavenumber energy_spectra forcing_spectra"
+    table = np.array([[float(v) for v in line.split()] for line in lines[1:]])
+    cfg = make_config(lattice="D2Q9", shape=shape, collision="BGK", forcing_scheme="Guo", force="Kolmogorov", tau=0.55,
+                      amplitude=(1e-4, 2e-4, 3e-4), wavelength=(8.0, 4.0, 16.0))
+    bins = O.max_wave_number(cfg)
+    assert table.shape == (2 * bins, 4) and all(line.endswith(" ") for line in lines[1:])
+    assert table[:, 0].tolist() == [50.0] * bins + [100.0] * bins and table[:bins, 1].tolist() == list(map(float, range(bins)))
+    density = np.ones(shape)
+    density[int((shape[0] - 1) * 0.4), int((shape[1] - 1) * 0.3), 0] = 3.0     # initDensity Peak (Initialize.h:30-46)
+    state = O.OracleState(cfg, O.init_equilibrium(cfg, density, np.zeros((2,) + shape)))
+    for iteration in range(1, 101):
+        state.step(iteration % 50 == 0)
+        if iteration % 50 == 0:
+            want = O.power_spectra(cfg, state.velocity, state.force)
+            got = table[(iteration // 50 - 1) * bins:(iteration // 50) * bins, 2:]
+            assert np.abs(got - want).max(axis=0)[0] <= 1e-9 * np.abs(want[:, 0]).max()
+            assert np.abs(got - want).max(axis=0)[1] <= 1e-9 * np.abs(want[:, 1]).max()
