@@ -127,21 +127,18 @@ _TWO_RANKS = """
 """
 
 
-def _torchrun(mode: str, timeout_s: int, port: int) -> subprocess.CompletedProcess:
+def _torchrun(mode: str, timeout_s: int, port: int, tmp_path: Path) -> subprocess.CompletedProcess:
     script = "import sys\nsys.path.insert(0, %r)\nimport bench\n" % str(ROOT) + textwrap.dedent(_TWO_RANKS)
-    path = ROOT / "tests" / "_bench_two_ranks_tmp.py"
+    path = tmp_path / "bench_two_ranks.py"
     path.write_text(script)
-    try:
-        return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                               "--master-addr", "127.0.0.1", "--master-port", str(port), str(path)],
-                              capture_output=True, text=True, timeout=180,
-                              env={**os.environ, "MODE": mode, "TIMEOUT": str(timeout_s), "OMP_NUM_THREADS": "1"})
-    finally:
-        path.unlink(missing_ok=True)
+    return subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                           "--master-addr", "127.0.0.1", "--master-port", str(port), str(path)],
+                          capture_output=True, text=True, timeout=180,
+                          env={**os.environ, "MODE": mode, "TIMEOUT": str(timeout_s), "OMP_NUM_THREADS": "1"})
 
 
-def test_two_ranks_stay_in_step_after_symmetric_and_one_sided_failures():
-    proc = _torchrun("ok,symmetric-failure,one-rank-fails,ok", 60, 29611)
+def test_two_ranks_stay_in_step_after_symmetric_and_one_sided_failures(tmp_path):
+    proc = _torchrun("ok,symmetric-failure,one-rank-fails,ok", 60, 29611, tmp_path)
     assert proc.returncode == 0, proc.stderr[-3000:]
     line = _only_line(proc.stdout)
     also = line["also"]
@@ -153,8 +150,8 @@ def test_two_ranks_stay_in_step_after_symmetric_and_one_sided_failures():
 
 
 @pytest.mark.timeout(240)
-def test_two_ranks_a_lost_rank_ends_in_the_watchdog_with_exit_code_zero():
-    proc = _torchrun("ok,rank1-dies,ok", 8, 29612)
+def test_two_ranks_a_lost_rank_ends_in_the_watchdog_with_exit_code_zero(tmp_path):
+    proc = _torchrun("ok,rank1-dies,ok", 8, 29612, tmp_path)
     # rank 0 is stuck in the workload's collective (or sees it fail): either way the line is out, once, and torchrun is happy
     assert proc.returncode == 0, proc.stderr[-3000:]
     line = _only_line(proc.stdout)
