@@ -15,6 +15,11 @@ The sources are taken from ``metalbm_b200/csrc`` at build time.  Edits, all mech
 ``cuda_runtime.h``, ``nccl.h`` and ``cufft.h`` resolve to the stand-ins under ``tests/emu/include``: device memory is host
 memory (poisoned at allocation), streams run immediately, there is one device and one rank.  Nothing under
 ``metalbm_b200/`` can reach this library; it says nothing about hardware behaviour or speed.
+
+Variants: ``MLBM_EMULATED_FLAGS="-DMLBM_ELBM_FASTPATH -DMLBM_PREFETCH_NEXT_PLANE"`` builds the experimental kernels;
+``MLBM_EMULATED_FLAGS="-fsanitize=address -DMLBM_EMU_ASAN" LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+ASAN_OPTIONS=detect_leaks=0 MLBM_EMULATED=1 MLBM_EMULATED_RANKS=1 pytest tests -m gpu`` runs the single-rank suites with
+"device" allocations on the sanitised heap, so that an index error of a kernel or of the host code lands in a red zone.
 """
 from __future__ import annotations
 
@@ -124,7 +129,7 @@ def transform(name: str) -> str:
 def build(flags: tuple = ()) -> Path:
     """``flags``: extra -D switches (the experimental kernel variants); every set of flags is its own library."""
     global BUILD, LIBRARY
-    suffix = "".join("_" + f.lstrip("-D").lower() for f in flags)
+    suffix = "".join("_" + re.sub(r"[^a-z0-9]+", "", f.lower()) for f in flags)
     BUILD = HERE / "_build" / ("context" + suffix)
     LIBRARY = HERE / "_build" / ("libmetalbm_emu" + suffix + ".so")
     BUILD.mkdir(parents=True, exist_ok=True)
@@ -150,7 +155,8 @@ def build(flags: tuple = ()) -> Path:
     with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
         objects = list(pool.map(compile_one, sources))
     # -Bsymbolic: the tests load libmetalbm_b200.so as well, with the very same exported names
-    cmd = ["g++", "-shared", "-Wl,-Bsymbolic", "-o", str(LIBRARY), *map(str, objects), "-ldl", "-lrt", "-pthread"]
+    cmd = ["g++", "-shared", "-Wl,-Bsymbolic", *[f for f in flags if f.startswith("-fsanitize")], "-o", str(LIBRARY), *map(str, objects),
+           "-ldl", "-lrt", "-pthread"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("emulated link failed:\n" + proc.stderr[-4000:])

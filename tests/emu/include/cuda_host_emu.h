@@ -53,6 +53,13 @@ inline void* mapSegment(const char* name, size_t bytes, bool create) {
 
 namespace cuda_emu {
 inline void* allocate(size_t bytes) {
+#ifdef MLBM_EMU_ASAN
+  // AddressSanitizer build (MLBM_EMULATED_FLAGS="-fsanitize=address -DMLBM_EMU_ASAN"): plain heap blocks, so that an index
+  // error of a kernel or of the host code lands in a red zone (single-rank runs only: nothing can be mapped by a peer)
+  void* heap = std::malloc(bytes ? bytes : 1);
+  if (heap) { std::memset(heap, 0xFF, bytes); allocations()[heap] = Allocation{"", bytes ? bytes : 1}; }
+  return heap;
+#endif
   static int counter = 0;
   char name[64];
   std::snprintf(name, sizeof(name), "/mlbm_emu_mem_%d_%d", (int)getpid(), counter++);
@@ -76,8 +83,12 @@ inline cudaError_t cudaFree(void* pointer) {
   if (!pointer) return cudaSuccess;
   auto found = cuda_emu::allocations().find(pointer);
   if (found == cuda_emu::allocations().end()) return cudaErrorInvalidValue;
+#ifdef MLBM_EMU_ASAN
+  std::free(pointer);
+#else
   munmap(pointer, found->second.bytes);
   shm_unlink(found->second.name.c_str());
+#endif
   cuda_emu::allocations().erase(found);
   return cudaSuccess;
 }
