@@ -64,3 +64,47 @@ def test_multi_rank_sample_passes_on_the_emulated_library(cuda_lib):
     tail = result.stdout[-3000:] + result.stderr[-1500:]
     assert result.returncode == 0, tail
     assert re.search(rf"{len(MULTI_RANK_SAMPLE)} passed", result.stdout), tail
+
+
+def test_bench_runs_end_to_end_on_the_emulated_library(monkeypatch, capsys, cuda_lib):
+    """bench.run_ours -- headline, per-launch kernel timing, the host-buffer e2e leg, the secondary workloads -- with the real
+    Algorithm class over the emulated library on an 8^3 cube (torch.cuda's device calls faked away): every C-ABI call the
+    bench makes exists and behaves; one complete JSON line comes out."""
+    import json
+    import types
+
+    import torch
+
+    sys.path.insert(0, str(ROOT / "tests" / "emu"))
+    import build_context
+    from metalbm_b200 import capi
+    import bench
+    monkeypatch.setattr(capi, "_library", capi.load_library(build_context.build()))
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "mem_get_info", lambda *a: (10 ** 11, 10 ** 11))
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{key: v for key, v in k.items() if key not in ("pin_memory", "device")}))
+    monkeypatch.setattr(bench, "cpu_baseline_leg", lambda: {"value": 50.0, "unit": "MLUPS", "cores": 4, "kind": "reference", "sample": "fake"})
+    monkeypatch.setattr(bench, "EDGE", 8)
+    for name, work in bench.WORKLOADS.items():
+        monkeypatch.setitem(work, "shape", (8, 8, 8) if work["shape"][2] > 1 else (16, 12, 1))
+        if work["store_every"]:
+            monkeypatch.setitem(work, "store_every", 2)
+    monkeypatch.setattr(bench, "ALSO_SINGLE", [(n, d, e, m, 3) for n, d, e, m, _ in bench.ALSO_SINGLE])
+    args = types.SimpleNamespace(gpus=1, steps=4, warmup=3, impl="ours", edge=8, variant=0, workload="d3q19_bgk_256", dtype="f64",
+                                 overlap="On", halo="peer", eps=None, store_every=None, no_e2e=False, no_cpu_baseline=False,
+                                 also="auto", also_timeout=600)
+    assert bench.run_ours(args) == 0
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["value"] > 0 and line["gpu_launches"] >= 4 and line["roofline"]["kernel_launches_timed"] == 4
+    assert line["e2e"]["value"] > 0 and "error" not in line["e2e"] and line["e2e"]["last_energy"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] == 19 * 8 ** 3 * 8 / 4
+    assert [e["name"] for e in line["also"]] == [e[0] for e in bench.ALSO_SINGLE]
+    for entry in line["also"]:
+        assert "error" not in entry and "skipped" not in entry and entry["value"] > 0, entry
+        assert abs(entry["mass_per_node"] - 1.0) < 1e-3, entry
+    entropic = [e for e in line["also"] if "elbm" in e["name"]]
+    assert entropic and all(0.0 <= e["alpha_off_shortcut_fraction_at_end"] <= 1.0 for e in entropic)
