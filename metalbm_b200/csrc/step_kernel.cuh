@@ -167,7 +167,8 @@ template <int I, int N, class F> __device__ __forceinline__ void staticFor(F&& f
 // N independent arguments advance in lock step: every Horner step is issued for all N before the next one, which
 // gives the FP64 pipe N independent dependency chains per warp.
 // `range` accumulates the maximum table index as an unsigned number: it stays below 512 exactly when every argument
-// was inside [0.25, 4) (smaller, negative, infinite and NaN arguments all map to indices >= 512).
+// was inside [0.25, 4) (smaller, negative, infinite and NaN arguments all map to indices >= 512: the high word minus that
+// of 0.25, in unsigned arithmetic, is either below 2^22 -- the table -- or at least 2^30).
 // ------------------------------------------------------------------------------------------------
 constexpr int kLogTableEntries = 512;
 static __device__ const double2 kLogTable[kLogTableEntries] = {
@@ -181,7 +182,7 @@ __device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[
   double r[N], p[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    const unsigned index = (unsigned)((__double2hiint(v[j]) - 0x3FD00000) >> 13);
+    const unsigned index = ((unsigned)__double2hiint(v[j]) - 0x3FD00000u) >> 13;  // unsigned: negative arguments wrap, they do not overflow
     range = max(range, index);
     entry[j] = table[index & (kLogTableEntries - 1)];
   }
