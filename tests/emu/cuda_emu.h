@@ -138,6 +138,26 @@ inline void fiberEntry() {
   swapcontext(&s.fibers[s.current].context, &s.scheduler);
 }
 
+inline unsigned scheduleOrder(unsigned slot, unsigned block) {
+  static const int mode = [] {
+    const char* e = std::getenv("MLBM_EMU_SCHEDULE");
+    return !e ? 0 : (std::strcmp(e, "reverse") == 0 ? 1 : (std::strcmp(e, "random") == 0 ? 2 : 0));
+  }();
+  if (mode == 1) return block - 1 - slot;
+  if (mode == 2) {  // a fresh pseudo-random rotation + stride per round (coprime stride: a permutation)
+    static unsigned long long state = 0x9E3779B97F4A7C15ull;
+    static unsigned offset = 0, stride = 1, lastBlock = 0;
+    if (slot == 0 || lastBlock != block) {
+      state = state * 6364136223846793005ull + 1442695040888963407ull;
+      offset = (unsigned)(state >> 33) % block;
+      do { state = state * 6364136223846793005ull + 1442695040888963407ull; stride = (unsigned)(state >> 33) % block; } while (stride == 0 || std::__gcd(stride, block) != 1);
+      lastBlock = block;
+    }
+    return (offset + slot * stride) % block;
+  }
+  return slot;
+}
+
 // one block after the other; every thread of a block is a fiber
 inline void runGrid(dim3 grid, unsigned block, size_t sharedBytes) {
   State& s = state();
@@ -167,7 +187,10 @@ inline void runGrid(dim3 grid, unsigned block, size_t sharedBytes) {
         while (remaining > 0) {
           const unsigned long long before = s.progress;
           remaining = 0;
-          for (unsigned t = 0; t < block; ++t) {
+          for (unsigned slot = 0; slot < block; ++slot) {
+            // MLBM_EMU_SCHEDULE=reverse|random: other legal interleavings of the block's threads -- a kernel that misses a
+            // barrier computes something else under them (a poor man's race detector)
+            const unsigned t = scheduleOrder(slot, block);
             Fiber& f = s.fibers[t];
             if (f.done) continue;
             s.current = (int)t;
