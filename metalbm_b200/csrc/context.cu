@@ -13,11 +13,7 @@
 #include <string>
 #include <vector>
 
-#include "../../include/metalbm_b200.h"
-#include "nccl_loader.h"
-#include "shell_force.h"
-#include "spectral.h"
-#include "step_kernel.cuh"
+#include "context.h"
 
 namespace mlbm {
 
@@ -56,37 +52,6 @@ StepKernel lookupStepKernel(int lattice, int collision, int equilibrium, int sch
   }
 }
 
-const NcclApi* loadNccl(const char** error) {
-  static NcclApi api;
-  static bool tried = false, ok = false;
-  static std::string message;
-  if (!tried) {
-    tried = true;
-    void* handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!handle) handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!handle) {
-      message = std::string("cannot load libnccl: ") + dlerror();
-    } else {
-      ok = true;
-      auto resolve = [&](const char* name) -> void* {
-        void* symbol = dlsym(handle, name);
-        if (!symbol) { ok = false; message = std::string("libnccl lacks ") + name; }
-        return symbol;
-      };
-      api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(resolve("ncclGetUniqueId"));
-      api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(resolve("ncclCommInitRank"));
-      api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(resolve("ncclCommDestroy"));
-      api.Send = reinterpret_cast<decltype(api.Send)>(resolve("ncclSend"));
-      api.Recv = reinterpret_cast<decltype(api.Recv)>(resolve("ncclRecv"));
-      api.GroupStart = reinterpret_cast<decltype(api.GroupStart)>(resolve("ncclGroupStart"));
-      api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(resolve("ncclGroupEnd"));
-      api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(resolve("ncclAllReduce"));
-      api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(resolve("ncclGetErrorString"));
-    }
-  }
-  if (!ok) { if (error) *error = message.c_str(); return nullptr; }
-  return &api;
-}
 
 // ------------------------------------------------------------------------------------------------
 // small device kernels around the fused step
@@ -94,7 +59,6 @@ const NcclApi* loadNccl(const char** error) {
 
 // Deterministic reduction of the per-block partials written by the fused kernel on stored steps: every block sums a
 // fixed contiguous share into `stage`, the block that finishes last (atomic ticket) adds the shares in index order.
-constexpr int kReduceBlocks = 296;  // two per SM
 constexpr int kReduceThreads = 256;
 
 __global__ void __launch_bounds__(kReduceThreads)
@@ -196,30 +160,6 @@ __global__ void addPaddingKernel(const StoreT* __restrict__ dense, StoreT* __res
   padded[j] = r < NR ? dense[row * NR + r] : (StoreT)0;   // the padding values arrive as zeros (they are scratch: Domain.h:53-57)
 }
 
-// one block: count of alpha != 2, min and max of the alpha field (a diagnostic, not on the step path)
-template <typename StoreT>
-__global__ void __launch_bounds__(256) alphaStatisticsKernel(const StoreT* __restrict__ alpha, long long nodes, double* __restrict__ out) {
-  __shared__ double scratch[3][256];
-  double count = 0.0, low = 1e300, high = -1e300;
-  for (long long i = threadIdx.x; i < nodes; i += blockDim.x) {
-    const double a = (double)alpha[i];
-    count += a != 2.0 ? 1.0 : 0.0;
-    low = fmin(low, a);
-    high = fmax(high, a);
-  }
-  scratch[0][threadIdx.x] = count; scratch[1][threadIdx.x] = low; scratch[2][threadIdx.x] = high;
-  __syncthreads();
-  for (int width = 128; width > 0; width >>= 1) {
-    if ((int)threadIdx.x < width) {
-      scratch[0][threadIdx.x] += scratch[0][threadIdx.x + width];
-      scratch[1][threadIdx.x] = fmin(scratch[1][threadIdx.x], scratch[1][threadIdx.x + width]);
-      scratch[2][threadIdx.x] = fmax(scratch[2][threadIdx.x], scratch[2][threadIdx.x + width]);
-    }
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) { out[0] = scratch[0][0]; out[1] = -scratch[1][0]; out[2] = scratch[2][0]; }   // -min: reduced with max over ranks
-}
-
 template <typename StoreT> __global__ void fillKernel(StoreT* data, long long count, StoreT value) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) data[i] = value;
@@ -308,13 +248,6 @@ __global__ void perturbKernel(StoreT* __restrict__ populations, long long stride
   }
 }
 
-__global__ void fastLogKernel(const double* __restrict__ in, double* __restrict__ out, long long count) {
-  __shared__ double2 table[kLogTableEntries];
-  for (int i = threadIdx.x; i < kLogTableEntries; i += blockDim.x) table[i] = kLogTable[i];
-  __syncthreads();
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = fastLog(in[i], table);
-}
 
 template <int EQ, typename StoreT>
 static void launchInitEquilibrium(int lattice, cudaStream_t stream, StoreT* populations, const StoreT* density,
@@ -371,11 +304,13 @@ static void launchInitSynthetic(int lattice, cudaStream_t stream, StoreT* popula
 using namespace mlbm;
 
 // ------------------------------------------------------------------------------------------------
-// error plumbing
+// error plumbing and slab geometry (declared in context.h)
 // ------------------------------------------------------------------------------------------------
 static thread_local std::string g_lastError;
 
-static int fail(int status, const char* format, ...) {
+namespace mlbm {
+
+int fail(int status, const char* format, ...) {
   char buffer[1024];
   va_list arguments;
   va_start(arguments, format);
@@ -385,114 +320,9 @@ static int fail(int status, const char* format, ...) {
   return status;
 }
 
-#define MLBM_CUDA(call)                                                                                  \
-  do {                                                                                                   \
-    cudaError_t error_ = (call);                                                                         \
-    if (error_ != cudaSuccess)                                                                           \
-      return fail(error_ == cudaErrorMemoryAllocation ? MLBM_ERR_NOMEM : MLBM_ERR_CUDA, "[%s:%d] CUDA failed with %s", \
-                  __FILE__, __LINE__, cudaGetErrorString(error_));                                       \
-  } while (0)
+const char* lastError() { return g_lastError.c_str(); }
 
-#define MLBM_NCCL(ctx, call)                                                                             \
-  do {                                                                                                   \
-    ncclResult_t result_ = (call);                                                                       \
-    if (result_ != ncclSuccess)                                                                          \
-      return fail(MLBM_ERR_COMM, "[%s:%d] NCCL failed with %s", __FILE__, __LINE__,                      \
-                  (ctx)->nccl->GetErrorString(result_));                                                 \
-  } while (0)
-
-// ------------------------------------------------------------------------------------------------
-// the context
-// ------------------------------------------------------------------------------------------------
-struct mlbm_ctx {
-  mlbm_config config;
-  int device = 0;
-  int D = 0, Q = 0, faceQ = 0;
-  int LX = 0, NM = 0, NR = 0;           // local extents on the kernel axes (x, m, r)
-  size_t elementSize = 8;
-  long long plane = 0, stride = 0, fieldStride = 0, nodes = 0;
-  int H = 1;                            // halo planes per side in x
-  long long interior = 0;               // elements from the start of a population to its first interior plane (H * plane)
-  long long partialBlocks = 0;
-  int gridR = 0;
-
-  void* populations[2] = {nullptr, nullptr};  // ping-pong SoA pair (Distribution.h:19-20)
-  int current = 0;                             // buffer the next step reads ("previous")
-  void* alpha = nullptr;
-  void* density = nullptr;
-  void* velocity = nullptr;
-  void* force = nullptr;
-  bool fieldsStored = false;
-  double* partials = nullptr;
-  unsigned char* hints = nullptr;        // entropic contexts: one byte per block and plane (StepParams::hints)
-  void* staging = nullptr;               // staged pack / unpack: one padded population block
-  size_t stagingBytes = 0;
-  double* reduceStage = nullptr;         // [kReduceBlocks][kObservableSlots] second-stage partials
-  unsigned* reduceTicket = nullptr;
-  double* deviceObservables = nullptr;   // [energy sum, mass, max speed^2, enstrophy sum]
-  SpectralEnstrophy* spectral = nullptr; // created on the first step that stores the fields
-  ShellForce* shell = nullptr;           // ConstantShell / EnergyRemoval / Turbulent2D (2-D): maker of the force field
-  bool forceStale = false;               // the fields changed since the force field was made (Force::update is due)
-  bool enstrophyValid = false;           // the last stored step stored the velocity field (bit 0 of isStored)
-  double* forceTables[3] = {nullptr, nullptr, nullptr};
-  int forceAxis[3] = {-1, -1, -1};
-  bool observablesValid = false;
-
-  StepKernel kernel = nullptr;
-  int sharedBytes = 0;  // dynamic shared memory of the fused kernel (entropic kernels stage f / fNeq there)
-  int hydroShift = 0;
-  cudaStream_t computeStream = nullptr;
-  cudaStream_t commStream = nullptr;
-  cudaEvent_t boundaryDone = nullptr, exchangeDone = nullptr, bulkDone = nullptr;
-  cudaEvent_t timeStart = nullptr, timeMid = nullptr, timeStop = nullptr;
-  cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  double lastCommunication = 0.0, lastComputation = 0.0;
-  unsigned long long launches = 0;
-
-  // per-launch timing of the fused kernel (mlbm_kernel_time)
-  bool profiling = false;
-  std::vector<cudaEvent_t> profileEvents;
-  size_t profileUsed = 0;
-  double profileMs = 0.0;
-  unsigned long long profileLaunches = 0;
-
-  const NcclApi* nccl = nullptr;
-  ncclComm_t comm = nullptr;
-  // direct peer halos (mlbm_comm_peer_export / _attach)
-  unsigned long long* peerFlags = nullptr;       // this rank's two handshake words (+ padding), written by the neighbours
-  int* peerTimedOut = nullptr;
-  void* mapped[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [left, right][populations 0, 1, flags]
-  bool mappedOwned[2] = {false, false};          // right shares left's mapping when both are the same rank
-  bool peerAttached = false;
-  unsigned long long peerEpoch = 0;
-  cudaEvent_t stepStart = nullptr;
-  bool halosValid = false;  // halo planes of populations[current] hold the neighbours' data
-  std::vector<mlbm_halo_message> haloMessages;
-};
-
-static inline void* offsetElements(void* base, long long elements, size_t elementSize) {
-  return static_cast<char*>(base) + elements * (long long)elementSize;
-}
-
-static int collectProfile(mlbm_ctx* ctx) {
-  for (size_t i = 0; i + 1 < ctx->profileUsed; i += 2) {
-    float ms = 0.f;
-    MLBM_CUDA(cudaEventElapsedTime(&ms, ctx->profileEvents[i], ctx->profileEvents[i + 1]));
-    ctx->profileMs += ms;
-    ctx->profileLaunches += 1;
-  }
-  ctx->profileUsed = 0;
-  return MLBM_OK;
-}
-
-// geometry shared by the context and the (device-free) halo plan
-struct SlabGeometry {
-  int D, Q, faceQ, LX, NM, NR;
-  int H;                 // halo planes per side in x (Lattice dimH: 1 but for the multi-speed lattices)
-  long long plane, stride;
-};
-
-static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
+bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
   g->Q = latticeQ(config->lattice);
   if (!g->Q || config->nranks < 1 || config->global_length[0] % config->nranks) return false;
   g->H = latticeHalo(config->lattice);
@@ -506,6 +336,22 @@ static bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
   const long long perPopulation = g->plane * (g->LX + 2 * g->H);
   g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
   return true;
+}
+
+}  // namespace mlbm
+
+// ------------------------------------------------------------------------------------------------
+// launches of the fused kernel and the per-step orchestration
+// ------------------------------------------------------------------------------------------------
+static int collectProfile(mlbm_ctx* ctx) {
+  for (size_t i = 0; i + 1 < ctx->profileUsed; i += 2) {
+    float ms = 0.f;
+    MLBM_CUDA(cudaEventElapsedTime(&ms, ctx->profileEvents[i], ctx->profileEvents[i + 1]));
+    ctx->profileMs += ms;
+    ctx->profileLaunches += 1;
+  }
+  ctx->profileUsed = 0;
+  return MLBM_OK;
 }
 
 // Everything of a launch that does not depend on device memory: the scalar kernel parameters and the grid.  Shared by
@@ -594,53 +440,6 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
   ctx->kernel<<<grid, kStepBlock, ctx->sharedBytes, stream>>>(p);
   if (profile) MLBM_CUDA(cudaEventRecord(stop, stream));
   MLBM_CUDA(cudaGetLastError());
-  ctx->launches += 1;
-  return MLBM_OK;
-}
-
-// Communication::communicateHalos (Communication.h:494-500) as a list of messages: the last interior plane of
-// the c_x > 0 populations goes to the right neighbour's plane 0, the first interior plane of the c_x < 0
-// populations to the left neighbour's plane LX+1 (Communication.h:134-180).
-static int haloPlan(const mlbm_config* config, std::vector<mlbm_halo_message>* plan) {
-  SlabGeometry g;
-  if (!slabGeometry(config, &g)) return MLBM_ERR_INVALID;
-  plan->clear();
-  if (config->nranks == 1) return MLBM_OK;
-  const int left = (config->rank + config->nranks - 1) % config->nranks;  // MPIInitializer.h:56
-  const int right = (config->rank + 1) % config->nranks;                  // MPIInitializer.h:57
-  auto add = [&](int q, int peer, int isSend, long long xPlane) {
-    mlbm_halo_message message;
-    message.population = q;
-    message.peer = peer;
-    message.is_send = isSend;
-    message.reserved = 0;
-    message.offset = (uint64_t)(q * g.stride + xPlane * g.plane);
-    message.count = (uint64_t)(g.H * g.plane);   // dimH adjacent planes travel together (Communication.h:145-150: sizeStripeX)
-    plan->push_back(message);
-  };
-  for (int q = g.faceQ + 1; q < 2 * g.faceQ + 1; ++q) {
-    add(q, right, 1, g.LX);  // last H interior planes (interior planes are H .. LX + H - 1)
-    add(q, left, 0, 0);      // left halo planes
-  }
-  for (int q = 1; q < g.faceQ + 1; ++q) {
-    add(q, left, 1, g.H);          // first H interior planes
-    add(q, right, 0, g.LX + g.H);  // right halo planes
-  }
-  return MLBM_OK;
-}
-
-static int exchangeHalos(mlbm_ctx* ctx, int which, cudaStream_t stream) {
-  if (ctx->config.nranks == 1) return MLBM_OK;
-  if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
-  const ncclDataType_t type = ctx->config.dtype == MLBM_F64 ? ncclDouble : ncclFloat;
-  void* base = ctx->populations[which];
-  MLBM_NCCL(ctx, ctx->nccl->GroupStart());
-  for (const mlbm_halo_message& message : ctx->haloMessages) {
-    void* pointer = offsetElements(base, (long long)message.offset, ctx->elementSize);
-    if (message.is_send) MLBM_NCCL(ctx, ctx->nccl->Send(pointer, message.count, type, message.peer, ctx->comm, stream));
-    else MLBM_NCCL(ctx, ctx->nccl->Recv(pointer, message.count, type, message.peer, ctx->comm, stream));
-  }
-  MLBM_NCCL(ctx, ctx->nccl->GroupEnd());
   ctx->launches += 1;
   return MLBM_OK;
 }
@@ -969,17 +768,6 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   return MLBM_OK;
 }
 
-int mlbm_halo_plan(const mlbm_config* config, mlbm_halo_message* out, int capacity, int* count) {
-  if (!config || !count) return fail(MLBM_ERR_INVALID, "null argument");
-  std::vector<mlbm_halo_message> plan;
-  if (haloPlan(config, &plan)) return fail(MLBM_ERR_INVALID, "bad lattice or nranks does not divide globalLengthX");
-  *count = (int)plan.size();
-  if (out) {
-    if (capacity < (int)plan.size()) return fail(MLBM_ERR_INVALID, "capacity %d < %d messages", capacity, (int)plan.size());
-    memcpy(out, plan.data(), plan.size() * sizeof(mlbm_halo_message));
-  }
-  return MLBM_OK;
-}
 
 int mlbm_launch_plan_for(const mlbm_config* config, int x0, int x1, int isStored, int planeStep, mlbm_launch_plan* out) {
   if (!config || !out) return fail(MLBM_ERR_INVALID, "null argument");
@@ -1004,115 +792,6 @@ int mlbm_launch_plan_for(const mlbm_config* config, int x0, int x1, int isStored
   out->wrap_x = p.wrapX; out->is_stored = p.isStored; out->hydro_shift = p.hydroShift; out->has_force = p.hasForce;
   out->stride = (uint64_t)p.stride; out->plane = (uint64_t)p.plane;
   out->beta = p.beta; out->guo_factor = p.guoFactor;
-  return MLBM_OK;
-}
-
-int mlbm_comm_unique_id(void* id128) {
-  if (!id128) return fail(MLBM_ERR_INVALID, "null argument");
-  const char* error = nullptr;
-  const NcclApi* api = loadNccl(&error);
-  if (!api) return fail(MLBM_ERR_COMM, "%s", error);
-  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
-  ncclUniqueId id;
-  ncclResult_t result = api->GetUniqueId(&id);
-  if (result != ncclSuccess) return fail(MLBM_ERR_COMM, "ncclGetUniqueId: %s", api->GetErrorString(result));
-  memcpy(id128, &id, sizeof(id));
-  return MLBM_OK;
-}
-
-int mlbm_comm_init(mlbm_ctx* ctx, const void* id128) {
-  if (!ctx || !id128) return fail(MLBM_ERR_INVALID, "null argument");
-  if (ctx->comm) return fail(MLBM_ERR_STATE, "communicator already initialised");
-  const char* error = nullptr;
-  ctx->nccl = loadNccl(&error);
-  if (!ctx->nccl) return fail(MLBM_ERR_COMM, "%s", error);
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  ncclUniqueId id;
-  memcpy(&id, id128, sizeof(id));
-  MLBM_NCCL(ctx, ctx->nccl->CommInitRank(&ctx->comm, ctx->config.nranks, id, ctx->config.rank));
-  return MLBM_OK;
-}
-
-// ---- direct peer halos ---------------------------------------------------------------------------
-struct PeerBlob {  // MLBM_PEER_HANDLE_BYTES = 256
-  cudaIpcMemHandle_t populations[2];
-  cudaIpcMemHandle_t flags;
-  uint64_t bufferBytes;
-  int32_t rank, device;
-  int64_t process;
-  char padding[256 - 3 * sizeof(cudaIpcMemHandle_t) - 8 - 8 - 8];
-};
-static_assert(sizeof(PeerBlob) == MLBM_PEER_HANDLE_BYTES, "peer handle blob size");
-
-int mlbm_comm_peer_export(mlbm_ctx* ctx, void* handle) {
-  if (!ctx || !handle) return fail(MLBM_ERR_INVALID, "null argument");
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  if (!ctx->peerFlags) {
-    MLBM_CUDA(cudaMalloc(&ctx->peerFlags, 256));
-    MLBM_CUDA(cudaMemset(ctx->peerFlags, 0, 256));
-    MLBM_CUDA(cudaHostAlloc(&ctx->peerTimedOut, sizeof(int), cudaHostAllocMapped));
-    *ctx->peerTimedOut = 0;
-  }
-  PeerBlob blob;
-  memset(&blob, 0, sizeof(blob));
-  for (int i = 0; i < 2; ++i) {
-    cudaError_t error = cudaIpcGetMemHandle(&blob.populations[i], ctx->populations[i]);
-    if (error != cudaSuccess) return fail(MLBM_ERR_COMM, "cudaIpcGetMemHandle: %s", cudaGetErrorString(error));
-  }
-  cudaError_t error = cudaIpcGetMemHandle(&blob.flags, ctx->peerFlags);
-  if (error != cudaSuccess) return fail(MLBM_ERR_COMM, "cudaIpcGetMemHandle: %s", cudaGetErrorString(error));
-  blob.bufferBytes = (uint64_t)ctx->stride * ctx->Q * ctx->elementSize;
-  blob.rank = ctx->config.rank;
-  blob.device = ctx->device;
-  blob.process = (int64_t)getpid();
-  memcpy(handle, &blob, sizeof(blob));
-  return MLBM_OK;
-}
-
-int mlbm_comm_peer_attach(mlbm_ctx* ctx, const void* leftHandle, const void* rightHandle) {
-  if (!ctx || !leftHandle || !rightHandle) return fail(MLBM_ERR_INVALID, "null argument");
-  if (ctx->config.nranks < 2) return fail(MLBM_ERR_STATE, "a single rank has no neighbours");
-  if (ctx->peerAttached) return fail(MLBM_ERR_STATE, "peer halos already attached");
-  if (!ctx->peerFlags) return fail(MLBM_ERR_STATE, "mlbm_comm_peer_export has to be called first");
-  if (!ctx->comm) return fail(MLBM_ERR_STATE, "mlbm_comm_init has to be called first (initial halo exchange and shutdown barrier)");
-  if (ctx->H > 1) return fail(MLBM_ERR_INVALID, "direct peer halos are built for the single-speed lattices (one halo plane); the multi-speed ones exchange over NCCL");
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  PeerBlob blobs[2];
-  memcpy(&blobs[0], leftHandle, sizeof(PeerBlob));
-  memcpy(&blobs[1], rightHandle, sizeof(PeerBlob));
-  const int expected[2] = {(ctx->config.rank + ctx->config.nranks - 1) % ctx->config.nranks, (ctx->config.rank + 1) % ctx->config.nranks};
-  const uint64_t bufferBytes = (uint64_t)ctx->stride * ctx->Q * ctx->elementSize;
-  for (int side = 0; side < 2; ++side) {
-    if (blobs[side].rank != expected[side]) return fail(MLBM_ERR_INVALID, "handle of rank %d where the %s neighbour %d was expected", blobs[side].rank, side ? "right" : "left", expected[side]);
-    if (blobs[side].bufferBytes != bufferBytes) return fail(MLBM_ERR_INVALID, "neighbour %d has a different slab geometry", blobs[side].rank);
-    if (blobs[side].process == (int64_t)getpid()) return fail(MLBM_ERR_INVALID, "peer halos need one process per rank (CUDA IPC)");
-  }
-  auto closeAll = [&]() {
-    for (int side = 0; side < 2; ++side) {
-      if (ctx->mappedOwned[side]) for (void*& pointer : ctx->mapped[side]) if (pointer) cudaIpcCloseMemHandle(pointer);
-      for (void*& pointer : ctx->mapped[side]) pointer = nullptr;
-      ctx->mappedOwned[side] = false;
-    }
-  };
-  for (int side = 0; side < 2; ++side) {
-    if (side == 1 && expected[1] == expected[0]) {  // two ranks: both neighbours are the same process, map it once
-      for (int i = 0; i < 3; ++i) ctx->mapped[1][i] = ctx->mapped[0][i];
-      break;
-    }
-    ctx->mappedOwned[side] = true;
-    const cudaIpcMemHandle_t* handles[3] = {&blobs[side].populations[0], &blobs[side].populations[1], &blobs[side].flags};
-    for (int i = 0; i < 3; ++i) {
-      cudaError_t error = cudaIpcOpenMemHandle(&ctx->mapped[side][i], *handles[i], cudaIpcMemLazyEnablePeerAccess);
-      if (error != cudaSuccess) {
-        cudaGetLastError();
-        closeAll();
-        return fail(MLBM_ERR_COMM, "cudaIpcOpenMemHandle (rank %d, device %d): %s", blobs[side].rank, blobs[side].device, cudaGetErrorString(error));
-      }
-    }
-  }
-  ctx->peerAttached = true;
-  ctx->peerEpoch = 0;
-  ctx->halosValid = false;
   return MLBM_OK;
 }
 
@@ -1349,155 +1028,6 @@ int mlbm_download_fields(mlbm_ctx* ctx, void* density, void* velocity, void* alp
     }
   }
   MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
-  return MLBM_OK;
-}
-
-int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
-  if (!ctx || !out) return fail(MLBM_ERR_INVALID, "null argument");
-  if (!ctx->observablesValid) return fail(MLBM_ERR_STATE, "no stored step yet (Algorithm::isStored was never set)");
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  double local[4];
-  if (ctx->config.nranks > 1) {
-    if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
-    // Communication::reduce (Communication.h:76-89): sums over ranks (max for the Mach number)
-    double* values = ctx->deviceObservables;
-    const ncclDataType_t type = ncclDouble;
-    MLBM_NCCL(ctx, ctx->nccl->GroupStart());
-    MLBM_NCCL(ctx, ctx->nccl->AllReduce(values, values, 2, type, ncclSum, ctx->comm, ctx->computeStream));
-    MLBM_NCCL(ctx, ctx->nccl->AllReduce(values + 2, values + 2, 1, type, ncclMax, ctx->comm, ctx->computeStream));
-    MLBM_NCCL(ctx, ctx->nccl->AllReduce(values + 3, values + 3, 1, type, ncclSum, ctx->comm, ctx->computeStream));
-    MLBM_NCCL(ctx, ctx->nccl->GroupEnd());
-    ctx->observablesValid = false;  // reduced in place: valid again after the next stored step
-  }
-  MLBM_CUDA(cudaMemcpyAsync(local, ctx->deviceObservables, sizeof(local), cudaMemcpyDeviceToHost, ctx->computeStream));
-  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
-  double globalVolume = 1.0;
-  for (int d = 0; d < ctx->D; ++d) globalVolume *= ctx->config.global_length[d];
-  out[0] = local[0] / globalVolume;          // AnalysisScalar::normalize (Analysis.h:30)
-  out[1] = ctx->enstrophyValid ? local[3] / globalVolume : NAN;  // Analysis.h:85-93; needs the stored velocity field
-  out[2] = sqrt(local[2] * latticeInvCs2(ctx->config.lattice));  // |u| / c_s, c_s^2 = 1 / inv_cs2 (1/3 but for the multi-speed lattices)
-  out[3] = local[1];
-  return MLBM_OK;
-}
-
-int mlbm_power_spectra(mlbm_ctx* ctx, double* energySpectrum, double* forcingSpectrum, int capacity, int* count) {
-  if (!ctx || !count) return fail(MLBM_ERR_INVALID, "null argument");
-  const int* L = ctx->config.global_length;
-  const int rest = L[1] < L[2] ? L[1] : L[2];                     // unused dimensions are 1
-  const int bins = (L[0] > rest ? L[0] : rest) / 2;               // gFD::maxWaveNumber(): arrayMax is max(first, MIN of the rest)
-  *count = bins;
-  if (!energySpectrum && !forcingSpectrum) return MLBM_OK;
-  if (capacity < bins) return fail(MLBM_ERR_INVALID, "capacity %d < %d wave numbers", capacity, bins);
-  if (!ctx->fieldsStored || !ctx->velocity) return fail(MLBM_ERR_STATE, "no stored step yet (Algorithm::isStored was never set)");
-  if (bins == 0) return MLBM_OK;
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->config.nranks > 1 && !ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
-  std::string error;
-  if (!ctx->spectral) {
-    SpectralGeometry geometry = {ctx->D, ctx->LX, ctx->NM, ctx->NR, ctx->config.rank, ctx->config.nranks, (int)ctx->elementSize};
-    ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->comm, &error);
-    if (!ctx->spectral) return fail(MLBM_ERR_CUDA, "power spectra: %s", error.c_str());
-  }
-  double* device = nullptr;
-  MLBM_CUDA(cudaMalloc(&device, sizeof(double) * 2 * (size_t)bins));
-  int status = MLBM_OK;
-  cudaStream_t stream = ctx->computeStream;
-  if (spectralPowerSpectrum(ctx->spectral, ctx->velocity, ctx->fieldStride, bins, device, stream, &ctx->launches, &error) ||
-      spectralPowerSpectrum(ctx->spectral, ctx->force, ctx->fieldStride, bins, device + bins, stream, &ctx->launches, &error))
-    status = fail(MLBM_ERR_CUDA, "power spectra: %s", error.c_str());
-  if (status == MLBM_OK && ctx->config.nranks > 1) {
-    const ncclResult_t result = ctx->nccl->AllReduce(device, device, 2 * (size_t)bins, ncclDouble, ncclSum, ctx->comm, stream);
-    if (result != ncclSuccess) status = fail(MLBM_ERR_COMM, "ncclAllReduce: %s", ctx->nccl->GetErrorString(result));
-  }
-  std::vector<double> host(2 * (size_t)bins);
-  cudaError_t copyError = cudaSuccess;
-  if (status == MLBM_OK) copyError = cudaMemcpyAsync(host.data(), device, sizeof(double) * host.size(), cudaMemcpyDeviceToHost, stream);
-  const cudaError_t syncError = cudaStreamSynchronize(stream);
-  cudaFree(device);
-  if (status != MLBM_OK) return status;
-  if (copyError != cudaSuccess || syncError != cudaSuccess)
-    return fail(MLBM_ERR_CUDA, "power spectra: %s", cudaGetErrorString(copyError != cudaSuccess ? copyError : syncError));
-  double volume = 1.0;
-  for (int d = 0; d < ctx->D; ++d) volume *= L[d];
-  for (int k = 0; k < bins; ++k) {
-    if (energySpectrum) energySpectrum[k] = host[k] / volume;      // normalizeAnalyses: the energy spectrum only (AnalysisList.h:189)
-    if (forcingSpectrum) forcingSpectrum[k] = host[bins + k];
-  }
-  return MLBM_OK;
-}
-
-int mlbm_alpha_statistics(mlbm_ctx* ctx, double out[3]) {
-  if (!ctx || !out) return fail(MLBM_ERR_INVALID, "null argument");
-  if (!ctx->alpha) { out[0] = 0.0; out[1] = 2.0; out[2] = 2.0; return MLBM_OK; }   // BGK: alpha == 2 (Collision.h:121)
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  if (ctx->config.nranks > 1 && !ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
-  double* device = nullptr;
-  MLBM_CUDA(cudaMalloc(&device, 3 * sizeof(double)));
-  cudaStream_t stream = ctx->computeStream;
-  if (ctx->config.dtype == MLBM_F64) alphaStatisticsKernel<double><<<1, 256, 0, stream>>>(static_cast<const double*>(ctx->alpha), ctx->nodes, device);
-  else alphaStatisticsKernel<float><<<1, 256, 0, stream>>>(static_cast<const float*>(ctx->alpha), ctx->nodes, device);
-  ctx->launches += 1;
-  int status = MLBM_OK;
-  if (ctx->config.nranks > 1) {
-    ncclResult_t result = ctx->nccl->GroupStart();
-    if (result == ncclSuccess) result = ctx->nccl->AllReduce(device, device, 1, ncclDouble, ncclSum, ctx->comm, stream);
-    if (result == ncclSuccess) result = ctx->nccl->AllReduce(device + 1, device + 1, 2, ncclDouble, ncclMax, ctx->comm, stream);
-    const ncclResult_t end = ctx->nccl->GroupEnd();
-    if (result == ncclSuccess) result = end;
-    if (result != ncclSuccess) status = fail(MLBM_ERR_COMM, "ncclAllReduce: %s", ctx->nccl->GetErrorString(result));
-  }
-  double host[3] = {0.0, 0.0, 0.0};
-  cudaError_t error = cudaGetLastError();
-  if (error == cudaSuccess && status == MLBM_OK) error = cudaMemcpyAsync(host, device, sizeof(host), cudaMemcpyDeviceToHost, stream);
-  const cudaError_t syncError = cudaStreamSynchronize(stream);
-  cudaFree(device);
-  if (status != MLBM_OK) return status;
-  if (error != cudaSuccess || syncError != cudaSuccess) return fail(MLBM_ERR_CUDA, "alpha statistics: %s", cudaGetErrorString(error != cudaSuccess ? error : syncError));
-  double globalNodes = 1.0;
-  for (int d = 0; d < ctx->D; ++d) globalNodes *= ctx->config.global_length[d];
-  out[0] = host[0] / globalNodes;
-  out[1] = -host[1];
-  out[2] = host[2];
-  return MLBM_OK;
-}
-
-int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count) {
-  if (!ctx || !values || count < 0) return fail(MLBM_ERR_INVALID, "null argument");
-  if (ctx->config.nranks == 1 || count == 0) return MLBM_OK;
-  if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
-  MLBM_CUDA(cudaSetDevice(ctx->device));
-  double* staging = nullptr;
-  MLBM_CUDA(cudaMalloc(&staging, sizeof(double) * (size_t)count));
-  int status = MLBM_OK;
-  cudaError_t error = cudaMemcpyAsync(staging, values, sizeof(double) * (size_t)count, cudaMemcpyHostToDevice, ctx->computeStream);
-  if (error == cudaSuccess) {
-    ncclResult_t result = ctx->nccl->AllReduce(staging, staging, (size_t)count, ncclDouble, ncclSum, ctx->comm, ctx->computeStream);
-    if (result != ncclSuccess) status = fail(MLBM_ERR_COMM, "ncclAllReduce: %s", ctx->nccl->GetErrorString(result));
-  }
-  if (error == cudaSuccess && status == MLBM_OK)
-    error = cudaMemcpyAsync(values, staging, sizeof(double) * (size_t)count, cudaMemcpyDeviceToHost, ctx->computeStream);
-  if (error == cudaSuccess) error = cudaStreamSynchronize(ctx->computeStream);
-  cudaFree(staging);
-  if (error != cudaSuccess) return fail(MLBM_ERR_CUDA, "mlbm_reduce_sum: %s", cudaGetErrorString(error));
-  ctx->launches += 1;
-  return status;
-}
-
-int mlbm_selftest_log(const double* in, double* out, size_t count) {
-  if (!in || !out) return fail(MLBM_ERR_INVALID, "null argument");
-  if (!count) return MLBM_OK;
-  double *deviceIn = nullptr, *deviceOut = nullptr;
-  MLBM_CUDA(cudaMalloc(&deviceIn, count * sizeof(double)));
-  cudaError_t error = cudaMalloc(&deviceOut, count * sizeof(double));
-  if (error == cudaSuccess) error = cudaMemcpy(deviceIn, in, count * sizeof(double), cudaMemcpyHostToDevice);
-  if (error == cudaSuccess) {
-    fastLogKernel<<<(unsigned)((count + 127) / 128), 128>>>(deviceIn, deviceOut, (long long)count);
-    error = cudaGetLastError();
-  }
-  if (error == cudaSuccess) error = cudaMemcpy(out, deviceOut, count * sizeof(double), cudaMemcpyDeviceToHost);
-  cudaFree(deviceIn);
-  cudaFree(deviceOut);
-  if (error != cudaSuccess) return fail(MLBM_ERR_CUDA, "mlbm_selftest_log: %s", cudaGetErrorString(error));
   return MLBM_OK;
 }
 

@@ -1,6 +1,6 @@
 """tests/emu/build_context.py -- TEST INFRASTRUCTURE ONLY.
 
-Builds ``tests/emu/_build/libmetalbm_emu.so``: the WHOLE product library (csrc/context.cu, shell_force.cu, spectral.cu and
+Builds ``tests/emu/_build/libmetalbm_emu.so``: the WHOLE product library (csrc/context.cu, communication.cu, analysis.cu, shell_force.cu, spectral.cu and
 the kernel instantiations) compiled for the HOST, so that the CPU test-suite can execute the library's host logic -- the
 C-ABI entry points, allocation and pitched copies, the per-step orchestration, the observables and spectral pipelines --
 around the emulated kernels (``cuda_emu.h``) without a GPU.  ``tests/test_emulated_library.py`` points the ctypes binding at
@@ -11,7 +11,7 @@ The sources are taken from ``metalbm_b200/csrc`` at build time.  Edits, all mech
   * the one ``extern __shared__`` declaration of each file -> the emulator's shared-memory buffer;
   * ``asm volatile("trap;")`` -> ``abort()``;
   * spectral.cu resolves its cuFFT entry points from the naive host transforms of ``include/cufft.h`` instead of dlopen,
-    context.cu its NCCL entry points from the shared-memory NCCL of ``include/nccl.h`` (one process per rank).
+    communication.cu its NCCL entry points from the shared-memory NCCL of ``include/nccl.h`` (one process per rank).
 ``cuda_runtime.h``, ``nccl.h`` and ``cufft.h`` resolve to the stand-ins under ``tests/emu/include``: device memory is host
 memory (poisoned at allocation), streams run immediately, there is one device and one rank.  Nothing under
 ``metalbm_b200/`` can reach this library; it says nothing about hardware behaviour or speed.
@@ -111,7 +111,7 @@ def transform(name: str) -> str:
     text = DYNAMIC_SHARED.sub(lambda m: f"{m.group(1)}* const {m.group(2)} = reinterpret_cast<{m.group(1)}*>(cuda_emu::dynamicSharedBase());", text)
     text = text.replace('asm volatile("trap;");', "abort();")
     text = text.replace('#include "../../include/metalbm_b200.h"', f'#include "{ROOT / "include" / "metalbm_b200.h"}"')
-    if name == "context.cu":
+    if name == "communication.cu":
         start = text.index("const NcclApi* loadNccl(const char** error) {")
         end = _matching(text, text.index("{", start), "{", "}")
         text = (text[:start] + "const NcclApi* loadNccl(const char** error) {\n  (void)error;\n"
@@ -139,7 +139,7 @@ def build(flags: tuple = ()) -> Path:
     if LIBRARY.is_file() and all(s.stat().st_mtime <= LIBRARY.stat().st_mtime for s in inputs):
         return LIBRARY
     for header in [*CSRC.glob("*.cuh"), *CSRC.glob("*.h"), *CSRC.glob("*.inc")]:
-        (BUILD / header.name).write_text(transform(header.name) if header.suffix == ".cuh" else header.read_text())
+        (BUILD / header.name).write_text(transform(header.name) if header.suffix in (".cuh", ".h") else header.read_text())
 
     def compile_one(source: Path) -> Path:
         translated = BUILD / (source.stem + ".cpp")

@@ -72,7 +72,7 @@ def force_field(cfg, seed=5, amplitude=2e-4):
 
 
 def shell_force_direct(cfg):
-    """The sum shellForceKernel (csrc/context.cu) evaluates, mode list and integer angle reduction included, in numpy."""
+    """The sum injectionKernel (csrc/shell_force.cu) evaluates, mode list and integer angle reduction included, in numpy."""
     nx, ny, _ = O.shape_of(cfg)
     scale = cfg.force_amplitude[0] / (nx * ny)
     x, y = np.arange(nx)[:, None], np.arange(ny)[None, :]

@@ -1,5 +1,5 @@
 """The single-rank GPU parity suites, executed on the CPU against the WHOLE library compiled for the host
-(tests/emu/build_context.py: csrc/context.cu, shell_force.cu, spectral.cu and every kernel instantiation, with the kernel
+(tests/emu/build_context.py: csrc/context.cu, communication.cu, analysis.cu, shell_force.cu, spectral.cu and every kernel instantiation, with the kernel
 launches rewritten onto the CUDA execution-model emulator and the CUDA runtime / cuFFT replaced by host stand-ins).
 
 `MLBM_EMULATED=1 pytest -m gpu` re-points the ctypes binding (tests/conftest.py) and runs the very same test functions the

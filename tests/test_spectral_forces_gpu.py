@@ -72,7 +72,7 @@ def test_force_field_needs_a_field_force_context():
 
 @pytest.mark.parametrize("name", ["d2q9_bgk_guo_constantshell", "d2q9_elbm_edm_constantshell", "d2q9_bgk_shanchen_turbulent2d"])
 def test_native_constant_shell_against_the_reference(name):
-    """Force "ConstantShell" synthesised on the device at mlbm_create (csrc/context.cu: shellForceKernel) against golden
+    """Force "ConstantShell" synthesised on the device at mlbm_create (csrc/shell_force.cu: injectionKernel) against golden
     vectors of the reference run with its own ConstantShell / Turbulent2D force: the force array and the populations."""
     from golden_util import load_golden
     meta, _, data = load_golden(name)
