@@ -10,6 +10,10 @@ so every timed step streams from HBM -- no L2 flush needed).  N > 1 (launched wi
 GPU): weak scaling, the same 256^3 slab per GPU, global (256 N) x 256 x 256, x-slab halo exchange
 overlapped with the bulk kernel.
 
+With the default headline workload the same line also carries the other BASELINE configs at this GPU count under "also"
+(device-resident throughput, kernel time, roofline fraction; N > 1: D3Q19 1024^3 strong-scaled, the entropic configs
+strong-scaled), measured after the headline is final and under a watchdog (`run_secondary`); `--also off` skips them.
+
 One JSON line on stdout from rank 0 (see the keys at the bottom).  `value` is device-timed with inputs
 resident in HBM; `e2e` is the same metric through the public C-ABI with HOST buffers: the timed region
 uploads the populations from pinned host memory (Algorithm::unpack), runs the K steps reading the scalar
