@@ -261,3 +261,16 @@ def test_launch_plan_rejects_bad_ranges(cuda_lib):
     plan = capi.MlbmLaunchPlan()
     for x0, x1, step in ((0, 0, 1), (-1, 4, 1), (0, 17, 1), (0, 2, 16), (3, 2, 1)):
         assert cuda_lib.mlbm_launch_plan_for(ctypes.byref(cfg), x0, x1, 0, step, ctypes.byref(plan)) == -1
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path, cuda_lib):
+    """include/metalbm_b200.h compiles as C99 with -pedantic and the library links from a C program (what a cgo / JNI / Fortran
+    binding relies on); without a device the program reports the loud mlbm_create failure."""
+    binary = tmp_path / "capi_minimal"
+    command = ["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", str(ROOT / "include"), str(ROOT / "examples" / "capi_minimal.c"),
+               "-L", str(ROOT / "metalbm_b200"), "-lmetalbm_b200", f"-Wl,-rpath,{ROOT / 'metalbm_b200'}", "-o", str(binary)]
+    result = subprocess.run(command, capture_output=True, text=True)
+    assert result.returncode == 0, result.stderr[-3000:]
+    run = subprocess.run([str(binary)], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert ("no CPU fallback" in run.stdout) if _no_gpu() else run.stdout.startswith("energy ")
