@@ -142,7 +142,7 @@ __global__ void signalPeersKernel(unsigned long long* leftNeighbourFlags, unsign
   __threadfence_system();
 }
 
-// Staged pack / unpack (EXPERIMENT, MLBM_STAGED_COPY=1): the host keeps every population as rows of NR values with a pitch of
+// Staged pack / unpack (large blocks, or MLBM_STAGED_COPY=1): the host keeps every population as rows of NR values with a pitch of
 // `pitch` >= NR values (the FFTW padding of lSD, Domain.h:53-57).  Instead of one pitched DMA per population (2 KB rows),
 // the padded block crosses PCIe as ONE contiguous copy and the padding is stripped / added on the device at HBM speed.
 template <typename StoreT>
@@ -804,9 +804,13 @@ static int copyDistribution(mlbm_ctx* ctx, void* host, size_t componentStride, s
   const size_t hostPitch = threeD ? paddedZ : paddedY;  // elements between consecutive host rows
   if (hostPitch < (size_t)ctx->NR || (threeD && paddedY < (size_t)ctx->NM)) return fail(MLBM_ERR_INVALID, "padded lengths smaller than the local lengths");
   const bool uniform = !threeD || paddedY == (size_t)ctx->NM;
-  static const bool stagedCopy = getenv("MLBM_STAGED_COPY") && atoi(getenv("MLBM_STAGED_COPY")) != 0;   // experiment, see stripPaddingKernel
-  if (stagedCopy && uniform) {
-    const long long rows = (long long)ctx->LX * ctx->NM;
+  // MLBM_STAGED_COPY=1 / 0 forces the staged route (see stripPaddingKernel) on / off; unset: staged for blocks of 32 MB and
+  // more, where one contiguous DMA per population beats hundreds of thousands of 2 KB rows, pitched copies below
+  static const int stagedCopy = getenv("MLBM_STAGED_COPY") ? (atoi(getenv("MLBM_STAGED_COPY")) != 0 ? 1 : 0) : -1;
+  const long long stagedRows = (long long)ctx->LX * ctx->NM;
+  const bool staged = uniform && (stagedCopy == 1 || (stagedCopy == -1 && (size_t)stagedRows * hostPitch * es >= ((size_t)32 << 20)));
+  if (staged) {
+    const long long rows = stagedRows;
     const size_t blockBytes = (size_t)rows * hostPitch * es;
     if (ctx->stagingBytes < blockBytes) {
       if (ctx->staging) MLBM_CUDA(cudaFree(ctx->staging));

@@ -7,7 +7,7 @@ nproc > gpurun_out/nproc.txt
 timeout 1800 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/pytest_gpu.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke rc=$?" | tee -a gpurun_out/smoke.log
 timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; echo "bench rc=$?"
-MLBM_STAGED_COPY=1 timeout 600 python bench.py --no-cpu-baseline --also off > gpurun_out/bench_staged_copy.json 2> gpurun_out/bench_staged_copy.err; echo "bench (staged pack/unpack) rc=$?"
+MLBM_STAGED_COPY=0 timeout 600 python bench.py --no-cpu-baseline --also off > gpurun_out/bench_pitched_copy.json 2> gpurun_out/bench_pitched_copy.err; echo "bench (pitched pack/unpack) rc=$?"
 timeout 600 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 20 --warmup 3 --no-cpu-baseline --also off > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu list rc=$?"
