@@ -78,7 +78,7 @@ def test_native_constant_shell_against_the_reference(name):
     meta, _, data = load_golden(name)
     cfg = native_shell_config(meta)
     got = run_cuda(cfg, data["f0"], meta["steps"])
-    assert np.abs(got["force"] - data["force"]).max() <= 4e-15 * np.abs(data["force"]).max()
+    assert np.abs(got["force"] - data["force"]).max() <= 2e-14 * np.abs(data["force"]).max()   # device sinpi: a few ulp per mode
     if meta["collision"] == "BGK":
         assert relative_error(got["f"], data["f"]) <= POPULATION_TOLERANCE
     else:
@@ -96,7 +96,7 @@ def test_native_constant_shell_odd_sizes_and_nyquist_shells(shape, shell, dtype)
     got = run_cuda(cfg, f0, 2)
     ref = run_oracle(cfg, f0, 2)
     scale = np.abs(ref.force).max()
-    assert scale > 0 and np.abs(got["force"] - ref.force).max() <= (4e-15 if dtype == "F64" else 1e-7) * scale
+    assert scale > 0 and np.abs(got["force"] - ref.force).max() <= (2e-14 if dtype == "F64" else 1e-7) * scale
     assert relative_error(got["f"], ref.f) <= (POPULATION_TOLERANCE if dtype == "F64" else 1e-5)
 
 
