@@ -96,7 +96,7 @@ def test_native_constant_shell_odd_sizes_and_nyquist_shells(shape, shell, dtype)
     got = run_cuda(cfg, f0, 2)
     ref = run_oracle(cfg, f0, 2)
     scale = np.abs(ref.force).max()
-    assert scale > 0 and np.abs(got["force"] - ref.force).max() <= (2e-14 if dtype == "F64" else 1e-7) * scale
+    assert scale > 0 and np.abs(got["force"] - ref.force).max() <= (1e-13 if dtype == "F64" else 1e-7) * scale   # up to ~150 modes, a few ulp of the device sinpi each
     assert relative_error(got["f"], ref.f) <= (POPULATION_TOLERANCE if dtype == "F64" else 1e-5)
 
 
