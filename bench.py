@@ -440,6 +440,10 @@ def run_ours(args) -> int:
     if args.edge != EDGE and args.workload == "d3q19_bgk_256":
         work["shape"] = (args.edge,) * 3
         work["text"] = work["text"].replace("256^3", f"{args.edge}^3")
+    if args.shape:
+        work["shape"] = tuple(int(n) for n in args.shape.split(","))
+        work["scaling"] = "strong"
+        work["text"] += f" [shape overridden: {args.shape}]"
     if args.eps is not None:
         work["eps"] = args.eps
     if args.store_every is not None:
@@ -639,6 +643,7 @@ def main() -> int:
     parser.add_argument("--impl", default="ours", choices=["ours", "reference"])
     parser.add_argument("--edge", type=int, default=EDGE, help="edge of the per-GPU cube (default: the BASELINE 256)")
     parser.add_argument("--variant", type=int, default=0)
+    parser.add_argument("--shape", default=None, help="global X,Y,Z overriding the workload's grid (experiments: slab shapes)")
     parser.add_argument("--workload", default="d3q19_bgk_256", choices=sorted(WORKLOADS))
     parser.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     parser.add_argument("--overlap", default="On", choices=["On", "Off"])

@@ -90,7 +90,9 @@ class Context {
       // Overlapping::On: the boundary kernel stores into the neighbours' halo planes over NVLink (CUDA IPC mappings);
       // MLBM_PEER_HALOS=0 keeps the NCCL send/recv exchange
       const char* peerHalos = std::getenv("MLBM_PEER_HALOS");
-      if (overlappingT == Overlapping::On && !(peerHalos && peerHalos[0] == '0')) {
+      // (the multi-speed lattices carry dimH > 1 halo planes per side: they keep the overlapped NCCL exchange,
+      // mlbm_comm_peer_attach is built for one plane)
+      if (overlappingT == Overlapping::On && L::dimH == 1 && !(peerHalos && peerHalos[0] == '0')) {
         unsigned char mine[MLBM_PEER_HANDLE_BYTES];
         std::vector<unsigned char> all((size_t)MLBM_PEER_HANDLE_BYTES * numProcs);
         LBM_B200_CALL(mlbm_comm_peer_export(handle, mine));

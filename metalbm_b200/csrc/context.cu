@@ -335,6 +335,10 @@ bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
   g->plane = (long long)g->NM * g->NR;
   const long long perPopulation = g->plane * (g->LX + 2 * g->H);
   g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
+  // experiment hook (bench only): extra elements between populations, to move the Q concurrent streams off a common
+  // power-of-two alignment (1024^2 planes make the stride a multiple of 16 MB)
+  static const long long stridePad = getenv("MLBM_STRIDE_PAD") ? atoll(getenv("MLBM_STRIDE_PAD")) / 32 * 32 : 0;
+  g->stride += stridePad;
   return true;
 }
 

@@ -43,6 +43,7 @@ struct StepParams {
   void* velocity;          // [D] components, fieldStride apart
   void* force;             // [D] components, fieldStride apart
   double* partials;        // [LX * NM * ceil(NR / kStepBlock)][kObservableSlots] block partial sums (only when isStored)
+  unsigned long long* newtonCounters;  // entropic kernels: [0] += nodes that took the Newton solve, [1] += evaluations of (F, F') they needed
   unsigned char* hints;    // [LX * NM * ceil(NR / kStepBlock)] entropic kernels built with MLBM_ELBM_FASTPATH: 1 = this block's
                            // plane had a node off the small-deviation shortcut in the previous step (else unused)
   const double* forceTable[3];  // per force component: amplitude * profile along forceAxis (host libm values)
@@ -403,7 +404,7 @@ __device__ __forceinline__ void entropicEvaluateClass(const double* fColumn, con
 
 // solveAlpha (Collision.h:328-349) -> NewtonRaphsonSolver (EntropicStep.h:111-140), see the banner above.
 template <class L>
-__device__ __forceinline__ double entropicNewton(const EntropicShared& s, int column, double alphaGuess, double alphaMax) {
+__device__ __forceinline__ double entropicNewton(const EntropicShared& s, int column, double alphaGuess, double alphaMax, int& evaluations) {
   using C = SpeedClasses<L>;
   const double* fColumn = s.f + column;
   const double* nColumn = s.fNeq + column;
@@ -428,6 +429,7 @@ __device__ __forceinline__ double entropicNewton(const EntropicShared& s, int co
   bool converged = false;
   for (int iteration = 1; iteration <= 50; ++iteration) {
     x = x - step;
+    evaluations = iteration;
     double total = 0.0, slope = 0.0;
     staticFor<0, L::maxNorm2() + 1>([&](auto nc) {
       constexpr int n2 = decltype(nc)::value;
@@ -860,7 +862,15 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       if (t < total) {
         const int column = s.list[t];
         const double guess = (double)alphaField[rowNode + blockIdx.x * kStepBlock + column];  // previous step's alpha (Algorithm.h:103-106)
-        s.alpha[column] = entropicNewton<L>(s, column, guess, s.alpha[column]);
+        int evaluations = 0;
+        s.alpha[column] = entropicNewton<L>(s, column, guess, s.alpha[column], evaluations);
+        // statistics of the solve (mlbm_newton_statistics: the FP64 side of the roofline); one atomic per solving warp
+        const unsigned solving = __activemask();
+        for (int offset = 16; offset > 0; offset >>= 1) evaluations += __shfl_xor_sync(solving, evaluations, offset) * (((lane ^ offset) < 32 && (solving >> (lane ^ offset) & 1u)) ? 1 : 0);
+        if (lane == 0 && p.newtonCounters) {
+          atomicAdd(p.newtonCounters, (unsigned long long)__popc(solving));
+          atomicAdd(p.newtonCounters + 1, (unsigned long long)evaluations);
+        }
       }
       __syncthreads();
       if (needsNewton) alpha = s.alpha[t];
@@ -898,7 +908,10 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
 // grid = (ceil(NR / kStepBlock), NM, number of x planes [/ planesPerBlock]), block = kStepBlock threads along r.
 // ------------------------------------------------------------------------------------------------
 template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
-__global__ void __launch_bounds__(kStepBlock, COLLISION != kBGK ? entropicBlocksPerSM(L::Q) : 1)
+#ifndef MLBM_BGK_BLOCKS
+#define MLBM_BGK_BLOCKS 1
+#endif
+__global__ void __launch_bounds__(kStepBlock, COLLISION != kBGK ? entropicBlocksPerSM(L::Q) : MLBM_BGK_BLOCKS)
 fusedStepKernel(const __grid_constant__ StepParams p) {
   if constexpr (COLLISION != kBGK) {
     entropicStepBody<L, EQ, SCHEME, StoreT, COLLISION == kELBMForcing>(p);

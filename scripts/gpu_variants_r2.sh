@@ -12,7 +12,7 @@ mkdir -p gpurun_out
 out=gpurun_out/elbm_variants_r2.txt
 : > $out
 one() { python -c "import json,sys; d=json.loads(sys.stdin.readline()); r=d['roofline']; print('$1', d['config']['name'], d['dtype'][:3], d['config']['perturbation_eps'], round(d['value']), 'MLUPS', round(d['ms_per_step'],3), 'ms  frac', round(r['frac'],3))"; }
-for v in "" fast pf fastpf; do
+for v in "" fast pf; do
   if [ -n "$v" ] && [ ! -f metalbm_b200/libmetalbm_b200_$v.so ]; then echo "variant $v not built" >> $out; continue; fi
   # parity of the variant before its speed means anything
   MLBM_VARIANT=$v timeout 600 python -m pytest tests/test_parity_gpu.py tests/test_golden_gpu.py -q -x -m gpu -k "elbm or ELBM" > gpurun_out/parity_variant_${v:-default}.log 2>&1
