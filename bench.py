@@ -233,6 +233,16 @@ def cpu_baseline_leg() -> dict:
 # --------------------------------------------------------------------------------------------------
 # secondary workloads ("also")
 # --------------------------------------------------------------------------------------------------
+def newton_work(algorithm, iteration, nodes_local) -> dict:
+    """One extra (untimed) step with the kernel's Newton counters on: which share of this rank's nodes took the solve
+    (solveAlpha, Collision.h:328-349) and how many evaluations of (F, F') a solved node needed -- the FP64 side of the
+    entropic roofline, at the END of the timed region."""
+    algorithm.newton_statistics(start=True)
+    algorithm.run(iteration, 1, 0)
+    solved, evaluations = algorithm.newton_statistics()
+    return {"solved_node_fraction": solved / nodes_local, "evaluations_per_solved_node": evaluations / solved if solved else 0.0}
+
+
 def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, min_over_ranks, peak) -> dict:
     """Device-resident throughput of one named workload at this GPU count: fresh context, synthetic field made on
     the device, 5 warm-up steps, `steps` timed steps between barriers (CUDA events, max over ranks)."""
@@ -304,6 +314,7 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
             stored_ms = max_over_ranks(algorithm.elapsed_ms(2, 3))
         # what the entropic collision was doing at the end of the timed region: share of nodes off the alpha = 2 shortcut
         newton_fraction, alpha_min, alpha_max = algorithm.alpha_statistics() if entropic else (None, None, None)
+        newton = newton_work(algorithm, warmup + steps + 1, nodes_local) if entropic else None
         # liveness of the state that was timed: one more step reducing energy / mass / Mach only
         algorithm.run(0, 1, 1, stored_mode=2)
         observables = algorithm.observables()
@@ -321,7 +332,8 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
             "mass_per_node": float(observables[3]) / nodes_global,
         })
         if entropic:
-            result.update({"alpha_off_shortcut_fraction_at_end": newton_fraction, "alpha_min": alpha_min, "alpha_max": alpha_max})
+            result.update({"alpha_off_shortcut_fraction_at_end": newton_fraction, "alpha_min": alpha_min, "alpha_max": alpha_max,
+                           "newton": newton})
     finally:
         algorithm.close()
     return result
@@ -440,7 +452,7 @@ def run_ours(args) -> int:
     if args.edge != EDGE and args.workload == "d3q19_bgk_256":
         work["shape"] = (args.edge,) * 3
         work["text"] = work["text"].replace("256^3", f"{args.edge}^3")
-    if args.shape:
+    if getattr(args, "shape", None):
         work["shape"] = tuple(int(n) for n in args.shape.split(","))
         work["scaling"] = "strong"
         work["text"] += f" [shape overridden: {args.shape}]"
@@ -512,6 +524,11 @@ def run_ours(args) -> int:
     kernel_ms, kernel_launches = algorithm.kernel_time()
     clocks = sampler.stop(begin, end) if rank == 0 else None
     value = nodes_global * args.steps / (device_ms * 1e-3) / 1e6
+    entropic_state = None
+    if entropic:
+        off_shortcut, alpha_min, alpha_max = algorithm.alpha_statistics()
+        entropic_state = {"alpha_off_shortcut_fraction_at_end": off_shortcut, "alpha_min": alpha_min, "alpha_max": alpha_max,
+                          "newton": newton_work(algorithm, args.warmup + args.steps + 1, nodes_local)}
 
     # ---- cost of one stored step (fields + energy / spectral enstrophy / Mach reductions), timed on its own -------------
     stored_ms = None
@@ -618,6 +635,8 @@ def run_ours(args) -> int:
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
+        if entropic_state is not None:
+            line["entropic"] = entropic_state
 
     # ---- the other BASELINE configs at this GPU count.  The headline line above is final; whatever happens below
     # (an exception, a rank that stops answering) it is printed, by the watchdog if need be.

@@ -271,6 +271,12 @@ int mlbm_power_spectra(mlbm_ctx* ctx, double* energy_spectrum, double* forcing_s
  * Characterises a benchmark state (how much of the grid pays for the Newton solve); BGK contexts report {0, 2, 2}. */
 int mlbm_alpha_statistics(mlbm_ctx* ctx, double out[3]);
 
+/* Work of the entropic Newton solve (solveAlpha, Collision.h:328-349; NewtonRaphsonSolver, EntropicStep.h:111-140) on THIS
+ * rank, counted by the step kernel between the two calls: mode 1 starts counting (zeroes the counters); mode 0 stops and
+ * returns out[0] = nodes that took the solve, out[1] = evaluations of (F, F') they needed.  The FP64 side of the entropic
+ * roofline (bench.py); costs two atomics per solved node while it counts, nothing otherwise. */
+int mlbm_newton_statistics(mlbm_ctx* ctx, int mode, unsigned long long out[2]);
+
 /* Communication::reduce(T* localSumPtr, numberComponents) (Communication.h:76-89): element-wise sum of `count` host
  * doubles over all ranks, result on EVERY rank (the reference leaves it on rank 0 only); a no-op for one rank. */
 int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count);

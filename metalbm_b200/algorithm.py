@@ -275,6 +275,12 @@ class Algorithm:
         check(self._lib.mlbm_alpha_statistics(self._ctx, out))
         return float(out[0]), float(out[1]), float(out[2])
 
+    def newton_statistics(self, start: bool = False) -> tuple:
+        """start=True: begin counting; else (nodes that took the Newton solve, evaluations of F and F') on this rank since then."""
+        out = (ctypes.c_ulonglong * 2)()
+        check(self._lib.mlbm_newton_statistics(self._ctx, 1 if start else 0, out))
+        return int(out[0]), int(out[1])
+
     def getCommunicationTime(self) -> float:
         c, _ = ctypes.c_double(), ctypes.c_double()
         check(self._lib.mlbm_timers(self._ctx, ctypes.byref(c), None))

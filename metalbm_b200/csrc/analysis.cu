@@ -155,6 +155,26 @@ int mlbm_alpha_statistics(mlbm_ctx* ctx, double out[3]) {
   return MLBM_OK;
 }
 
+int mlbm_newton_statistics(mlbm_ctx* ctx, int mode, unsigned long long out[2]) {
+  if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (mode == 1) {
+    if (!ctx->alpha) return MLBM_OK;  // BGK: nothing is solved
+    if (!ctx->newtonCounters) MLBM_CUDA(cudaMalloc(&ctx->newtonCounters, 2 * sizeof(unsigned long long)));
+    MLBM_CUDA(cudaMemsetAsync(ctx->newtonCounters, 0, 2 * sizeof(unsigned long long), ctx->computeStream));
+    return MLBM_OK;
+  }
+  if (!out) return fail(MLBM_ERR_INVALID, "null argument");
+  out[0] = out[1] = 0ull;
+  if (!ctx->newtonCounters) return MLBM_OK;
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  MLBM_CUDA(cudaStreamSynchronize(ctx->commStream));
+  MLBM_CUDA(cudaMemcpy(out, ctx->newtonCounters, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  MLBM_CUDA(cudaFree(ctx->newtonCounters));
+  ctx->newtonCounters = nullptr;
+  return MLBM_OK;
+}
+
 int mlbm_reduce_sum(mlbm_ctx* ctx, double* values, int count) {
   if (!ctx || !values || count < 0) return fail(MLBM_ERR_INVALID, "null argument");
   if (ctx->config.nranks == 1 || count == 0) return MLBM_OK;

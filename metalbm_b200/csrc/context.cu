@@ -414,6 +414,7 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
   p.force = ctx->force;
   p.partials = ctx->partials;
   p.hints = ctx->hints;
+  p.newtonCounters = ctx->newtonCounters;
   for (int d = 0; d < 3; ++d) { p.forceTable[d] = ctx->forceTables[d]; p.forceAxis[d] = ctx->forceAxis[d]; }
   p.fieldStride = ctx->fieldStride;
   p.peerLow = peerLow;
@@ -595,7 +596,7 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   if (ctx->shell) shellForceDestroy(ctx->shell);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
-                        (void*)ctx->partials, (void*)ctx->hints, ctx->staging, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
+                        (void*)ctx->partials, (void*)ctx->hints, (void*)ctx->newtonCounters, ctx->staging, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
                         (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
     if (pointer) cudaFree(pointer);
   for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->stepStart, ctx->timeStart, ctx->timeMid, ctx->timeStop})

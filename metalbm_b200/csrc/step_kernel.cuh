@@ -864,11 +864,9 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
         const double guess = (double)alphaField[rowNode + blockIdx.x * kStepBlock + column];  // previous step's alpha (Algorithm.h:103-106)
         int evaluations = 0;
         s.alpha[column] = entropicNewton<L>(s, column, guess, s.alpha[column], evaluations);
-        // statistics of the solve (mlbm_newton_statistics: the FP64 side of the roofline); one atomic per solving warp
-        const unsigned solving = __activemask();
-        for (int offset = 16; offset > 0; offset >>= 1) evaluations += __shfl_xor_sync(solving, evaluations, offset) * (((lane ^ offset) < 32 && (solving >> (lane ^ offset) & 1u)) ? 1 : 0);
-        if (lane == 0 && p.newtonCounters) {
-          atomicAdd(p.newtonCounters, (unsigned long long)__popc(solving));
+        // statistics of the solve (mlbm_newton_statistics: the FP64 side of the roofline); counted only while a caller asks
+        if (p.newtonCounters) {
+          atomicAdd(p.newtonCounters, 1ull);
           atomicAdd(p.newtonCounters + 1, (unsigned long long)evaluations);
         }
       }

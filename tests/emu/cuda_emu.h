@@ -265,6 +265,7 @@ using std::sqrt;
 
 // ---- intrinsics used by the kernels of csrc/context.cu, shell_force.cu and spectral.cu -----------------------------
 inline unsigned atomicAdd(unsigned* address, unsigned value) { const unsigned old = *address; *address = old + value; return old; }
+inline unsigned long long atomicAdd(unsigned long long* address, unsigned long long value) { const unsigned long long old = *address; *address = old + value; return old; }
 inline double atomicAdd(double* address, double value) { const double old = *address; *address = old + value; return old; }
 inline void __threadfence() {}
 inline void __threadfence_system() {}

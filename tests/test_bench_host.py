@@ -190,6 +190,7 @@ class _FakeAlgorithm:
         for n in self.cfg.global_length: nodes *= n
         return [1e-3, float("nan"), 0.1, float(nodes)]
     def alpha_statistics(self): return 0.5, 1.2, 2.1
+    def newton_statistics(self, start=False): return (0, 0) if start else (10, 30)
     def close(self): self.closed = True
 
 
