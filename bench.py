@@ -186,28 +186,48 @@ def distributed_setup(gpus: int):
 # reference arm: the reference's own CPU implementation (oracle/_ref, compiled from /root/reference by
 # oracle/refbuild.py in the build container) on the host cores, on a bounded x-slab sample of the workload
 # --------------------------------------------------------------------------------------------------
+def _host_cores() -> int:
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def _reference_sample_text(refbuild, cfg, full: bool) -> str:
+    planes = cfg.nx // cfg.nprocs
+    what = ("the WHOLE 256^3 cube of BASELINE configs[1]" if full else
+            f"bounded x-slab sample {cfg.nx}x256x256 of the 256^3 cube")
+    return (f"{what}: reference CPU build ({refbuild.TIMING_FLAGS}), {cfg.nprocs} forked MPI-shim ranks x {planes} x-planes of "
+            f"256x256 D3Q19 BGK FP64 nodes, timers of Algorithm::iterate (computation + communication)")
+
+
 def run_reference(args) -> int:
+    """The reference's own CPU implementation on the host cores.  Preferred sample: the whole 256^3 cube (the GPU arm's
+    configuration, one x-slab per core); if K + W steps of it would not end within a few minutes on this host, the
+    thin-slab sample (2 x-planes per rank) instead."""
     rank, world, _ = distributed_setup(args.gpus)
     if rank != 0:
         return 0
     from oracle import refbuild
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cfg = refbuild.best_timing_config(cores)
-    if cfg is None:
+    cores = _host_cores()
+    full_cfg = refbuild.best_timing_config(cores)
+    thin_cfg = refbuild.best_timing_config(cores, refbuild.TIMING_PLANES_PER_RANK)
+    if full_cfg is None and thin_cfg is None:
         print(json.dumps({"impl": "reference", "unavailable": "no prebuilt reference binary in oracle/_ref"}))
         return 0
+    cfg, full = thin_cfg, False
+    if full_cfg is not None:
+        probe = refbuild.time_reference(full_cfg, 1, 1)
+        if thin_cfg is None or probe["seconds"] * (args.steps + args.warmup) <= 150.0:
+            cfg, full = full_cfg, True
     result = refbuild.time_reference(cfg, args.steps, args.warmup)
-    sample = (f"reference CPU build ({refbuild.TIMING_FLAGS}), {cfg.nprocs} forked MPI-shim ranks x "
-              f"{refbuild.TIMING_PLANES_PER_RANK} x-planes of 256x256 D3Q19 BGK FP64 nodes per step "
-              f"({cfg.nx}x256x256 per step), timers of Algorithm::iterate")
+    sample = _reference_sample_text(refbuild, cfg, full)
     line = {
         "impl": "reference", "metric": METRIC, "value": result["mlups"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": result["seconds"] / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"D3Q19 SRT-BGK periodic 256^3 FP64 per GPU (BASELINE configs[1]); bounded sample: {sample}",
-                   "lattice": LATTICE, "collision": "BGK", "host_cores": cores, "ranks": cfg.nprocs},
+        "config": {"workload": f"D3Q19 SRT-BGK periodic 256^3 FP64 per GPU (BASELINE configs[1]); {sample}",
+                   "lattice": LATTICE, "collision": "BGK", "host_cores": cores, "ranks": cfg.nprocs,
+                   "global_length": [cfg.nx, cfg.ny, cfg.nz], "same_config_as_gpu_arm_at_n1": full},
         "cpu_baseline": {"value": result["mlups"], "unit": UNIT, "cores": cfg.nprocs, "kind": "reference",
-                         "sample": sample},
+                         "sample": sample, "communication_share": result["communication_share"]},
         "e2e": {"value": result["mlups"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -216,23 +236,138 @@ def run_reference(args) -> int:
 
 
 def cpu_baseline_leg() -> dict:
-    """The reference CPU build timed on this box's host cores on a bounded sample (about 10-20 s)."""
+    """The reference CPU build timed on this box's host cores: about 12 s on the whole 256^3 cube (one x-slab per core), and
+    the thin-slab sample of round 1 (2 x-planes per rank, where the reference's halo exchange and boundary copies weigh as
+    much as its node update) beside it."""
     from oracle import refbuild
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-    cfg = refbuild.best_timing_config(cores)
-    if cfg is None:
+    cores = _host_cores()
+
+    def timed(cfg, budget):
+        probe = refbuild.time_reference(cfg, 2, 1)
+        steps = int(max(3, min(200, budget / max(probe["seconds"] / 2, 1e-3))))
+        return refbuild.time_reference(cfg, steps, 1), steps
+
+    full_cfg = refbuild.best_timing_config(cores)
+    thin_cfg = refbuild.best_timing_config(cores, refbuild.TIMING_PLANES_PER_RANK)
+    if full_cfg is None and thin_cfg is None:
         return {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "no prebuilt reference binary"}
-    probe = refbuild.time_reference(cfg, 3, 1)
-    steps = int(max(5, min(200, 12.0 / max(probe["seconds"] / 3, 1e-3))))
-    result = refbuild.time_reference(cfg, steps, 2)
-    return {"value": result["mlups"], "unit": UNIT, "cores": cfg.nprocs, "kind": "reference",
-            "sample": (f"{steps} steps of {cfg.nx}x256x256 D3Q19 BGK FP64 ({refbuild.TIMING_PLANES_PER_RANK} x-planes per rank), "
-                       f"reference CPU build {refbuild.TIMING_FLAGS}, {cfg.nprocs} forked MPI-shim ranks on {cores} host cores")}
+    out = None
+    if full_cfg is not None:
+        result, steps = timed(full_cfg, 12.0)
+        out = {"value": result["mlups"], "unit": UNIT, "cores": full_cfg.nprocs, "kind": "reference",
+               "sample": f"{steps} steps of " + _reference_sample_text(refbuild, full_cfg, True) + f", on {cores} host cores",
+               "communication_share": result["communication_share"]}
+    if thin_cfg is not None:
+        result, steps = timed(thin_cfg, 5.0)
+        thin = {"value": result["mlups"], "unit": UNIT, "cores": thin_cfg.nprocs,
+                "sample": f"{steps} steps of " + _reference_sample_text(refbuild, thin_cfg, False),
+                "communication_share": result["communication_share"]}
+        if out is None:
+            out = {**thin, "kind": "reference"}
+        else:
+            out["thin_slab_sample"] = thin
+    return out
 
 
 # --------------------------------------------------------------------------------------------------
 # secondary workloads ("also")
 # --------------------------------------------------------------------------------------------------
+def device_bytes_needed(q_count, plane_nodes, lx, element, entropic, dim, stored_mode) -> int:
+    """Device memory of a workload: two population buffers with their x-halo planes, the alpha field of the entropic
+    collisions and, when whole fields are stored, density / velocity / force plus the three spectral work arrays."""
+    nodes_local = plane_nodes * lx
+    need = 2 * q_count * plane_nodes * (lx + 2) * element + (nodes_local * element if entropic else 0)
+    if stored_mode == 1:
+        need += (1 + 2 * dim) * nodes_local * element + 3 * dim * nodes_local * 8
+    return need
+
+
+def fp64_peak():
+    """DFMA lane-operations per second measured by tools/fp64_peak.cu on this pool's B200 (profiles/FP64_PEAK.json;
+    MEASURED_PEAKS.json has no FP64 figure), else the nominal 64 DFMA per clock and SM at 1965 MHz."""
+    path = ROOT / "profiles" / "FP64_PEAK.json"
+    if path.is_file():
+        try:
+            return float(json.loads(path.read_text())["dfma_lane_ops_per_s"]), "measured (profiles/FP64_PEAK.json, tools/fp64_peak.cu)"
+        except Exception:
+            pass
+    return 148 * 64 * 1.965e9, "nominal (64 DFMA / clock / SM x 148 SMs x 1965 MHz)"
+
+
+# FP64 lane-operations per node of the shipped kernels, counted from their SASS (profiles/r02_sass_fp64_counts.md:
+# D* instructions on the node's path; `base` = every node, `solve` = once per node that takes the Newton solve
+# (the hoisted sum), `evaluation` = per evaluation of (F, F')).  The FP64 side of the entropic roofline.
+FP64_OPS = {
+    # (lattice, collision): (base, solve, evaluation)
+}
+
+
+def fp64_fraction(lattice, collision, kernel_nodes, kernel_ms, newton) -> dict | None:
+    counts = FP64_OPS.get((lattice, collision))
+    if not counts or not kernel_ms:
+        return None
+    base, solve, evaluation = counts
+    solved = (newton or {}).get("solved_node_fraction", 0.0)
+    per_solved = (newton or {}).get("evaluations_per_solved_node", 0.0)
+    per_node = base + solved * (solve + per_solved * evaluation)
+    peak, source = fp64_peak()
+    achieved = per_node * kernel_nodes / (kernel_ms * 1e-3)
+    return {"fp64_ops_per_node": per_node, "fp64_achieved_lane_ops_per_s": achieved, "fp64_peak_lane_ops_per_s": peak,
+            "fp64_frac": achieved / peak, "fp64_peak_source": source}
+
+
+def bind_near_gpu(device_index: int):
+    """Restrict this process to the host cores of the GPU's NUMA node, so that the pinned staging buffer of the end-to-end
+    leg is allocated (first touch) in the memory next to the GPU's PCIe root.  Returns the previous affinity (or None)."""
+    try:
+        import torch
+        props = torch.cuda.get_device_properties(device_index)
+        address = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        node = int((Path("/sys/bus/pci/devices") / address / "numa_node").read_text())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in (Path("/sys/devices/system/node") / f"node{node}" / "cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        before = os.sched_getaffinity(0)
+        wanted = cpus & before
+        if not wanted:
+            return None
+        os.sched_setaffinity(0, wanted)
+        return before
+    except Exception:  # noqa: BLE001 -- placement is best effort
+        return None
+
+
+def host_memory_available() -> int:
+    try:
+        for row in Path("/proc/meminfo").read_text().splitlines():
+            if row.startswith("MemAvailable:"):
+                return int(row.split()[1]) * 1024
+    except Exception:  # noqa: BLE001
+        pass
+    return 0
+
+
+def summarize_also(also) -> list:
+    """One short string per secondary workload: the line's LAST key, so that it survives a truncated log tail."""
+    rows = []
+    for entry in also:
+        if "value" not in entry:
+            rows.append(f"{entry.get('name')}: {entry.get('skipped') or entry.get('error') or '?'}"[:90])
+            continue
+        text = (f"{entry['name']} {entry.get('dtype')} {entry['global_length'][0]}x{entry['global_length'][1]}x{entry['global_length'][2]}"
+                + (f" eps={entry['eps']:g}" if entry.get("eps") else "") + (f" store{entry['stored_mode']}" if entry.get("stored_mode") else "")
+                + f": {entry['value']:.0f} MLUPS hbm={entry['roofline_frac']:.3f}")
+        if entry.get("fp64_frac") is not None:
+            text += f" fp64={entry['fp64_frac']:.2f}"
+        if entry.get("stored_step_ms") is not None:
+            text += f" stored_ms={entry['stored_step_ms']:.2f}/{entry['ms_per_step']:.2f}"
+        rows.append(text)
+    return rows
+
+
 def newton_work(algorithm, iteration, nodes_local) -> dict:
     """One extra (untimed) step with the kernel's Newton counters on: which share of this rank's nodes took the solve
     (solveAlpha, Collision.h:328-349) and how many evaluations of (F, F') a solved node needed -- the FP64 side of the
@@ -270,9 +405,7 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
     dim = 3 if shape[2] > 1 else 2
     # device memory this workload needs (populations with halo planes, alpha, and on fully stored steps the fields
     # plus the spectra of the enstrophy), agreed over the ranks before anybody allocates
-    need = 2 * q_count * (nodes_local // lx) * (lx + 2) * element + (nodes_local * element if entropic else 0)
-    if work["store_every"] and stored_mode == 1:
-        need += (1 + 2 * dim) * nodes_local * element + 3 * dim * nodes_local * 8
+    need = device_bytes_needed(q_count, nodes_local // lx, lx, element, entropic, dim, stored_mode if work["store_every"] else 0)
     free = torch.cuda.mem_get_info()[0]
     fits = min_over_ranks(1.0 if need + (3 << 30) < free else 0.0)
     result["device_bytes_needed"] = need
@@ -334,6 +467,9 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
         if entropic:
             result.update({"alpha_off_shortcut_fraction_at_end": newton_fraction, "alpha_min": alpha_min, "alpha_max": alpha_max,
                            "newton": newton})
+            fp64 = fp64_fraction(work["lattice"], work["collision"], kernel_nodes, kernel_ms, newton)
+            if fp64:
+                result.update(fp64)
     finally:
         algorithm.close()
     return result
@@ -363,6 +499,8 @@ def run_secondary(entries, measure, line, rank, world, max_over_ranks, sum_over_
                 line["also"] = list(also)
             if note:
                 line["also_note"] = note
+            if also:
+                line["also_summary"] = summarize_also(also)
             stream.write(json.dumps(line) + "\n")
             stream.flush()
 
@@ -448,8 +586,13 @@ def run_ours(args) -> int:
         dist.all_reduce(tensor, op=dist.ReduceOp.SUM)
         return float(tensor.item())
 
-    work = dict(WORKLOADS[args.workload])
-    if args.edge != EDGE and args.workload == "d3q19_bgk_256":
+    # N = 1: BASELINE configs[1] (256^3, the roofline calibration).  N > 1: BASELINE configs[4], D3Q19 1024^3 strong-scaled
+    # -- the configuration the north star's parallel-efficiency target is quoted on; the driver's efficiency
+    # v_N / (N v_1) is then SURVEY 8d's definition (1024^3 itself cannot run on one GPU).
+    workload_name = args.workload or ("d3q19_bgk_256" if world == 1 else "d3q19_bgk_1024")
+    default_headline = args.workload is None and args.dtype == "f64" and args.edge == EDGE and not getattr(args, "shape", None)
+    work = dict(WORKLOADS[workload_name])
+    if args.edge != EDGE and workload_name == "d3q19_bgk_256":
         work["shape"] = (args.edge,) * 3
         work["text"] = work["text"].replace("256^3", f"{args.edge}^3")
     if getattr(args, "shape", None):
@@ -469,42 +612,39 @@ def run_ours(args) -> int:
         shape = (work["shape"][0] * world,) + tuple(work["shape"][1:])
     else:
         shape = tuple(work["shape"])
+    if shape[0] % world:
+        raise SystemExit(f"{world} GPUs do not divide the x extent {shape[0]}")
+    nodes_global = shape[0] * shape[1] * shape[2]
+    nodes_local = nodes_global // world
+    lx = shape[0] // world
+    dim = 3 if shape[2] > 1 else 2
+    store_every = int(work["store_every"])
+    # stored steps: whole fields + energy / spectral enstrophy / Mach (mode 1) where the slab leaves room for the field
+    # arrays, else the energy / mass / Mach reductions alone (mode 2: no field arrays; 1024^3 on 2 GPUs fills them)
+    stored_mode = 0
+    if store_every:
+        free = torch.cuda.mem_get_info()[0]
+        full = device_bytes_needed(q_count, nodes_local // lx, lx, element, entropic, dim, 1) + (4 << 30) < free
+        stored_mode = args.stored_mode or (1 if min_over_ranks(1.0 if full else 0.0) else 2)
     cfg = make_config(lattice=work["lattice"], shape=shape, collision=work["collision"], equilibrium=work["equilibrium"],
                       forcing_scheme=work["scheme"], force=work["force"], tau=work["tau"], dtype=dtype,
                       amplitude=(1e-5, 1e-5, 1e-5), wavelength=(32.0, 32.0, 32.0),
                       overlap=args.overlap, rank=rank, nranks=world, device=local_rank, variant=args.variant)
-    algorithm = Algorithm(cfg, communication=Communication(rank, world), host_distribution=not args.no_e2e,
+    algorithm = Algorithm(cfg, communication=Communication(rank, world), host_distribution=False, host_fields=False,
                           peer_halos=(args.halo == "peer" and args.overlap == "On") if world > 1 else False)
     domain = algorithm.domain
-    nodes_global = shape[0] * shape[1] * shape[2]
-    nodes_local = nodes_global // world
 
-    # synthetic initial field of the named grid size: Taylor-Green-like velocity, density ripple (SURVEY 8d "Init B"),
-    # f = feq(rho, u) on the device, then (entropic workloads) a multiplicative perturbation of relative size eps
-    lx = domain.local_length[0]
-    x = (2 * np.pi * (np.arange(lx) + domain.offset_x) / shape[0])[:, None, None]
-    y = (2 * np.pi * np.arange(shape[1]) / shape[1])[None, :, None]
-    z = (2 * np.pi * np.arange(shape[2]) / shape[2])[None, None, :]
-    fields = algorithm.fieldList
-    field_dtype = domain.dtype
-    domain.interior(fields.density)[0] = (1.0 + 0.05 * np.sin(x) * np.cos(y) * np.cos(z)).astype(field_dtype)
-    if domain.dim == 3:
-        domain.interior(fields.velocity)[0] = (0.05 * np.sin(x) * np.cos(y) * np.cos(z)).astype(field_dtype)
-        domain.interior(fields.velocity)[1] = (-0.05 * np.cos(x) * np.sin(y) * np.cos(z)).astype(field_dtype)
-        domain.interior(fields.velocity)[2] = (0.025 * np.cos(x) * np.cos(y) * np.sin(z)).astype(field_dtype)
-    else:
-        domain.interior(fields.velocity)[0] = (0.05 * np.sin(y) * np.ones_like(x) * np.ones_like(z)).astype(field_dtype)
-        domain.interior(fields.velocity)[1] = (0.05 * np.cos(x) * np.ones_like(y) * np.ones_like(z)).astype(field_dtype)
-    algorithm.init_equilibrium()
+    # synthetic initial field of the named grid size, made on the device (SURVEY 8d "Init B": Taylor-Green-like velocity,
+    # density ripple, f = feq(rho, u)), then (entropic workloads) a multiplicative perturbation of relative size eps
+    algorithm.init_synthetic(0.05, 0.05)
     if work["eps"]:
         algorithm.perturb(work["eps"])
-    store_every = int(work["store_every"])
 
     # ---- device-resident throughput: W warm-up steps, then exactly K timed steps -------------------------
     if store_every:
         # the first stored step allocates the field arrays and plans the transforms of the spectral enstrophy: warm-up
-        check(algorithm._lib.mlbm_step(algorithm._ctx, 0, 1))
-    algorithm.run(1, args.warmup, store_every)
+        algorithm.run(0, 1, 1, stored_mode=stored_mode)
+    algorithm.run(1, args.warmup, store_every, stored_mode=stored_mode or 1)
     algorithm.kernel_time()                      # switches the per-launch CUDA event pairs on
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -514,7 +654,7 @@ def run_ours(args) -> int:
     barrier()
     begin = time.time()
     algorithm.mark(0)
-    algorithm.run(args.warmup + 1, args.steps, store_every, sync=False)
+    algorithm.run(args.warmup + 1, args.steps, store_every, sync=False, stored_mode=stored_mode or 1)
     algorithm.mark(1)
     algorithm.synchronize()
     barrier()
@@ -524,6 +664,7 @@ def run_ours(args) -> int:
     kernel_ms, kernel_launches = algorithm.kernel_time()
     clocks = sampler.stop(begin, end) if rank == 0 else None
     value = nodes_global * args.steps / (device_ms * 1e-3) / 1e6
+    stored_in_region = sum(1 for i in range(args.warmup + 1, args.warmup + args.steps + 1) if store_every and i % store_every == 0)
     entropic_state = None
     if entropic:
         off_shortcut, alpha_min, alpha_max = algorithm.alpha_statistics()
@@ -535,7 +676,7 @@ def run_ours(args) -> int:
     if store_every:
         barrier()
         algorithm.mark(2)
-        check(algorithm._lib.mlbm_run_async(algorithm._ctx, store_every, 1, store_every))
+        algorithm.run(store_every, 1, store_every, sync=False, stored_mode=stored_mode)
         algorithm.mark(3)
         algorithm.synchronize()
         stored_ms = max_over_ranks(algorithm.elapsed_ms(2, 3))
@@ -543,12 +684,25 @@ def run_ours(args) -> int:
     # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
     e2e = None
     if not args.no_e2e:
+        affinity = None
         try:
-            algorithm.pack()                         # current state -> host array (also first-touches the host pages)
-            host = algorithm.distribution.array
-            pinned = torch.empty(host.shape, dtype=torch.float64 if element == 8 else torch.float32, pin_memory=True)
-            pinned.numpy()[...] = host
+            # the host side of Distribution<T, GPU> (Distribution.h:15-43): the local padded SoA array, in pinned memory
+            # next to this GPU's PCIe root
+            host_bytes = q_count * domain.number_elements * element
+            available = host_memory_available()
+            roomy = min_over_ranks(1.0 if (available == 0 or host_bytes * world < 0.45 * available) else 0.0)
+            if not roomy:
+                raise RuntimeError(f"host staging buffers of {host_bytes * world / 1e9:.0f} GB do not fit {available / 1e9:.0f} GB of host memory")
+            affinity = bind_near_gpu(local_rank)
+            pinned = torch.empty((q_count,) + domain.padded_length, dtype=torch.float64 if element == 8 else torch.float32,
+                                 pin_memory=True)
             algorithm.distribution.array = pinned.numpy()
+            algorithm.pack()                         # current state -> host array (first-touches the pages)
+            # warm-up of everything the timed region uses for the first time: the observables' partial sums and their
+            # all-reduce (NCCL sets its channels up on the first collective of a communicator), the SM clocks
+            for iteration in range(1, 1 + max(args.warmup, 20)):
+                algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)
+                algorithm.observables()
             barrier()
             t0 = time.perf_counter()
             algorithm.unpack()                       # H2D of the whole SoA distribution from pinned host memory
@@ -562,34 +716,23 @@ def run_ours(args) -> int:
             t3 = time.perf_counter()
             barrier()
             e2e_seconds = max_over_ranks(time.perf_counter() - t0)
-            # outside the timed region: what the same bytes cost as ONE contiguous copy each way (the upload / download above
-            # move 2 KB rows of a padded host array with cudaMemcpy2DAsync); tells whether a staged contiguous copy would pay
-            contiguous = {}
-            try:
-                device_copy = torch.empty(pinned.shape, dtype=pinned.dtype, device="cuda")
-                for name, source, target in (("h2d", pinned, device_copy), ("d2h", device_copy, pinned)):
-                    torch.cuda.synchronize()
-                    c0 = time.perf_counter()
-                    target.copy_(source, non_blocking=True)
-                    torch.cuda.synchronize()
-                    contiguous[name + "_contiguous_GBps"] = pinned.numel() * element / (time.perf_counter() - c0) / 1e9
-                del device_copy
-            except Exception as error:  # noqa: BLE001 -- a diagnostic, never fatal
-                contiguous = {"contiguous_probe_error": str(error)[:200]}
             e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
             distribution_bytes = q_count * nodes_local * element
             e2e = {"value": e2e_value, "unit": UNIT,
                    "h2d_bytes_per_step": distribution_bytes / args.steps,
                    "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
-                   "note": "timed region: unpack (H2D of all populations from pinned host memory) + K synchronous mlbm_step calls "
-                           "each followed by a D2H read of the observables + pack (D2H of all populations); population bytes "
-                           "amortised over K", "last_energy": energy,
-                   "unpack_ms": (t1 - t0) * 1e3, "steps_ms": (t2 - t1) * 1e3, "pack_ms": (t3 - t2) * 1e3,
-                   "h2d_GBps": q_count * nodes_local * element / (t1 - t0) / 1e9,
-                   "d2h_GBps": q_count * nodes_local * element / (t3 - t2) / 1e9, **contiguous}
-
+                   "note": "per rank; timed region: unpack (H2D of all populations from pinned host memory) + K synchronous "
+                           "mlbm_step calls each followed by a D2H read of the all-reduced observables + pack (D2H of all "
+                           "populations); population bytes amortised over K; max over ranks", "last_energy": energy,
+                   "unpack_ms": max_over_ranks((t1 - t0) * 1e3), "steps_ms": max_over_ranks((t2 - t1) * 1e3),
+                   "pack_ms": max_over_ranks((t3 - t2) * 1e3),
+                   "h2d_GBps": distribution_bytes / (t1 - t0) / 1e9, "d2h_GBps": distribution_bytes / (t3 - t2) / 1e9,
+                   "host_buffer_numa_bound": affinity is not None}
         except Exception as error:  # noqa: BLE001 -- the device-resident headline above stands; the line says what happened
             e2e = {"value": None, "unit": UNIT, "error": str(error)[:300]}
+        finally:
+            if affinity is not None:
+                os.sched_setaffinity(0, affinity)
 
     peak, peak_source = measured_peak()
     # the dominant kernel is the bulk launch of the fused step: all local planes at N = 1, all but the two boundary
@@ -601,31 +744,41 @@ def run_ours(args) -> int:
                    f"{'double' if element == 8 else 'float'}>")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak if achieved else None,
-                "traffic": recorded_traffic() if args.workload == "d3q19_bgk_256" and dtype == "F64" else None,
+                # ncu's dram bytes per launch exist for exactly one kernel and shape (profiles/traffic.json says which)
+                "traffic": recorded_traffic() if workload_name == "d3q19_bgk_256" and dtype == "F64" and world == 1
+                and args.edge == EDGE and not getattr(args, "shape", None) else None,
                 "peak_source": peak_source, "kernel": kernel_name,
                 "kernel_ms": kernel_ms, "kernel_launches_timed": kernel_launches,
+                "kernel_planes_per_launch": lx - 2 if overlapped else lx,
                 "algorithmic_bytes_per_node": bytes_per_node,
                 "algorithmic_bytes_per_launch": bytes_per_node * kernel_nodes,
                 "roofline_mlups_per_gpu": peak * 1e9 / bytes_per_node / 1e6}
+    if entropic_state is not None:
+        fp64 = fp64_fraction(work["lattice"], work["collision"], kernel_nodes, kernel_ms, entropic_state["newton"])
+        if fp64:
+            roofline.update(fp64)
 
     cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline
-                                 and args.workload == "d3q19_bgk_256") else None
+                                 and workload_name == "d3q19_bgk_256") else None
     algorithm_peer = algorithm.peer_halos
     algorithm.close()
 
     line = None
     if rank == 0:
         buffer_gb = q_count * nodes_local * element / 1e9
-        metric = METRIC if args.workload == "d3q19_bgk_256" and dtype == "F64" else \
+        metric = METRIC if work["lattice"] == "D3Q19" and dtype == "F64" else \
             f"MLUPS ({work['lattice']}, {'FP64' if element == 8 else 'FP32'})"
+        stored_text = {0: None, 1: "whole fields + energy / spectral enstrophy / Mach", 2: "energy / mass / Mach reductions, no field arrays"}
         line = {
             "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": work["scaling"], "vs_baseline": None,
             "dtype": "f64" if element == 8 else "f32 storage, f64 arithmetic", "data": "synthetic",
-            "config": {"workload": f"{work['text']}; global {shape[0]}x{shape[1]}x{shape[2]}", "name": args.workload,
+            "config": {"workload": f"{work['text']}; global {shape[0]}x{shape[1]}x{shape[2]}", "name": workload_name,
                        "lattice": work["lattice"], "collision": work["collision"], "equilibrium": work["equilibrium"],
                        "forcing": f"{work['scheme']}/{work['force']}", "tau": work["tau"], "perturbation_eps": work["eps"],
-                       "store_every": store_every, "stored_step_ms": stored_ms, "global_length": list(shape), "parallelism": f"x-slab x{world}",
+                       "store_every": store_every, "stored_mode": stored_text[stored_mode], "stored_step_ms": stored_ms,
+                       "stored_steps_in_timed_region": stored_in_region,
+                       "global_length": list(shape), "parallelism": f"x-slab x{world}",
                        "overlap": args.overlap,
                        "halo": ("direct peer stores over NVLink from the boundary kernel" if algorithm_peer else
                                 "NCCL send/recv") if world > 1 else "none (single rank: periodic wrap in the kernel)",
@@ -633,6 +786,11 @@ def run_ours(args) -> int:
                              "no flush between steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
         }
+        if store_every and stored_ms is not None:
+            # the configuration's cadence spelled out: K plain steps were timed; one step in store_every is a stored one
+            plain = device_ms / args.steps if not stored_in_region else None
+            if plain is not None:
+                line["config"]["mlups_at_cadence"] = nodes_global * store_every / ((plain * (store_every - 1) + stored_ms) * 1e-3) / 1e6
         if cpu is not None:
             line["cpu_baseline"] = cpu
         if entropic_state is not None:
@@ -640,8 +798,7 @@ def run_ours(args) -> int:
 
     # ---- the other BASELINE configs at this GPU count.  The headline line above is final; whatever happens below
     # (an exception, a rank that stops answering) it is printed, by the watchdog if need be.
-    run_also = args.also == "on" or (args.also == "auto" and args.workload == "d3q19_bgk_256" and dtype == "F64"
-                                     and args.edge == EDGE)
+    run_also = args.also == "on" or (args.also == "auto" and default_headline)
     entries = (ALSO_SINGLE if world == 1 else ALSO_MULTI) if run_also else []
 
     def measure(entry):
@@ -663,7 +820,10 @@ def main() -> int:
     parser.add_argument("--edge", type=int, default=EDGE, help="edge of the per-GPU cube (default: the BASELINE 256)")
     parser.add_argument("--variant", type=int, default=0)
     parser.add_argument("--shape", default=None, help="global X,Y,Z overriding the workload's grid (experiments: slab shapes)")
-    parser.add_argument("--workload", default="d3q19_bgk_256", choices=sorted(WORKLOADS))
+    parser.add_argument("--workload", default=None, choices=sorted(WORKLOADS),
+                        help="default: d3q19_bgk_256 on one GPU (BASELINE configs[1]), d3q19_bgk_1024 strong-scaled on several (configs[4])")
+    parser.add_argument("--stored-mode", type=int, default=0, choices=[0, 1, 2],
+                        help="stored steps: 1 = whole fields + spectral enstrophy, 2 = energy / mass / Mach only; 0 = 1 where it fits")
     parser.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     parser.add_argument("--overlap", default="On", choices=["On", "Off"])
     parser.add_argument("--halo", default="peer", choices=["peer", "nccl"],

@@ -907,7 +907,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
 // ------------------------------------------------------------------------------------------------
 template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
 #ifndef MLBM_BGK_BLOCKS
-#define MLBM_BGK_BLOCKS 1
+#define MLBM_BGK_BLOCKS 4
 #endif
 __global__ void __launch_bounds__(kStepBlock, COLLISION != kBGK ? entropicBlocksPerSM(L::Q) : MLBM_BGK_BLOCKS)
 fusedStepKernel(const __grid_constant__ StepParams p) {

@@ -234,27 +234,44 @@ def run_ref(cfg: RefConfig, populations: np.ndarray | None, steps: int, store_ev
 # compiled in the build container and timed on the GPU box, whose host CPU may differ.
 TIMING_FLAGS = "-O3 -march=x86-64-v3 -funroll-loops"
 TIMING_RANKS = (1, 2, 4, 8, 16, 32, 64, 128)
-TIMING_PLANES_PER_RANK = 2
+TIMING_PLANES_PER_RANK = 2   # the thin-slab sample of round 1 (kept as a second figure)
+TIMING_EDGE = 256
 
 
-def timing_config(nprocs: int) -> RefConfig:
-    """The headline workload (D3Q19 SRT-BGK, 256 x 256 cross-section, FP64) as a bounded x-slab sample:
-    TIMING_PLANES_PER_RANK planes of 256 x 256 nodes per rank, one rank per host core."""
-    return RefConfig(lattice="D3Q19", nx=TIMING_PLANES_PER_RANK * nprocs, ny=256, nz=256, collision="BGK",
+LARGE_EDGE = 1024            # cross-section of BASELINE configs[4] (D3Q19 1024^3, the multi-GPU headline)
+LARGE_MAX_RANKS = 32         # 2 planes of 1024^2 per rank: 3 arrays x 19 x 8 B x 2.1e6 nodes = 0.96 GB per rank
+
+
+def timing_config(nprocs: int, planes: int | None = None, edge: int = TIMING_EDGE) -> RefConfig:
+    """The headline workload (D3Q19 SRT-BGK, edge x edge cross-section, FP64).  planes=None: the WHOLE cube of
+    BASELINE configs[1] (edge 256) split into nprocs x-slabs, one rank per host core (256 / nprocs planes per rank) -- the
+    same configuration the GPU arm times.  planes=k: a bounded x-slab sample of k planes per rank (k = 2 makes the
+    reference's halo exchange and y/z boundary copies as expensive as its node update); edge=1024 samples configs[4]."""
+    nx = edge if planes is None else planes * nprocs
+    return RefConfig(lattice="D3Q19", nx=nx, ny=edge, nz=edge, collision="BGK",
                      forcing_scheme="None", force="None", tau=0.55, nprocs=nprocs, optimize=TIMING_FLAGS)
 
 
 def timing_configs() -> list:
     """Prebuilt by __graft_entry__.build() so that they travel to the GPU box (one binary per rank count,
-    numProcs is a compile-time constant of the reference)."""
-    return [timing_config(n) for n in TIMING_RANKS]
+    numProcs is a compile-time constant of the reference): the full 256^3 cube, its thin-slab sample, and the thin-slab
+    sample of the 1024^3 cube."""
+    configs = []
+    for n in TIMING_RANKS:
+        candidates = [timing_config(n, None), timing_config(n, TIMING_PLANES_PER_RANK)]
+        if n <= LARGE_MAX_RANKS:
+            candidates.append(timing_config(n, TIMING_PLANES_PER_RANK, LARGE_EDGE))
+        for cfg in candidates:
+            if all(cfg.name() != other.name() for other in configs):
+                configs.append(cfg)
+    return configs
 
 
-def best_timing_config(cores: int) -> RefConfig | None:
+def best_timing_config(cores: int, planes: int | None = None, edge: int = TIMING_EDGE) -> RefConfig | None:
     """Largest prebuilt rank count that fits the host cores."""
     for n in sorted(TIMING_RANKS, reverse=True):
-        if n <= cores and binary_path(timing_config(n)).is_file():
-            return timing_config(n)
+        if n <= cores and binary_path(timing_config(n, planes, edge)).is_file():
+            return timing_config(n, planes, edge)
     return None
 
 
@@ -266,7 +283,8 @@ def time_reference(cfg: RefConfig, steps: int, warmup: int = 0, timeout: float =
     # per-rank average of the reference's own timers (Algorithm.h:340-357) = time of the parallel run
     seconds = result["time_computation"] + result["time_communication"]
     return {"mlups": nodes * steps / seconds / 1e6, "seconds": seconds, "wall": result["time_wall"],
-            "nodes": nodes, "steps": steps, "ranks": cfg.nprocs}
+            "nodes": nodes, "steps": steps, "ranks": cfg.nprocs,
+            "communication_share": result["time_communication"] / seconds if seconds > 0 else None}
 
 
 if __name__ == "__main__":
