@@ -354,17 +354,26 @@ def summarize_also(also) -> list:
     """One short string per secondary workload: the line's LAST key, so that it survives a truncated log tail."""
     rows = []
     for entry in also:
-        if "value" not in entry:
-            rows.append(f"{entry.get('name')}: {entry.get('skipped') or entry.get('error') or '?'}"[:90])
-            continue
-        text = (f"{entry['name']} {entry.get('dtype')} {entry['global_length'][0]}x{entry['global_length'][1]}x{entry['global_length'][2]}"
-                + (f" eps={entry['eps']:g}" if entry.get("eps") else "") + (f" store{entry['stored_mode']}" if entry.get("stored_mode") else "")
-                + f": {entry['value']:.0f} MLUPS hbm={entry['roofline_frac']:.3f}")
-        if entry.get("fp64_frac") is not None:
-            text += f" fp64={entry['fp64_frac']:.2f}"
-        if entry.get("stored_step_ms") is not None:
-            text += f" stored_ms={entry['stored_step_ms']:.2f}/{entry['ms_per_step']:.2f}"
-        rows.append(text)
+        try:
+            if "value" not in entry:
+                rows.append(f"{entry.get('name')}: {entry.get('skipped') or entry.get('error') or '?'}"[:90])
+                continue
+            length = entry.get("global_length") or ["?"] * 3
+            text = f"{entry.get('name')} {entry.get('dtype')} {length[0]}x{length[1]}x{length[2]}"
+            if entry.get("eps"):
+                text += f" eps={entry['eps']:g}"
+            if entry.get("stored_mode"):
+                text += f" store{entry['stored_mode']}"
+            text += f": {entry['value']:.0f} MLUPS"
+            if entry.get("roofline_frac") is not None:
+                text += f" hbm={entry['roofline_frac']:.3f}"
+            if entry.get("fp64_frac") is not None:
+                text += f" fp64={entry['fp64_frac']:.2f}"
+            if entry.get("stored_step_ms") is not None and entry.get("ms_per_step") is not None:
+                text += f" stored_ms={entry['stored_step_ms']:.2f}/{entry['ms_per_step']:.2f}"
+            rows.append(text)
+        except Exception as error:  # noqa: BLE001 -- a summary must never cost the line
+            rows.append(f"{entry.get('name') if isinstance(entry, dict) else entry}: summary failed ({error})"[:90])
     return rows
 
 
@@ -590,7 +599,8 @@ def run_ours(args) -> int:
     # -- the configuration the north star's parallel-efficiency target is quoted on; the driver's efficiency
     # v_N / (N v_1) is then SURVEY 8d's definition (1024^3 itself cannot run on one GPU).
     workload_name = args.workload or ("d3q19_bgk_256" if world == 1 else "d3q19_bgk_1024")
-    default_headline = args.workload is None and args.dtype == "f64" and args.edge == EDGE and not getattr(args, "shape", None)
+    default_headline = (workload_name == ("d3q19_bgk_256" if world == 1 else "d3q19_bgk_1024") and args.dtype == "f64"
+                        and args.edge == EDGE and not getattr(args, "shape", None))
     work = dict(WORKLOADS[workload_name])
     if args.edge != EDGE and workload_name == "d3q19_bgk_256":
         work["shape"] = (args.edge,) * 3
@@ -625,7 +635,7 @@ def run_ours(args) -> int:
     if store_every:
         free = torch.cuda.mem_get_info()[0]
         full = device_bytes_needed(q_count, nodes_local // lx, lx, element, entropic, dim, 1) + (4 << 30) < free
-        stored_mode = args.stored_mode or (1 if min_over_ranks(1.0 if full else 0.0) else 2)
+        stored_mode = getattr(args, "stored_mode", 0) or (1 if min_over_ranks(1.0 if full else 0.0) else 2)
     cfg = make_config(lattice=work["lattice"], shape=shape, collision=work["collision"], equilibrium=work["equilibrium"],
                       forcing_scheme=work["scheme"], force=work["force"], tau=work["tau"], dtype=dtype,
                       amplitude=(1e-5, 1e-5, 1e-5), wavelength=(32.0, 32.0, 32.0),

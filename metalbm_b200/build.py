@@ -15,7 +15,8 @@ PACKAGE_DIR = Path(__file__).resolve().parent
 CSRC = PACKAGE_DIR / "csrc"
 # experiments: MLBM_VARIANT=name MLBM_EXTRA_FLAGS="-DX=1 ..." builds libmetalbm_b200_name.so next to the product library
 VARIANT = os.environ.get("MLBM_VARIANT", "")
-BUILD = PACKAGE_DIR / ("_build" + ("_" + VARIANT if VARIANT else ""))
+# variant objects live outside the tree: only their .so travels to the GPU box (the snapshot is capped at 512 MiB)
+BUILD = (Path("/tmp") / ("mlbm_build_" + VARIANT)) if VARIANT else PACKAGE_DIR / "_build"
 LIBRARY = PACKAGE_DIR / ("libmetalbm_b200" + ("_" + VARIANT if VARIANT else "") + ".so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -33,9 +33,11 @@ __global__ void __launch_bounds__(256) alphaStatisticsKernel(const StoreT* __res
 }
 
 __global__ void fastLogKernel(const double* __restrict__ in, double* __restrict__ out, long long count) {
-  __shared__ double2 table[kLogTableEntries];
-  for (int i = threadIdx.x; i < kLogTableEntries; i += blockDim.x) table[i] = kLogTable[i];
+  __shared__ double logc[kLogTableEntries];
+  __shared__ unsigned inverseHigh[kLogTableEntries];
+  for (int i = threadIdx.x; i < kLogTableEntries; i += blockDim.x) { logc[i] = kLogCentre[i]; inverseHigh[i] = kLogInverseHigh[i]; }
   __syncthreads();
+  const LogTable table = {inverseHigh, logc};
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < count) out[i] = fastLog(in[i], table);
 }

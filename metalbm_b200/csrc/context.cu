@@ -413,7 +413,6 @@ static int launchStep(mlbm_ctx* ctx, cudaStream_t stream, int x0, int x1, int is
   p.velocity = ctx->velocity;
   p.force = ctx->force;
   p.partials = ctx->partials;
-  p.hints = ctx->hints;
   p.newtonCounters = ctx->newtonCounters;
   for (int d = 0; d < 3; ++d) { p.forceTable[d] = ctx->forceTables[d]; p.forceAxis[d] = ctx->forceAxis[d]; }
   p.fieldStride = ctx->fieldStride;
@@ -596,7 +595,7 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   if (ctx->shell) shellForceDestroy(ctx->shell);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
-                        (void*)ctx->partials, (void*)ctx->hints, (void*)ctx->newtonCounters, ctx->staging, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
+                        (void*)ctx->partials, (void*)ctx->newtonCounters, ctx->staging, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
                         (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
     if (pointer) cudaFree(pointer);
   for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->stepStart, ctx->timeStart, ctx->timeMid, ctx->timeStop})
@@ -715,8 +714,6 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
     if (config->dtype == MLBM_F64) fillKernel<double><<<grid, 256, 0, ctx->computeStream>>>(static_cast<double*>(ctx->alpha), ctx->nodes, 2.0);
     else fillKernel<float><<<grid, 256, 0, ctx->computeStream>>>(static_cast<float*>(ctx->alpha), ctx->nodes, 2.0f);
     MLBM_CREATE_CUDA(cudaGetLastError());
-    MLBM_CREATE_CUDA(cudaMalloc(&ctx->hints, (size_t)ctx->partialBlocks));
-    MLBM_CREATE_CUDA(cudaMemsetAsync(ctx->hints, 0, (size_t)ctx->partialBlocks, ctx->computeStream));
   }
   MLBM_CREATE_CUDA(cudaMalloc(&ctx->deviceObservables, 4 * sizeof(double)));
   MLBM_CREATE_CUDA(cudaMemsetAsync(ctx->deviceObservables, 0, 4 * sizeof(double), ctx->computeStream));

@@ -79,7 +79,6 @@ struct mlbm_ctx {
   bool fieldsStored = false;
   double* partials = nullptr;
   unsigned long long* newtonCounters = nullptr;  // mlbm_newton_statistics: {nodes solved, evaluations}, counted while non-null
-  unsigned char* hints = nullptr;        // entropic contexts: one byte per block and plane (StepParams::hints)
   void* staging = nullptr;               // staged pack / unpack: one padded population block
   size_t stagingBytes = 0;
   double* reduceStage = nullptr;         // [kReduceBlocks][kObservableSlots] second-stage partials

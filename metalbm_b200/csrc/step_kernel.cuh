@@ -44,8 +44,6 @@ struct StepParams {
   void* force;             // [D] components, fieldStride apart
   double* partials;        // [LX * NM * ceil(NR / kStepBlock)][kObservableSlots] block partial sums (only when isStored)
   unsigned long long* newtonCounters;  // entropic kernels: [0] += nodes that took the Newton solve, [1] += evaluations of (F, F') they needed
-  unsigned char* hints;    // [LX * NM * ceil(NR / kStepBlock)] entropic kernels built with MLBM_ELBM_FASTPATH: 1 = this block's
-                           // plane had a node off the small-deviation shortcut in the previous step (else unused)
   const double* forceTable[3];  // per force component: amplitude * profile along forceAxis (host libm values)
   int forceAxis[3];        // 0 = x, 1 = m, 2 = r, -1 = component is identically zero
   long long stride;        // elements between populations
@@ -155,56 +153,65 @@ template <int I, int N, class F> __device__ __forceinline__ void staticFor(F&& f
 }
 
 // ------------------------------------------------------------------------------------------------
-// fastLogCore: natural logarithm of doubles in [0.25, 4) with an absolute error below 2.5e-16, 9 FP64 + 4 integer
+// fastLogCore: natural logarithm of doubles in [0.25, 4) with an absolute error below 2.5e-16, 8 FP64 + 4 integer
 // instructions instead of the ~30 FP64 + ~25 integer instructions of the CUDA math library's log().
-// The entropic solve evaluates (1 + iterations) * Q logarithms per node, which makes it FP64-issue bound (SURVEY.md
-// section 7); this is what moves it back towards the HBM roofline.  The arguments are f_q / w_q and
+// The entropic solve evaluates (1 + iterations) * Q logarithms per node, which makes it FP64-issue and shared-memory
+// bound; this is what moves it back towards the HBM roofline.  The arguments are f_q / w_q and
 // (f_q - alpha fNeq_q) / w_q, i.e. the local density times 1 + O(Mach) + O(non-equilibrium): [0.25, 4) covers every
 // state a lattice-Boltzmann run can sensibly be in, and anything else takes the library path (entropicNewtonLibrary).
-//   The top bits of the double (exponent and 7 mantissa bits, minus those of 0.25) index one of 512 sub-intervals with
-//   centre c; invc = double(1/c), logc = double(-ln invc) (log_table.inc, generated with 100-digit arithmetic by
-//   gen_log_table.py); r = fma(v, invc, -1) is exact to rounding and |r| < 2^-8, so
-//   ln v = logc + (r - r^2/2 + ... + r^7/7) with a truncation error below 1e-20.
+//   The top bits of the double (exponent and 8 mantissa bits, minus those of 0.25) index one of 1024 sub-intervals with
+//   centre c; invc = 1/c rounded to a double with a ZERO LOW WORD, logc = double(-ln invc) (log_table.inc, generated with
+//   100-digit arithmetic by gen_log_table.py); r = fma(v, invc, -1) is exact to rounding and |r| < 2^-9 + 2^-20, so
+//   ln v = logc + (r - r^2/2 + ... + r^5/5) with a truncation error below 1e-17.
+// The table is two arrays -- the high words of invc (4 bytes) and logc (8 bytes): 12 bytes of shared-memory traffic per
+// logarithm, not 16.  ncu (profiles/r02b_*): with 16-byte entries the shared-memory pipe was busier (65 %) than the FP64
+// pipe (53 %) in the D3Q27 entropic kernel.
 // N independent arguments advance in lock step: every Horner step is issued for all N before the next one, which
 // gives the FP64 pipe N independent dependency chains per warp.
-// `range` accumulates the maximum table index as an unsigned number: it stays below 512 exactly when every argument
-// was inside [0.25, 4) (smaller, negative, infinite and NaN arguments all map to indices >= 512: the high word minus that
+// `range` accumulates the maximum table index as an unsigned number: it stays below 1024 exactly when every argument
+// was inside [0.25, 4) (smaller, negative, infinite and NaN arguments all map to indices >= 1024: the high word minus that
 // of 0.25, in unsigned arithmetic, is either below 2^22 -- the table -- or at least 2^30).
 // ------------------------------------------------------------------------------------------------
-constexpr int kLogTableEntries = 512;
-static __device__ const double2 kLogTable[kLogTableEntries] = {
+constexpr int kLogTableEntries = 1024;
+static __device__ const unsigned kLogInverseHigh[kLogTableEntries] = {
+#define MLBM_LOG_ENTRY(inverseHigh, logc) inverseHigh,
 #include "log_table.inc"
+#undef MLBM_LOG_ENTRY
+};
+static __device__ const double kLogCentre[kLogTableEntries] = {
+#define MLBM_LOG_ENTRY(inverseHigh, logc) logc,
+#include "log_table.inc"
+#undef MLBM_LOG_ENTRY
+};
+struct LogTable {
+  const unsigned* inverseHigh;  // high word of invc (its low word is zero)
+  const double* logc;           // -ln(invc)
 };
 
 template <int N>
-__device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[N], const double2* __restrict__ table,
-                                            unsigned& range) {
-  double2 entry[N];
-  double r[N], p[N];
+__device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[N], const LogTable& table, unsigned& range) {
+  double invc[N], logc[N], r[N], p[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
-    const unsigned index = ((unsigned)__double2hiint(v[j]) - 0x3FD00000u) >> 13;  // unsigned: negative arguments wrap, they do not overflow
+    const unsigned index = ((unsigned)__double2hiint(v[j]) - 0x3FD00000u) >> 12;  // unsigned: negative arguments wrap, they do not overflow
     range = max(range, index);
-    entry[j] = table[index & (kLogTableEntries - 1)];
+    invc[j] = __hiloint2double((int)table.inverseHigh[index & (kLogTableEntries - 1)], 0);
+    logc[j] = table.logc[index & (kLogTableEntries - 1)];
   }
 #pragma unroll
-  for (int j = 0; j < N; ++j) r[j] = fma(v[j], entry[j].x, -1.0);
+  for (int j = 0; j < N; ++j) r[j] = fma(v[j], invc[j], -1.0);
 #pragma unroll
-  for (int j = 0; j < N; ++j) p[j] = fma(r[j], 1.0 / 7.0, -1.0 / 6.0);
-#pragma unroll
-  for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], 0.2);
-#pragma unroll
-  for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], -0.25);
+  for (int j = 0; j < N; ++j) p[j] = fma(r[j], 0.2, -0.25);
 #pragma unroll
   for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], 1.0 / 3.0);
 #pragma unroll
   for (int j = 0; j < N; ++j) p[j] = fma(r[j], p[j], -0.5);
 #pragma unroll
-  for (int j = 0; j < N; ++j) out[j] = entry[j].y + fma(r[j] * r[j], p[j], r[j]);
+  for (int j = 0; j < N; ++j) out[j] = logc[j] + fma(r[j] * r[j], p[j], r[j]);
 }
 
 // general entry point (self-test, tools): library logarithm outside [0.25, 4)
-__device__ __forceinline__ double fastLog(double v, const double2* __restrict__ table) {
+__device__ __forceinline__ double fastLog(double v, const LogTable& table) {
   const double in[1] = {v};
   double out[1];
   unsigned range = 0;
@@ -215,14 +222,17 @@ __device__ __forceinline__ double fastLog(double v, const double2* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 // Entropic alpha: Collision<ELBM>::calculateAlpha (Collision.h:351-375).
 //
-// Work layout.  The populations f_q and their non-equilibrium parts of the block's nodes live in SHARED memory
+// Work layout.  The populations f_q and their non-equilibrium parts of the block's nodes are parked in SHARED memory
 // ([row][node], conflict-free) while alpha is solved for.  That buys three things:
-//   * the Newton loops over q are rolled (a few dozen instructions, G logarithms in lock step for instruction-level
-//     parallelism) instead of Q copies of the logarithm per evaluation, which had overflowed the instruction cache;
-//   * the solve is COMPACTED over the block: the nodes that need it are listed in shared memory and thread i solves
-//     the i-th listed node (any thread can read any node's column), so the FP64 cost follows the number of such nodes
-//     instead of the number of warps that contain at least one of them;
+//   * the registers of the pull / moments / equilibrium phase are free during the solve;
+//   * the solve is COMPACTED over the block: the nodes that left the small-deviation shortcut are listed in shared
+//     memory and thread i solves the i-th listed node (any thread can read any node's column), so the FP64 cost follows
+//     the number of such nodes instead of the number of warps that contain at least one of them;
 //   * one block handles several x planes in a row, staging the logarithm table and the per-row constants once.
+// The solving thread reads the column of its node ONCE into registers where the register file allows (kColumnRegisters:
+// both F2 and N2 for Q <= 13, N2 only up to Q = 27) and unrolls the loops over q; the evaluations then cost 12 bytes of
+// shared-memory traffic per population (the table) instead of 28.  Lattices beyond that keep the rolled loops over the
+// shared-memory column.
 //
 // Arithmetic of one evaluation.  The populations of one speed class c (|c_q|^2 = 0, 1, 2, 3: same weight w_c) are
 // stored next to each other and SCALED by 2^k_c, k_c the integer with w_c 2^k_c in [0.7, 1.4): the scaling is exact
@@ -233,7 +243,7 @@ __device__ __forceinline__ double fastLog(double v, const double2* __restrict__ 
 //   F(a)  = sum f ln(f/w) - g ln(g/w) = H - [sum_c 2^-k_c sum_{q in c} v_q L_q + A - a B]          (EntropicStep.h:31-45)
 //   F'(a) = sum fNeq (1 + ln(g/w))    = sum fNeq + B + sum_c 2^-k_c sum_{q in c} N2_q L_q             (EntropicStep.h:47-62)
 // with L_q = fastLog(v_q), A = sum_c 2^-k_c C_c sum_{q in c} F2_q, B likewise over N2, and H = F's first sum, hoisted
-// out of the iteration: 12 FP64 instructions per population and evaluation (1 + 9 + 2), against ~3 x 60 as the
+// out of the iteration: 11 FP64 instructions per population and evaluation (1 + 8 + 2), against ~3 x 60 as the
 // reference writes it, and no per-population integer or constant traffic besides the table lookup.
 // ------------------------------------------------------------------------------------------------
 constexpr int logShift(double w) {
@@ -280,26 +290,22 @@ template <class L> struct SpeedClasses {
   // logarithms advanced in lock step inside a class
   static constexpr int group(int n2) {
     const int n = count(n2);
-#ifdef MLBM_LOG_GROUP_WIDE
-    return n % 6 == 0 ? 6 : (n % 4 == 0 ? 4 : (n < 3 ? (n > 0 ? n : 1) : 3));
-#else
     return n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n < 3 ? (n > 0 ? n : 1) : 3));
-#endif
   }
 };
 
 struct EntropicShared {
   double* f;             // [Q][kStepBlock]  F2, rows sorted by speed class
   double* fNeq;          // [Q][kStepBlock]  N2
-  double* alpha;         // [kStepBlock]     in: alphaMax of the nodes to solve, out: their alpha
+  double* alpha;         // [kStepBlock]     out: alpha of the solved nodes
   double* rowOffset;     // [kRowSlots]  C_c of the row's class       (library fallback only)
   double* rowInverse;    // [kRowSlots]  2^-k_c of the row's class    (library fallback only)
   int* warpCount;        // [kStepBlock / 32]
-  unsigned char* list;   // [kStepBlock]     nodes (thread indices) that need the Newton solve, ascending
-  const double2* table;  // fastLog table (shared or global memory)
+  unsigned char* list;   // [kStepBlock]     nodes (thread indices) that left the shortcut, ascending
+  LogTable table;        // fastLog table (shared or global memory)
 };
 
-constexpr int kLogTableBytes = kLogTableEntries * 16;
+constexpr int kLogTableBytes = kLogTableEntries * 12;
 constexpr int rowSlots(int Q) { return Q <= 32 ? 32 : 40; }  // D3Q33 has 33 rows
 constexpr int entropicSharedBytes(int Q, bool tableInShared) {
   return 2 * Q * kStepBlock * 8 + kStepBlock * 8 + 2 * rowSlots(Q) * 8 + 16 + kStepBlock + (tableInShared ? kLogTableBytes : 0);
@@ -312,6 +318,14 @@ constexpr int entropicSharedBytes(int Q, bool tableInShared) {
 constexpr int entropicBlocksPerSM(int Q) { return Q <= 9 ? MLBM_ENTROPIC_BLOCKS_Q9 : (Q >= 27 ? 3 : 4); }
 // the fastLog table is staged in shared memory whenever those blocks still fit (228 KB, 1 KB reserved per block)
 constexpr bool logTableInShared(int Q) { return entropicBlocksPerSM(Q) * (entropicSharedBytes(Q, true) + 1024) <= 233472; }
+// which part of its node's column the solving thread keeps in registers: 2 = F2 and N2, 1 = N2, 0 = nothing (rolled loops)
+#ifndef MLBM_COLUMN_REGISTERS_Q27
+#define MLBM_COLUMN_REGISTERS_Q27 1
+#endif
+#ifndef MLBM_COLUMN_REGISTERS_Q19
+#define MLBM_COLUMN_REGISTERS_Q19 1
+#endif
+constexpr int columnRegisters(int Q) { return Q <= 13 ? 2 : (Q <= 21 ? MLBM_COLUMN_REGISTERS_Q19 : (Q <= 27 ? MLBM_COLUMN_REGISTERS_Q27 : 0)); }
 
 // The same solve with the CUDA math library's logarithm, for the rare node whose arguments fall outside fastLogCore's
 // table (and with it the reference's NaN behaviour for mirror states that leave the positive cone: the iteration produces
@@ -344,84 +358,128 @@ __device__ __noinline__ double entropicNewtonLibrary(const double* fColumn, cons
   return 2.0;
 }
 
-// one speed class of the hoisted sums: hC = sum v ln v, sF = sum F2, sN = sum N2 over the class rows
-template <int FIRST, int COUNT, int G>
-__device__ __forceinline__ void entropicHoistClass(const double* fColumn, const double* nColumn, const double2* table, unsigned& range,
-                                                   double& hC, double& sF, double& sN) {
-  constexpr int groups = (COUNT + G - 1) / G;
-  double h[G], a[G], b[G];
+// The column of one node as the solve sees it: MODE 2 keeps F2 and N2 in registers, MODE 1 N2 only (F2 is read from shared
+// memory at compile-time offsets), MODE 0 nothing.  Rows are compile-time in MODE 1 / 2 (unrolled loops) and run-time in MODE 0.
+template <int Q, int MODE> struct EntropicColumn {
+  const double* fColumn;
+  const double* nColumn;
+  double fRegisters[MODE == 2 ? Q : 1];
+  double nRegisters[MODE >= 1 ? Q : 1];
+  __device__ __forceinline__ void load(const double* f, const double* n) {
+    fColumn = f;
+    nColumn = n;
+    if constexpr (MODE == 2) {
 #pragma unroll
-  for (int j = 0; j < G; ++j) h[j] = a[j] = b[j] = 0.0;
-#pragma unroll 1
-  for (int group = 0; group < groups; ++group) {
-    double v[G], lg[G];
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      const int row = FIRST + group * G + j;
-      const bool live = COUNT % G == 0 || group * G + j < COUNT;
-      v[j] = live ? fColumn[row * kStepBlock] : 1.0;
-      a[j] += live ? v[j] : 0.0;
-      b[j] += live ? nColumn[row * kStepBlock] : 0.0;
+      for (int row = 0; row < Q; ++row) fRegisters[row] = f[row * kStepBlock];
     }
-    fastLogCore<G>(v, lg, table, range);
+    if constexpr (MODE >= 1) {
 #pragma unroll
-    for (int j = 0; j < G; ++j) h[j] = fma(v[j], lg[j], h[j]);
-  }
-  hC = h[0]; sF = a[0]; sN = b[0];
-#pragma unroll
-  for (int j = 1; j < G; ++j) { hC += h[j]; sF += a[j]; sN += b[j]; }
-}
-
-// one speed class of an evaluation: sC = sum v L, dC = sum N2 L with v = F2 - x N2
-template <int FIRST, int COUNT, int G>
-__device__ __forceinline__ void entropicEvaluateClass(const double* fColumn, const double* nColumn, const double2* table, unsigned& range,
-                                                      double x, double& sC, double& dC) {
-  constexpr int groups = (COUNT + G - 1) / G;
-  double sum[G], derivative[G];
-#pragma unroll
-  for (int j = 0; j < G; ++j) sum[j] = derivative[j] = 0.0;
-#pragma unroll 1
-  for (int group = 0; group < groups; ++group) {
-    double n2[G], v[G], lg[G];
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      const int row = FIRST + group * G + j;
-      const bool live = COUNT % G == 0 || group * G + j < COUNT;
-      n2[j] = live ? nColumn[row * kStepBlock] : 0.0;
-      v[j] = live ? fma(-x, n2[j], fColumn[row * kStepBlock]) : 1.0;
-    }
-    fastLogCore<G>(v, lg, table, range);
-#pragma unroll
-    for (int j = 0; j < G; ++j) {
-      sum[j] = fma(v[j], lg[j], sum[j]);
-      derivative[j] = fma(n2[j], lg[j], derivative[j]);
+      for (int row = 0; row < Q; ++row) nRegisters[row] = n[row * kStepBlock];
     }
   }
-  sC = sum[0]; dC = derivative[0];
+  __device__ __forceinline__ double F(int row) const { if constexpr (MODE == 2) return fRegisters[row]; else return fColumn[row * kStepBlock]; }
+  __device__ __forceinline__ double N(int row) const { if constexpr (MODE >= 1) return nRegisters[row]; else return nColumn[row * kStepBlock]; }
+};
+
+// one group of G rows: hC += v ln v, sF += F2, sN += N2
+template <int G, int COUNT, class Column>
+__device__ __forceinline__ void entropicHoistGroup(const Column& column, int firstRow, int inClass, const LogTable& table, unsigned& range,
+                                                   double (&h)[G], double (&a)[G], double (&b)[G]) {
+  double v[G], lg[G];
 #pragma unroll
-  for (int j = 1; j < G; ++j) { sC += sum[j]; dC += derivative[j]; }
+  for (int j = 0; j < G; ++j) {
+    const bool live = COUNT % G == 0 || inClass + j < COUNT;
+    v[j] = live ? column.F(firstRow + j) : 1.0;
+    a[j] += live ? v[j] : 0.0;
+    b[j] += live ? column.N(firstRow + j) : 0.0;
+  }
+  fastLogCore<G>(v, lg, table, range);
+#pragma unroll
+  for (int j = 0; j < G; ++j) h[j] = fma(v[j], lg[j], h[j]);
 }
 
-// solveAlpha (Collision.h:328-349) -> NewtonRaphsonSolver (EntropicStep.h:111-140), see the banner above.
+// one group of G rows of an evaluation: sum += v L, derivative += N2 L with v = F2 - x N2
+template <int G, int COUNT, class Column>
+__device__ __forceinline__ void entropicEvaluateGroup(const Column& column, int firstRow, int inClass, const LogTable& table, unsigned& range,
+                                                      double x, double (&sum)[G], double (&derivative)[G]) {
+  double n2[G], v[G], lg[G];
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    const bool live = COUNT % G == 0 || inClass + j < COUNT;
+    n2[j] = live ? column.N(firstRow + j) : 0.0;
+    v[j] = live ? fma(-x, n2[j], column.F(firstRow + j)) : 1.0;
+  }
+  fastLogCore<G>(v, lg, table, range);
+#pragma unroll
+  for (int j = 0; j < G; ++j) {
+    sum[j] = fma(v[j], lg[j], sum[j]);
+    derivative[j] = fma(n2[j], lg[j], derivative[j]);
+  }
+}
+
+// the groups of one speed class: unrolled when the column sits in registers (compile-time rows), rolled otherwise
+template <int FIRST, int COUNT, int G, int MODE, class Body>
+__device__ __forceinline__ void forEachGroup(Body&& body) {
+  constexpr int groups = (COUNT + G - 1) / G;
+  if constexpr (MODE >= 1) {
+    staticFor<0, groups>([&](auto gc) { body(FIRST + decltype(gc)::value * G, decltype(gc)::value * G); });
+  } else {
+#pragma unroll 1
+    for (int group = 0; group < groups; ++group) body(FIRST + group * G, group * G);
+  }
+}
+
+// calculateAlpha for a node off the small-deviation shortcut (Collision.h:351-375; FORCED: :792-808), by the thread that
+// solves it: calculateAlphaMax (Collision.h:305-326: min(2.5, min over fNeq_q > 0 of |f_q| / fNeq_q), tracked as a fraction;
+// the 2^k scaling of a class cancels in the ratio), alphaMax < 2 -> 0.95 alphaMax, else solveAlpha (Collision.h:328-349) ->
+// NewtonRaphsonSolver (EntropicStep.h:111-140), see the banner above.  `evaluations` returns the evaluations of (F, F').
 template <class L>
-__device__ __forceinline__ double entropicNewton(const EntropicShared& s, int column, double alphaGuess, double alphaMax, int& evaluations) {
+__device__ __forceinline__ double entropicAlpha(const EntropicShared& s, int node, double alphaGuess, int& evaluations) {
   using C = SpeedClasses<L>;
-  const double* fColumn = s.f + column;
-  const double* nColumn = s.fNeq + column;
+  constexpr int MODE = columnRegisters(L::Q);
+  EntropicColumn<L::Q, MODE> column;
+  column.load(s.f + node, s.fNeq + node);
+
+  double num = 2.5, den = 1.0;
+  auto screen = [&](int row) {
+    const double n2 = column.N(row);
+    if (n2 > 0.0) {
+      const double af = fabs(column.F(row));
+      if (af * den < num * n2) { num = af; den = n2; }
+    }
+  };
+  if constexpr (MODE >= 1) {
+    staticFor<0, L::Q>([&](auto rc) { screen(decltype(rc)::value); });
+  } else {
+#pragma unroll 1
+    for (int row = 0; row < L::Q; ++row) screen(row);
+  }
+  const double alphaMax = num / den;
+  evaluations = 0;
+  if (alphaMax < 2.0) return 0.95 * alphaMax;
+
   unsigned range = 0;
   double hoisted = 0.0, offsetF = 0.0, offsetN = 0.0, sumN = 0.0;
   staticFor<0, L::maxNorm2() + 1>([&](auto nc) {
     constexpr int n2 = decltype(nc)::value;
     if constexpr (C::count(n2) > 0) {
-      double hC, sF, sN;
-      entropicHoistClass<C::first(n2), C::count(n2), C::group(n2)>(fColumn, nColumn, s.table, range, hC, sF, sN);
+      constexpr int G = C::group(n2);
+      double h[G], a[G], b[G];
+#pragma unroll
+      for (int j = 0; j < G; ++j) h[j] = a[j] = b[j] = 0.0;
+      forEachGroup<C::first(n2), C::count(n2), G, MODE>([&](int firstRow, int inClass) {
+        entropicHoistGroup<G, C::count(n2)>(column, firstRow, inClass, s.table, range, h, a, b);
+      });
+      double hC = h[0], sF = a[0], sN = b[0];
+#pragma unroll
+      for (int j = 1; j < G; ++j) { hC += h[j]; sF += a[j]; sN += b[j]; }
       hoisted = fma(C::inverseScale(n2), hC, hoisted);
       offsetF = fma(C::inverseScale(n2) * C::offset(n2), sF, offsetF);
       offsetN = fma(C::inverseScale(n2) * C::offset(n2), sN, offsetN);
       sumN = fma(C::inverseScale(n2), sN, sumN);
     }
   });
-  if (range >= kLogTableEntries) return entropicNewtonLibrary<L::Q>(fColumn, nColumn, s.rowOffset, s.rowInverse, alphaGuess, alphaMax);
+  if (range >= kLogTableEntries) return entropicNewtonLibrary<L::Q>(column.fColumn, column.nColumn, s.rowOffset, s.rowInverse, alphaGuess, alphaMax);
   hoisted += offsetF;
   const double derivativeBase = sumN + offsetN;
 
@@ -434,13 +492,21 @@ __device__ __forceinline__ double entropicNewton(const EntropicShared& s, int co
     staticFor<0, L::maxNorm2() + 1>([&](auto nc) {
       constexpr int n2 = decltype(nc)::value;
       if constexpr (C::count(n2) > 0) {
-        double sC, dC;
-        entropicEvaluateClass<C::first(n2), C::count(n2), C::group(n2)>(fColumn, nColumn, s.table, range, x, sC, dC);
+        constexpr int G = C::group(n2);
+        double sum[G], derivative[G];
+#pragma unroll
+        for (int j = 0; j < G; ++j) sum[j] = derivative[j] = 0.0;
+        forEachGroup<C::first(n2), C::count(n2), G, MODE>([&](int firstRow, int inClass) {
+          entropicEvaluateGroup<G, C::count(n2)>(column, firstRow, inClass, s.table, range, x, sum, derivative);
+        });
+        double sC = sum[0], dC = derivative[0];
+#pragma unroll
+        for (int j = 1; j < G; ++j) { sC += sum[j]; dC += derivative[j]; }
         total = fma(C::inverseScale(n2), sC, total);
         slope = fma(C::inverseScale(n2), dC, slope);
       }
     });
-    if (range >= kLogTableEntries) return entropicNewtonLibrary<L::Q>(fColumn, nColumn, s.rowOffset, s.rowInverse, alphaGuess, alphaMax);
+    if (range >= kLogTableEntries) return entropicNewtonLibrary<L::Q>(column.fColumn, column.nColumn, s.rowOffset, s.rowInverse, alphaGuess, alphaMax);
     step = (hoisted - (total + fma(-x, offsetN, offsetF))) / (derivativeBase + slope);
     if (fabs(step) <= 1e-8) { converged = (x > 1.0 && x < alphaMax); break; }
   }
@@ -505,26 +571,6 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
     const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
     f[q] = STREAMING ? loadPopulationStreaming(source) : loadPopulation(source);
   }
-}
-
-// EXPERIMENT (MLBM_PREFETCH_NEXT_PLANE): the entropic blocks walk several planes and spend most of a plane computing, so
-// too few loads are in flight per SM to keep HBM busy; ask L2 for the populations of the block's NEXT plane while this one
-// is being solved.  One request per 32-byte sector.
-template <class L, typename StoreT>
-__device__ __forceinline__ void prefetchPopulations(const StepParams& p, const NodeIndex& n) {
-#if defined(__CUDA_ARCH__)
-  if (L::H > 1) return;
-  if ((threadIdx.x & (32 / (int)sizeof(StoreT) - 1)) != 0) return;
-  const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
-#pragma unroll
-  for (int q = 0; q < L::Q; ++q) {
-    const int xs = L::cx(q) == 1 ? n.xPrev : (L::cx(q) == -1 ? n.xNext : n.xh);
-    const int ms = L::cm(q) == 1 ? n.mPrev : (L::cm(q) == -1 ? n.mNext : n.m);
-    const int rs = L::cr(q) == 1 ? n.rPrev : (L::cr(q) == -1 ? n.rNext : n.r);
-    const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(source));
-  }
-#endif
 }
 
 // Moment::calculateDensity / calculateVelocity (Moment.h:14-47)
@@ -665,7 +711,7 @@ __device__ __forceinline__ void reduceBlockObservables(const StepParams& p, int 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Entropic body: Collision<ELBM> (Collision.h:182-376); see the banner above entropicNewton.
+// Entropic body: Collision<ELBM> (Collision.h:182-376); see the banner above entropicAlpha.
 // grid = (ceil(NR / kStepBlock), NM, ceil(planes / planesPerBlock)); the block walks planesPerBlock planes.
 // ------------------------------------------------------------------------------------------------
 //
@@ -687,7 +733,8 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
   s.rowInverse = s.rowOffset + rowSlots(Q);
   s.warpCount = reinterpret_cast<int*>(s.rowInverse + rowSlots(Q));
   s.list = reinterpret_cast<unsigned char*>(s.warpCount + 4);
-  s.table = kLogTable;
+  s.table.inverseHigh = kLogInverseHigh;
+  s.table.logc = kLogCentre;
   staticFor<0, Q>([&](auto qc) {
     constexpr int q = decltype(qc)::value;
     if (threadIdx.x == q) {
@@ -697,10 +744,15 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
   });
   if (logTableInShared(Q)) {
     static_assert(kLogTableEntries % kStepBlock == 0, "whole table entries per thread");
-    double2* table = reinterpret_cast<double2*>(dynamicShared + entropicSharedBytes(Q, false));
+    double* logc = reinterpret_cast<double*>(dynamicShared + entropicSharedBytes(Q, false));
+    unsigned* inverseHigh = reinterpret_cast<unsigned*>(logc + kLogTableEntries);
 #pragma unroll
-    for (int i = 0; i < kLogTableEntries / kStepBlock; ++i) table[i * kStepBlock + threadIdx.x] = kLogTable[i * kStepBlock + threadIdx.x];
-    s.table = table;
+    for (int i = 0; i < kLogTableEntries / kStepBlock; ++i) {
+      logc[i * kStepBlock + threadIdx.x] = kLogCentre[i * kStepBlock + threadIdx.x];
+      inverseHigh[i * kStepBlock + threadIdx.x] = kLogInverseHigh[i * kStepBlock + threadIdx.x];
+    }
+    s.table.inverseHigh = inverseHigh;
+    s.table.logc = logc;
   }
 
   const int t = threadIdx.x;
@@ -719,159 +771,89 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
     const long long rowNode = (long long)x * p.plane + (long long)m * p.NR;  // field / alpha index of r = 0
     __syncthreads();  // constants staged (first plane) / shared columns of the previous plane no longer read
 
-#ifdef MLBM_ELBM_FASTPATH
-    // EXPERIMENT.  Where the flow is resolved every node of a block takes the small-deviation shortcut alpha = 2
-    // (Collision.h:284-303, 357-359) and the shared-memory staging, the compaction and three of the four barriers below
-    // buy nothing.  A one-byte hint per block and plane remembers whether the previous step found a node off the
-    // shortcut; if not, the block finishes the plane OPTIMISTICALLY from registers (exactly the BGK data flow) and votes
-    // afterwards.  The decision stays exact: a block in which some node turns out to be off the shortcut runs the general
-    // path after all, which overwrites everything the optimistic pass stored (same threads, same addresses), and raises
-    // the hint.
-    unsigned char* const hint = (!FORCED && p.hints) ? p.hints + (((long long)x * p.NM + m) * gridDim.x + blockIdx.x) : nullptr;
-    if (hint && *hint == 0) {  // block-uniform
-      bool large = false;
-      double rhoFast = 0.0, energyFast = 0.0, speed2Fast = 0.0;
-      if (active) {
-        const NodeIndex n = nodeIndex<L>(p, x, m, r);
-        double f[Q];
-        pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
-        double invRhoFast, u2, uFast[3], forceFast[3];
-        moments<L>(f, rhoFast, invRhoFast, uFast, u2);
-        bodyForce<L, StoreT>(p, x, m, r, forceFast);
-        EquilibriumCoefficients<L, EQ> eqFast;
-        eqFast.set(uFast, u2);
-        const long long node = rowNode + r;
-        const long long out = (long long)(x + L::H) * p.plane + (long long)m * p.NR + r;
-        StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
-        StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
-        alphaField[node] = (StoreT)2.0;
-        const double omega = 2.0 * p.beta;
-        SourceTerm<L, EQ, SCHEME> source;
-        source.set(p, rhoFast, invRhoFast, uFast, forceFast);
-        staticFor<0, Q>([&](auto qc) {
-          constexpr int q = decltype(qc)::value;
-          const double feq = rhoFast * L::w(q) * eqFast.template shape<q>();
-          const double nq = f[q] - feq;
-          const double a = fabs(nq);
-          large = large || (f[q] > 0.0 ? (a > 1.0e-3 * f[q]) : (f[q] == 0.0 ? a > 0.0 : false));
-          // the general path's (F2 - omega N2) 2^-k + S with F2 = 2^k f, N2 = 2^k fNeq: the power of two commutes with the rounding
-          const double value = fma(-omega, nq, f[q]) + source.template value<q>(f[q] - nq);
-          storePopulation(next + q * p.stride + out, value);
-          if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
-          if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
-        });
-        if (p.isStored) storeNodeFields<L, StoreT>(p, node, rhoFast, invRhoFast, uFast, forceFast, energyFast, speed2Fast);
-      }
-      if (p.isStored) reduceBlockObservables(p, x, energyFast, active ? rhoFast : 0.0, speed2Fast);
-      const unsigned largeBallot = __ballot_sync(0xffffffffu, large);
-      if ((t & 31) == 0) s.warpCount[t >> 5] = largeBallot != 0u;
-      __syncthreads();
-      int anyLarge = 0;
-#pragma unroll
-      for (int w = 0; w < kStepBlock / 32; ++w) anyLarge |= s.warpCount[w];
-      if (!anyLarge) continue;  // block-uniform: the plane is done
-      __syncthreads();          // the compaction below writes the warp counters again
-    }
-#endif
-
     double rho = 0.0, invRho = 0.0, energy = 0.0, speed2 = 0.0, alpha = 2.0;
     double u[3] = {0.0, 0.0, 0.0}, F[3] = {0.0, 0.0, 0.0};
-    bool needsNewton = false;
-#ifdef MLBM_ELBM_FASTPATH
     bool offShortcut = false;
-#endif
     if (active) {
       const NodeIndex n = nodeIndex<L>(p, x, m, r);
       double f[Q];
       pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
-#ifdef MLBM_PREFETCH_NEXT_PLANE
-      if (i + 1 < p.planesPerBlock && planeIndex + 1 < p.planeCount) prefetchPopulations<L, StoreT>(p, nodeIndex<L>(p, x + p.planeStep, m, r));
-#endif
       double u2;
       moments<L>(f, rho, invRho, u, u2);
       bodyForce<L, StoreT>(p, x, m, r, F);
       EquilibriumCoefficients<L, EQ> eq;
       eq.set(u, u2);
-      // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241): fNeq, then alpha.  While fNeq is formed the
-      // two cheap screens of calculateAlpha run on the register values:
-      //   isDeviationSmall (Collision.h:284-303): no |fNeq_q| / f_q above 1e-3
-      //   calculateAlphaMax (Collision.h:305-326): min(2.5, min over fNeq_q > 0 of |f_q| / fNeq_q), tracked as a fraction
-      bool small = !FORCED;  // the forced variant has no isDeviationSmall shortcut
-      double num = 2.5, den = 1.0;
-      SourceTerm<L, EQ, SCHEME> forcedSource;
-      if (FORCED) forcedSource.set(p, rho, invRho, u, F);
-      staticFor<0, Q>([&](auto qc) {
-        constexpr int q = decltype(qc)::value;
-        constexpr double scale = C::scale(L::norm2(q));
-        const double feq = rho * L::w(q) * eq.template shape<q>();
-        const double nq = f[q] - feq;
-        // the population the entropy condition is written for: f_q, or f_q + S_q for the forced variant
-        const double fq = FORCED ? f[q] + forcedSource.template value<q>(feq) : f[q];
-        myF[C::row(q) * kStepBlock] = fq * scale;  // exact
-        myN[C::row(q) * kStepBlock] = nq * scale;
-        const double a = fabs(nq);
-        const bool large = fq > 0.0 ? (a > 1.0e-3 * fq) : (fq == 0.0 ? a > 0.0 : false);
-        small = small && !large;
-        if (nq > 0.0) {
-          const double af = fabs(fq);
-          if (af * den < num * nq) { num = af; den = nq; }
+      // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241): fNeq, then alpha.  While fNeq is formed the cheap
+      // screen of calculateAlpha runs on the register values: isDeviationSmall (Collision.h:284-303), no |fNeq_q| / f_q
+      // above 1e-3.  Written as |N2_q| > 1e-3 F2_q, which is the reference's predicate for every F2_q >= 0 (the
+      // division by zero included: inf > 1e-3 when fNeq_q != 0, NaN > 1e-3 false when it is 0); a node with a NEGATIVE
+      // population -- sign bit of any F2_q, collected with integer ORs -- repeats the screen literally below.
+      bool large = false;
+      int signs = 0;
+      if constexpr (FORCED) {
+        SourceTerm<L, EQ, SCHEME> forcedSource;
+        forcedSource.set(p, rho, invRho, u, F);
+        staticFor<0, Q>([&](auto qc) {
+          constexpr int q = decltype(qc)::value;
+          constexpr double scale = C::scale(L::norm2(q));
+          const double feq = rho * L::w(q) * eq.template shape<q>();
+          // the population the entropy condition is written for: f_q + S_q
+          myF[C::row(q) * kStepBlock] = (f[q] + forcedSource.template value<q>(feq)) * scale;  // exact
+          myN[C::row(q) * kStepBlock] = (f[q] - feq) * scale;
+        });
+        offShortcut = true;  // the forced variant has no isDeviationSmall shortcut
+      } else {
+        staticFor<0, Q>([&](auto qc) {
+          constexpr int q = decltype(qc)::value;
+          constexpr double scale = C::scale(L::norm2(q));
+          // (f - feq) 2^k = f 2^k - feq 2^k and feq 2^k = (rho (w 2^k)) shape, all exact: one multiply less per population
+          const double f2 = f[q] * scale;
+          const double n2 = f2 - rho * (L::w(q) * scale) * eq.template shape<q>();
+          myF[C::row(q) * kStepBlock] = f2;
+          myN[C::row(q) * kStepBlock] = n2;
+          large = large || fabs(n2) > 1.0e-3 * f2;
+          signs |= __double2hiint(f2);
+        });
+        if (signs < 0) {  // some population is negative (or -0): the reference's predicate, literally
+          large = false;
+#pragma unroll 1
+          for (int row = 0; row < Q; ++row) {
+            const double f2 = myF[row * kStepBlock], a = fabs(myN[row * kStepBlock]);
+            large = large || (f2 > 0.0 ? (a > 1.0e-3 * f2) : (f2 == 0.0 ? a > 0.0 : false));
+          }
         }
-      });
-#ifdef MLBM_ELBM_FASTPATH
-      offShortcut = !small;
-#endif
-      if (!small) {
-        // Collision<ELBM>::calculateAlpha (Collision.h:351-375) / Collision<ForcedNR_ELBM_Forcing>::calculateAlpha (:792-808)
-        const double alphaMax = num / den;
-        if (alphaMax < 2.0) alpha = 0.95 * alphaMax;
-        else { needsNewton = true; s.alpha[t] = alphaMax; }
+        offShortcut = large;
       }
     }
 
-    // compaction: the i-th node (in thread order) that needs the Newton solve is solved by thread i
-    const unsigned ballot = __ballot_sync(0xffffffffu, needsNewton);
+    // compaction: the i-th node (in thread order) that left the shortcut is solved by thread i
+    const unsigned ballot = __ballot_sync(0xffffffffu, offShortcut);
     const int warp = t >> 5, lane = t & 31;
-#ifdef MLBM_ELBM_FASTPATH
-    const unsigned offBallot = __ballot_sync(0xffffffffu, offShortcut);
-    if (lane == 0) s.warpCount[warp] = __popc(ballot) | (offBallot != 0u ? 0x10000 : 0);
-#else
     if (lane == 0) s.warpCount[warp] = __popc(ballot);
-#endif
     __syncthreads();
     int before = 0, total = 0;
-#ifdef MLBM_ELBM_FASTPATH
-    int anyOff = 0;
-#endif
 #pragma unroll
     for (int w = 0; w < kStepBlock / 32; ++w) {
-#ifdef MLBM_ELBM_FASTPATH
-      const int count = s.warpCount[w] & 0xffff;
-      anyOff |= s.warpCount[w] >> 16;
-#else
       const int count = s.warpCount[w];
-#endif
       if (w < warp) before += count;
       total += count;
     }
-#ifdef MLBM_ELBM_FASTPATH
-    if (hint && t == 0) *hint = anyOff ? 1 : 0;  // the next step of this block and plane starts from what this one saw
-#endif
     if (total > 0) {  // block-uniform
-      if (needsNewton) s.list[before + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)t;
+      if (offShortcut) s.list[before + __popc(ballot & ((1u << lane) - 1u))] = (unsigned char)t;
       __syncthreads();
       if (t < total) {
-        const int column = s.list[t];
-        const double guess = (double)alphaField[rowNode + blockIdx.x * kStepBlock + column];  // previous step's alpha (Algorithm.h:103-106)
+        const int node = s.list[t];
+        const double guess = (double)alphaField[rowNode + blockIdx.x * kStepBlock + node];  // previous step's alpha (Algorithm.h:103-106)
         int evaluations = 0;
-        s.alpha[column] = entropicNewton<L>(s, column, guess, s.alpha[column], evaluations);
+        s.alpha[node] = entropicAlpha<L>(s, node, guess, evaluations);
         // statistics of the solve (mlbm_newton_statistics: the FP64 side of the roofline); counted only while a caller asks
-        if (p.newtonCounters) {
+        if (p.newtonCounters && evaluations > 0) {
           atomicAdd(p.newtonCounters, 1ull);
           atomicAdd(p.newtonCounters + 1, (unsigned long long)evaluations);
         }
       }
       __syncthreads();
-      if (needsNewton) alpha = s.alpha[t];
+      if (offShortcut) alpha = s.alpha[t];
     }
 
     if (active) {

@@ -5,7 +5,7 @@ import sys
 from pathlib import Path
 
 import os
-build = Path(__file__).resolve().parent.parent / "metalbm_b200" / ("_build" + ("_" + os.environ["MLBM_VARIANT"] if os.environ.get("MLBM_VARIANT") else ""))
+build = (Path("/tmp") / ("mlbm_build_" + os.environ["MLBM_VARIANT"])) if os.environ.get("MLBM_VARIANT") else Path(__file__).resolve().parent.parent / "metalbm_b200" / "_build"
 names = {"0": "D2Q5", "1": "D2Q9", "2": "D3Q15", "3": "D3Q19", "4": "D3Q27", "5": "D2Q13", "6": "D2Q17", "7": "D2Q21", "8": "D3Q33"}
 pattern = sys.argv[1] if len(sys.argv) > 1 else ""
 for log in sorted(build.glob("instantiate_*.ptxas.log")):

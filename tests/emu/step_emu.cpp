@@ -17,7 +17,6 @@ struct EmuLaunch {
   void* peerLow; void* peerHigh;
   int wrapX, isStored, hydroShift, hasForce;
   double beta, guoFactor;
-  unsigned char* hints;
 };
 
 template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
@@ -32,7 +31,6 @@ static int run(const EmuLaunch& e) {
   p.planesPerBlock = e.planesPerBlock; p.peerLow = e.peerLow; p.peerHigh = e.peerHigh;
   p.wrapX = e.wrapX; p.isStored = e.isStored; p.hydroShift = e.hydroShift; p.hasForce = e.hasForce;
   p.beta = e.beta; p.guoFactor = e.guoFactor;
-  p.hints = e.hints;
   const int gridR = (e.NR + kStepBlock - 1) / kStepBlock;
   const dim3 grid((unsigned)gridR, (unsigned)e.NM, (unsigned)((e.planeCount + e.planesPerBlock - 1) / e.planesPerBlock));
   const size_t shared = COLLISION != kBGK ? (size_t)entropicSharedBytes(L::Q, logTableInShared(L::Q)) : 0;

@@ -35,7 +35,7 @@ class EmuLaunch(ctypes.Structure):
                 ("planeStep", ctypes.c_int), ("planesPerBlock", ctypes.c_int),
                 ("peerLow", ctypes.c_void_p), ("peerHigh", ctypes.c_void_p),
                 ("wrapX", ctypes.c_int), ("isStored", ctypes.c_int), ("hydroShift", ctypes.c_int), ("hasForce", ctypes.c_int),
-                ("beta", ctypes.c_double), ("guoFactor", ctypes.c_double), ("hints", ctypes.c_void_p)]
+                ("beta", ctypes.c_double), ("guoFactor", ctypes.c_double)]
 
 
 def _load_emulator(flags=()):
@@ -48,13 +48,6 @@ def _load_emulator(flags=()):
 @pytest.fixture(scope="session")
 def emu(cuda_lib):
     return _load_emulator()
-
-
-@pytest.fixture(scope="session")
-def emu_fastpath(cuda_lib):
-    """The experimental entropic variants (not the product build): register fast path for all-shortcut blocks with its
-    per-block hint, and the next-plane L2 prefetch (a no-op under the emulator)."""
-    return _load_emulator(("-DMLBM_ELBM_FASTPATH", "-DMLBM_PREFETCH_NEXT_PLANE"))
 
 
 SCHEME_KERNEL = {0: 0, 1: 1, 2: 0, 3: 2}   # None, Guo, ShanChen (kernel of None), ExactDifferenceMethod  (context.cu: schemeOf)
@@ -81,7 +74,6 @@ class Slab:
         self.force = np.zeros(self.dim * self.field_stride, dtype=dtype)
         grid_r = -(-self.nr // 128)
         self.partials = np.full(grid_r * self.nm * self.lx * 3, np.nan)
-        self.hints = np.zeros(grid_r * self.nm * self.lx, dtype=np.uint8)   # context.cu: one byte per block and plane
         if cfg.force == capi.Force.ConstantShell:
             # mlbm_create synthesises the shell force into the force field (shellForceKernel); this rank's slab of it
             from helpers import shell_force_direct
@@ -152,7 +144,6 @@ class Slab:
         e.peerHigh = peer_high.ctypes.data if peer_high is not None else None
         e.wrapX, e.isStored, e.hydroShift, e.hasForce = plan.wrap_x, plan.is_stored, plan.hydro_shift, plan.has_force
         e.beta, e.guoFactor = plan.beta, plan.guo_factor
-        e.hints = self.hints.ctypes.data if self.entropic else None
         assert self.emu.emu_fused_step(ctypes.byref(e)) == 0, "no such kernel instantiation"
 
     def fields(self):
@@ -178,7 +169,7 @@ def kernel_shape(cfg, array):
     return array.reshape(lead + ((nx, ny, nz) if dim == 3 else (nx, 1, ny)))
 
 
-def run_single(emu, cfg, f0, steps, planes_per_block=None, dtype=np.float64, force=None, hints_seen=None):
+def run_single(emu, cfg, f0, steps, planes_per_block=None, dtype=np.float64, force=None):
     slab = Slab(emu, cfg, dtype)
     slab.upload(kernel_shape(cfg, f0).astype(dtype))
     if force is not None:
@@ -186,8 +177,6 @@ def run_single(emu, cfg, f0, steps, planes_per_block=None, dtype=np.float64, for
     for step in range(1, steps + 1):
         slab.launch(0, slab.lx, 1 if step == steps else 0, planes_per_block=planes_per_block)
         slab.current ^= 1
-        if hints_seen is not None:
-            hints_seen.append(slab.hints.copy())
     out = slab.fields()
     shape = f0.shape[1:]
     got = {"f": slab.download().reshape(f0.shape), "alpha": out["alpha"].reshape(shape), "density": out["density"].reshape(shape),
@@ -350,54 +339,6 @@ def test_entropic_blocks_walking_several_planes(emu, lattice, shape, planes_per_
 
 
 # ---- the experimental entropic variants (scripts/gpu_variants_r2.sh measures them; not the product build) ----
-FASTPATH_CASES = [c for c in SINGLE_CASES if c[2] in ("ELBM", "ForcedNR_ELBM", "Malaspinas_ELBM")] + [
-    ("D2Q9", (6, 140, 1), "ELBM", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 1e-5, 3),      # every block stays on the fast path
-    ("D3Q27", (4, 3, 4), "ELBM", "TruncationMa3", "ExactDifferenceMethod", "Kolmogorov", 0.55, 1e-5, 2),
-    ("D3Q19", (4, 3, 4), "ForcedNR_ELBM_Forcing", "TruncationMa3", "Guo", "Kolmogorov", 0.55, 2e-2, 2),   # has no shortcut: never fast
-]
-
-
-@pytest.mark.parametrize("case", FASTPATH_CASES, ids=lambda c: "-".join(map(str, (c[0], "x".join(map(str, c[1])), c[2], c[3], c[4], c[7]))))
-def test_fastpath_variant_reproduces_the_oracle(emu_fastpath, case):
-    lattice, shape, collision, equilibrium, scheme, force, tau, eps, steps = case
-    cfg = _config(lattice, shape, collision, equilibrium, scheme, force, tau)
-    f0 = O.synthetic_populations(cfg, eps=eps, **_flow(eps))
-    hints = []
-    got = run_single(emu_fastpath, cfg, f0, steps, hints_seen=hints)
-    ref = run_oracle(cfg, f0, steps)
-    _compare(cfg, got, ref, steps, True)
-    if collision == "ForcedNR_ELBM_Forcing":
-        assert not any(h.any() for h in hints)          # never consulted, never written
-    elif eps <= 1e-4:
-        assert not any(h.any() for h in hints) and np.all(got["alpha"] == 2.0)
-
-
-def test_fastpath_hint_follows_the_flow(emu_fastpath, emu):
-    """A fluid at rest with a few strongly perturbed nodes: blocks that contain a node off the shortcut fall through to the
-    general path (a misprediction in the first step) and raise their hint, the others finish from registers.  After every
-    step the hints are exactly "the oracle took a non-shortcut branch somewhere in this block", and the fast and the
-    general build agree."""
-    cfg = _config("D2Q9", (6, 300, 1), "ELBM", tau=0.8)
-    f0 = O.synthetic_populations(cfg, eps=1e-6, amplitude=0.0, ripple=0.0)
-    rng = np.random.default_rng(11)
-    for _ in range(3):
-        x, y = rng.integers(0, 6), rng.integers(0, 300)
-        f0[:, x, y, 0] *= 1.0 + 0.02 * rng.standard_normal(9)
-    hints = []
-    steps = 4
-    got = run_single(emu_fastpath, cfg, f0, steps, hints_seen=hints, planes_per_block=3)
-    plain = run_single(emu, cfg, f0, steps, planes_per_block=3)
-    state = O.OracleState(cfg, f0)
-    for step in range(steps):
-        state.step(True)
-        off = state.branch[:, :, 0] != 0                                          # [x, y]: node left the shortcut
-        blocks = np.stack([off[:, b * 128:(b + 1) * 128].any(axis=1) for b in range(3)], axis=1)   # [x, block along r]
-        assert np.array_equal(hints[step].reshape(6, 3).astype(bool), blocks), f"step {step + 1}"
-    assert 0 < hints[0].sum() < hints[0].size                                     # both paths were exercised
-    assert relative_error(got["f"], state.f) <= 1e-11 and relative_error(got["f"], plain["f"]) <= 1e-13
-    assert np.abs(got["alpha"] - plain["alpha"]).max() <= 1e-10
-
-
 def test_sparse_newton_nodes_are_compacted_correctly(emu):
     """A fluid at rest with a few strongly perturbed nodes: most threads of a block skip the solve, the listed ones are
     solved by OTHER threads (block-level compaction) and must land in the right columns."""
@@ -469,16 +410,6 @@ MULTI_CASES = [
 @pytest.mark.parametrize("case", MULTI_CASES, ids=lambda c: "-".join(map(str, (c[0], c[2], c[3]))))
 def test_slab_decomposition_logic(emu, case, world, mode):
     _decomposition(emu, case, world, mode, 1e-2)
-
-
-@pytest.mark.parametrize("eps", [1e-2, 1e-5])
-@pytest.mark.parametrize("mode", ["overlap", "peer"])
-@pytest.mark.parametrize("world", [2, 8])
-@pytest.mark.parametrize("case", [c for c in MULTI_CASES if c[2] == "ELBM"], ids=lambda c: "-".join(map(str, (c[0], c[2], c[3]))))
-def test_slab_decomposition_logic_fastpath_variant(emu_fastpath, case, world, mode, eps):
-    """The experimental fast path on slabs: optimistic passes that store into the neighbours' halo planes (eps = 1e-5: every
-    block stays on the shortcut) and mispredicted ones whose stores, remote ones included, the general path overwrites."""
-    _decomposition(emu_fastpath, case, world, mode, eps)
 
 
 def _decomposition(emu, case, world, mode, eps):
