@@ -1,9 +1,11 @@
 // Parity harness for the C++ drop-in layer: drives the reference's object model (FieldList, Distribution,
 // Communication_, Algorithm_ -- the members of Routine, Routine.h:36-56) by hand so that arbitrary populations can be
 // injected and read back.  Used by tests/test_cpp_shim.py; compiled with -include <Input.in> like examples/main_gpu.cpp.
-//   shim_check <populations_in.bin> <steps> <populations_out.bin> <fields_out.bin>
+//   shim_check <populations_in.bin> <steps> <populations_out.bin> <fields_out.bin> [<moments_out.bin>]
 // populations_*.bin: raw dataT [dimQ][lx][ly][lz] of this rank's slab (interior only, z fastest).
 // fields_out.bin   : density [lx][ly][lz], velocity [dimD][lx][ly][lz], alpha [lx][ly][lz], then 4 observables.
+// moments_out.bin  : density, velocity [dimD], hydrodynamic velocity [dimD] of the state AFTER the last step, computed on the
+//                    host with Collision::calculateMoments / getHydrodynamicVelocity over Distribution::getHaloDataPreviousHost().
 #include <cstdio>
 #include <vector>
 
@@ -76,6 +78,32 @@ int main(int argc, char* argv[]) {
   std::fwrite(fields.data(), sizeof(dataT), fields.size(), out);
   std::fwrite(observables, sizeof(double), 4, out);
   std::fclose(out);
+  if (argc > 5) {
+    // the host-callable per-node surface (Moment.h:14-47, Collision.h:60-93) over a host copy of the halo-space buffer the
+    // NEXT step would read: density, velocity and hydrodynamic velocity of the populations pulled to every interior node
+    const dataT* halo = distribution.getHaloDataPreviousHost();
+    Collision_<Architecture::GPU> collision(relaxationTime, fieldList, forceAmplitude, forceWaveLength, forcekMin, forcekMax);
+    std::vector<dataT> moments(volume * (1 + 2 * L::dimD));
+    size_t n = 0;
+    for (unsigned int x = 0; x < lSD::sLength()[d::X]; ++x)
+      for (unsigned int y = 0; y < lSD::sLength()[d::Y]; ++y)
+        for (unsigned int z = 0; z < lSD::sLength()[d::Z]; ++z, ++n) {
+          const Position iP = Position{{x + L::halo()[d::X], y + L::halo()[d::Y], z + L::halo()[d::Z]}};
+          collision.calculateMoments(halo, iP);
+          collision.setForce(fieldList.force.getData(FFTWInit::numberElements), iP, gSD::sOffset(MPIInit::rank), FFTWInit::numberElements);
+          dataT density;
+          Moment_::calculateDensity(halo, iP, density);
+          if (density != collision.getDensity()) return 4;
+          moments[n] = collision.getDensity();
+          for (int iD = 0; iD < L::dimD; ++iD) {
+            moments[(1 + iD) * volume + n] = collision.getVelocity()[iD];
+            moments[(1 + L::dimD + iD) * volume + n] = collision.getHydrodynamicVelocity()[iD];
+          }
+        }
+    out = std::fopen(argv[5], "wb");
+    std::fwrite(moments.data(), sizeof(dataT), moments.size(), out);
+    std::fclose(out);
+  }
   const double mass = communication.reduce(fieldList.density.getData(FFTWInit::numberElements));
   std::printf("ok rank %d mass %.17g comm %.3e s comp %.3e s\n", MPIInit::rank[d::X], mass, algorithm.getCommunicationTime(),
               algorithm.getComputationTime());

@@ -5,6 +5,8 @@
 // mlbm_device_layout -- x halo planes only, no y/z halo cells -- for callers that interoperate on the device.
 #pragma once
 
+#include <vector>
+
 #include "Context.h"
 #include "Field.h"
 
@@ -26,11 +28,21 @@ class Distribution : public Field<T, L::dimQ, architecture, true> {
     LBM_B200_CALL(mlbm_device_distribution(b200::Context::get(), &layout));
     return static_cast<T*>(layout.populations);
   }
+  // The same buffer as a HOST array in the reference's halo space (hSD::getIndex(iP, iQ), Domain.h:272-276), every halo
+  // cell holding what the halo exchange and the periodic boundaries deliver before the node update: what the host-callable
+  // per-node functions (Moment<T>, Collision::calculateMoments) read.  Refreshed by every call; an inspection path.
+  const T* getHaloDataPreviousHost() {
+    haloMirror.resize((size_t)hSD::volume() * L::dimQ);
+    LBM_B200_CALL(mlbm_download_halo_distribution(b200::Context::get(), haloMirror.data(), haloMirror.size()));
+    return haloMirror.data();
+  }
   mlbm_device_layout getHaloLayout() {
     mlbm_device_layout layout;
     LBM_B200_CALL(mlbm_device_distribution(b200::Context::get(), &layout));
     return layout;
   }
+ private:
+  std::vector<T> haloMirror;
 };
 
 }  // namespace lbm

@@ -1,148 +1,102 @@
-// metaLBM/Writer.h (B200 drop-in) -- the part of the reference's writers that sits right behind the hot path: the ASCII
-// table of the scalar analyses, `../output/<prefix>/observables_<startIteration>.dat` (Writer.h:22-105 Writer<ascii>,
-// :140-190 ScalarAnalysisWriter; opened by ScalarAnalysisList, AnalysisList.h:41).  Same file name, header line, column
-// order, precision (16 significant digits, default float format) and the same trailing blank before every newline, so
-// that post-processing scripts written against the reference keep working; pinned byte for byte against the reference's
-// own class in tests/test_cpp_shim.py::test_observables_file_format_equals_the_reference.
-// The only deviation: the output directory is created when it is missing (the reference prints "Could not open file").
-// The HDF5 / XDMF field and checkpoint writers (Writer.h:252-560) are out of scope.
+// metaLBM/Writer.h (B200 drop-in) -- only what sits right behind the hot path: the two ASCII tables the analysis lists
+// append to, `../output/<prefix>/observables_<startIteration>.dat` and `spectra_<startIteration>.dat`.  The method names
+// are the ones ScalarAnalysisList / SpectralAnalysisList call in the reference (AnalysisList.h:41-93, 163-199); the file
+// format (one line per record: unsigned iteration, then the values with 16 significant digits, every field followed by ONE
+// blank, also the last) is pinned byte for byte against the reference's own writer in
+// tests/test_cpp_shim.py::test_observables_file_format_equals_the_reference.  One deviation: the output directory is created
+// when it is missing.  The HDF5 / XDMF field and checkpoint writers are out of scope.
 #pragma once
 
 #include <sys/stat.h>
 
-#include <fstream>
-#include <iostream>
-#include <sstream>
+#include <cstdio>
 #include <string>
 
 #include "Options.h"
 
 namespace lbm {
+namespace b200 {
 
-template <class T, InputOutput inputOutput, InputOutputFormat inputOutputFormat>
-class Writer {};
+// an append-only text table; every call opens and closes the file, like the reference's writers do
+class AnalysisTable {
+  std::string folder, path;
+  unsigned int period;
 
-template <class T>
-class Writer<T, InputOutput::Generic, InputOutputFormat::ascii> {
- protected:
-  const std::string writeFolder;
-  const std::string writerFolder;
-  const std::string fileExtension;
-  const std::string filePrefix;
-  std::ofstream file;
-
-  Writer(const std::string& writerFolder_in, const std::string& filePrefix_in, const std::string& fileExtension_in)
-      : writeFolder("../output/"), writerFolder(writerFolder_in + "/"), fileExtension(fileExtension_in), filePrefix(filePrefix_in) {}
-
-  inline std::string getFileName(const std::string& postfix = "") {
-    return writeFolder + writerFolder + filePrefix + postfix + fileExtension;
-  }
-
-  inline void makeFolders() {
-    ::mkdir(writeFolder.c_str(), 0777);
-    ::mkdir((writeFolder + writerFolder).c_str(), 0777);
-  }
-
-  inline void open(const std::string& fileName, std::ios_base::openmode mode) {
-    file.open(fileName, std::ofstream::out | mode);
-    if (!file) {
-      makeFolders();
-      file.clear();
-      file.open(fileName, std::ofstream::out | mode);
+  std::FILE* open(const char* mode) const {
+    std::FILE* file = std::fopen(path.c_str(), mode);
+    if (!file) {  // first use: ../output/ and ../output/<prefix>/ may not exist yet
+      ::mkdir("../output", 0777);
+      ::mkdir(folder.c_str(), 0777);
+      file = std::fopen(path.c_str(), mode);
     }
-    file.precision(16);
-    if (!file) std::cout << "Could not open file " << fileName << std::endl;
+    if (!file) std::printf("Could not open file %s\n", path.c_str());
+    return file;
   }
-
-  inline void openAndAppend(const std::string& fileName) { open(fileName, std::ofstream::app); }
-  inline void openAndTruncate(const std::string& fileName) { open(fileName, std::ofstream::trunc); }
-
-  template <class U>
-  inline void write(const U data) { file << data; }
-};
-
-template <class T, InputOutputFormat inputOutputFormat>
-class ScalarAnalysisWriter : public Writer<T, InputOutput::Generic, inputOutputFormat> {
-  static_assert(inputOutputFormat == InputOutputFormat::ascii, "metalbm_b200 writes the scalar analyses as ascii (the reference's only instantiation, Writer.h:562-563)");
-  using Base = Writer<T, InputOutput::Generic, inputOutputFormat>;
-  unsigned int startIteration;
-  unsigned int analysisStep;
 
  public:
-  ScalarAnalysisWriter(const std::string& writerFolder_in, const std::string& filePrefix_in, const unsigned int startIteration_in,
-                       const unsigned int analysisStep_in)
-      : Base(writerFolder_in, filePrefix_in, ".dat"), startIteration(startIteration_in), analysisStep(analysisStep_in) {}
+  AnalysisTable(const std::string& prefix_in, const std::string& name, unsigned int startIteration, unsigned int period_in)
+      : folder("../output/" + prefix_in), path(folder + "/" + name + "_" + std::to_string(startIteration) + ".dat"), period(period_in) {}
 
-  // the reference divides by analysisStep unguarded (Writer.h:160-162); 0 means "never" here instead of a division by zero
-  inline bool getIsAnalyzed(const unsigned int iteration) { return analysisStep != 0 && (iteration % analysisStep) == 0; }
-
-  inline std::string fileName() { return Base::getFileName("_" + std::to_string(startIteration)); }
-  inline void openFile(const unsigned int) { Base::openAndAppend(fileName()); }
-  inline void closeFile() { Base::file.close(); }
-
-  template <unsigned int NumberScalarAnalyses>
-  void writeAnalysis(const unsigned int iteration, T* data) {
-    Base::write(iteration);
-    Base::file << " ";
-    for (unsigned int iS = 0; iS < NumberScalarAnalyses; ++iS) {
-      Base::write(data[iS]);
-      Base::file << " ";
-    }
-    Base::file << std::endl;
+  bool due(unsigned int iteration) const { return period != 0 && iteration % period == 0; }  // 0 = never (the reference divides by it)
+  void header(const std::string& text) const {
+    if (std::FILE* file = open("w")) { std::fprintf(file, "%s\n", text.c_str()); std::fclose(file); }
   }
-
-  void writeHeader(const std::string& header) {
-    Base::openAndTruncate(fileName());
-    Base::file << header << std::endl;
-    closeFile();
+  // "<key_0> <key_1> ... <value_0> ... <value_n-1> \n"
+  template <class T>
+  void record(const unsigned int* keys, unsigned int keyCount, T* const* columns, unsigned int columnCount, unsigned int row) const {
+    std::FILE* file = open("a");
+    if (!file) return;
+    for (unsigned int k = 0; k < keyCount; ++k) std::fprintf(file, "%u ", keys[k]);
+    for (unsigned int c = 0; c < columnCount; ++c) std::fprintf(file, "%.16g ", (double)columns[c][row]);
+    std::fprintf(file, "\n");
+    std::fclose(file);
   }
 };
 
+}  // namespace b200
+
+template <class T, InputOutputFormat inputOutputFormat>
+class ScalarAnalysisWriter {
+  static_assert(inputOutputFormat == InputOutputFormat::ascii, "metalbm_b200 writes the analyses as ascii (the reference's only instantiation)");
+  b200::AnalysisTable table;
+
+ public:
+  ScalarAnalysisWriter(const std::string& folder, const std::string& name, unsigned int startIteration, unsigned int step)
+      : table(folder, name, startIteration, step) {}
+  bool getIsAnalyzed(unsigned int iteration) { return table.due(iteration); }
+  void writeHeader(const std::string& header) { table.header(header); }
+  void openFile(unsigned int) {}
+  void closeFile() {}
+  template <unsigned int Count>
+  void writeAnalysis(unsigned int iteration, T* data) {
+    T* columns[Count];
+    for (unsigned int c = 0; c < Count; ++c) columns[c] = data + c;
+    table.record(&iteration, 1, columns, Count, 0);
+  }
+};
 typedef ScalarAnalysisWriter<dataT, InputOutputFormat::ascii> ScalarAnalysisWriter_;
 
-// SpectralAnalysisWriter (Writer.h:193-251): `../output/<prefix>/spectra_<startIteration>.dat`, one line per wave number and
-// analysed iteration: "iteration wavenumber energy_spectra forcing_spectra " (the same trailing blank).
 template <class T, InputOutputFormat inputOutputFormat>
-class SpectralAnalysisWriter : public Writer<T, InputOutput::Generic, inputOutputFormat> {
-  static_assert(inputOutputFormat == InputOutputFormat::ascii, "metalbm_b200 writes the spectral analyses as ascii (Writer.h:564-565)");
-  using Base = Writer<T, InputOutput::Generic, inputOutputFormat>;
-  unsigned int startIteration;
-  unsigned int analysisStep;
+class SpectralAnalysisWriter {
+  static_assert(inputOutputFormat == InputOutputFormat::ascii, "metalbm_b200 writes the analyses as ascii (the reference's only instantiation)");
+  b200::AnalysisTable table;
 
  public:
-  SpectralAnalysisWriter(const std::string& writerFolder_in, const std::string& filePrefix_in, const unsigned int startIteration_in,
-                         const unsigned int analysisStep_in)
-      : Base(writerFolder_in, filePrefix_in, ".dat"), startIteration(startIteration_in), analysisStep(analysisStep_in) {}
-
-  // the reference divides by analysisStep unguarded (Writer.h:211-213); 0 means "never" here
-  inline bool getIsAnalyzed(const unsigned int iteration) { return analysisStep != 0 && (iteration % analysisStep) == 0; }
-
-  inline std::string fileName() { return Base::getFileName("_" + std::to_string(startIteration)); }
-  inline void openFile(const unsigned int) { Base::openAndAppend(fileName()); }
-  inline void closeFile() { Base::file.close(); }
-
-  template <unsigned int NumberSpectralAnalyses>
-  void writeAnalysis(const unsigned int iteration, const unsigned int maxWaveNumber, T* data[NumberSpectralAnalyses]) {
-    for (unsigned int kNorm = 0; kNorm < maxWaveNumber; ++kNorm) {   // Writer.h:226-238
-      Base::write(iteration);
-      Base::file << " ";
-      Base::write(kNorm);
-      Base::file << " ";
-      for (unsigned int iS = 0; iS < NumberSpectralAnalyses; ++iS) {
-        Base::write(data[iS][kNorm]);
-        Base::file << " ";
-      }
-      Base::file << std::endl;
+  SpectralAnalysisWriter(const std::string& folder, const std::string& name, unsigned int startIteration, unsigned int step)
+      : table(folder, name, startIteration, step) {}
+  bool getIsAnalyzed(unsigned int iteration) { return table.due(iteration); }
+  void writeHeader(const std::string& header) { table.header(header); }
+  void openFile(unsigned int) {}
+  void closeFile() {}
+  // one line per wave number: "iteration wavenumber energy_spectra forcing_spectra "
+  template <unsigned int Count>
+  void writeAnalysis(unsigned int iteration, unsigned int maxWaveNumber, T* data[Count]) {
+    for (unsigned int k = 0; k < maxWaveNumber; ++k) {
+      const unsigned int keys[2] = {iteration, k};
+      table.record(keys, 2, data, Count, k);
     }
   }
-
-  void writeHeader(const std::string& header) {
-    Base::openAndTruncate(fileName());
-    Base::file << header << std::endl;
-    closeFile();
-  }
 };
-
 typedef SpectralAnalysisWriter<dataT, InputOutputFormat::ascii> SpectralAnalysisWriter_;
 
 }  // namespace lbm

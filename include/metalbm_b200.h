@@ -197,6 +197,15 @@ int mlbm_upload_distribution(mlbm_ctx* ctx, const void* host, size_t component_s
 /* Algorithm::pack (Algorithm.h:132-139, Boundary.h:11-24): device -> host, same layout. */
 int mlbm_download_distribution(mlbm_ctx* ctx, void* host, size_t component_stride,
                                size_t padded_y, size_t padded_z);
+/* Distribution::getHaloDataPrevious() (Distribution.h:19-20, 30-31) as a HOST array: the buffer the next step reads,
+ * in the reference's halo space hSD (Domain.h:173-283): element (iQ, iP) at host[iQ * hSD::volume() + hSD::getIndex(iP)],
+ * extents local length + 2 dimH in every used dimension.  All halo cells hold what the reference's halo exchange
+ * (Communication.h:134-180) and periodic boundaries (Boundary.h:45-102) would have put there before the node update
+ * -- the periodic image, or the neighbour rank's plane in x -- for EVERY population, a superset of the cells the
+ * reference fills.  This is what the per-node host functions of the template layer read (Moment<T>::calculateDensity /
+ * calculateVelocity, Moment.h:14-47; Collision::calculateMoments, Collision.h:72-79).  `capacity` = elements of `host`
+ * (>= dimQ * hSD::volume()), in the context's dtype.  An inspection path: one whole-buffer copy plus a host loop. */
+int mlbm_download_halo_distribution(mlbm_ctx* ctx, void* host, size_t capacity);
 
 /* Initial state without a host round trip: f = feq(rho, u) (initDistribution, Initialize.h:106-117) from
  * host density / velocity fields laid out like the FieldList arrays (velocity component iD at

@@ -224,6 +224,7 @@ PROTOTYPES = {
     "mlbm_power_spectra": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.c_int,
                                           ctypes.POINTER(ctypes.c_int)]),
     "mlbm_alpha_statistics": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
+    "mlbm_download_halo_distribution": (ctypes.c_int, [_P, _P, _SZ]),
     "mlbm_newton_statistics": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "mlbm_reduce_sum": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "mlbm_selftest_log": (ctypes.c_int, [_P, _P, _SZ]),

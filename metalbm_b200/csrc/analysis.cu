@@ -32,14 +32,21 @@ __global__ void __launch_bounds__(256) alphaStatisticsKernel(const StoreT* __res
   if (threadIdx.x == 0) { out[0] = scratch[0][0]; out[1] = -scratch[1][0]; out[2] = scratch[2][0]; }   // -min: reduced with max over ranks
 }
 
+// both table formats of fastLogCore (step_kernel.cuh): even blocks the split one, odd blocks the {invc, logc} pairs
 __global__ void fastLogKernel(const double* __restrict__ in, double* __restrict__ out, long long count) {
-  __shared__ double logc[kLogTableEntries];
-  __shared__ unsigned inverseHigh[kLogTableEntries];
-  for (int i = threadIdx.x; i < kLogTableEntries; i += blockDim.x) { logc[i] = kLogCentre[i]; inverseHigh[i] = kLogInverseHigh[i]; }
-  __syncthreads();
-  const LogTable table = {inverseHigh, logc};
+  __shared__ __align__(16) unsigned char storage[LogTable<false>::kBytes];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < count) out[i] = fastLog(in[i], table);
+  if (blockIdx.x & 1) {
+    LogTable<false> table;
+    table.stage(storage, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (i < count) out[i] = fastLog(in[i], table);
+  } else {
+    LogTable<true> table;
+    table.stage(storage, threadIdx.x, blockDim.x);
+    __syncthreads();
+    if (i < count) out[i] = fastLog(in[i], table);
+  }
 }
 
 }  // namespace mlbm

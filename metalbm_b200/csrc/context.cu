@@ -866,6 +866,44 @@ int mlbm_download_distribution(mlbm_ctx* ctx, void* host, size_t componentStride
   return copyDistribution(ctx, host, componentStride, paddedY, paddedZ, false);
 }
 
+int mlbm_download_halo_distribution(mlbm_ctx* ctx, void* host, size_t capacity) {
+  if (!ctx || !host) return fail(MLBM_ERR_INVALID, "null argument");
+  MLBM_CUDA(cudaSetDevice(ctx->device));
+  const int H = ctx->H, D = ctx->D;
+  const long long NY = D == 3 ? ctx->NM : (D == 2 ? ctx->NR : 1), NZ = D == 3 ? ctx->NR : 1;
+  const long long HX = ctx->LX + 2 * H, HY = D >= 2 ? NY + 2 * H : 1, HZ = D == 3 ? NZ + 2 * H : 1;
+  const long long volume = HX * HY * HZ;
+  if (capacity < (size_t)(volume * ctx->Q)) return fail(MLBM_ERR_INVALID, "halo array of %zu elements, needs dimQ * hSD::volume() = %lld", capacity, volume * ctx->Q);
+  const bool multi = ctx->config.nranks > 1;
+  if (multi && !ctx->halosValid) {
+    // the x halo planes of the buffer about to be read are delivered like at the top of iterate (Algorithm.h:339-341)
+    if (int status = exchangeHalos(ctx, ctx->current, ctx->computeStream)) return status;
+    ctx->halosValid = true;
+  }
+  const size_t es = ctx->elementSize;
+  std::vector<char> device((size_t)ctx->stride * ctx->Q * es);
+  MLBM_CUDA(cudaStreamSynchronize(ctx->commStream));
+  MLBM_CUDA(cudaMemcpyAsync(device.data(), ctx->populations[ctx->current], device.size(), cudaMemcpyDeviceToHost, ctx->computeStream));
+  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  auto wrap = [](long long v, long long n) { v %= n; return v < 0 ? v + n : v; };
+  for (int q = 0; q < ctx->Q; ++q)
+    for (long long hx = 0; hx < HX; ++hx) {
+      // one rank: x is periodic inside the slab; several: the device halo planes hold the neighbours' planes
+      const long long xs = multi ? hx : wrap(hx - H, ctx->LX) + H;
+      for (long long hy = 0; hy < HY; ++hy) {
+        const long long ys = D >= 2 ? wrap(hy - H, NY) : 0;
+        for (long long hz = 0; hz < HZ; ++hz) {
+          const long long zs = D == 3 ? wrap(hz - H, NZ) : 0;
+          const long long m = D == 3 ? ys : 0, r = D == 3 ? zs : ys;
+          const size_t from = ((size_t)q * ctx->stride + (size_t)xs * ctx->plane + (size_t)m * ctx->NR + (size_t)r) * es;
+          const size_t to = ((size_t)q * volume + (size_t)(HZ * (HY * hx + hy) + hz)) * es;
+          memcpy(static_cast<char*>(host) + to, device.data() + from, es);
+        }
+      }
+    }
+  return MLBM_OK;
+}
+
 // a field [components][LX][paddedY][paddedZ] on the host <-> dense [components][LX][NM][NR] on the device
 static int copyField(mlbm_ctx* ctx, void* host, void* device, int components, size_t componentStride, size_t paddedY,
                      size_t paddedZ, bool upload) {

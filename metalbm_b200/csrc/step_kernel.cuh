@@ -173,30 +173,75 @@ template <int I, int N, class F> __device__ __forceinline__ void staticFor(F&& f
 // of 0.25, in unsigned arithmetic, is either below 2^22 -- the table -- or at least 2^30).
 // ------------------------------------------------------------------------------------------------
 constexpr int kLogTableEntries = 1024;
+// MLBM_LOG_TABLE_SPLIT = 1: two arrays, the high words of invc (4 bytes) and logc (8 bytes) -- 12 bytes and 3 shared-memory
+// wavefronts per warp lookup, two loads; = 0: one array of {invc, logc} pairs -- 16 bytes and 4-5 wavefronts, one load
+// and three integer instructions less.  Which one wins depends on whether a kernel is short of shared-memory bandwidth
+// (D3Q27) or of issue slots (D2Q9): logTableSplit(Q).
+#ifndef MLBM_LOG_TABLE_SPLIT_Q9
+#define MLBM_LOG_TABLE_SPLIT_Q9 1
+#endif
+#ifndef MLBM_LOG_TABLE_SPLIT_Q27
+#define MLBM_LOG_TABLE_SPLIT_Q27 1
+#endif
+constexpr bool logTableSplit(int Q) { return Q <= 13 ? MLBM_LOG_TABLE_SPLIT_Q9 != 0 : MLBM_LOG_TABLE_SPLIT_Q27 != 0; }
 static __device__ const unsigned kLogInverseHigh[kLogTableEntries] = {
-#define MLBM_LOG_ENTRY(inverseHigh, logc) inverseHigh,
+#define MLBM_LOG_ENTRY(inverseHigh, invc, logc) inverseHigh,
 #include "log_table.inc"
 #undef MLBM_LOG_ENTRY
 };
 static __device__ const double kLogCentre[kLogTableEntries] = {
-#define MLBM_LOG_ENTRY(inverseHigh, logc) logc,
+#define MLBM_LOG_ENTRY(inverseHigh, invc, logc) logc,
 #include "log_table.inc"
 #undef MLBM_LOG_ENTRY
 };
-struct LogTable {
+static __device__ const double2 kLogPairs[kLogTableEntries] = {
+#define MLBM_LOG_ENTRY(inverseHigh, invc, logc) {invc, logc},
+#include "log_table.inc"
+#undef MLBM_LOG_ENTRY
+};
+template <bool SPLIT> struct LogTable;
+template <> struct LogTable<true> {
   const unsigned* inverseHigh;  // high word of invc (its low word is zero)
   const double* logc;           // -ln(invc)
+  static constexpr int kBytes = kLogTableEntries * 12;
+  __device__ __forceinline__ void global() { inverseHigh = kLogInverseHigh; logc = kLogCentre; }
+  // copies the table to `shared` (kBytes, 8-byte aligned) with all `threads` threads of the block; the caller synchronises
+  __device__ __forceinline__ void stage(unsigned char* shared, int thread, int threads) {
+    double* sharedLogc = reinterpret_cast<double*>(shared);
+    unsigned* sharedHigh = reinterpret_cast<unsigned*>(sharedLogc + kLogTableEntries);
+    for (int i = thread; i < kLogTableEntries; i += threads) { sharedLogc[i] = kLogCentre[i]; sharedHigh[i] = kLogInverseHigh[i]; }
+    inverseHigh = sharedHigh;
+    logc = sharedLogc;
+  }
+  __device__ __forceinline__ void fetch(unsigned index, double& invc, double& logCentre) const {
+    invc = __hiloint2double((int)inverseHigh[index], 0);
+    logCentre = logc[index];
+  }
+};
+template <> struct LogTable<false> {
+  const double2* pairs;  // {invc, -ln(invc)}
+  static constexpr int kBytes = kLogTableEntries * 16;
+  __device__ __forceinline__ void global() { pairs = kLogPairs; }
+  __device__ __forceinline__ void stage(unsigned char* shared, int thread, int threads) {
+    double2* sharedPairs = reinterpret_cast<double2*>(shared);
+    for (int i = thread; i < kLogTableEntries; i += threads) sharedPairs[i] = kLogPairs[i];
+    pairs = sharedPairs;
+  }
+  __device__ __forceinline__ void fetch(unsigned index, double& invc, double& logCentre) const {
+    const double2 entry = pairs[index];
+    invc = entry.x;
+    logCentre = entry.y;
+  }
 };
 
-template <int N>
-__device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[N], const LogTable& table, unsigned& range) {
+template <int N, class Table>
+__device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[N], const Table& table, unsigned& range) {
   double invc[N], logc[N], r[N], p[N];
 #pragma unroll
   for (int j = 0; j < N; ++j) {
     const unsigned index = ((unsigned)__double2hiint(v[j]) - 0x3FD00000u) >> 12;  // unsigned: negative arguments wrap, they do not overflow
     range = max(range, index);
-    invc[j] = __hiloint2double((int)table.inverseHigh[index & (kLogTableEntries - 1)], 0);
-    logc[j] = table.logc[index & (kLogTableEntries - 1)];
+    table.fetch(index & (kLogTableEntries - 1), invc[j], logc[j]);
   }
 #pragma unroll
   for (int j = 0; j < N; ++j) r[j] = fma(v[j], invc[j], -1.0);
@@ -211,7 +256,8 @@ __device__ __forceinline__ void fastLogCore(const double (&v)[N], double (&out)[
 }
 
 // general entry point (self-test, tools): library logarithm outside [0.25, 4)
-__device__ __forceinline__ double fastLog(double v, const LogTable& table) {
+template <class Table>
+__device__ __forceinline__ double fastLog(double v, const Table& table) {
   const double in[1] = {v};
   double out[1];
   unsigned range = 0;
@@ -294,21 +340,21 @@ template <class L> struct SpeedClasses {
   }
 };
 
-struct EntropicShared {
+template <int Q> struct EntropicShared {
   double* f;             // [Q][kStepBlock]  F2, rows sorted by speed class
   double* fNeq;          // [Q][kStepBlock]  N2
-  double* alpha;         // [kStepBlock]     out: alpha of the solved nodes
+  double* alpha;         // [kStepBlock]     in: alphaMax of the nodes off the shortcut (when screened in registers), out: their alpha
   double* rowOffset;     // [kRowSlots]  C_c of the row's class       (library fallback only)
   double* rowInverse;    // [kRowSlots]  2^-k_c of the row's class    (library fallback only)
   int* warpCount;        // [kStepBlock / 32]
   unsigned char* list;   // [kStepBlock]     nodes (thread indices) that left the shortcut, ascending
-  LogTable table;        // fastLog table (shared or global memory)
+  LogTable<logTableSplit(Q)> table;  // fastLog table (shared or global memory)
 };
 
-constexpr int kLogTableBytes = kLogTableEntries * 12;
+constexpr int logTableBytes(int Q) { return logTableSplit(Q) ? LogTable<true>::kBytes : LogTable<false>::kBytes; }
 constexpr int rowSlots(int Q) { return Q <= 32 ? 32 : 40; }  // D3Q33 has 33 rows
 constexpr int entropicSharedBytes(int Q, bool tableInShared) {
-  return 2 * Q * kStepBlock * 8 + kStepBlock * 8 + 2 * rowSlots(Q) * 8 + 16 + kStepBlock + (tableInShared ? kLogTableBytes : 0);
+  return 2 * Q * kStepBlock * 8 + kStepBlock * 8 + 2 * rowSlots(Q) * 8 + 16 + kStepBlock + (tableInShared ? logTableBytes(Q) : 0);
 }
 // blocks per SM the entropic kernels are compiled for (registers) and sized for (shared memory)
 // (measured, D3Q27 512^3: three blocks with the table in shared memory beat four blocks with the table in L1 by 10-14 %)
@@ -320,11 +366,21 @@ constexpr int entropicBlocksPerSM(int Q) { return Q <= 9 ? MLBM_ENTROPIC_BLOCKS_
 constexpr bool logTableInShared(int Q) { return entropicBlocksPerSM(Q) * (entropicSharedBytes(Q, true) + 1024) <= 233472; }
 // which part of its node's column the solving thread keeps in registers: 2 = F2 and N2, 1 = N2, 0 = nothing (rolled loops)
 #ifndef MLBM_COLUMN_REGISTERS_Q27
-#define MLBM_COLUMN_REGISTERS_Q27 1
+#define MLBM_COLUMN_REGISTERS_Q27 0
 #endif
 #ifndef MLBM_COLUMN_REGISTERS_Q19
-#define MLBM_COLUMN_REGISTERS_Q19 1
+#define MLBM_COLUMN_REGISTERS_Q19 0
 #endif
+// calculateAlphaMax (Collision.h:305-326) while fNeq is formed in registers (0: two multiplies and two compares per population
+// on EVERY node) or by the thread that solves the node, from its column (1: only on the nodes that left the shortcut, but
+// through shared memory when the column is not in registers)
+#ifndef MLBM_ALPHAMAX_IN_SOLVER_Q9
+#define MLBM_ALPHAMAX_IN_SOLVER_Q9 1
+#endif
+#ifndef MLBM_ALPHAMAX_IN_SOLVER_Q27
+#define MLBM_ALPHAMAX_IN_SOLVER_Q27 1
+#endif
+constexpr bool alphaMaxInSolver(int Q) { return Q <= 13 ? MLBM_ALPHAMAX_IN_SOLVER_Q9 != 0 : MLBM_ALPHAMAX_IN_SOLVER_Q27 != 0; }
 constexpr int columnRegisters(int Q) { return Q <= 13 ? 2 : (Q <= 21 ? MLBM_COLUMN_REGISTERS_Q19 : (Q <= 27 ? MLBM_COLUMN_REGISTERS_Q27 : 0)); }
 
 // The same solve with the CUDA math library's logarithm, for the rare node whose arguments fall outside fastLogCore's
@@ -382,8 +438,8 @@ template <int Q, int MODE> struct EntropicColumn {
 };
 
 // one group of G rows: hC += v ln v, sF += F2, sN += N2
-template <int G, int COUNT, class Column>
-__device__ __forceinline__ void entropicHoistGroup(const Column& column, int firstRow, int inClass, const LogTable& table, unsigned& range,
+template <int G, int COUNT, class Column, class Table>
+__device__ __forceinline__ void entropicHoistGroup(const Column& column, int firstRow, int inClass, const Table& table, unsigned& range,
                                                    double (&h)[G], double (&a)[G], double (&b)[G]) {
   double v[G], lg[G];
 #pragma unroll
@@ -399,8 +455,8 @@ __device__ __forceinline__ void entropicHoistGroup(const Column& column, int fir
 }
 
 // one group of G rows of an evaluation: sum += v L, derivative += N2 L with v = F2 - x N2
-template <int G, int COUNT, class Column>
-__device__ __forceinline__ void entropicEvaluateGroup(const Column& column, int firstRow, int inClass, const LogTable& table, unsigned& range,
+template <int G, int COUNT, class Column, class Table>
+__device__ __forceinline__ void entropicEvaluateGroup(const Column& column, int firstRow, int inClass, const Table& table, unsigned& range,
                                                       double x, double (&sum)[G], double (&derivative)[G]) {
   double n2[G], v[G], lg[G];
 #pragma unroll
@@ -434,27 +490,30 @@ __device__ __forceinline__ void forEachGroup(Body&& body) {
 // the 2^k scaling of a class cancels in the ratio), alphaMax < 2 -> 0.95 alphaMax, else solveAlpha (Collision.h:328-349) ->
 // NewtonRaphsonSolver (EntropicStep.h:111-140), see the banner above.  `evaluations` returns the evaluations of (F, F').
 template <class L>
-__device__ __forceinline__ double entropicAlpha(const EntropicShared& s, int node, double alphaGuess, int& evaluations) {
+__device__ __forceinline__ double entropicAlpha(const EntropicShared<L::Q>& s, int node, double alphaGuess, double alphaMaxScreened, int& evaluations) {
   using C = SpeedClasses<L>;
   constexpr int MODE = columnRegisters(L::Q);
   EntropicColumn<L::Q, MODE> column;
   column.load(s.f + node, s.fNeq + node);
 
-  double num = 2.5, den = 1.0;
-  auto screen = [&](int row) {
-    const double n2 = column.N(row);
-    if (n2 > 0.0) {
-      const double af = fabs(column.F(row));
-      if (af * den < num * n2) { num = af; den = n2; }
-    }
-  };
-  if constexpr (MODE >= 1) {
-    staticFor<0, L::Q>([&](auto rc) { screen(decltype(rc)::value); });
-  } else {
+  double alphaMax = alphaMaxScreened;
+  if constexpr (alphaMaxInSolver(L::Q)) {
+    double num = 2.5, den = 1.0;
+    auto screen = [&](int row) {
+      const double n2 = column.N(row);
+      if (n2 > 0.0) {
+        const double af = fabs(column.F(row));
+        if (af * den < num * n2) { num = af; den = n2; }
+      }
+    };
+    if constexpr (MODE >= 1) {
+      staticFor<0, L::Q>([&](auto rc) { screen(decltype(rc)::value); });
+    } else {
 #pragma unroll 1
-    for (int row = 0; row < L::Q; ++row) screen(row);
+      for (int row = 0; row < L::Q; ++row) screen(row);
+    }
+    alphaMax = num / den;
   }
-  const double alphaMax = num / den;
   evaluations = 0;
   if (alphaMax < 2.0) return 0.95 * alphaMax;
 
@@ -725,7 +784,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
   constexpr int Q = L::Q;
   using C = SpeedClasses<L>;
   extern __shared__ __align__(16) unsigned char dynamicShared[];
-  EntropicShared s;
+  EntropicShared<Q> s;
   s.f = reinterpret_cast<double*>(dynamicShared);
   s.fNeq = s.f + Q * kStepBlock;
   s.alpha = s.fNeq + Q * kStepBlock;
@@ -733,8 +792,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
   s.rowInverse = s.rowOffset + rowSlots(Q);
   s.warpCount = reinterpret_cast<int*>(s.rowInverse + rowSlots(Q));
   s.list = reinterpret_cast<unsigned char*>(s.warpCount + 4);
-  s.table.inverseHigh = kLogInverseHigh;
-  s.table.logc = kLogCentre;
+  s.table.global();
   staticFor<0, Q>([&](auto qc) {
     constexpr int q = decltype(qc)::value;
     if (threadIdx.x == q) {
@@ -742,18 +800,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       s.rowInverse[C::row(q)] = C::inverseScale(L::norm2(q));
     }
   });
-  if (logTableInShared(Q)) {
-    static_assert(kLogTableEntries % kStepBlock == 0, "whole table entries per thread");
-    double* logc = reinterpret_cast<double*>(dynamicShared + entropicSharedBytes(Q, false));
-    unsigned* inverseHigh = reinterpret_cast<unsigned*>(logc + kLogTableEntries);
-#pragma unroll
-    for (int i = 0; i < kLogTableEntries / kStepBlock; ++i) {
-      logc[i * kStepBlock + threadIdx.x] = kLogCentre[i * kStepBlock + threadIdx.x];
-      inverseHigh[i * kStepBlock + threadIdx.x] = kLogInverseHigh[i * kStepBlock + threadIdx.x];
-    }
-    s.table.inverseHigh = inverseHigh;
-    s.table.logc = logc;
-  }
+  if (logTableInShared(Q)) s.table.stage(dynamicShared + entropicSharedBytes(Q, false), threadIdx.x, kStepBlock);
 
   const int t = threadIdx.x;
   const int r = blockIdx.x * kStepBlock + t;
@@ -790,6 +837,15 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       // population -- sign bit of any F2_q, collected with integer ORs -- repeats the screen literally below.
       bool large = false;
       int signs = 0;
+      double num = 2.5, den = 1.0;  // calculateAlphaMax as a fraction, when it is screened here (alphaMaxInSolver(Q) == false)
+      auto trackAlphaMax = [&](double f2, double n2) {
+        if constexpr (!alphaMaxInSolver(Q)) {
+          if (n2 > 0.0) {
+            const double af = fabs(f2);
+            if (af * den < num * n2) { num = af; den = n2; }
+          }
+        }
+      };
       if constexpr (FORCED) {
         SourceTerm<L, EQ, SCHEME> forcedSource;
         forcedSource.set(p, rho, invRho, u, F);
@@ -798,8 +854,11 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
           constexpr double scale = C::scale(L::norm2(q));
           const double feq = rho * L::w(q) * eq.template shape<q>();
           // the population the entropy condition is written for: f_q + S_q
-          myF[C::row(q) * kStepBlock] = (f[q] + forcedSource.template value<q>(feq)) * scale;  // exact
-          myN[C::row(q) * kStepBlock] = (f[q] - feq) * scale;
+          const double f2 = (f[q] + forcedSource.template value<q>(feq)) * scale;  // exact
+          const double n2 = (f[q] - feq) * scale;
+          myF[C::row(q) * kStepBlock] = f2;
+          myN[C::row(q) * kStepBlock] = n2;
+          trackAlphaMax(f2, n2);
         });
         offShortcut = true;  // the forced variant has no isDeviationSmall shortcut
       } else {
@@ -813,6 +872,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
           myN[C::row(q) * kStepBlock] = n2;
           large = large || fabs(n2) > 1.0e-3 * f2;
           signs |= __double2hiint(f2);
+          trackAlphaMax(f2, n2);
         });
         if (signs < 0) {  // some population is negative (or -0): the reference's predicate, literally
           large = false;
@@ -823,6 +883,9 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
           }
         }
         offShortcut = large;
+      }
+      if constexpr (!alphaMaxInSolver(Q)) {
+        if (offShortcut) s.alpha[t] = num / den;  // read by the thread that solves this node
       }
     }
 
@@ -845,7 +908,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
         const int node = s.list[t];
         const double guess = (double)alphaField[rowNode + blockIdx.x * kStepBlock + node];  // previous step's alpha (Algorithm.h:103-106)
         int evaluations = 0;
-        s.alpha[node] = entropicAlpha<L>(s, node, guess, evaluations);
+        s.alpha[node] = entropicAlpha<L>(s, node, guess, alphaMaxInSolver(Q) ? 0.0 : s.alpha[node], evaluations);
         // statistics of the solve (mlbm_newton_statistics: the FP64 side of the roofline); counted only while a caller asks
         if (p.newtonCounters && evaluations > 0) {
           atomicAdd(p.newtonCounters, 1ull);

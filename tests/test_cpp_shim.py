@@ -97,7 +97,7 @@ def _run_shim(tmp_path, binary, f0_slabs, steps, env_extra=None):
                    MLBM_SESSION=f"shim{os.getpid()}")
         env.update(env_extra or {})
         procs.append(subprocess.Popen([str(binary), str(tmp_path / f"in{rank}.bin"), str(steps), str(tmp_path / f"out{rank}.bin"),
-                                       str(tmp_path / f"fields{rank}.bin")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                                       str(tmp_path / f"fields{rank}.bin"), str(tmp_path / f"moments{rank}.bin")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                                       text=True, env=env))
     outputs = []
     for rank, p in enumerate(procs):
@@ -173,6 +173,21 @@ def check_template_api(tmp_path, world, case):
     if collision != "BGK":
         assert (~alpha_ok).mean() <= 1e-3
         assert node_error[alpha_ok].max() <= 1e-12 * np.abs(ref.f).max() + 2e-10 * ref.fneq_max.max()
+    # the host-callable per-node surface (Moment<T>, Collision::calculateMoments / setForce / getHydrodynamicVelocity) over the
+    # halo-space host copy: moments of the populations PULLED to every node of the state after the last step (Moment.h:14-47),
+    # against the same sums over the device result itself, periodic images from np.roll
+    _, _, celerity, _ = O.lattice(lattice)
+    pulled = np.stack([np.roll(got[iq], tuple(int(c) for c in celerity[iq]), axis=(0, 1, 2)) for iq in range(q)])
+    density = pulled.sum(axis=0)
+    velocity = np.stack([(pulled * celerity[:, d, None, None, None]).sum(axis=0) for d in range(dim)]) / density
+    force = ref.force            # Kolmogorov: a profile along y, the same at local and global coordinates
+    for r in range(world):
+        raw = np.fromfile(tmp_path / f"moments{r}.bin").reshape((1 + 2 * dim, lx) + tuple(shape[1:]))
+        part = slice(r * lx, (r + 1) * lx)
+        assert relative_error(raw[0], density[part]) <= 1e-14
+        assert np.abs(raw[1:1 + dim] - velocity[:, part]).max() <= 1e-14
+        hydro = velocity[:, part] + (0.5 / density[part]) * force[:, part] if scheme != "None" else velocity[:, part]
+        assert np.abs(raw[1 + dim:] - hydro).max() <= 1e-14
 
 
 def test_observables_file_format_equals_the_reference(tmp_path):
