@@ -34,7 +34,8 @@ __global__ void __launch_bounds__(256) alphaStatisticsKernel(const StoreT* __res
 
 // both table formats of fastLogCore (step_kernel.cuh): even blocks the split one, odd blocks the {invc, logc} pairs
 __global__ void fastLogKernel(const double* __restrict__ in, double* __restrict__ out, long long count) {
-  __shared__ __align__(16) unsigned char storage[LogTable<false>::kBytes];
+  __shared__ double2 pairs[kLogTableEntries];   // large enough for either format
+  unsigned char* storage = reinterpret_cast<unsigned char*>(pairs);
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (blockIdx.x & 1) {
     LogTable<false> table;
@@ -59,6 +60,7 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]) {
   if (!ctx || !out) return fail(MLBM_ERR_INVALID, "null argument");
   if (!ctx->observablesValid) return fail(MLBM_ERR_STATE, "no stored step yet (Algorithm::isStored was never set)");
   MLBM_CUDA(cudaSetDevice(ctx->device));
+  if (int status = joinAnalysis(ctx)) return status;  // the enstrophy of the last stored step comes from the analysis stream
   double local[4];
   if (ctx->config.nranks > 1) {
     if (!ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
@@ -95,10 +97,11 @@ int mlbm_power_spectra(mlbm_ctx* ctx, double* energySpectrum, double* forcingSpe
   if (bins == 0) return MLBM_OK;
   MLBM_CUDA(cudaSetDevice(ctx->device));
   if (ctx->config.nranks > 1 && !ctx->comm) return fail(MLBM_ERR_STATE, "nranks > 1 but mlbm_comm_init was not called");
+  if (int status = joinAnalysis(ctx)) return status;  // the transforms below reuse the buffers of the enstrophy analysis
   std::string error;
   if (!ctx->spectral) {
     SpectralGeometry geometry = {ctx->D, ctx->LX, ctx->NM, ctx->NR, ctx->config.rank, ctx->config.nranks, (int)ctx->elementSize};
-    ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->comm, &error);
+    ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->analysisComm, &error);
     if (!ctx->spectral) return fail(MLBM_ERR_CUDA, "power spectra: %s", error.c_str());
   }
   double* device = nullptr;

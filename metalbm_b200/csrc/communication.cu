@@ -35,6 +35,7 @@ const NcclApi* loadNccl(const char** error) {
       api.GroupEnd = reinterpret_cast<decltype(api.GroupEnd)>(resolve("ncclGroupEnd"));
       api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(resolve("ncclAllReduce"));
       api.GetErrorString = reinterpret_cast<decltype(api.GetErrorString)>(resolve("ncclGetErrorString"));
+      api.CommSplit = reinterpret_cast<decltype(api.CommSplit)>(dlsym(handle, "ncclCommSplit"));  // optional
     }
   }
   if (!ok) { if (error) *error = message.c_str(); return nullptr; }
@@ -129,6 +130,15 @@ int mlbm_comm_init(mlbm_ctx* ctx, const void* id128) {
   ncclUniqueId id;
   memcpy(&id, id128, sizeof(id));
   MLBM_NCCL(ctx, ctx->nccl->CommInitRank(&ctx->comm, ctx->config.nranks, id, ctx->config.rank));
+  // The spectral analyses of a stored step run on their own stream next to the following steps (context.cu: enqueueStep):
+  // their all-to-all gets its own communicator, so that it never queues in front of a step's halo exchange or of the
+  // all-reduce of the observables on ctx->comm.  Without ncclCommSplit the one communicator serves both (NCCL orders them).
+  ctx->analysisComm = ctx->comm;
+  static const bool shareComm = getenv("MLBM_ANALYSIS_COMM") && atoi(getenv("MLBM_ANALYSIS_COMM")) == 0;
+  if (ctx->nccl->CommSplit && !shareComm) {
+    ncclComm_t second = nullptr;
+    if (ctx->nccl->CommSplit(ctx->comm, 0, ctx->config.rank, &second, nullptr) == ncclSuccess && second) ctx->analysisComm = second;
+  }
   return MLBM_OK;
 }
 

@@ -335,10 +335,9 @@ bool slabGeometry(const mlbm_config* config, SlabGeometry* g) {
   g->plane = (long long)g->NM * g->NR;
   const long long perPopulation = g->plane * (g->LX + 2 * g->H);
   g->stride = (perPopulation + 31) / 32 * 32;  // keep every population 128-byte aligned
-  // experiment hook (bench only): extra elements between populations, to move the Q concurrent streams off a common
-  // power-of-two alignment (1024^2 planes make the stride a multiple of 16 MB)
-  static const long long stridePad = getenv("MLBM_STRIDE_PAD") ? atoll(getenv("MLBM_STRIDE_PAD")) / 32 * 32 : 0;
-  g->stride += stridePad;
+  // the kernels address a node INSIDE one population with 32-bit element offsets (NodeIndex, step_kernel.cuh); the
+  // offsets BETWEEN populations are 64-bit.  1024^3 on 2 GPUs has 5.4e8 elements per population.
+  if (perPopulation >= (1LL << 32)) return false;
   return true;
 }
 
@@ -469,12 +468,22 @@ static int ensurePartials(mlbm_ctx* ctx) {
   return MLBM_OK;
 }
 
+// the compute stream waits for the analysis of the last stored step (a no-op when none is in flight)
+int joinAnalysis(mlbm_ctx* ctx) {
+  if (!ctx->analysisPending) return MLBM_OK;
+  MLBM_CUDA(cudaStreamWaitEvent(ctx->computeStream, ctx->analysisDone, 0));
+  ctx->analysisPending = false;
+  return MLBM_OK;
+}
+
 // enqueue one Algorithm::iterate; `timed` records the events behind mlbm_timers
 static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
   const bool multi = ctx->config.nranks > 1;
   if (isStored & 1) { if (int status = ensureFields(ctx)) return status; }
   if (isStored) { if (int status = ensurePartials(ctx)) return status; }
   cudaStream_t compute = ctx->computeStream;
+  // the analysis of the previous stored step still reads the velocity field this step is about to overwrite
+  if ((isStored & 1) && ctx->analysisPending) { if (int status = joinAnalysis(ctx)) return status; }
   if (ctx->shell && ctx->forceStale) {
     // Collision::update -> Force::update at the top of iterate (Algorithm.h:338, Collision.h:97-100, Force.h:552-558)
     std::string error;
@@ -552,11 +561,25 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
       std::string error;
       if (!ctx->spectral) {
         SpectralGeometry geometry = {ctx->D, ctx->LX, ctx->NM, ctx->NR, ctx->config.rank, ctx->config.nranks, (int)ctx->elementSize};
-        ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->comm, &error);
+        ctx->spectral = spectralCreate(geometry, ctx->nccl, ctx->analysisComm, &error);
         if (!ctx->spectral) return fail(MLBM_ERR_CUDA, "spectral enstrophy: %s", error.c_str());
       }
-      if (spectralEnqueue(ctx->spectral, ctx->velocity, ctx->fieldStride, ctx->deviceObservables + 3, compute, &ctx->launches, &error))
+      // The transforms, their all-to-all and the vorticity norm run on the analysis stream, next to the steps that follow
+      // (the fields are only written on stored steps); whoever needs the result or the fields' buffers joins it first
+      // (joinAnalysis: mlbm_observables, mlbm_power_spectra, the next stored step, mlbm_sync).  MLBM_ASYNC_ANALYSIS=0 keeps
+      // everything on the compute stream.
+      static const bool asyncAnalysis = !(getenv("MLBM_ASYNC_ANALYSIS") && atoi(getenv("MLBM_ASYNC_ANALYSIS")) == 0);
+      cudaStream_t analysis = asyncAnalysis ? ctx->analysisStream : compute;
+      if (asyncAnalysis) {
+        MLBM_CUDA(cudaEventRecord(ctx->fieldsReady, compute));
+        MLBM_CUDA(cudaStreamWaitEvent(analysis, ctx->fieldsReady, 0));
+      }
+      if (spectralEnqueue(ctx->spectral, ctx->velocity, ctx->fieldStride, ctx->deviceObservables + 3, analysis, &ctx->launches, &error))
         return fail(MLBM_ERR_CUDA, "spectral enstrophy: %s", error.c_str());
+      if (asyncAnalysis) {
+        MLBM_CUDA(cudaEventRecord(ctx->analysisDone, analysis));
+        ctx->analysisPending = true;
+      }
       ctx->fieldsStored = true;
       ctx->enstrophyValid = true;
       if (ctx->shell && shellForceIsTimeDependent(ctx->shell)) ctx->forceStale = true;  // fieldList changed
@@ -581,6 +604,7 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->computeStream) cudaStreamSynchronize(ctx->computeStream);
   if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
+  if (ctx->analysisStream) cudaStreamSynchronize(ctx->analysisStream);
   if (ctx->peerAttached && ctx->comm && ctx->nccl && ctx->deviceObservables) {
     // the neighbours store into this rank's halo planes and flags: nobody frees before everybody has drained its streams
     if (ctx->nccl->AllReduce(ctx->deviceObservables, ctx->deviceObservables, 1, ncclDouble, ncclSum, ctx->comm, ctx->computeStream) == ncclSuccess)
@@ -593,17 +617,19 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   if (ctx->peerTimedOut) cudaFreeHost(ctx->peerTimedOut);
   if (ctx->spectral) spectralDestroy(ctx->spectral);
   if (ctx->shell) shellForceDestroy(ctx->shell);
+  if (ctx->analysisComm && ctx->analysisComm != ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->analysisComm);
   if (ctx->comm && ctx->nccl) ctx->nccl->CommDestroy(ctx->comm);
   for (void* pointer : {ctx->populations[0], ctx->populations[1], ctx->alpha, ctx->density, ctx->velocity, ctx->force,
                         (void*)ctx->partials, (void*)ctx->newtonCounters, ctx->staging, (void*)ctx->reduceStage, (void*)ctx->reduceTicket, (void*)ctx->deviceObservables,
                         (void*)ctx->forceTables[0], (void*)ctx->forceTables[1], (void*)ctx->forceTables[2]})
     if (pointer) cudaFree(pointer);
-  for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->stepStart, ctx->timeStart, ctx->timeMid, ctx->timeStop})
+  for (cudaEvent_t event : {ctx->boundaryDone, ctx->exchangeDone, ctx->bulkDone, ctx->stepStart, ctx->timeStart, ctx->timeMid, ctx->timeStop, ctx->fieldsReady, ctx->analysisDone})
     if (event) cudaEventDestroy(event);
   for (cudaEvent_t event : ctx->profileEvents) cudaEventDestroy(event);
   for (cudaEvent_t event : ctx->marks) if (event) cudaEventDestroy(event);
   if (ctx->computeStream) cudaStreamDestroy(ctx->computeStream);
   if (ctx->commStream) cudaStreamDestroy(ctx->commStream);
+  if (ctx->analysisStream) cudaStreamDestroy(ctx->analysisStream);
   delete ctx;
   return MLBM_OK;
 }
@@ -659,7 +685,10 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   ctx->device = device;
   ctx->D = D; ctx->Q = Q; ctx->faceQ = latticeFaceQ(config->lattice);
   SlabGeometry geometry;
-  slabGeometry(config, &geometry);
+  if (!slabGeometry(config, &geometry)) {
+    delete ctx;
+    return fail(MLBM_ERR_INVALID, "a population of this slab has 2^32 elements or more (32-bit in-population offsets); use more ranks");
+  }
   ctx->LX = geometry.LX;
   ctx->NM = geometry.NM;
   ctx->NR = geometry.NR;
@@ -698,6 +727,8 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   MLBM_CREATE_CUDA(cudaDeviceGetStreamPriorityRange(&leastPriority, &greatestPriority));
   MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->computeStream, cudaStreamNonBlocking, leastPriority));
   MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->commStream, cudaStreamNonBlocking, greatestPriority));
+  MLBM_CREATE_CUDA(cudaStreamCreateWithPriority(&ctx->analysisStream, cudaStreamNonBlocking, leastPriority));
+  for (cudaEvent_t* event : {&ctx->fieldsReady, &ctx->analysisDone}) MLBM_CREATE_CUDA(cudaEventCreateWithFlags(event, cudaEventDisableTiming));
   for (cudaEvent_t* event : {&ctx->boundaryDone, &ctx->exchangeDone, &ctx->bulkDone, &ctx->stepStart})
     MLBM_CREATE_CUDA(cudaEventCreateWithFlags(event, cudaEventDisableTiming));
   for (cudaEvent_t* event : {&ctx->timeStart, &ctx->timeMid, &ctx->timeStop}) MLBM_CREATE_CUDA(cudaEventCreate(event));
@@ -1045,6 +1076,7 @@ int mlbm_sync(mlbm_ctx* ctx) {
   MLBM_CUDA(cudaSetDevice(ctx->device));
   MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
   MLBM_CUDA(cudaStreamSynchronize(ctx->commStream));
+  MLBM_CUDA(cudaStreamSynchronize(ctx->analysisStream));
   return MLBM_OK;
 }
 

@@ -97,6 +97,10 @@ struct mlbm_ctx {
   int hydroShift = 0;
   cudaStream_t computeStream = nullptr;
   cudaStream_t commStream = nullptr;
+  cudaStream_t analysisStream = nullptr;   // spectral enstrophy of a stored step, next to the steps that follow it
+  cudaEvent_t fieldsReady = nullptr, analysisDone = nullptr;
+  bool analysisPending = false;            // analysisDone was recorded and nobody has waited for it on the compute stream yet
+  ncclComm_t analysisComm = nullptr;       // == comm where ncclCommSplit is unavailable
   cudaEvent_t boundaryDone = nullptr, exchangeDone = nullptr, bulkDone = nullptr;
   cudaEvent_t timeStart = nullptr, timeMid = nullptr, timeStop = nullptr;
   cudaEvent_t marks[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -126,6 +130,7 @@ struct mlbm_ctx {
 
 namespace mlbm {
 int exchangeHalos(mlbm_ctx* ctx, int which, cudaStream_t stream);
+int joinAnalysis(mlbm_ctx* ctx);  // the compute stream waits for the spectral analysis of the last stored step
 inline void* offsetElements(void* base, long long elements, size_t elementSize) {
   return static_cast<char*>(base) + elements * (long long)elementSize;
 }

@@ -18,6 +18,8 @@ struct NcclApi {
   ncclResult_t (*GroupEnd)();
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
   const char* (*GetErrorString)(ncclResult_t);
+  // optional (NCCL >= 2.18; nullptr otherwise): a second communicator over the same ranks for the analysis stream
+  ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, ncclConfig_t*);
 };
 
 // nullptr (and a message in *error) when libnccl cannot be loaded

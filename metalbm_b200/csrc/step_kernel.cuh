@@ -178,10 +178,10 @@ constexpr int kLogTableEntries = 1024;
 // and three integer instructions less.  Which one wins depends on whether a kernel is short of shared-memory bandwidth
 // (D3Q27) or of issue slots (D2Q9): logTableSplit(Q).
 #ifndef MLBM_LOG_TABLE_SPLIT_Q9
-#define MLBM_LOG_TABLE_SPLIT_Q9 1
+#define MLBM_LOG_TABLE_SPLIT_Q9 0
 #endif
 #ifndef MLBM_LOG_TABLE_SPLIT_Q27
-#define MLBM_LOG_TABLE_SPLIT_Q27 1
+#define MLBM_LOG_TABLE_SPLIT_Q27 0
 #endif
 constexpr bool logTableSplit(int Q) { return Q <= 13 ? MLBM_LOG_TABLE_SPLIT_Q9 != 0 : MLBM_LOG_TABLE_SPLIT_Q27 != 0; }
 static __device__ const unsigned kLogInverseHigh[kLogTableEntries] = {
@@ -336,7 +336,11 @@ template <class L> struct SpeedClasses {
   // logarithms advanced in lock step inside a class
   static constexpr int group(int n2) {
     const int n = count(n2);
+#if defined(MLBM_LOG_GROUP_WIDE)
+    return n % 6 == 0 ? 6 : (n % 8 == 0 ? 8 : (n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n < 3 ? (n > 0 ? n : 1) : 3))));
+#else
     return n % 4 == 0 ? 4 : (n % 3 == 0 ? 3 : (n < 3 ? (n > 0 ? n : 1) : 3));
+#endif
   }
 };
 
@@ -378,7 +382,7 @@ constexpr bool logTableInShared(int Q) { return entropicBlocksPerSM(Q) * (entrop
 #define MLBM_ALPHAMAX_IN_SOLVER_Q9 1
 #endif
 #ifndef MLBM_ALPHAMAX_IN_SOLVER_Q27
-#define MLBM_ALPHAMAX_IN_SOLVER_Q27 1
+#define MLBM_ALPHAMAX_IN_SOLVER_Q27 0
 #endif
 constexpr bool alphaMaxInSolver(int Q) { return Q <= 13 ? MLBM_ALPHAMAX_IN_SOLVER_Q9 != 0 : MLBM_ALPHAMAX_IN_SOLVER_Q27 != 0; }
 constexpr int columnRegisters(int Q) { return Q <= 13 ? 2 : (Q <= 21 ? MLBM_COLUMN_REGISTERS_Q19 : (Q <= 27 ? MLBM_COLUMN_REGISTERS_Q27 : 0)); }
@@ -473,6 +477,11 @@ __device__ __forceinline__ void entropicEvaluateGroup(const Column& column, int 
   }
 }
 
+#ifndef MLBM_GROUP_UNROLL
+#define MLBM_GROUP_UNROLL 1
+#endif
+constexpr int kGroupUnroll = MLBM_GROUP_UNROLL;  // groups of the rolled loops in flight per thread
+
 // the groups of one speed class: unrolled when the column sits in registers (compile-time rows), rolled otherwise
 template <int FIRST, int COUNT, int G, int MODE, class Body>
 __device__ __forceinline__ void forEachGroup(Body&& body) {
@@ -480,7 +489,7 @@ __device__ __forceinline__ void forEachGroup(Body&& body) {
   if constexpr (MODE >= 1) {
     staticFor<0, groups>([&](auto gc) { body(FIRST + decltype(gc)::value * G, decltype(gc)::value * G); });
   } else {
-#pragma unroll 1
+#pragma unroll kGroupUnroll
     for (int group = 0; group < groups; ++group) body(FIRST + group * G, group * G);
   }
 }
@@ -576,7 +585,11 @@ __device__ __forceinline__ double entropicAlpha(const EntropicShared<L::Q>& s, i
 // Pieces shared by the two kernel bodies
 // ------------------------------------------------------------------------------------------------
 struct NodeIndex {
-  int xPrev, xh, xNext, mPrev, m, mNext, rPrev, r, rNext;
+  int xh, m, r;  // the node itself: plane index counted from the first halo plane, row, column
+  // element offsets INSIDE one population of the upstream plane / row / column for a celerity component +1, 0, -1 (pull from
+  // x - c).  32-bit: a population (LX + 2 H planes) holds fewer than 2^32 elements (checked by mlbm_create), so that an
+  // address costs one three-input add and one widening multiply-add instead of a chain of 64-bit operations.
+  unsigned plane[3], row[3], column[3];
 };
 
 template <class L>
@@ -584,18 +597,23 @@ __device__ __forceinline__ NodeIndex nodeIndex(const StepParams& p, int x, int m
   // upstream coordinates: pull from (x - cx, m - cm, r - cr) of the periodic image
   NodeIndex n;
   n.xh = x + L::H;  // L::H halo planes (one but for the multi-speed lattices) precede the interior
-  n.xPrev = n.xh - 1;
-  n.xNext = n.xh + 1;
-  if (p.wrapX) {
-    if (n.xPrev == 0) n.xPrev = p.LX;
-    if (n.xNext == p.LX + 1) n.xNext = 1;
-  }
   n.m = m;
-  n.mPrev = m == 0 ? p.NM - 1 : m - 1;
-  n.mNext = m == p.NM - 1 ? 0 : m + 1;
   n.r = r;
-  n.rPrev = r == 0 ? p.NR - 1 : r - 1;
-  n.rNext = r == p.NR - 1 ? 0 : r + 1;
+  int xPrev = n.xh - 1, xNext = n.xh + 1;
+  if (p.wrapX) {
+    if (xPrev == 0) xPrev = p.LX;
+    if (xNext == p.LX + 1) xNext = 1;
+  }
+  const unsigned planeElements = (unsigned)p.plane, NR = (unsigned)p.NR;
+  n.plane[0] = (unsigned)xPrev * planeElements;
+  n.plane[1] = (unsigned)n.xh * planeElements;
+  n.plane[2] = (unsigned)xNext * planeElements;
+  n.row[0] = (unsigned)(m == 0 ? p.NM - 1 : m - 1) * NR;
+  n.row[1] = (unsigned)m * NR;
+  n.row[2] = (unsigned)(m == p.NM - 1 ? 0 : m + 1) * NR;
+  n.column[0] = (unsigned)(r == 0 ? p.NR - 1 : r - 1);
+  n.column[1] = (unsigned)r;
+  n.column[2] = (unsigned)(r == p.NR - 1 ? 0 : r + 1);
   return n;
 }
 
@@ -624,13 +642,14 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
   }
 #pragma unroll
   for (int q = 0; q < L::Q; ++q) {
-    const int xs = L::cx(q) == 1 ? n.xPrev : (L::cx(q) == -1 ? n.xNext : n.xh);
-    const int ms = L::cm(q) == 1 ? n.mPrev : (L::cm(q) == -1 ? n.mNext : n.m);
-    const int rs = L::cr(q) == 1 ? n.rPrev : (L::cr(q) == -1 ? n.rNext : n.r);
-    const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
+    const unsigned offset = n.plane[1 - L::cx(q)] + n.row[1 - L::cm(q)] + n.column[1 - L::cr(q)];
+    const StoreT* source = prev + q * p.stride + offset;
     f[q] = STREAMING ? loadPopulationStreaming(source) : loadPopulation(source);
   }
 }
+
+// element offset of the node itself inside one population of `next` (32-bit, see NodeIndex)
+__device__ __forceinline__ unsigned ownOffset(const NodeIndex& n) { return n.plane[1] + n.row[1] + n.column[1]; }
 
 // Moment::calculateDensity / calculateVelocity (Moment.h:14-47)
 template <class L>
@@ -921,7 +940,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
 
     if (active) {
       const long long node = rowNode + r;
-      const long long out = (long long)(x + L::H) * p.plane + (long long)m * p.NR + r;
+      const unsigned out = (unsigned)(x + L::H) * (unsigned)p.plane + (unsigned)m * (unsigned)p.NR + (unsigned)r;
       StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
       StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
       alphaField[node] = (StoreT)alpha;
@@ -979,7 +998,7 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
       source.set(p, rho, invRho, u, F);
 
       const long long node = (long long)x * p.plane + (long long)m * p.NR + r;  // field index
-      const long long out = (long long)n.xh * p.plane + (long long)m * p.NR + r;
+      const unsigned out = ownOffset(n);
       // halo planes of the neighbours this node's outgoing populations belong to (block-uniform conditions)
       StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
       StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;

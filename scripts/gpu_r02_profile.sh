@@ -20,8 +20,8 @@ B="python bench.py --no-cpu-baseline --no-e2e --also off"
 out=${T}_bgk_experiments.txt; : > $out
 for shape in 256,256,256 512,512,512 128,1024,1024; do
   timeout 300 $B --shape $shape --steps 50 2>>${T}_err.log | one "default" >> $out
-  MLBM_STRIDE_PAD=8480 timeout 300 $B --shape $shape --steps 50 2>>${T}_err.log | one "stride+8480" >> $out
-  MLBM_STRIDE_PAD=33824 timeout 300 $B --shape $shape --steps 50 2>>${T}_err.log | one "stride+33824" >> $out
+  
+  
   MLBM_VARIANT=bgk4 timeout 300 $B --shape $shape --steps 50 2>>${T}_err.log | one "bgk4(128regs)" >> $out
 done
 timeout 300 $B --shape 256,256,256 --dtype f32 --steps 50 2>>${T}_err.log | one "default" >> $out

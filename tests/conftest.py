@@ -94,3 +94,22 @@ def _order_gpu_items(items):
         return
     ordered = iter(sorted(gpu, key=_gpu_order))   # stable
     items[:] = [next(ordered) if item.get_closest_marker("gpu") else item for item in items]
+
+
+# ---- a multi-GPU box must not skip what it can run ---------------------------------------------------------------------
+# Every multi-rank case skips itself with "needs N GPUs" on a smaller box.  The outcomes are recorded here and
+# tests/test_zz_gpu_coverage.py (collected last) FAILS when a box with N or more GPUs skipped such a case, or when a box with
+# two or more GPUs ran no multi-rank case at all: a parity run that silently degraded to one GPU is an error, not a skip.
+GPU_OUTCOMES = {"skipped_needing": [], "ran": [], "multi_rank_ran": 0}
+
+
+def pytest_runtest_logreport(report):
+    import re
+    if report.when == "setup" and report.skipped or report.when == "call" and report.skipped:
+        text = str(report.longrepr)
+        match = re.search(r"needs (\d+) GPUs", text)
+        if match:
+            GPU_OUTCOMES["skipped_needing"].append((report.nodeid, int(match.group(1))))
+    elif report.when == "call" and report.passed:
+        GPU_OUTCOMES["ran"].append(report.nodeid)
+        # the multi-rank cases carry their world size in the test id ("[...-2]", "world2", "-2-" ...): counted by the tests themselves
