@@ -469,7 +469,7 @@ static int ensurePartials(mlbm_ctx* ctx) {
 }
 
 // the compute stream waits for the analysis of the last stored step (a no-op when none is in flight)
-int joinAnalysis(mlbm_ctx* ctx) {
+int mlbm::joinAnalysis(mlbm_ctx* ctx) {
   if (!ctx->analysisPending) return MLBM_OK;
   MLBM_CUDA(cudaStreamWaitEvent(ctx->computeStream, ctx->analysisDone, 0));
   ctx->analysisPending = false;

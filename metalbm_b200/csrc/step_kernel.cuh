@@ -68,15 +68,15 @@ struct StepParams {
   double guoFactor;        // (1 - 1/(2 tau)) * inv_cs2        (ForcingScheme.h:115)
 };
 
-template <typename StoreT> __device__ __forceinline__ double loadPopulation(const StoreT* p) {
-  return (double)__ldg(p);
+template <typename CT = double, typename StoreT> __device__ __forceinline__ CT loadPopulation(const StoreT* p) {
+  return (CT)__ldg(p);
 }
 // L2-only load: the entropic kernels keep their logarithm table (and little else) in what the shared-memory carve-out
 // leaves of L1; the once-read population stream must not evict it
-template <typename StoreT> __device__ __forceinline__ double loadPopulationStreaming(const StoreT* p) {
-  return (double)__ldcg(p);
+template <typename CT = double, typename StoreT> __device__ __forceinline__ CT loadPopulationStreaming(const StoreT* p) {
+  return (CT)__ldcg(p);
 }
-template <typename StoreT> __device__ __forceinline__ void storePopulation(StoreT* p, double v) {
+template <typename StoreT, typename CT> __device__ __forceinline__ void storePopulation(StoreT* p, CT v) {
   __stcs(p, (StoreT)v);
 }
 
@@ -87,58 +87,59 @@ template <typename StoreT> __device__ __forceinline__ void storePopulation(Store
 //     A0 = 1 - s/2 u2 + s^2/8 u2^2, A1 = s - s^2/2 u2, A2 = s^2/2 - s^3/4 u2, A3 = s^3/6, A4 = s^4/24
 //   Exact (Equilibrium.h:60-81, 106-126): product form, three factors per dimension precomputed.
 // ------------------------------------------------------------------------------------------------
-template <class L, int EQ> struct EquilibriumCoefficients;
+// CT: the arithmetic type -- double, or float for the BGK kernels on FP32 storage (the reference computes in its dataT)
+template <class L, int EQ, typename CT = double> struct EquilibriumCoefficients;
 
 // c_q . v for a compile-time celerity: additions and subtractions for the unit components, one multiply for the others
-template <class L, int q> __device__ __forceinline__ double celerityDot(const double* v) {
-  double r = 0.0;
+template <class L, int q, typename CT> __device__ __forceinline__ CT celerityDot(const CT* v) {
+  CT r = (CT)0;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) {
     if (L::c(q, d) == 1) r += v[d];
     else if (L::c(q, d) == -1) r -= v[d];
-    else if (L::c(q, d) != 0) r += (double)L::c(q, d) * v[d];
+    else if (L::c(q, d) != 0) r += (CT)L::c(q, d) * v[d];
   }
   return r;
 }
 
-template <class L> struct EquilibriumCoefficients<L, kTruncationMa3> {
+template <class L, typename CT> struct EquilibriumCoefficients<L, kTruncationMa3, CT> {
   // s = L::inv_cs2: 3 for the single-speed lattices, where these constants are exactly 1.5, 1.125, 3, 4.5, 4.5, 6.75, 4.5, 3.375
   static constexpr double s = L::inv_cs2;
-  static constexpr double kA0u2 = 0.5 * s, kA0u4 = 0.125 * s * s, kA1 = s, kA1u2 = 0.5 * s * s, kA2 = 0.5 * s * s,
-                          kA2u2 = 0.25 * s * s * s, kA3 = s * s * s / 6.0, kA4 = s * s * s * s / 24.0;
-  double a0, a1, a2;
-  double u[3];
-  __device__ __forceinline__ void set(const double* velocity, double u2) {
-    a0 = 1.0 - kA0u2 * u2 + kA0u4 * u2 * u2;
+  static constexpr CT kA0u2 = (CT)(0.5 * s), kA0u4 = (CT)(0.125 * s * s), kA1 = (CT)s, kA1u2 = (CT)(0.5 * s * s), kA2 = (CT)(0.5 * s * s),
+                      kA2u2 = (CT)(0.25 * s * s * s), kA3 = (CT)(s * s * s / 6.0), kA4 = (CT)(s * s * s * s / 24.0);
+  CT a0, a1, a2;
+  CT u[3];
+  __device__ __forceinline__ void set(const CT* velocity, CT u2) {
+    a0 = (CT)1 - kA0u2 * u2 + kA0u4 * u2 * u2;
     a1 = kA1 - kA1u2 * u2;
     a2 = kA2 - kA2u2 * u2;
 #pragma unroll
-    for (int d = 0; d < 3; ++d) u[d] = d < L::D ? velocity[d] : 0.0;
+    for (int d = 0; d < 3; ++d) u[d] = d < L::D ? velocity[d] : (CT)0;
   }
   // returns feq / (rho * w_q)
-  template <int q> __device__ __forceinline__ double shape() const {
-    const double cu = celerityDot<L, q>(u);
+  template <int q> __device__ __forceinline__ CT shape() const {
+    const CT cu = celerityDot<L, q, CT>(u);
     if (L::norm2(q) == 0) return a0;
     return a0 + cu * (a1 + cu * (a2 + cu * (kA3 + cu * kA4)));
   }
 };
 
-template <class L> struct EquilibriumCoefficients<L, kExact> {
-  double factor[3][3];  // [d][c+1]: (2 - sqrt(1+3u^2)) * ((2u + sqrt(1+3u^2)) / (1-u))^c
-  __device__ __forceinline__ void set(const double* velocity, double) {
+template <class L, typename CT> struct EquilibriumCoefficients<L, kExact, CT> {
+  CT factor[3][3];  // [d][c+1]: (2 - sqrt(1+3u^2)) * ((2u + sqrt(1+3u^2)) / (1-u))^c
+  __device__ __forceinline__ void set(const CT* velocity, CT) {
 #pragma unroll
     for (int d = 0; d < L::D; ++d) {
-      const double ud = velocity[d];
-      const double root = sqrt(1.0 + 3.0 * ud * ud);
-      const double a = 2.0 - root;
-      const double b = (2 * ud + root) / (1.0 - ud);
-      factor[d][0] = a * (1.0 / b);
+      const CT ud = velocity[d];
+      const CT root = sqrt((CT)1 + (CT)3 * ud * ud);
+      const CT a = (CT)2 - root;
+      const CT b = ((CT)2 * ud + root) / ((CT)1 - ud);
+      factor[d][0] = a * ((CT)1 / b);
       factor[d][1] = a;
       factor[d][2] = a * b;
     }
   }
-  template <int q> __device__ __forceinline__ double shape() const {
-    double r = factor[0][L::c(q, 0) + 1];
+  template <int q> __device__ __forceinline__ CT shape() const {
+    CT r = factor[0][L::c(q, 0) + 1];
 #pragma unroll
     for (int d = 1; d < L::D; ++d) r *= factor[d][L::c(q, d) + 1];
     return r;
@@ -623,8 +624,8 @@ __device__ __forceinline__ int wrapCoordinate(int v, int n) {
   return v < 0 ? v + n : v;
 }
 
-template <class L, typename StoreT, bool STREAMING = false>
-__device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeIndex& n, double (&f)[L::Q]) {
+template <class L, typename StoreT, bool STREAMING = false, typename CT = double>
+__device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeIndex& n, CT (&f)[L::Q]) {
   const StoreT* __restrict__ prev = static_cast<const StoreT*>(p.prev);
   if constexpr (L::H > 1) {
     // multi-speed lattices (Lattice.h:213-458, 706-803): m and r wrap by index arithmetic whatever the length of the jump;
@@ -636,7 +637,7 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
       const int ms = L::cm(q) == 0 ? n.m : wrapCoordinate(n.m - L::cm(q), p.NM);
       const int rs = L::cr(q) == 0 ? n.r : wrapCoordinate(n.r - L::cr(q), p.NR);
       const StoreT* source = prev + q * p.stride + xs * p.plane + (long long)ms * p.NR + rs;
-      f[q] = STREAMING ? loadPopulationStreaming(source) : loadPopulation(source);
+      f[q] = STREAMING ? loadPopulationStreaming<CT>(source) : loadPopulation<CT>(source);
     }
     return;
   }
@@ -644,7 +645,7 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
   for (int q = 0; q < L::Q; ++q) {
     const unsigned offset = n.plane[1 - L::cx(q)] + n.row[1 - L::cm(q)] + n.column[1 - L::cr(q)];
     const StoreT* source = prev + q * p.stride + offset;
-    f[q] = STREAMING ? loadPopulationStreaming(source) : loadPopulation(source);
+    f[q] = STREAMING ? loadPopulationStreaming<CT>(source) : loadPopulation<CT>(source);
   }
 }
 
@@ -652,23 +653,23 @@ __device__ __forceinline__ void pullPopulations(const StepParams& p, const NodeI
 __device__ __forceinline__ unsigned ownOffset(const NodeIndex& n) { return n.plane[1] + n.row[1] + n.column[1]; }
 
 // Moment::calculateDensity / calculateVelocity (Moment.h:14-47)
-template <class L>
-__device__ __forceinline__ void moments(const double (&f)[L::Q], double& rho, double& invRho, double (&u)[3], double& u2) {
+template <class L, typename CT>
+__device__ __forceinline__ void moments(const CT (&f)[L::Q], CT& rho, CT& invRho, CT (&u)[3], CT& u2) {
   rho = f[0];
 #pragma unroll
   for (int q = 1; q < L::Q; ++q) rho += f[q];
-  u[0] = u[1] = u[2] = 0.0;
+  u[0] = u[1] = u[2] = (CT)0;
 #pragma unroll
   for (int q = 1; q < L::Q; ++q) {
 #pragma unroll
     for (int d = 0; d < L::D; ++d) {
       if (L::c(q, d) == 1) u[d] += f[q];
       else if (L::c(q, d) == -1) u[d] -= f[q];
-      else if (L::c(q, d) != 0) u[d] += (double)L::c(q, d) * f[q];
+      else if (L::c(q, d) != 0) u[d] += (CT)L::c(q, d) * f[q];
     }
   }
-  invRho = 1.0 / rho;
-  u2 = 0.0;
+  invRho = (CT)1 / rho;
+  u2 = (CT)0;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) {
     u[d] *= invRho;
@@ -679,30 +680,30 @@ __device__ __forceinline__ void moments(const double (&f)[L::Q], double& rho, do
 // Force::setForce at local interior coordinates (Collision.h:81-88): profiles precomputed on the host for the analytic
 // forces, or Force<Generic>::setForce (Force.h:39-48) for the array-type forces: component iD of the force FIELD at the
 // node's local index.  storeNodeFields writes the same values back on stored steps, like Algorithm::storeFields does.
-template <class L, typename StoreT>
-__device__ __forceinline__ void bodyForce(const StepParams& p, int x, int m, int r, double (&F)[3]) {
-  F[0] = F[1] = F[2] = 0.0;
+template <class L, typename StoreT, typename CT>
+__device__ __forceinline__ void bodyForce(const StepParams& p, int x, int m, int r, CT (&F)[3]) {
+  F[0] = F[1] = F[2] = (CT)0;
   if (p.hasForce == 1) {
 #pragma unroll
     for (int d = 0; d < L::D; ++d) {
       const int axis = p.forceAxis[d];
-      if (axis >= 0) F[d] = __ldg(p.forceTable[d] + (axis == 0 ? x : (axis == 1 ? m : r)));
+      if (axis >= 0) F[d] = (CT)__ldg(p.forceTable[d] + (axis == 0 ? x : (axis == 1 ? m : r)));
     }
   } else if (p.hasForce == 2) {
     const StoreT* field = static_cast<const StoreT*>(p.force) + ((long long)x * p.plane + (long long)m * p.NR + r);
 #pragma unroll
-    for (int d = 0; d < L::D; ++d) F[d] = (double)field[d * p.fieldStride];
+    for (int d = 0; d < L::D; ++d) F[d] = (CT)field[d * p.fieldStride];
   }
 }
 
 // collision source term S_q (ForcingScheme.h:99-117 Guo, :184-197 ExactDifferenceMethod; None / ShanChen: 0)
-template <class L, int EQ, int SCHEME> struct SourceTerm {
-  double uF = 0.0, guoFactor = 0.0, rho = 0.0;
-  double u[3], F[3];
-  EquilibriumCoefficients<L, EQ> shifted;  // EDM: feq at u + F / rho
-  __device__ __forceinline__ void set(const StepParams& p, double density, double invRho, const double (&velocity)[3], const double (&force)[3]) {
+template <class L, int EQ, int SCHEME, typename CT = double> struct SourceTerm {
+  CT uF = (CT)0, guoFactor = (CT)0, rho = (CT)0;
+  CT u[3], F[3];
+  EquilibriumCoefficients<L, EQ, CT> shifted;  // EDM: feq at u + F / rho
+  __device__ __forceinline__ void set(const StepParams& p, CT density, CT invRho, const CT (&velocity)[3], const CT (&force)[3]) {
     rho = density;
-    guoFactor = p.guoFactor;
+    guoFactor = (CT)p.guoFactor;
 #pragma unroll
     for (int d = 0; d < 3; ++d) { u[d] = velocity[d]; F[d] = force[d]; }
     if (SCHEME == kSchemeGuo) {
@@ -710,8 +711,8 @@ template <class L, int EQ, int SCHEME> struct SourceTerm {
       for (int d = 0; d < L::D; ++d) uF += u[d] * F[d];
     }
     if (SCHEME == kSchemeEDM) {
-      double v[3] = {0.0, 0.0, 0.0};
-      double v2 = 0.0;
+      CT v[3] = {(CT)0, (CT)0, (CT)0};
+      CT v2 = (CT)0;
 #pragma unroll
       for (int d = 0; d < L::D; ++d) {
         v[d] = u[d] + F[d] * invRho;
@@ -721,38 +722,38 @@ template <class L, int EQ, int SCHEME> struct SourceTerm {
     }
   }
   // feq is the equilibrium the scheme is handed: feq_q for BGK, f_q - fNeq_q for ELBM (Collision.h:252)
-  template <int q> __device__ __forceinline__ double value(double feq) const {
+  template <int q> __device__ __forceinline__ CT value(CT feq) const {
     if (SCHEME == kSchemeGuo) {
-      double cF = 0.0, cu = 0.0;
+      CT cF = (CT)0, cu = (CT)0;
 #pragma unroll
       for (int d = 0; d < L::D; ++d) {
         if (L::c(q, d) == 1) { cF += F[d]; cu += u[d]; }
         else if (L::c(q, d) == -1) { cF -= F[d]; cu -= u[d]; }
-        else if (L::c(q, d) != 0) { cF += (double)L::c(q, d) * F[d]; cu += (double)L::c(q, d) * u[d]; }
+        else if (L::c(q, d) != 0) { cF += (CT)L::c(q, d) * F[d]; cu += (CT)L::c(q, d) * u[d]; }
       }
-      return guoFactor * L::w(q) * (cF - uF + L::inv_cs2 * cu * cF);
+      return guoFactor * (CT)L::w(q) * (cF - uF + (CT)L::inv_cs2 * cu * cF);
     }
-    if (SCHEME == kSchemeEDM) return rho * L::w(q) * shifted.template shape<q>() - feq;
-    return 0.0;
+    if (SCHEME == kSchemeEDM) return rho * (CT)L::w(q) * shifted.template shape<q>() - feq;
+    return (CT)0;
   }
 };
 
-// Algorithm::storeFields (Algorithm.h:150-194) and the per-node terms of the scalar analyses (Analysis.h:53-61)
-template <class L, typename StoreT>
-__device__ __forceinline__ void storeNodeFields(const StepParams& p, long long node, double rho, double invRho, const double (&u)[3],
-                                                const double (&F)[3], double& energy, double& speed2) {
+// Algorithm::storeFields (Algorithm.h:150-194) and the per-node terms of the scalar analyses (Analysis.h:53-61; summed in double)
+template <class L, typename StoreT, typename CT>
+__device__ __forceinline__ void storeNodeFields(const StepParams& p, long long node, CT rho, CT invRho, const CT (&u)[3],
+                                                const CT (&F)[3], double& energy, double& speed2) {
   const bool fields = (p.isStored & 1) != 0;
   if (fields) static_cast<StoreT*>(p.density)[node] = (StoreT)rho;
-  const double half = p.hydroShift ? 0.5 * invRho : 0.0;
+  const CT half = p.hydroShift ? (CT)0.5 * invRho : (CT)0;
 #pragma unroll
   for (int d = 0; d < L::D; ++d) {
-    const double v = u[d] + half * F[d];
+    const CT v = u[d] + half * F[d];
     if (fields) {
       static_cast<StoreT*>(p.velocity)[d * p.fieldStride + node] = (StoreT)v;
       static_cast<StoreT*>(p.force)[d * p.fieldStride + node] = (StoreT)F[d];
     }
-    energy += 0.5 * rho * v * v;  // TotalEnergy (Analysis.h:53-61)
-    speed2 += v * v;
+    energy += 0.5 * (double)rho * (double)v * (double)v;  // TotalEnergy (Analysis.h:53-61)
+    speed2 += (double)v * (double)v;
   }
 }
 
@@ -845,8 +846,8 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
       double f[Q];
       pullPopulations<L, StoreT, !logTableInShared(Q)>(p, n, f);
       double u2;
-      moments<L>(f, rho, invRho, u, u2);
-      bodyForce<L, StoreT>(p, x, m, r, F);
+      moments<L, double>(f, rho, invRho, u, u2);
+      bodyForce<L, StoreT, double>(p, x, m, r, F);
       EquilibriumCoefficients<L, EQ> eq;
       eq.set(u, u2);
       // Collision<ELBM>::calculateRelaxationTime (Collision.h:227-241): fNeq, then alpha.  While fNeq is formed the cheap
@@ -959,7 +960,7 @@ __device__ __forceinline__ void entropicStepBody(const StepParams& p) {
         if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
         if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
       });
-      if (p.isStored) storeNodeFields<L, StoreT>(p, node, rho, invRho, u, F, energy, speed2);
+      if (p.isStored) storeNodeFields<L, StoreT, double>(p, node, rho, invRho, u, F, energy, speed2);
     }
     if (p.isStored) reduceBlockObservables(p, x, energy, active ? rho : 0.0, speed2);
   }
@@ -979,22 +980,25 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
     entropicStepBody<L, EQ, SCHEME, StoreT, COLLISION == kELBMForcing>(p);
   } else {
     constexpr int Q = L::Q;
+    // the reference computes in its dataT (Algorithm<T, ...>): FP32 storage means FP32 arithmetic here too, which is what
+    // lets the FP32 kernels reach their (twice as high) HBM roofline instead of the FP64 pipe's; the observables' sums stay double
+    using CT = StoreT;
     const int r = blockIdx.x * kStepBlock + threadIdx.x;
     const int m = blockIdx.y;
     const int x = p.x0 + (int)blockIdx.z * p.planeStep;
     const bool active = r < p.NR;
-    double rho = 0.0, energy = 0.0, speed2 = 0.0;
+    double mass = 0.0, energy = 0.0, speed2 = 0.0;
     if (active) {
       const NodeIndex n = nodeIndex<L>(p, x, m, r);
       StoreT* __restrict__ next = static_cast<StoreT*>(p.next);
-      double f[Q];
-      pullPopulations<L, StoreT>(p, n, f);
-      double invRho, u2, u[3], F[3];
-      moments<L>(f, rho, invRho, u, u2);
-      bodyForce<L, StoreT>(p, x, m, r, F);
-      EquilibriumCoefficients<L, EQ> eq;
+      CT f[Q];
+      pullPopulations<L, StoreT, false, CT>(p, n, f);
+      CT rho, invRho, u2, u[3], F[3];
+      moments<L, CT>(f, rho, invRho, u, u2);
+      bodyForce<L, StoreT, CT>(p, x, m, r, F);
+      EquilibriumCoefficients<L, EQ, CT> eq;
       eq.set(u, u2);
-      SourceTerm<L, EQ, SCHEME> source;
+      SourceTerm<L, EQ, SCHEME, CT> source;
       source.set(p, rho, invRho, u, F);
 
       const long long node = (long long)x * p.plane + (long long)m * p.NR + r;  // field index
@@ -1003,20 +1007,21 @@ fusedStepKernel(const __grid_constant__ StepParams p) {
       StoreT* const remoteHigh = (p.peerHigh && x == p.LX - 1) ? static_cast<StoreT*>(p.peerHigh) + ((long long)m * p.NR + r) : nullptr;
       StoreT* const remoteLow = (p.peerLow && x == 0) ? static_cast<StoreT*>(p.peerLow) + ((long long)(p.LX + 1) * p.plane + (long long)m * p.NR + r) : nullptr;
       // Collision<BGK>::collideAndStream (Collision.h:134-151)
-      const double keep = 1.0 - 2.0 * p.beta;
-      const double relax = 2.0 * p.beta;
+      const CT keep = (CT)(1.0 - 2.0 * p.beta);
+      const CT relax = (CT)(2.0 * p.beta);
       staticFor<0, Q>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
-        const double feq = rho * L::w(q) * eq.template shape<q>();
-        const double value = keep * f[q] + relax * feq + source.template value<q>(feq);
+        const CT feq = rho * (CT)L::w(q) * eq.template shape<q>();
+        const CT value = keep * f[q] + relax * feq + source.template value<q>(feq);
         storePopulation(next + q * p.stride + out, value);
         if (L::cx(q) == 1 && remoteHigh) remoteHigh[q * p.stride] = (StoreT)value;
         if (L::cx(q) == -1 && remoteLow) remoteLow[q * p.stride] = (StoreT)value;
       });
       // BGK's alpha field is the constant 2 (Collision.h:121) and is not stored
-      if (p.isStored) storeNodeFields<L, StoreT>(p, node, rho, invRho, u, F, energy, speed2);
+      mass = (double)rho;
+      if (p.isStored) storeNodeFields<L, StoreT, CT>(p, node, rho, invRho, u, F, energy, speed2);
     }
-    if (p.isStored) reduceBlockObservables(p, x, energy, active ? rho : 0.0, speed2);
+    if (p.isStored) reduceBlockObservables(p, x, energy, mass, speed2);
   }
 }
 

@@ -139,6 +139,7 @@ inline ncclResult_t issue(Comm* c, const Operation& operation) {
 }  // namespace nccl_emu
 
 typedef nccl_emu::Comm* ncclComm_t;
+typedef struct ncclConfig_v21700 { int unused; } ncclConfig_t;   // only named in the optional ncclCommSplit entry (never resolved here)
 
 inline ncclResult_t ncclGetUniqueId(ncclUniqueId* id) {
   static int counter = 0;
