@@ -294,16 +294,20 @@ def fp64_peak():
     return 148 * 64 * 1.965e9, "nominal (64 DFMA / clock / SM x 148 SMs x 1965 MHz)"
 
 
-# FP64 lane-operations per node of the shipped kernels, counted from their SASS (profiles/r02_sass_fp64_counts.md:
-# D* instructions on the node's path; `base` = every node, `solve` = once per node that takes the Newton solve
-# (the hoisted sum), `evaluation` = per evaluation of (F, F')).  The FP64 side of the entropic roofline.
+# FP64-pipe instructions per node of the shipped entropic kernels, counted from their SASS by scripts/fp64_counts.py
+# (profiles/r02_sass_fp64_counts.md): `base` = every node (pull, moments, equilibrium, screens, collide), `solve` = once per node
+# that leaves the shortcut (alphaMax where the solving thread forms it, the hoisted sum of f ln f), `evaluation` = per evaluation
+# of (F, F') of the Newton solve.  The FP64 side of the entropic roofline; one warp instruction = 32 lane operations = 32 nodes.
 FP64_OPS = {
-    # (lattice, collision): (base, solve, evaluation)
+    # workload: (base, solve, evaluation)
+    "d3q27_elbm_512": (780, 270, 309),
+    "d2q9_elbm_shanchen_8192": (211, 136, 123),
+    "d2q9_elbm_edm_8192": (290, 136, 123),
 }
 
 
-def fp64_fraction(lattice, collision, kernel_nodes, kernel_ms, newton) -> dict | None:
-    counts = FP64_OPS.get((lattice, collision))
+def fp64_fraction(workload, kernel_nodes, kernel_ms, newton) -> dict | None:
+    counts = FP64_OPS.get(workload)
     if not counts or not kernel_ms:
         return None
     base, solve, evaluation = counts
@@ -476,7 +480,7 @@ def measure_also(entry, args, rank, world, local_rank, barrier, max_over_ranks, 
         if entropic:
             result.update({"alpha_off_shortcut_fraction_at_end": newton_fraction, "alpha_min": alpha_min, "alpha_max": alpha_max,
                            "newton": newton})
-            fp64 = fp64_fraction(work["lattice"], work["collision"], kernel_nodes, kernel_ms, newton)
+            fp64 = fp64_fraction(name, kernel_nodes, kernel_ms, newton)
             if fp64:
                 result.update(fp64)
     finally:
@@ -764,7 +768,7 @@ def run_ours(args) -> int:
                 "algorithmic_bytes_per_launch": bytes_per_node * kernel_nodes,
                 "roofline_mlups_per_gpu": peak * 1e9 / bytes_per_node / 1e6}
     if entropic_state is not None:
-        fp64 = fp64_fraction(work["lattice"], work["collision"], kernel_nodes, kernel_ms, entropic_state["newton"])
+        fp64 = fp64_fraction(workload_name, kernel_nodes, kernel_ms, entropic_state["newton"])
         if fp64:
             roofline.update(fp64)
 

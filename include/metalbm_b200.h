@@ -274,6 +274,16 @@ int mlbm_observables(mlbm_ctx* ctx, double out[4]);
  * length of the arrays given.  Unlike the reference, the fields are left untouched (its transforms run in place). */
 int mlbm_power_spectra(mlbm_ctx* ctx, double* energy_spectrum, double* forcing_spectrum, int capacity, int* count);
 
+/* Checkpoint of the distribution in the reference's data-set layout: DistributionWriter::writeDistribution
+ * (Writer.h:400-445) writes dimQ data sets "distribution<iQ>", each the padded global box gSD::pLength() of doubles with rank r
+ * at the hyperslab gSD::pOffset(r); DistributionReader::readDistribution (Reader.h:119-157) reads them back.  The container
+ * is a flat file (no HDF5 in this build): a 4096-byte JSON header, then the data sets back to back in that order and layout;
+ * tools/checkpoint_to_hdf5.py turns it into the reference's .h5 and back.  Every rank calls with the SAME path and moves only
+ * its own hyperslab (one contiguous range per data set); a file written on n ranks can be read on m.  FP32 contexts widen /
+ * narrow.  `iteration` is stored in / returned from the header (may be NULL when reading).  Host-side I/O: synchronous. */
+int mlbm_checkpoint_write(mlbm_ctx* ctx, const char* path, unsigned iteration);
+int mlbm_checkpoint_read(mlbm_ctx* ctx, const char* path, unsigned* iteration);
+
 /* What the entropic collision did in the last step, from the alpha field (Algorithm.h:103-106), over all ranks:
  *   out[0] fraction of nodes whose alpha differs from 2, i.e. that left the small-deviation shortcut (Collision.h:357-359)
  *   out[1] smallest alpha, out[2] largest alpha.

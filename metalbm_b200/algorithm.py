@@ -208,6 +208,17 @@ class Algorithm:
         stride, py, pz = self._layout()
         check(self._lib.mlbm_download_distribution(self._ctx, self.distribution.array.ctypes.data, stride, py, pz))
 
+    # -- DistributionWriter / DistributionReader (Writer.h:400-445, Reader.h:119-157) ----------------
+    def write_checkpoint(self, path, iteration: int = 0) -> None:
+        """This rank's hyperslab of the dimQ "distribution<iQ>" data sets (padded global box, doubles) into `path`."""
+        check(self._lib.mlbm_checkpoint_write(self._ctx, os.fsencode(str(path)), int(iteration)))
+
+    def read_checkpoint(self, path) -> int:
+        """The inverse: loads this rank's hyperslab, returns the iteration the file was written at."""
+        iteration = ctypes.c_uint(0)
+        check(self._lib.mlbm_checkpoint_read(self._ctx, os.fsencode(str(path)), ctypes.byref(iteration)))
+        return int(iteration.value)
+
     def init_equilibrium(self) -> None:
         """initDistribution (Initialize.h:106-117) from fieldList.density / velocity, on the device."""
         stride, py, pz = self._layout()

@@ -225,6 +225,8 @@ PROTOTYPES = {
                                           ctypes.POINTER(ctypes.c_int)]),
     "mlbm_alpha_statistics": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double)]),
     "mlbm_download_halo_distribution": (ctypes.c_int, [_P, _P, _SZ]),
+    "mlbm_checkpoint_write": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_uint]),
+    "mlbm_checkpoint_read": (ctypes.c_int, [_P, ctypes.c_char_p, ctypes.POINTER(ctypes.c_uint)]),
     "mlbm_newton_statistics": (ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_ulonglong)]),
     "mlbm_reduce_sum": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_double), ctypes.c_int]),
     "mlbm_selftest_log": (ctypes.c_int, [_P, _P, _SZ]),

@@ -9,7 +9,10 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cerrno>
 #include <cstring>
+#include <fcntl.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -933,6 +936,124 @@ int mlbm_download_halo_distribution(mlbm_ctx* ctx, void* host, size_t capacity) 
       }
     }
   return MLBM_OK;
+}
+
+// ---- checkpoint container ------------------------------------------------------------------------------
+// DistributionWriter::writeDistribution (Writer.h:400-445) / DistributionReader (Reader.h:119-157) move dimQ data sets
+// "distribution<iQ>": each the PADDED GLOBAL box gSD::pLength() of doubles (H5T_NATIVE_DOUBLE), rank r owning the hyperslab at
+// gSD::pOffset(r) of extent lSD::pLength(), filled from / into the local padded array.  HDF5 is not in this image, so the
+// container is a flat file: a 4096-byte text header, then the dimQ data sets back to back in exactly that order and layout
+// (tools/checkpoint_to_hdf5.py wraps them into the reference's .h5 where h5py exists).  x is the slowest index, so a rank's
+// hyperslab of a data set is ONE contiguous range: every rank writes / reads its part with pwrite / pread, any number of
+// ranks at once, and a file written by n ranks restarts on m.
+namespace {
+constexpr size_t kCheckpointHeaderBytes = 4096;
+
+struct CheckpointLayout {
+  long long paddedY, paddedZ, localElements, globalElements;  // per data set
+};
+
+CheckpointLayout checkpointLayout(const mlbm_ctx* ctx) {
+  CheckpointLayout c;
+  const int* L = ctx->config.global_length;
+  const long long ny = ctx->D >= 2 ? L[1] : 1, nz = ctx->D == 3 ? L[2] : 1;
+  c.paddedY = ctx->D == 2 ? 2 * (ny / 2 + 1) : ny;   // lSD::pLength: the last used dimension is padded (Domain.h:53-57)
+  c.paddedZ = ctx->D == 3 ? 2 * (nz / 2 + 1) : nz;
+  c.localElements = (long long)ctx->LX * c.paddedY * c.paddedZ;
+  c.globalElements = c.localElements * ctx->config.nranks;
+  return c;
+}
+}  // namespace
+
+int mlbm_checkpoint_write(mlbm_ctx* ctx, const char* path, unsigned iteration) {
+  if (!ctx || !path) return fail(MLBM_ERR_INVALID, "null argument");
+  const CheckpointLayout c = checkpointLayout(ctx);
+  const size_t es = ctx->elementSize;
+  std::vector<char> local((size_t)c.localElements * ctx->Q * es);
+  if (int status = mlbm_download_distribution(ctx, local.data(), (size_t)c.localElements, (size_t)c.paddedY, (size_t)c.paddedZ)) return status;
+  const int fd = open(path, O_CREAT | O_WRONLY, 0644);
+  if (fd < 0) return fail(MLBM_ERR_INVALID, "cannot open %s for writing: %s", path, strerror(errno));
+  int status = MLBM_OK;
+  if (ctx->config.rank == 0) {
+    char header[kCheckpointHeaderBytes];
+    memset(header, ' ', sizeof(header));
+    const int* L = ctx->config.global_length;
+    const int written = snprintf(header, sizeof(header),
+                                 "{\"format\": \"metalbm_b200 checkpoint 1\", \"datasets\": \"distribution<iQ>, iQ = 0 .. dimQ - 1 (Writer.h:400-445)\", "
+                                 "\"dtype\": \"float64\", \"dimD\": %d, \"dimQ\": %d, \"global_length\": [%d, %d, %d], "
+                                 "\"padded_global_length\": [%d, %lld, %lld], \"header_bytes\": %zu, \"iteration\": %u, \"written_by_ranks\": %d}",
+                                 ctx->D, ctx->Q, L[0], ctx->D >= 2 ? L[1] : 1, ctx->D == 3 ? L[2] : 1, L[0], c.paddedY, c.paddedZ,
+                                 kCheckpointHeaderBytes, iteration, ctx->config.nranks);
+    header[written] = ' ';
+    header[sizeof(header) - 1] = '\n';
+    if (pwrite(fd, header, sizeof(header), 0) != (ssize_t)sizeof(header)) status = fail(MLBM_ERR_INVALID, "short write to %s", path);
+  }
+  std::vector<double> widened;
+  for (int q = 0; q < ctx->Q && status == MLBM_OK; ++q) {
+    const char* source = local.data() + (size_t)q * c.localElements * es;
+    if (es == 4) {   // the data sets are doubles whatever the context stores
+      widened.resize((size_t)c.localElements);
+      for (long long i = 0; i < c.localElements; ++i) widened[(size_t)i] = (double)reinterpret_cast<const float*>(source)[i];
+      source = reinterpret_cast<const char*>(widened.data());
+    }
+    const off_t offset = (off_t)kCheckpointHeaderBytes + (off_t)sizeof(double) * ((off_t)q * c.globalElements + (off_t)ctx->config.rank * c.localElements);
+    const size_t bytes = sizeof(double) * (size_t)c.localElements;
+    size_t done = 0;
+    while (done < bytes) {
+      const ssize_t step = pwrite(fd, source + done, bytes - done, offset + (off_t)done);
+      if (step <= 0) { status = fail(MLBM_ERR_INVALID, "write to %s failed: %s", path, strerror(errno)); break; }
+      done += (size_t)step;
+    }
+  }
+  if (close(fd) != 0 && status == MLBM_OK) status = fail(MLBM_ERR_INVALID, "closing %s: %s", path, strerror(errno));
+  return status;
+}
+
+int mlbm_checkpoint_read(mlbm_ctx* ctx, const char* path, unsigned* iteration) {
+  if (!ctx || !path) return fail(MLBM_ERR_INVALID, "null argument");
+  const CheckpointLayout c = checkpointLayout(ctx);
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) return fail(MLBM_ERR_INVALID, "cannot open %s: %s", path, strerror(errno));
+  char header[kCheckpointHeaderBytes];
+  int status = MLBM_OK;
+  if (pread(fd, header, sizeof(header), 0) != (ssize_t)sizeof(header)) status = fail(MLBM_ERR_INVALID, "%s is not a checkpoint (short header)", path);
+  header[sizeof(header) - 1] = 0;
+  int D = 0, Q = 0, L[3] = {0, 0, 0};
+  unsigned stored = 0;
+  if (status == MLBM_OK) {
+    const char* dims = strstr(header, "\"dimD\": ");
+    const char* lengths = strstr(header, "\"global_length\": [");
+    const char* it = strstr(header, "\"iteration\": ");
+    if (!strstr(header, "metalbm_b200 checkpoint 1") || !dims || !lengths || !it || sscanf(dims, "\"dimD\": %d, \"dimQ\": %d", &D, &Q) != 2 ||
+        sscanf(lengths, "\"global_length\": [%d, %d, %d]", &L[0], &L[1], &L[2]) != 3 || sscanf(it, "\"iteration\": %u", &stored) != 1)
+      status = fail(MLBM_ERR_INVALID, "%s: not a metalbm_b200 checkpoint header", path);
+  }
+  if (status == MLBM_OK) {
+    const int* G = ctx->config.global_length;
+    if (D != ctx->D || Q != ctx->Q || L[0] != G[0] || L[1] != (ctx->D >= 2 ? G[1] : 1) || L[2] != (ctx->D == 3 ? G[2] : 1))
+      status = fail(MLBM_ERR_INVALID, "%s holds D%dQ%d %dx%dx%d, the context is D%dQ%d %dx%dx%d", path, D, Q, L[0], L[1], L[2], ctx->D, ctx->Q, G[0],
+                    ctx->D >= 2 ? G[1] : 1, ctx->D == 3 ? G[2] : 1);
+  }
+  const size_t es = ctx->elementSize;
+  std::vector<double> slab((size_t)c.localElements);
+  std::vector<char> local(status == MLBM_OK ? (size_t)c.localElements * ctx->Q * es : 0);
+  for (int q = 0; q < ctx->Q && status == MLBM_OK; ++q) {
+    const off_t offset = (off_t)kCheckpointHeaderBytes + (off_t)sizeof(double) * ((off_t)q * c.globalElements + (off_t)ctx->config.rank * c.localElements);
+    const size_t bytes = sizeof(double) * (size_t)c.localElements;
+    size_t done = 0;
+    while (done < bytes) {
+      const ssize_t step = pread(fd, reinterpret_cast<char*>(slab.data()) + done, bytes - done, offset + (off_t)done);
+      if (step <= 0) { status = fail(MLBM_ERR_INVALID, "%s: data set distribution%d is truncated", path, q); break; }
+      done += (size_t)step;
+    }
+    char* target = local.data() + (size_t)q * c.localElements * es;
+    if (es == 8) memcpy(target, slab.data(), bytes);
+    else for (long long i = 0; i < c.localElements; ++i) reinterpret_cast<float*>(target)[i] = (float)slab[(size_t)i];
+  }
+  close(fd);
+  if (status != MLBM_OK) return status;
+  if (iteration) *iteration = stored;
+  return mlbm_upload_distribution(ctx, local.data(), (size_t)c.localElements, (size_t)c.paddedY, (size_t)c.paddedZ);
 }
 
 // a field [components][LX][paddedY][paddedZ] on the host <-> dense [components][LX][NM][NR] on the device

@@ -58,6 +58,8 @@ else:  # the asynchronous run loop with a stored step at the end
     algorithm.isStored = True
     algorithm.iterate(steps)
 observables = algorithm.observables()
+if case.get("checkpoint"):
+    algorithm.write_checkpoint(out + "/checkpoint.mlbm", steps)   # every rank its hyperslab of the same file
 algorithm.pack()
 fields = algorithm.fieldList
 np.savez(out + f"/rank{rank}.npz", f=algorithm.distribution.get_interior(), density=domain.interior(fields.density)[0],
@@ -77,9 +79,9 @@ def _device_count():
         return 0
 
 
-def _run_ranks(tmp_path, world, config, f0, steps, mode, peer=False):
+def _run_ranks(tmp_path, world, config, f0, steps, mode, peer=False, checkpoint=False):
     import json
-    (tmp_path / "case.json").write_text(json.dumps({"config": config, "steps": steps, "mode": mode, "peer": peer}))
+    (tmp_path / "case.json").write_text(json.dumps({"config": config, "steps": steps, "mode": mode, "peer": peer, "checkpoint": checkpoint}))
     np.save(tmp_path / "f0.npy", f0)
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
@@ -156,3 +158,21 @@ def test_slabs_reproduce_the_single_rank_result(tmp_path, world, case):
         assert abs(rank_observables[3] - obs[3]) <= 1e-12 * abs(obs[3])
         assert abs(rank_observables[2] - obs[2]) <= 1e-12 * abs(obs[2])
         assert np.array_equal(rank_observables, got["observables"][0])
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_checkpoint_written_on_slabs_restarts_on_one_rank(tmp_path, world):
+    """DistributionWriter / DistributionReader (Writer.h:400-445, Reader.h:119-157): `world` ranks write their hyperslabs of the
+    dimQ padded-global-box data sets into ONE file; a single-rank context reads the whole box back, bit for bit."""
+    if _device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    from metalbm_b200.algorithm import Algorithm
+    config = dict(lattice="D3Q19", shape=[16, 6, 10], collision="BGK", forcing_scheme="Guo", force="Kolmogorov", tau=0.55,
+                  amplitude=[1e-4, 2e-4, 3e-4], wavelength=[8.0, 4.0, 16.0], overlap="On")
+    single = make_config(**config)
+    f0 = O.synthetic_populations(single, eps=1e-2)
+    got = _run_ranks(tmp_path, world, config, f0, 3, "sync", peer=True, checkpoint=True)
+    with Algorithm(single) as algorithm:
+        assert algorithm.read_checkpoint(tmp_path / "checkpoint.mlbm") == 3
+        algorithm.pack()
+        assert np.array_equal(algorithm.distribution.get_interior(), got["f"])
