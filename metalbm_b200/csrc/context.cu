@@ -594,6 +594,20 @@ static int enqueueStep(mlbm_ctx* ctx, int isStored, bool timed, bool profile) {
   return MLBM_OK;
 }
 
+// A synchronisation that failed: say so, and say WHY when the direct peer halos are in use and the handshake kernel gave up
+// (waitPeerFlagsKernel traps after ~20 s without the neighbour's flag; it raises *peerTimedOut first).  The context is
+// unusable afterwards (sticky CUDA error); mlbm_destroy then skips its shutdown barrier, which the lost neighbour would hang.
+static int synchronizeOrDiagnose(mlbm_ctx* ctx, cudaStream_t stream) {
+  const cudaError_t error = cudaStreamSynchronize(stream);
+  if (error == cudaSuccess) return MLBM_OK;
+  ctx->poisoned = true;
+  if (ctx->peerTimedOut && *ctx->peerTimedOut)
+    return fail(MLBM_ERR_COMM, "peer halo handshake timed out on rank %d: a neighbour (rank %d or %d) never delivered its halo planes (%s)",
+                ctx->config.rank, (ctx->config.rank + ctx->config.nranks - 1) % ctx->config.nranks, (ctx->config.rank + 1) % ctx->config.nranks,
+                cudaGetErrorString(error));
+  return fail(MLBM_ERR_CUDA, "CUDA failed with %s", cudaGetErrorString(error));
+}
+
 // ------------------------------------------------------------------------------------------------
 // C entry points
 // ------------------------------------------------------------------------------------------------
@@ -608,7 +622,7 @@ int mlbm_destroy(mlbm_ctx* ctx) {
   if (ctx->computeStream) cudaStreamSynchronize(ctx->computeStream);
   if (ctx->commStream) cudaStreamSynchronize(ctx->commStream);
   if (ctx->analysisStream) cudaStreamSynchronize(ctx->analysisStream);
-  if (ctx->peerAttached && ctx->comm && ctx->nccl && ctx->deviceObservables) {
+  if (ctx->peerAttached && ctx->comm && ctx->nccl && ctx->deviceObservables && !ctx->poisoned) {
     // the neighbours store into this rank's halo planes and flags: nobody frees before everybody has drained its streams
     if (ctx->nccl->AllReduce(ctx->deviceObservables, ctx->deviceObservables, 1, ncclDouble, ncclSum, ctx->comm, ctx->computeStream) == ncclSuccess)
       cudaStreamSynchronize(ctx->computeStream);
@@ -672,7 +686,13 @@ int mlbm_create(const mlbm_config* config, mlbm_ctx** out) {
   }
   if (config->equilibrium != MLBM_TRUNCATION_MA3 && config->equilibrium != MLBM_EXACT) return fail(MLBM_ERR_INVALID, "unknown equilibrium %d", config->equilibrium);
   StepKernel kernel = lookupStepKernel(config->lattice, collision, config->equilibrium, scheme, config->dtype);
-  if (!kernel) return fail(MLBM_ERR_INVALID, "no kernel for this lattice/equilibrium combination (the exact equilibrium exists for D2Q9 and D3Q27 only, Equilibrium.h:36-126)");
+  if (!kernel) return fail(MLBM_ERR_INVALID, "no kernel for this lattice/equilibrium combination (the exact equilibrium is built for D2Q9 and D3Q27, Equilibrium.h:60-81, 106-126; the reference also defines it for D1Q3 and D2Q13, :36-58, 83-103, which this library does not cover)");
+  // the launch grid is (ceil(NR / 128), NM, x planes [/ planes per block]): CUDA caps grid.y and grid.z at 65535
+  {
+    SlabGeometry check;
+    if (slabGeometry(config, &check) && (check.NM > 65535 || (collision == kBGK && check.LX > 65535) || check.LX > 65535 * 16))
+      return fail(MLBM_ERR_INVALID, "local extents %d x %d planes exceed the launch grid (65535 rows; 65535 x planes per rank for BGK, 16 times that for the entropic collisions): use more ranks or the transposed orientation", check.LX, check.NM);
+  }
 
   int deviceCount = 0;
   cudaError_t error = cudaGetDeviceCount(&deviceCount);
@@ -1166,7 +1186,7 @@ int mlbm_step(mlbm_ctx* ctx, unsigned iteration, int isStored) {
   MLBM_CUDA(cudaSetDevice(ctx->device));
   if (int status = enqueueStep(ctx, isStored ? (isStored & 3 ? isStored & 3 : 1) : 0, true, ctx->profiling)) return status;
   // the reference's iterate returns after cudaDeviceSynchronize (Algorithm.h:355)
-  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
+  if (int status = synchronizeOrDiagnose(ctx, ctx->computeStream)) return status;
   float communication = 0.f, computation = 0.f;
   MLBM_CUDA(cudaEventElapsedTime(&communication, ctx->timeStart, ctx->timeMid));
   MLBM_CUDA(cudaEventElapsedTime(&computation, ctx->timeMid, ctx->timeStop));
@@ -1195,9 +1215,9 @@ int mlbm_run_async(mlbm_ctx* ctx, unsigned firstIteration, unsigned count, unsig
 int mlbm_sync(mlbm_ctx* ctx) {
   if (!ctx) return fail(MLBM_ERR_INVALID, "null argument");
   MLBM_CUDA(cudaSetDevice(ctx->device));
-  MLBM_CUDA(cudaStreamSynchronize(ctx->computeStream));
-  MLBM_CUDA(cudaStreamSynchronize(ctx->commStream));
-  MLBM_CUDA(cudaStreamSynchronize(ctx->analysisStream));
+  if (int status = synchronizeOrDiagnose(ctx, ctx->computeStream)) return status;
+  if (int status = synchronizeOrDiagnose(ctx, ctx->commStream)) return status;
+  if (int status = synchronizeOrDiagnose(ctx, ctx->analysisStream)) return status;
   return MLBM_OK;
 }
 

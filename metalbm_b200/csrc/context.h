@@ -99,6 +99,7 @@ struct mlbm_ctx {
   cudaStream_t commStream = nullptr;
   cudaStream_t analysisStream = nullptr;   // spectral enstrophy of a stored step, next to the steps that follow it
   cudaEvent_t fieldsReady = nullptr, analysisDone = nullptr;
+  bool poisoned = false;                   // a synchronisation failed (sticky CUDA error): no collectives at shutdown
   bool analysisPending = false;            // analysisDone was recorded and nobody has waited for it on the compute stream yet
   ncclComm_t analysisComm = nullptr;       // == comm where ncclCommSplit is unavailable
   cudaEvent_t boundaryDone = nullptr, exchangeDone = nullptr, bulkDone = nullptr;

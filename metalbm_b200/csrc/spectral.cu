@@ -160,28 +160,48 @@ __global__ void finishKernel(const double* __restrict__ blockSums, long long cou
 }
 
 // PowerSpectra::operator() (Analysis.h:148-168) over this rank's part of the half spectrum: sum_d |a^_d|^2, halved where the
-// wave number of the last (halved) dimension is 0, into bin floor(|k|) when that is below `bins`.  Shared-memory bins per
-// block, then one partial row per block (summed in block order by binSumKernel).
+// wave number of the last (halved) dimension is 0, into bin floor(|k|) when that is below `bins`.  Bit-reproducible: a block
+// is ONE warp with private bins in shared memory; per round the 32 lanes publish (bin, value) and lane l adds, in lane order,
+// the values of the bins it owns (bin % 32 == l) -- no atomics, a fixed summation order; then one partial row per block
+// (summed in block order by binSumKernel).
+constexpr int kBinBlock = 32;
 template <int D>
-__global__ void powerBinKernel(const double2* __restrict__ ax, const double2* __restrict__ ay, const double2* __restrict__ az, int NX, int NM,
+__global__ void __launch_bounds__(kBinBlock) powerBinKernel(const double2* __restrict__ ax, const double2* __restrict__ ay, const double2* __restrict__ az, int NX, int NM,
                                int NR, long long myColumns, long long firstColumn, int bins, double* __restrict__ blockBins) {
   extern __shared__ double shared[];
+  __shared__ int keys[kBinBlock];
+  __shared__ double values[kBinBlock];
   for (int b = threadIdx.x; b < bins; b += blockDim.x) shared[b] = 0.0;
   __syncthreads();
   const int NRc = NR / 2 + 1;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (long long)NX * myColumns; i += (long long)gridDim.x * blockDim.x) {
-    const int ix = (int)(i / myColumns);
-    const long long column = firstColumn + i % myColumns;
-    const int im = (int)(column / NRc), ir = (int)(column % NRc);
-    const long long kx = ix <= NX / 2 ? ix : ix - NX, ky = D == 3 ? (im <= NM / 2 ? im : im - NM) : 0, kr = ir;  // AnalysisList.h:141-149
-    const unsigned kNorm = (unsigned)sqrt((double)(kx * kx + ky * ky + kr * kr));
-    if (kNorm >= (unsigned)bins) continue;
-    const double2 a = ax[i], b = ay[i];
-    double energy = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
-    if (D == 3) { const double2 c = az[i]; energy += c.x * c.x + c.y * c.y; }
-    atomicAdd(shared + kNorm, (ir == 0 ? 0.5 : 1.0) * energy);
+  const long long total = (long long)NX * myColumns, stride = (long long)gridDim.x * blockDim.x;
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < total; base += stride) {   // block-uniform trip count
+    const long long i = base + threadIdx.x;
+    int key = -1;
+    double value = 0.0;
+    if (i < total) {
+      const int ix = (int)(i / myColumns);
+      const long long column = firstColumn + i % myColumns;
+      const int im = (int)(column / NRc), ir = (int)(column % NRc);
+      const long long kx = ix <= NX / 2 ? ix : ix - NX, ky = D == 3 ? (im <= NM / 2 ? im : im - NM) : 0, kr = ir;  // AnalysisList.h:141-149
+      const unsigned kNorm = (unsigned)sqrt((double)(kx * kx + ky * ky + kr * kr));
+      if (kNorm < (unsigned)bins) {
+        const double2 a = ax[i], b = ay[i];
+        double energy = a.x * a.x + a.y * a.y + b.x * b.x + b.y * b.y;
+        if (D == 3) { const double2 c = az[i]; energy += c.x * c.x + c.y * c.y; }
+        key = (int)kNorm;
+        value = (ir == 0 ? 0.5 : 1.0) * energy;
+      }
+    }
+    keys[threadIdx.x] = key;
+    values[threadIdx.x] = value;
+    __syncthreads();
+    for (int source = 0; source < kBinBlock; ++source) {
+      const int k = keys[source];
+      if (k >= 0 && (k % kBinBlock) == (int)threadIdx.x) shared[k] += values[source];
+    }
+    __syncthreads();
   }
-  __syncthreads();
   for (int b = threadIdx.x; b < bins; b += blockDim.x) blockBins[(long long)blockIdx.x * bins + b] = shared[b];
 }
 
@@ -388,10 +408,10 @@ int spectralPowerSpectrum(SpectralEnstrophy* s, const void* field, long long fie
   if (transformComponents(s, field, fieldStride, stream, count, error)) return -1;
   if (s->myColumns > 0) {
     if (g.D == 3)
-      powerBinKernel<3><<<(unsigned)blocks, kBlock, bins * sizeof(double), stream>>>(s->spectrum[0], s->spectrum[1], s->spectrum[2], s->NX, g.NM, g.NR,
+      powerBinKernel<3><<<(unsigned)blocks, kBinBlock, bins * sizeof(double), stream>>>(s->spectrum[0], s->spectrum[1], s->spectrum[2], s->NX, g.NM, g.NR,
                                                                                     s->myColumns, s->firstColumn, bins, s->blockBins);
     else
-      powerBinKernel<2><<<(unsigned)blocks, kBlock, bins * sizeof(double), stream>>>(s->spectrum[0], s->spectrum[1], nullptr, s->NX, g.NM, g.NR,
+      powerBinKernel<2><<<(unsigned)blocks, kBinBlock, bins * sizeof(double), stream>>>(s->spectrum[0], s->spectrum[1], nullptr, s->NX, g.NM, g.NR,
                                                                                     s->myColumns, s->firstColumn, bins, s->blockBins);
     binSumKernel<<<(unsigned)((bins + 127) / 128), 128, 0, stream>>>(s->blockBins, blocks, bins, out);
     count += 2;
