@@ -192,23 +192,32 @@ def _host_cores() -> int:
 
 def _reference_sample_text(refbuild, cfg, full: bool) -> str:
     planes = cfg.nx // cfg.nprocs
-    what = ("the WHOLE 256^3 cube of BASELINE configs[1]" if full else
-            f"bounded x-slab sample {cfg.nx}x256x256 of the 256^3 cube")
+    edge = cfg.ny
+    what = (f"the WHOLE {edge}^3 cube of BASELINE configs[1]" if full else
+            f"bounded x-slab sample {cfg.nx}x{edge}x{edge} of the {edge}^3 cube")
     return (f"{what}: reference CPU build ({refbuild.TIMING_FLAGS}), {cfg.nprocs} forked MPI-shim ranks x {planes} x-planes of "
-            f"256x256 D3Q19 BGK FP64 nodes, timers of Algorithm::iterate (computation + communication)")
+            f"{edge}x{edge} D3Q19 BGK FP64 nodes, timers of Algorithm::iterate (computation + communication)")
 
 
 def run_reference(args) -> int:
-    """The reference's own CPU implementation on the host cores.  Preferred sample: the whole 256^3 cube (the GPU arm's
-    configuration, one x-slab per core); if K + W steps of it would not end within a few minutes on this host, the
-    thin-slab sample (2 x-planes per rank) instead."""
+    """The reference's own CPU implementation on the host cores, on this repository's arm's configuration.
+    N = 1 (D3Q19 256^3): the whole cube, one x-slab per core; if K + W steps of it would not end within a few minutes on this
+    host, the thin-slab sample (2 x-planes per rank).  N > 1 (D3Q19 1024^3 strong-scaled; 490 GB on a CPU): a bounded x-slab
+    sample of the 1024 x 1024 cross-section, 2 planes per rank on at most 32 ranks."""
     rank, world, _ = distributed_setup(args.gpus)
     if rank != 0:
         return 0
     from oracle import refbuild
     cores = _host_cores()
-    full_cfg = refbuild.best_timing_config(cores)
-    thin_cfg = refbuild.best_timing_config(cores, refbuild.TIMING_PLANES_PER_RANK)
+    large = args.gpus > 1
+    if large:
+        full_cfg = None
+        thin_cfg = refbuild.best_timing_config(min(cores, refbuild.LARGE_MAX_RANKS), refbuild.TIMING_PLANES_PER_RANK, refbuild.LARGE_EDGE)
+        if thin_cfg is None:   # binaries of the large cross-section missing: the 256^2 sample rather than nothing
+            large = False
+    if not large:
+        full_cfg = refbuild.best_timing_config(cores)
+        thin_cfg = refbuild.best_timing_config(cores, refbuild.TIMING_PLANES_PER_RANK)
     if full_cfg is None and thin_cfg is None:
         print(json.dumps({"impl": "reference", "unavailable": "no prebuilt reference binary in oracle/_ref"}))
         return 0
@@ -219,13 +228,15 @@ def run_reference(args) -> int:
             cfg, full = full_cfg, True
     result = refbuild.time_reference(cfg, args.steps, args.warmup)
     sample = _reference_sample_text(refbuild, cfg, full)
+    workload = ("D3Q19 SRT-BGK 1024^3 strong-scaled (BASELINE configs[4])" if large else
+                "D3Q19 SRT-BGK periodic 256^3 FP64 per GPU (BASELINE configs[1])")
     line = {
         "impl": "reference", "metric": METRIC, "value": result["mlups"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": result["seconds"] / args.steps * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"D3Q19 SRT-BGK periodic 256^3 FP64 per GPU (BASELINE configs[1]); {sample}",
+        "higher_is_better": True, "scaling": "strong" if large else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{workload}; {sample}",
                    "lattice": LATTICE, "collision": "BGK", "host_cores": cores, "ranks": cfg.nprocs,
-                   "global_length": [cfg.nx, cfg.ny, cfg.nz], "same_config_as_gpu_arm_at_n1": full},
+                   "global_length": [cfg.nx, cfg.ny, cfg.nz], "same_config_as_gpu_arm": full},
         "cpu_baseline": {"value": result["mlups"], "unit": UNIT, "cores": cfg.nprocs, "kind": "reference",
                          "sample": sample, "communication_share": result["communication_share"]},
         "e2e": {"value": result["mlups"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -974,7 +974,10 @@ template <class L, int COLLISION, int EQ, int SCHEME, typename StoreT>
 #ifndef MLBM_BGK_BLOCKS
 #define MLBM_BGK_BLOCKS 4
 #endif
-__global__ void __launch_bounds__(kStepBlock, COLLISION != kBGK ? entropicBlocksPerSM(L::Q) : MLBM_BGK_BLOCKS)
+#ifndef MLBM_BGK_BLOCKS_F32
+#define MLBM_BGK_BLOCKS_F32 4
+#endif
+__global__ void __launch_bounds__(kStepBlock, COLLISION != kBGK ? entropicBlocksPerSM(L::Q) : (sizeof(StoreT) == 4 ? MLBM_BGK_BLOCKS_F32 : MLBM_BGK_BLOCKS))
 fusedStepKernel(const __grid_constant__ StepParams p) {
   if constexpr (COLLISION != kBGK) {
     entropicStepBody<L, EQ, SCHEME, StoreT, COLLISION == kELBMForcing>(p);
