@@ -188,6 +188,84 @@ def test_secondary_workloads_of_the_bench_on_several_ranks(tmp_path, world):
         assert r["value"] > 0 and r["halo"] == "peer" and abs(r["mass_per_node"] - 1.0) < 1e-3 and r["energy"] > 0, r
 
 
+_HEADLINE_WORKER = r'''
+import json, os, sys, types
+root, rank, world, port = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+sys.path.insert(0, root)
+os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=port)
+import torch
+import torch.distributed as dist
+from metalbm_b200 import capi
+if os.environ.get("MLBM_EMULATED") == "1":   # tests/conftest.py: the library compiled for the host; no CUDA in this process
+    capi._library = capi.load_library(os.environ["MLBM_EMULATED_LIBRARY"])
+    torch.cuda.mem_get_info = lambda *a: (10 ** 11, 10 ** 11)
+    torch.cuda.set_device = lambda *a: None
+    torch.cuda.synchronize = lambda *a: None
+    real_init, real_tensor, real_empty = dist.init_process_group, torch.tensor, torch.empty
+    dist.init_process_group = lambda backend=None, device_id=None, **k: real_init("gloo", **k)
+    torch.tensor = lambda *a, **k: real_tensor(*a, **{key: v for key, v in k.items() if key != "device"})
+    torch.empty = lambda *a, **k: real_empty(*a, **{key: v for key, v in k.items() if key not in ("pin_memory", "device")})
+import bench
+for name, work in bench.WORKLOADS.items():
+    work["shape"] = (8, 6, 5) if work["shape"][2] > 1 else (16, 10, 1)
+    if work["store_every"]:
+        work["store_every"] = 2
+bench.ALSO_MULTI = [(n, d, e, m, 3) for n, d, e, m, _ in bench.ALSO_MULTI[:2]]
+bench.ClockSampler.start = lambda self: None
+args = types.SimpleNamespace(gpus=world, steps=4, warmup=3, impl="ours", edge=bench.EDGE, variant=0, workload=None, dtype="f64",
+                             overlap="On", halo="peer", eps=None, store_every=None, no_e2e=False, no_cpu_baseline=True,
+                             also="auto", also_timeout=600, shape=None, stored_mode=0)
+assert bench.run_ours(args) == 0
+print("ok", rank)
+'''
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_the_multi_gpu_headline_of_the_bench_on_several_ranks(tmp_path, world):
+    """bench.run_ours as the driver launches it on N > 1 GPUs, on a toy box: the headline is BASELINE configs[4] strong-scaled
+    (stored steps with whole fields + the spectral enstrophy on the analysis stream), the end-to-end leg reads the all-reduced
+    observables back every step, the secondary workloads follow; ONE line from rank 0."""
+    import json
+    import os
+    import socket
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    root = Path(__file__).resolve().parent.parent
+    script = tmp_path / "worker.py"
+    script.write_text(_HEADLINE_WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, str(script), str(root), str(r), str(world), str(port)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True, env=dict(os.environ, OMP_NUM_THREADS="1")) for r in range(world)]
+    outputs = []
+    for r, p in enumerate(procs):
+        try:
+            out, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            out, _ = p.communicate()
+        assert p.returncode == 0 and f"ok {r}" in out, out[-3000:]
+        outputs.append(out)
+    lines = [l for l in outputs[0].splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and not any(l.startswith("{") for out in outputs[1:] for l in out.splitlines())
+    line = json.loads(lines[0])
+    assert line["metric"] == "MLUPS (D3Q19, FP64)" and line["scaling"] == "strong" and line["n_gpus"] == world and line["value"] > 0
+    assert line["config"]["name"] == "d3q19_bgk_1024" and line["config"]["store_every"] == 2
+    assert line["config"]["stored_mode"].startswith("whole fields") and line["config"]["stored_steps_in_timed_region"] == 2
+    assert line["config"]["stored_step_ms"] >= 0 and line["config"]["stored_step_with_analysis_ms"] >= 0
+    assert line["config"]["halo"].startswith("direct peer stores") and line["roofline"]["traffic"] is None
+    assert line["e2e"]["value"] > 0 and "error" not in line["e2e"] and line["e2e"]["last_energy"] > 0
+    assert [e["name"] for e in line["also"]] == ["d3q19_bgk_256", "d3q19_bgk_512"] and len(line["also_summary"]) == 2
+    assert all(e.get("value", 0) > 0 for e in line["also"]), line["also"]
+
+
 _STAGED_WORKER = r'''
 import os, sys
 root, out = sys.argv[1], sys.argv[2]

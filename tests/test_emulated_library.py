@@ -50,6 +50,9 @@ MULTI_RANK_SAMPLE = [
     "tests/test_multi_gpu.py::test_slabs_reproduce_the_single_rank_result[D3Q27-ELBM-Guo-On-sync-peer-4]",
     "tests/test_multi_gpu.py::test_slabs_reproduce_the_single_rank_result[D2Q9-ELBM-ExactDifferenceMethod-Off-async-2]",
     "tests/test_spectral_forces_gpu.py::test_spectral_forces_on_slabs[Turbulent2D-4-nccl]",
+    # bench.run_ours as the driver launches it on N > 1 GPUs (1024^3 strong-scaled headline on a toy box, e2e leg, secondary rows)
+    "tests/test_bench_support_gpu.py::test_the_multi_gpu_headline_of_the_bench_on_several_ranks[2]",
+    "tests/test_multi_gpu.py::test_checkpoint_written_on_slabs_restarts_on_one_rank[2]",
 ]
 
 
