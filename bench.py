@@ -7,16 +7,19 @@
 N = 1 workload: BASELINE.json configs[1], D3Q19 SRT-BGK periodic 256^3 FP64 (one step = one pass of the
 fused kernel over all 256^3 nodes; the two 2.6 GB population buffers are far larger than the 126 MB L2,
 so every timed step streams from HBM -- no L2 flush needed).  N > 1 (launched with torchrun, one rank per
-GPU): weak scaling, the same 256^3 slab per GPU, global (256 N) x 256 x 256, x-slab halo exchange
-overlapped with the bulk kernel.
+GPU): BASELINE.json configs[4], D3Q19 SRT-BGK 1024^3 STRONG-scaled over the N GPUs (x-slabs of 1024 / N planes),
+halo exchange by direct peer stores overlapped with the bulk kernel, energy / enstrophy / Mach reductions every 50 steps
+(the reductions alone where the field arrays do not fit next to the slab: 2 GPUs).  The driver's efficiency
+v_N / (N v_1) is then the parallel efficiency the north star quotes its 85 % target on.
 
 With the default headline workload the same line also carries the other BASELINE configs at this GPU count under "also"
-(device-resident throughput, kernel time, roofline fraction; N > 1: D3Q19 1024^3 strong-scaled, the entropic configs
-strong-scaled), measured after the headline is final and under a watchdog (`run_secondary`); `--also off` skips them.
+(device-resident throughput, kernel time, both roofline fractions; N > 1: the weak-scaled 256^3-per-GPU cube, 512^3 and the
+entropic configs strong-scaled, 1024^3 with whole fields), measured after the headline is final and under a watchdog
+(`run_secondary`), and a one-string-per-row "also_summary" as the line's LAST key; `--also off` skips them.
 
 One JSON line on stdout from rank 0 (see the keys at the bottom).  `value` is device-timed with inputs
 resident in HBM; `e2e` is the same metric through the public C-ABI with HOST buffers: the timed region
-uploads the populations from pinned host memory (Algorithm::unpack), runs the K steps reading the scalar
+uploads the populations from pinned host memory (Algorithm::unpack), runs the K steps reading the all-reduced scalar
 observables back to the host after every step, and downloads the populations (Algorithm::pack).
 """
 from __future__ import annotations

@@ -27,7 +27,7 @@ def pytest_configure(config):
                 except OSError:
                     pass
         from metalbm_b200 import capi
-        library = build_context.build(tuple(os.environ.get("MLBM_EMULATED_FLAGS", "").split()))   # e.g. -DMLBM_ELBM_FASTPATH
+        library = build_context.build(tuple(os.environ.get("MLBM_EMULATED_FLAGS", "").split()))   # e.g. -DMLBM_COLUMN_REGISTERS_Q27=1
         capi._library = capi.load_library(library)
         shim_dir = library.parent / "shim_lib"
         shim_dir.mkdir(exist_ok=True)

@@ -16,7 +16,7 @@ The sources are taken from ``metalbm_b200/csrc`` at build time.  Edits, all mech
 memory (poisoned at allocation), streams run immediately, there is one device and one rank.  Nothing under
 ``metalbm_b200/`` can reach this library; it says nothing about hardware behaviour or speed.
 
-Variants: ``MLBM_EMULATED_FLAGS="-DMLBM_ELBM_FASTPATH -DMLBM_PREFETCH_NEXT_PLANE"`` builds the experimental kernels;
+Variants: ``MLBM_EMULATED_FLAGS="-DMLBM_COLUMN_REGISTERS_Q27=1 -DMLBM_LOG_TABLE_SPLIT_Q9=1"`` builds the kernel variants of step_kernel.cuh;
 ``MLBM_EMULATED_FLAGS="-fsanitize=address -DMLBM_EMU_ASAN" LD_PRELOAD=$(gcc -print-file-name=libasan.so)
 ASAN_OPTIONS=detect_leaks=0 MLBM_EMULATED=1 MLBM_EMULATED_RANKS=1 pytest tests -m gpu`` runs the single-rank suites with
 "device" allocations on the sanitised heap, so that an index error of a kernel or of the host code lands in a red zone.
