@@ -727,66 +727,6 @@ def run_ours(args) -> int:
             algorithm.synchronize()
             stored_with_analysis_ms = max_over_ranks(algorithm.elapsed_ms(2, 4))
 
-    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        affinity = None
-        try:
-            # the host side of Distribution<T, GPU> (Distribution.h:15-43): the local padded SoA array, in pinned memory
-            # next to this GPU's PCIe root
-            host_bytes = q_count * domain.number_elements * element
-            available = host_memory_available()
-            # pinned where the ranks' buffers take less than 45 % of the host's free memory, pageable up to 80 % (1024^3 on 2
-            # GPUs: 2 x 82 GB), else no end-to-end leg
-            pin = min_over_ranks(1.0 if (available == 0 or host_bytes * world < 0.45 * available) else 0.0) > 0
-            fits = min_over_ranks(1.0 if (available == 0 or host_bytes * world < 0.80 * available) else 0.0) > 0
-            if not fits:
-                raise RuntimeError(f"host staging buffers of {host_bytes * world / 1e9:.0f} GB do not fit {available / 1e9:.0f} GB of host memory")
-            affinity = bind_near_gpu(local_rank)
-            if pin:
-                pinned = torch.empty((q_count,) + domain.padded_length, dtype=torch.float64 if element == 8 else torch.float32,
-                                     pin_memory=True)
-                algorithm.distribution.array = pinned.numpy()
-            else:
-                algorithm.distribution.array = np.empty((q_count,) + domain.padded_length, dtype=domain.dtype)
-            algorithm.pack()                         # current state -> host array (first-touches the pages)
-            # warm-up of everything the timed region uses for the first time: the observables' partial sums and their
-            # all-reduce (NCCL sets its channels up on the first collective of a communicator), the SM clocks
-            for iteration in range(1, 1 + max(args.warmup, 20)):
-                algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)
-                algorithm.observables()
-            barrier()
-            t0 = time.perf_counter()
-            algorithm.unpack()                       # H2D of the whole SoA distribution from pinned host memory
-            t1 = time.perf_counter()
-            energy = 0.0
-            for iteration in range(1, args.steps + 1):
-                algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
-                energy = algorithm.observables()[0]  # D2H read of the step's scalar results
-            t2 = time.perf_counter()
-            algorithm.pack()                         # D2H of the whole distribution
-            t3 = time.perf_counter()
-            barrier()
-            e2e_seconds = max_over_ranks(time.perf_counter() - t0)
-            e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
-            distribution_bytes = q_count * nodes_local * element
-            e2e = {"value": e2e_value, "unit": UNIT,
-                   "h2d_bytes_per_step": distribution_bytes / args.steps,
-                   "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
-                   "note": "per rank; timed region: unpack (H2D of all populations from pinned host memory) + K synchronous "
-                           "mlbm_step calls each followed by a D2H read of the all-reduced observables + pack (D2H of all "
-                           "populations); population bytes amortised over K; max over ranks", "last_energy": energy,
-                   "unpack_ms": max_over_ranks((t1 - t0) * 1e3), "steps_ms": max_over_ranks((t2 - t1) * 1e3),
-                   "pack_ms": max_over_ranks((t3 - t2) * 1e3),
-                   "h2d_GBps": distribution_bytes / (t1 - t0) / 1e9, "d2h_GBps": distribution_bytes / (t3 - t2) / 1e9,
-                   "host_buffer": "pinned" if pin else "pageable (pinning it would take more than 45 % of the host's free memory)",
-                   "host_buffer_numa_bound": affinity is not None}
-        except Exception as error:  # noqa: BLE001 -- the device-resident headline above stands; the line says what happened
-            e2e = {"value": None, "unit": UNIT, "error": str(error)[:300]}
-        finally:
-            if affinity is not None:
-                os.sched_setaffinity(0, affinity)
-
     peak, peak_source = measured_peak()
     # the dominant kernel is the bulk launch of the fused step: all local planes at N = 1, all but the two boundary
     # planes when the halo exchange is overlapped
@@ -811,10 +751,7 @@ def run_ours(args) -> int:
         if fp64:
             roofline.update(fp64)
 
-    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline
-                                 and workload_name == "d3q19_bgk_256") else None
     algorithm_peer = algorithm.peer_halos
-    algorithm.close()
 
     line = None
     if rank == 0:
@@ -838,17 +775,110 @@ def run_ours(args) -> int:
                                 "NCCL send/recv") if world > 1 else "none (single rank: periodic wrap in the kernel)",
                        "l2": f"inputs (2 x {buffer_gb:.2f} GB population buffers per GPU) larger than the 126 MB L2; "
                              "no flush between steps"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline,
+            "clocks": clocks, "e2e": None, "gpu_launches": launches, "roofline": roofline,
         }
         if store_every and stored_ms is not None:
             # the configuration's cadence spelled out: K plain steps were timed; one step in store_every is a stored one
             plain = device_ms / args.steps if not stored_in_region else None
             if plain is not None:
                 line["config"]["mlups_at_cadence"] = nodes_global * store_every / ((plain * (store_every - 1) + stored_ms) * 1e-3) / 1e6
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
         if entropic_state is not None:
             line["entropic"] = entropic_state
+
+    # ---- end to end through the C-ABI with host buffers ---------------------------------------------------
+    # After the headline is final and under a watchdog: should the leg stop answering (a rank lost inside a collective, a host
+    # allocation that never returns) the line is printed without it, by every rank's timer, instead of never.
+    def end_to_end() -> dict:
+        def agree(ok: bool, what: str) -> None:
+            """every rank learns whether ALL ranks got through a step that can fail on one of them alone"""
+            if min_over_ranks(1.0 if ok else 0.0) <= 0:
+                raise RuntimeError(what)
+
+        affinity = None
+        try:
+            # the host side of Distribution<T, GPU> (Distribution.h:15-43): the local padded SoA array, in pinned memory
+            # next to this GPU's PCIe root
+            host_bytes = q_count * domain.number_elements * element
+            available = host_memory_available()
+            # pinned where the ranks' buffers take less than 45 % of the host's free memory, pageable up to 80 % (1024^3 on 2
+            # GPUs: 2 x 82 GB), else no end-to-end leg
+            pin = min_over_ranks(1.0 if (available == 0 or host_bytes * world < 0.45 * available) else 0.0) > 0
+            fits = min_over_ranks(1.0 if (available == 0 or host_bytes * world < 0.80 * available) else 0.0) > 0
+            if not fits:
+                raise RuntimeError(f"host staging buffers of {host_bytes * world / 1e9:.0f} GB do not fit {available / 1e9:.0f} GB of host memory")
+            affinity = bind_near_gpu(local_rank)
+            failure = None
+            try:
+                if pin:
+                    pinned = torch.empty((q_count,) + domain.padded_length, dtype=torch.float64 if element == 8 else torch.float32,
+                                         pin_memory=True)
+                    algorithm.distribution.array = pinned.numpy()
+                else:
+                    algorithm.distribution.array = np.empty((q_count,) + domain.padded_length, dtype=domain.dtype)
+                algorithm.pack()                     # current state -> host array (first-touches the pages)
+            except Exception as error:  # noqa: BLE001 -- reported by every rank below
+                failure = str(error)[:200]
+            agree(failure is None, f"host buffer or first download failed on a rank ({failure or 'another rank'})")
+            # warm-up of everything the timed region uses for the first time: the observables' partial sums and their
+            # all-reduce (NCCL sets its channels up on the first collective of a communicator), the SM clocks
+            for iteration in range(1, 1 + max(args.warmup, 20)):
+                check(algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2))
+                algorithm.observables()
+            barrier()
+            t0 = time.perf_counter()
+            algorithm.unpack()                       # H2D of the whole SoA distribution from pinned host memory
+            t1 = time.perf_counter()
+            energy = 0.0
+            for iteration in range(1, args.steps + 1):
+                algorithm._lib.mlbm_step(algorithm._ctx, iteration, 2)   # isStored = observables only
+                energy = algorithm.observables()[0]  # D2H read of the step's scalar results
+            t2 = time.perf_counter()
+            algorithm.pack()                         # D2H of the whole distribution
+            t3 = time.perf_counter()
+            barrier()
+            e2e_seconds = max_over_ranks(time.perf_counter() - t0)
+            e2e_value = nodes_global * args.steps / e2e_seconds / 1e6
+            distribution_bytes = q_count * nodes_local * element
+            return {"value": e2e_value, "unit": UNIT,
+                    "h2d_bytes_per_step": distribution_bytes / args.steps,
+                    "d2h_bytes_per_step": distribution_bytes / args.steps + 32,
+                    "note": "per rank; timed region: unpack (H2D of all populations from pinned host memory) + K synchronous "
+                            "mlbm_step calls each followed by a D2H read of the all-reduced observables + pack (D2H of all "
+                            "populations); population bytes amortised over K; max over ranks", "last_energy": energy,
+                    "unpack_ms": max_over_ranks((t1 - t0) * 1e3), "steps_ms": max_over_ranks((t2 - t1) * 1e3),
+                    "pack_ms": max_over_ranks((t3 - t2) * 1e3),
+                    "h2d_GBps": distribution_bytes / (t1 - t0) / 1e9, "d2h_GBps": distribution_bytes / (t3 - t2) / 1e9,
+                    "host_buffer": "pinned" if pin else "pageable (pinning it would take more than 45 % of the host's free memory)",
+                    "host_buffer_numa_bound": affinity is not None}
+        except Exception as error:  # noqa: BLE001 -- the device-resident headline above stands; the line says what happened
+            return {"value": None, "unit": UNIT, "error": str(error)[:300]}
+        finally:
+            if affinity is not None:
+                os.sched_setaffinity(0, affinity)
+
+    if not args.no_e2e:
+        timeout = float(getattr(args, "e2e_timeout", 300))
+
+        def give_up():
+            if rank == 0:
+                line["e2e"] = {"value": None, "unit": UNIT, "error": f"the end-to-end leg did not finish within {timeout:.0f} s"}
+                sys.stdout.write(json.dumps(line) + "\n")
+                sys.stdout.flush()
+            os._exit(0)
+
+        watchdog = threading.Timer(timeout, give_up)
+        watchdog.daemon = True
+        watchdog.start()
+        e2e = end_to_end()
+        watchdog.cancel()
+        if rank == 0:
+            line["e2e"] = e2e
+
+    cpu = cpu_baseline_leg() if (rank == 0 and world == 1 and not args.no_cpu_baseline
+                                 and workload_name == "d3q19_bgk_256") else None
+    if rank == 0 and cpu is not None:
+        line["cpu_baseline"] = cpu
+    algorithm.close()
 
     # ---- the other BASELINE configs at this GPU count.  The headline line above is final; whatever happens below
     # (an exception, a rank that stops answering) it is printed, by the watchdog if need be.
@@ -889,6 +919,7 @@ def main() -> int:
     parser.add_argument("--also", default="auto", choices=["auto", "on", "off"],
                         help="secondary workloads (the other BASELINE configs at this GPU count) under \"also\" in the "
                              "JSON line; auto = with the default headline workload only")
+    parser.add_argument("--e2e-timeout", type=int, default=300, help="watchdog of the host-buffer end-to-end leg, seconds")
     parser.add_argument("--also-timeout", type=int, default=300, help="watchdog of the secondary workloads, seconds")
     args = parser.parse_args()
     args.warmup = max(args.warmup, 3)
