@@ -345,3 +345,51 @@ def test_alpha_statistics_follow_the_alpha_field():
     assert abs(low - ref.alpha.min()) <= 1e-9 and abs(high - ref.alpha.max()) <= 1e-9
     with Algorithm(make_config(lattice="D2Q9", shape=(8, 8, 1))) as bgk:
         assert bgk.alpha_statistics() == (0.0, 2.0, 2.0)
+
+
+def test_newton_statistics_count_the_solves_of_a_step():
+    """mlbm_newton_statistics: nodes that took the Newton solve and the evaluations of (F, F') they needed in the steps between
+    the two calls, against the oracle's branch and iteration bookkeeping (solveAlpha, Collision.h:328-349; EntropicStep.h:111-140).
+    A node within rounding of a branch threshold may fall on the other side: a budget of 1 % of the nodes."""
+    from helpers import run_oracle
+    for lattice, shape in (("D2Q9", (12, 140, 1)), ("D3Q27", (6, 5, 9))):
+        cfg = make_config(lattice=lattice, shape=shape, collision="ELBM", forcing_scheme="Guo", force="Kolmogorov", tau=0.55,
+                          amplitude=(1e-4, 1e-4, 1e-4), wavelength=(8.0, 8.0, 8.0))
+        f0 = O.synthetic_populations(cfg, eps=2e-2)
+        with Algorithm(cfg) as algorithm:
+            algorithm.distribution.set_interior(f0)
+            algorithm.unpack()
+            assert algorithm.newton_statistics(start=True) == (0, 0)
+            algorithm.iterate(1)
+            solved, evaluations = algorithm.newton_statistics()
+            assert algorithm.newton_statistics() == (0, 0)      # counting stopped with the read
+        ref = run_oracle(cfg, f0, 1)
+        newton = ref.branch >= 2
+        budget = max(2, int(0.01 * newton.size))
+        assert abs(solved - int(newton.sum())) <= budget
+        assert abs(evaluations - int(ref.iterations[newton].sum())) <= 4 * budget
+        assert solved > 0.5 * newton.size and evaluations >= solved
+    with Algorithm(make_config(lattice="D2Q9", shape=(8, 8, 1))) as bgk:
+        assert bgk.newton_statistics(start=True) == (0, 0) and bgk.newton_statistics() == (0, 0)
+
+
+@pytest.mark.parametrize("lattice,shape", [("D2Q9", (5, 7, 1)), ("D3Q19", (4, 3, 5)), ("D2Q13", (6, 5, 1))])
+def test_halo_space_download_is_the_periodic_padding_of_the_distribution(lattice, shape):
+    """mlbm_download_halo_distribution: Distribution::getHaloDataPrevious() as a host array in the reference's halo space hSD
+    (Domain.h:173-283) -- local extents + 2 dimH per used dimension, every halo cell the periodic image (one rank)."""
+    import ctypes
+    from metalbm_b200.capi import check
+    cfg = make_config(lattice=lattice, shape=shape, tau=0.6)
+    f0 = O.synthetic_populations(cfg, eps=1e-2)
+    dim, q, celerity, _ = O.lattice(lattice)
+    halo = int(np.abs(celerity).max())
+    with Algorithm(cfg) as algorithm:
+        algorithm.distribution.set_interior(f0)
+        algorithm.unpack()
+        extents = [n + 2 * halo if d < dim else 1 for d, n in enumerate(shape)]
+        out = np.full([q] + extents, np.nan)
+        check(algorithm._lib.mlbm_download_halo_distribution(algorithm._ctx, out.ctypes.data, out.size))
+        pad = [(0, 0)] + [(halo, halo) if d < dim else (0, 0) for d in range(3)]
+        assert np.array_equal(out, np.pad(f0, pad, mode="wrap"))
+        with pytest.raises(RuntimeError, match="needs dimQ"):
+            check(algorithm._lib.mlbm_download_halo_distribution(algorithm._ctx, out.ctypes.data, out.size - 1))
