@@ -367,7 +367,8 @@ def test_newton_statistics_count_the_solves_of_a_step():
         newton = ref.branch >= 2
         budget = max(2, int(0.01 * newton.size))
         assert abs(solved - int(newton.sum())) <= budget
-        assert abs(evaluations - int(ref.iterations[newton].sum())) <= 4 * budget
+        expected = int(ref.iterations[newton].sum())
+        assert abs(evaluations - expected) <= max(4 * budget, 0.05 * expected)   # a convergence test within rounding of 1e-8 costs one more
         assert solved > 0.5 * newton.size and evaluations >= solved
     with Algorithm(make_config(lattice="D2Q9", shape=(8, 8, 1))) as bgk:
         assert bgk.newton_statistics(start=True) == (0, 0) and bgk.newton_statistics() == (0, 0)
