@@ -1,5 +1,6 @@
 // metaLBM/Initialize.h (B200 drop-in) -- initDensity / initVelocity / initForce / initAlpha / initDistribution
-// (Initialize.h:19-148).  The field initialisers fill host arrays; initDistribution evaluates f = feq(rho, u) ON THE
+// (Initialize.h:19-148).  The field initialisers fill host arrays; initDistribution reads the checkpoint of startIteration
+// when that is not 0 (Initialize.h:119-124) and otherwise evaluates f = feq(rho, u) ON THE
 // DEVICE (mlbm_init_equilibrium) and brings the result back into the Distribution's local array, so the host copy
 // is what the reference would hold before Algorithm::unpack.
 #pragma once
@@ -9,6 +10,7 @@
 #include "Context.h"
 #include "Distribution.h"
 #include "Field.h"
+#include "Writer.h"
 
 namespace lbm {
 
@@ -57,8 +59,16 @@ Distribution<T, architecture> initDistribution(Field<T, 1, architecture, true>& 
   Distribution<T, architecture> distributionR;
   mlbm_ctx* context = b200::Context::get();
   const size_t n = FFTWInit::numberElements, pY = lSD::pLength()[d::Y], pZ = lSD::pLength()[d::Z];
-  LBM_B200_CALL(mlbm_init_equilibrium(context, densityField.getData(n), velocityField.getData(n), n, pY, pZ));
-  LBM_B200_CALL(mlbm_download_distribution(context, distributionR.getData(n), n, pY, pZ));
+  if (startIteration == 0) {
+    LBM_B200_CALL(mlbm_init_equilibrium(context, densityField.getData(n), velocityField.getData(n), n, pY, pZ));
+    LBM_B200_CALL(mlbm_download_distribution(context, distributionR.getData(n), n, pY, pZ));
+  } else {
+    // restart (Initialize.h:119-124): the checkpoint DistributionWriter left at startIteration
+    DistributionReader_ distributionReader(prefix);
+    distributionReader.openFile(startIteration);
+    distributionReader.readDistribution(distributionR);
+    distributionReader.closeFile();
+  }
   return distributionR;
 }
 

@@ -2,9 +2,10 @@
 // communicationT, overlappingT>` with the reference's constructor-and-compute() shape (Routine.h:23-241): builds the
 // field list, the equilibrium distribution, the communication and the algorithm, then runs the time loop
 //     algorithm.unpack; for it: algorithm.isStored = ...; algorithm.iterate(...); analyses      (Routine.h:90-154)
-// The HDF5 field / checkpoint writers, the FFT analyses and the performance table of the reference are the CALLERS
-// of the hot path and are out of scope; the scalar observables are kept because they are
-// device reductions of the step itself.
+// The HDF5 / XDMF field writers and the performance table of the reference are CALLERS of the hot path and out of scope
+// (SURVEY.md section 2); the scalar observables and spectra are kept because they are device reductions of the step itself,
+// and the checkpoint of the distribution (backUpStep, Routine.h:212-216; restart from startIteration, Initialize.h:119-124)
+// because it is the data format either side of the path.
 #pragma once
 
 #include <chrono>
@@ -34,6 +35,7 @@ class Routine {
   Algorithm_ algorithm;
   ScalarAnalysisList<T, architecture> scalarAnalysisList;
   SpectralAnalysisList<T, architecture> spectralAnalysisList;   // Routine.h:52, 78-79
+  DistributionWriter_ distributionWriter;                        // Routine.h:45, 67
   double computationTime = 0, communicationTime = 0, totalTime = 0;
 
  public:
@@ -43,7 +45,7 @@ class Routine {
         distribution(initDistribution<T, architecture>(fieldList.density, fieldList.velocity, defaultStream)),
         algorithm(fieldList, distribution, communication),
         scalarAnalysisList(algorithm, scalarAnalysisStep, startIteration),
-        spectralAnalysisList(algorithm, spectralAnalysisStep, startIteration) {}
+        spectralAnalysisList(algorithm, spectralAnalysisStep, startIteration), distributionWriter(prefix) {}
 
   FieldList<T, architecture>& getFieldList() { return fieldList; }
   Distribution<T, architecture>& getDistribution() { return distribution; }
@@ -62,6 +64,12 @@ class Routine {
       if (spectralAnalysisList.getIsAnalyzed(iteration)) spectralAnalysisList.writeAnalyses(iteration);   // Routine.h:227-229
       communicationTime += algorithm.getCommunicationTime();
       computationTime += algorithm.getComputationTime();
+      if (distributionWriter.getIsBackedUp(iteration)) {   // Routine.h:212-216
+        algorithm.pack(defaultStream);
+        distributionWriter.openFile(iteration);
+        distributionWriter.writeDistribution(distribution);
+        distributionWriter.closeFile();
+      }
     }
     defaultStream.synchronize();
     totalTime = std::chrono::duration<double>(Clock::now() - t0).count();

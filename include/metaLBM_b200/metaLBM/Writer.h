@@ -12,10 +12,14 @@
 #include <cstdio>
 #include <string>
 
+#include "Context.h"
 #include "Options.h"
 
 namespace lbm {
 namespace b200 {
+
+// iteration is a multiple of period; a period of 0 means never (the reference divides by it unguarded)
+inline bool isDue(unsigned int iteration, unsigned int period) { return period != 0 && iteration % period == 0; }
 
 // an append-only text table; every call opens and closes the file, like the reference's writers do
 class AnalysisTable {
@@ -37,7 +41,7 @@ class AnalysisTable {
   AnalysisTable(const std::string& prefix_in, const std::string& name, unsigned int startIteration, unsigned int period_in)
       : folder("../output/" + prefix_in), path(folder + "/" + name + "_" + std::to_string(startIteration) + ".dat"), period(period_in) {}
 
-  bool due(unsigned int iteration) const { return period != 0 && iteration % period == 0; }  // 0 = never (the reference divides by it)
+  bool due(unsigned int iteration) const { return isDue(iteration, period); }
   void header(const std::string& text) const {
     if (std::FILE* file = open("w")) { std::fprintf(file, "%s\n", text.c_str()); std::fclose(file); }
   }
@@ -98,5 +102,66 @@ class SpectralAnalysisWriter {
   }
 };
 typedef SpectralAnalysisWriter<dataT, InputOutputFormat::ascii> SpectralAnalysisWriter_;
+
+// DistributionWriter<T, InputOutput::HDF5> (Writer.h:400-445) and DistributionReader<T, InputOutput::HDF5> (Reader.h:119-157):
+// the checkpoint `../output/<prefix>/distribution-<iteration>` -- dimQ data sets "distribution<iQ>" of the padded global box,
+// every rank its hyperslab.  Same call sequence as the reference (getIsBackedUp / openFile / writeDistribution / closeFile;
+// openFile / readDistribution / closeFile), same data-set layout; the container is the flat one of mlbm_checkpoint_write
+// (extension .mlbm; tools/checkpoint_to_hdf5.py converts to and from the reference's .h5) because this build has no HDF5.
+// writeDistribution saves the DEVICE state, which is what Algorithm::pack has just copied into `distribution`
+// (Routine.h:212-216); readDistribution loads it to the device AND into the host array.
+namespace b200 {
+inline std::string checkpointPath(const std::string& filePrefix, unsigned int iteration, bool create) {
+  const std::string folder = "../output/" + filePrefix;
+  if (create) {
+    ::mkdir("../output", 0777);
+    ::mkdir(folder.c_str(), 0777);
+  }
+  return folder + "/distribution-" + std::to_string(iteration) + ".mlbm";
+}
+}  // namespace b200
+
+template <class T, InputOutput inputOutput>
+class DistributionWriter {};
+
+template <class T>
+class DistributionWriter<T, InputOutput::HDF5> {
+  const std::string filePrefix;
+  std::string path;
+  unsigned int iteration = 0;
+
+ public:
+  DistributionWriter(const std::string& filePrefix_in) : filePrefix(filePrefix_in) {}
+  bool getIsBackedUp(const unsigned int iteration_in) { return b200::isDue(iteration_in, backUpStep); }  // Writer.h:412-414
+  void openFile(const unsigned int iteration_in) {
+    iteration = iteration_in;
+    path = b200::checkpointPath(filePrefix, iteration_in, true);   // every rank: mkdir is idempotent, nobody waits for rank 0
+  }
+  template <class Distribution_>
+  void writeDistribution(Distribution_&) { LBM_B200_CALL(mlbm_checkpoint_write(b200::Context::get(), path.c_str(), iteration)); }
+  void closeFile() {}
+};
+typedef DistributionWriter<dataT, InputOutput::HDF5> DistributionWriter_;
+
+template <class T, InputOutput inputOutput>
+class DistributionReader {};
+
+template <class T>
+class DistributionReader<T, InputOutput::HDF5> {
+  const std::string filePrefix;
+  std::string path;
+
+ public:
+  DistributionReader(const std::string& filePrefix_in) : filePrefix(filePrefix_in) {}
+  void openFile(const unsigned int iteration) { path = b200::checkpointPath(filePrefix, iteration, false); }
+  template <class Distribution_>
+  void readDistribution(Distribution_& distribution) {
+    LBM_B200_CALL(mlbm_checkpoint_read(b200::Context::get(), path.c_str(), nullptr));
+    LBM_B200_CALL(mlbm_download_distribution(b200::Context::get(), distribution.getData(FFTWInit::numberElements), FFTWInit::numberElements,
+                                             lSD::pLength()[d::Y], lSD::pLength()[d::Z]));
+  }
+  void closeFile() {}
+};
+typedef DistributionReader<dataT, InputOutput::HDF5> DistributionReader_;
 
 }  // namespace lbm

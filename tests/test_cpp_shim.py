@@ -24,13 +24,13 @@ LIBDIR = Path(os.environ.get("MLBM_SHIM_LIBDIR", ROOT / "metalbm_b200"))   # tes
 
 def compile_example(tmp_path, source, name, lattice, shape, collision="BGK", equilibrium="TruncationMa3", scheme="Guo",
                     force="Kolmogorov", tau=0.55, nprocs=1, overlap="Off", link=True, input_file="Input_generic.in", steps=100,
-                    compile_only=False, spectral_step=0):
+                    compile_only=False, spectral_step=0, defines=()):
     output = tmp_path / name
     command = ["g++", "-std=c++14", "-O1", "-Wall", "-Wextra", "-Werror",
                f"-DNPROCS={nprocs}", "-DNTHREADS=1", f"-DGLOBAL_LENGTH_X={shape[0]}", f"-DGLOBAL_LENGTH_Y={shape[1]}",
                f"-DGLOBAL_LENGTH_Z={shape[2]}", '-DLBM_POSTFIX="test"', f"-DLBM_LATTICE={lattice}", f"-DLBM_COLLISION={collision}",
                f"-DLBM_EQUILIBRIUM={equilibrium}", f"-DLBM_SCHEME={scheme}", f"-DLBM_FORCE={force}", f"-DLBM_TAU={tau}",
-               f"-DLBM_OVERLAP={overlap}", f"-DLBM_STEPS={steps}", f"-DLBM_SPECTRAL_STEP={spectral_step}",
+               f"-DLBM_OVERLAP={overlap}", f"-DLBM_STEPS={steps}", f"-DLBM_SPECTRAL_STEP={spectral_step}", *defines,
                "-include", str(ROOT / "examples" / input_file), "-I", str(INCLUDE), str(ROOT / "examples" / source),
                "-o", str(output)]
     if compile_only:
@@ -247,3 +247,29 @@ def test_reference_style_routine_runs(tmp_path, cuda_lib):
             assert abs(row[1] - obs[0]) <= 1e-9 * abs(obs[0])
             assert abs(row[2] - obs[1]) <= 1e-9 * abs(obs[1])
             assert abs(extras[iteration // 50 - 1][2] - obs[3]) <= 1e-12 * abs(obs[3])
+
+
+@pytest.mark.gpu
+def test_routine_backs_up_and_restarts_from_the_checkpoint(tmp_path, cuda_lib):
+    """Routine::compute with backUpStep (Routine.h:212-216: pack + DistributionWriter) and a second binary with
+    startIteration != 0 (initDistribution reads the checkpoint, Initialize.h:119-124): the restarted run writes the SAME final
+    checkpoint as the uninterrupted one, bit for bit (BGK; the data sets are the reference's padded global box)."""
+    import json
+    shape = (24, 20, 1)
+    common = dict(lattice="D2Q9", shape=shape, scheme="Guo", force="Kolmogorov", tau=0.6)
+    whole = compile_example(tmp_path, "main_gpu.cpp", "whole", steps=8, defines=("-DLBM_BACKUP_STEP=4",), **common)
+    resumed = compile_example(tmp_path, "main_gpu.cpp", "resumed", steps=8, defines=("-DLBM_BACKUP_STEP=4", "-DLBM_START=4"), **common)
+    run = tmp_path / "run"
+    run.mkdir()
+    result = subprocess.run([str(whole)], capture_output=True, text=True, cwd=run, timeout=300)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    folder = tmp_path / "output" / "test"
+    first = (folder / "distribution-8.mlbm").read_bytes()
+    header = json.loads((folder / "distribution-4.mlbm").read_bytes()[:4096].decode())
+    assert header["iteration"] == 4 and header["dimQ"] == 9 and header["padded_global_length"] == [24, 22, 1]
+    (folder / "distribution-8.mlbm").unlink()
+    result = subprocess.run([str(resumed)], capture_output=True, text=True, cwd=run, timeout=300)
+    assert result.returncode == 0, result.stdout[-2000:] + result.stderr[-2000:]
+    assert (folder / "distribution-8.mlbm").read_bytes() == first
+    data = np.frombuffer(first[4096:], dtype=np.float64).reshape(9, 24, 22, 1)[:, :, :20]
+    assert abs(data.sum() / (24 * 20) - 1.0) < 1e-2 and np.isfinite(data).all()      # a density peak of 3 on a background of 1
