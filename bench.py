@@ -773,7 +773,7 @@ def run_ours(args) -> int:
         line = {
             "metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": device_ms / args.steps, "higher_is_better": True, "scaling": work["scaling"], "vs_baseline": None,
-            "dtype": "f64" if element == 8 else "f32 storage, f64 arithmetic", "data": "synthetic",
+            "dtype": "f64" if element == 8 else ("f32 storage, f64 arithmetic" if entropic else "f32"), "data": "synthetic",
             "config": {"workload": f"{work['text']}; global {shape[0]}x{shape[1]}x{shape[2]}", "name": workload_name,
                        "lattice": work["lattice"], "collision": work["collision"], "equilibrium": work["equilibrium"],
                        "forcing": f"{work['scheme']}/{work['force']}", "tau": work["tau"], "perturbation_eps": work["eps"],
