@@ -9,8 +9,11 @@ import pytest
 
 @pytest.mark.gpu
 def test_multi_rank_cases_ran_wherever_the_box_has_the_gpus(request):
+    import os
     import torch
     from conftest import GPU_OUTCOMES
+    if os.environ.get("PYTEST_XDIST_WORKER"):
+        pytest.skip("the outcomes of the other xdist workers are not visible here: the guard needs a serial run (the driver's)")
     devices = torch.cuda.device_count()
     wrongly_skipped = [(node, need) for node, need in GPU_OUTCOMES["skipped_needing"] if need <= devices]
     assert not wrongly_skipped, f"{devices} GPUs present, yet skipped: {wrongly_skipped[:5]}"
