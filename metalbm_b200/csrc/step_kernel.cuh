@@ -164,9 +164,9 @@ template <int I, int N, class F> __device__ __forceinline__ void staticFor(F&& f
 //   centre c; invc = 1/c rounded to a double with a ZERO LOW WORD, logc = double(-ln invc) (log_table.inc, generated with
 //   100-digit arithmetic by gen_log_table.py); r = fma(v, invc, -1) is exact to rounding and |r| < 2^-9 + 2^-20, so
 //   ln v = logc + (r - r^2/2 + ... + r^5/5) with a truncation error below 1e-17.
-// The table is two arrays -- the high words of invc (4 bytes) and logc (8 bytes): 12 bytes of shared-memory traffic per
-// logarithm, not 16.  ncu (profiles/r02b_*): with 16-byte entries the shared-memory pipe was busier (65 %) than the FP64
-// pipe (53 %) in the D3Q27 entropic kernel.
+// Two table formats (LogTable<SPLIT>): {invc, logc} pairs, one 16-byte load per logarithm, or two arrays -- the high words of
+// invc (4 bytes) and logc (8 bytes) -- 12 bytes and a third fewer shared-memory wavefronts, but one more load and two more
+// integer instructions.  Measured (profiles/r02d_table_alphamax_variants.txt): the pairs win by 1-3 % on every lattice.
 // N independent arguments advance in lock step: every Horner step is issued for all N before the next one, which
 // gives the FP64 pipe N independent dependency chains per warp.
 // `range` accumulates the maximum table index as an unsigned number: it stays below 1024 exactly when every argument
@@ -276,10 +276,11 @@ __device__ __forceinline__ double fastLog(double v, const Table& table) {
 //     memory and thread i solves the i-th listed node (any thread can read any node's column), so the FP64 cost follows
 //     the number of such nodes instead of the number of warps that contain at least one of them;
 //   * one block handles several x planes in a row, staging the logarithm table and the per-row constants once.
-// The solving thread reads the column of its node ONCE into registers where the register file allows (kColumnRegisters:
-// both F2 and N2 for Q <= 13, N2 only up to Q = 27) and unrolls the loops over q; the evaluations then cost 12 bytes of
-// shared-memory traffic per population (the table) instead of 28.  Lattices beyond that keep the rolled loops over the
-// shared-memory column.
+// Where the register file allows (columnRegisters(Q): both F2 and N2 for Q <= 13) the solving thread reads the column of its
+// node ONCE into registers and unrolls the loops over q: the evaluations then cost only the table lookup in shared-memory
+// traffic.  Larger lattices keep the rolled loops over the shared-memory column: with N2 (or both) in registers the D3Q27
+// kernel needs 168 registers, spills, and loses 20 % (profiles/r02c_results.txt).  The kernels are bound by instruction
+// issue, FP64 instructions counting double (profiles/r02_issue_model.md): every choice below is the one with fewer instructions.
 //
 // Arithmetic of one evaluation.  The populations of one speed class c (|c_q|^2 = 0, 1, 2, 3: same weight w_c) are
 // stored next to each other and SCALED by 2^k_c, k_c the integer with w_c 2^k_c in [0.7, 1.4): the scaling is exact
